@@ -1,0 +1,460 @@
+// Section A of include/soglu.h: context, device-resident block pool, task-graph upload,
+// factor and solve entry points.  All numeric work is done by the kernels in executor.cu
+// and trsv.cu; there is no CPU path -- every entry point fails if CUDA is unavailable.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../../include/soglu.h"
+#include "executor.cuh"
+#include "tasks.h"
+
+namespace soglu {
+void set_error(const std::string& s);
+}
+
+using namespace soglu;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct soglu_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int exec_grid = 0, trsv_grid = 0;
+    // options
+    int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
+    int64_t opt_fuse_sub = 1;
+    int64_t opt_grid = 0;          // override CTA count (0 = all resident)
+
+    // host-side description (borrowed arrays are copied)
+    int64_t n_ids = 0, n_input = 0;
+    std::vector<int32_t> input_ids;
+    DevBuf in_dense;               // staging for dense input blocks until slots are known
+    bool inputs_pending = false;
+    int64_t n_ops = 0;
+    std::vector<int32_t> src, src2, result, result2;
+    std::vector<uint8_t> op;
+    std::vector<int32_t> L_ids, L_brow, L_bcol, U_ids, U_brow, U_bcol;
+    int32_t n_block_rows = 0;
+    int symmetric = 0;
+    bool have_blocks = false, have_graph = false, have_factors = false;
+
+    // compiled state
+    bool compiled = false;
+    bool factored = false;
+    TaskGraph G;
+    std::vector<int32_t> level_order;   // tasks sorted by level (debug executor)
+    std::vector<int64_t> level_ptr;
+    DevBuf pool, tasks, pairs, succ, dep0, dep, ready, counters, initial;
+    // solve structures
+    DevBuf l_ptr, l_col, l_slot, l_diag, u_ptr, u_col, u_slot, u_diag, d_b, d_y, d_x, flags;
+    int64_t nL_off = 0, nU_off = 0;
+    int64_t launches = 0;
+    double h2d = 0, d2h = 0;
+};
+
+namespace {
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            soglu::set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                \
+            return SOGLU_ERR_CUDA;                                                                \
+        }                                                                                         \
+    } while (0)
+
+int fail(int code, const std::string& msg) { soglu::set_error(msg); return code; }
+
+template <typename T>
+int upload(DevBuf& b, const std::vector<T>& v, soglu_ctx* c) {
+    CU(b.alloc(std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    c->h2d += (double)(v.size() * sizeof(T));
+    return SOGLU_OK;
+}
+
+// CSR over off-diagonal factor blocks of one triangle; lower: cols < row, upper: cols > row.
+// transpose = true builds the structure of the transposed factor (CSC of L for L^T).
+int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<int32_t>& br, const std::vector<int32_t>& bc,
+              bool upper, bool transpose, DevBuf& dptr, DevBuf& dcol, DevBuf& dslot, DevBuf& ddiag, int64_t& n_off) {
+    const int n = c->n_block_rows;
+    std::vector<int64_t> ptr(n + 1, 0);
+    std::vector<int32_t> diag(n, -1);
+    const size_t m = ids.size();
+    for (size_t k = 0; k < m; k++) {
+        int r = transpose ? bc[k] : br[k], cc = transpose ? br[k] : bc[k];
+        if (r < 0 || r >= n || cc < 0 || cc >= n) return fail(SOGLU_ERR_ARG, "factor block coordinate out of range");
+        if (ids[k] <= 0 || ids[k] >= c->n_ids) return fail(SOGLU_ERR_ARG, "factor block id out of range");
+        if (r == cc) { diag[r] = c->G.slot_of[ids[k]]; continue; }
+        if (upper ? (cc < r) : (cc > r)) return fail(SOGLU_ERR_ARG, "factor block on the wrong side of the diagonal");
+        ptr[r + 1]++;
+    }
+    for (int r = 0; r < n; r++) {
+        if (diag[r] <= 0) return fail(SOGLU_ERR_GRAPH, "factor has no diagonal block in block row " + std::to_string(r));
+        ptr[r + 1] += ptr[r];
+    }
+    n_off = ptr[n];
+    std::vector<int32_t> col(n_off), slot(n_off);
+    std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
+    for (size_t k = 0; k < m; k++) {
+        int r = transpose ? bc[k] : br[k], cc = transpose ? br[k] : bc[k];
+        if (r == cc) continue;
+        col[pos[r]] = cc;
+        slot[pos[r]] = c->G.slot_of[ids[k]];
+        pos[r]++;
+    }
+    // ascending columns inside each row
+    std::vector<std::pair<int32_t, int32_t>> tmp;
+    for (int r = 0; r < n; r++) {
+        tmp.clear();
+        for (int64_t q = ptr[r]; q < ptr[r + 1]; q++) tmp.push_back({col[q], slot[q]});
+        std::sort(tmp.begin(), tmp.end());
+        for (int64_t q = ptr[r]; q < ptr[r + 1]; q++) { col[q] = tmp[q - ptr[r]].first; slot[q] = tmp[q - ptr[r]].second; }
+    }
+    for (int64_t q = 0; q < n_off; q++)
+        if (slot[q] <= 0) return fail(SOGLU_ERR_GRAPH, "factor block is never produced by the operation list");
+    int rc;
+    if ((rc = upload(dptr, ptr, c))) return rc;
+    if ((rc = upload(dcol, col, c))) return rc;
+    if ((rc = upload(dslot, slot, c))) return rc;
+    if ((rc = upload(ddiag, diag, c))) return rc;
+    return SOGLU_OK;
+}
+
+int pack_pending_inputs(soglu_ctx* c) {
+    if (!c->inputs_pending) return SOGLU_OK;
+    std::vector<int32_t> slots(c->n_input);
+    for (int64_t k = 0; k < c->n_input; k++) slots[k] = c->G.slot_of[c->input_ids[k]];
+    DevBuf dslots;
+    int rc = upload(dslots, slots, c);
+    if (rc) return rc;
+    CU(launch_pack_blocks(c->pool.as<double>(), c->in_dense.as<double>(), dslots.as<int32_t>(), c->n_input, c->stream));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    dslots.release();
+    c->in_dense.release();
+    c->inputs_pending = false;
+    return SOGLU_OK;
+}
+
+int finalize(soglu_ctx* c) {
+    if (c->compiled) return pack_pending_inputs(c);
+    if (!c->have_blocks || !c->have_graph || !c->have_factors)
+        return fail(SOGLU_ERR_ARG, "soglu_set_blocks, soglu_set_graph and soglu_set_factors must precede soglu_factor");
+    std::vector<int32_t> keep;
+    keep.reserve(c->L_ids.size() + c->U_ids.size());
+    keep.insert(keep.end(), c->L_ids.begin(), c->L_ids.end());
+    keep.insert(keep.end(), c->U_ids.begin(), c->U_ids.end());
+    CompileOptions co;
+    co.fuse_sub = c->opt_fuse_sub != 0;
+    std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
+                                    c->result.data(), c->result2.data(), keep, co, c->G);
+    if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
+    TaskGraph& G = c->G;
+    // the op arrays are no longer needed on the host
+    std::vector<int32_t>().swap(c->src); std::vector<int32_t>().swap(c->src2);
+    std::vector<int32_t>().swap(c->result); std::vector<int32_t>().swap(c->result2);
+    std::vector<uint8_t>().swap(c->op);
+
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t pool_bytes = (size_t)G.n_slots * BLK_BYTES;
+    const size_t aux = G.tasks.size() * (sizeof(Task) + 12) + G.pairs.size() * sizeof(Pair) + G.succ.size() * 4 + (256u << 20);
+    if (pool_bytes + aux > free_b) {
+        char m[256];
+        snprintf(m, sizeof m, "block pool needs %.1f GB (+%.1f GB graph) but only %.1f GB of HBM are free", pool_bytes * 1e-9, aux * 1e-9, free_b * 1e-9);
+        return fail(SOGLU_ERR_OOM, m);
+    }
+    CU(c->pool.alloc(pool_bytes));
+    CU(cudaMemsetAsync(c->pool.p, 0, pool_bytes, c->stream));
+    int rc;
+    if ((rc = upload(c->tasks, G.tasks, c))) return rc;
+    if ((rc = upload(c->pairs, G.pairs, c))) return rc;
+    if ((rc = upload(c->succ, G.succ, c))) return rc;
+    {
+        std::vector<int32_t> d0(G.tasks.size());
+        for (size_t t = 0; t < G.tasks.size(); t++) d0[t] = G.tasks[t].n_deps;
+        if ((rc = upload(c->dep0, d0, c))) return rc;
+    }
+    if ((rc = upload(c->initial, G.initial, c))) return rc;
+    CU(c->dep.alloc(std::max<size_t>(G.tasks.size(), 1) * 4));
+    CU(c->ready.alloc(std::max<size_t>(G.tasks.size(), 1) * 4));
+    CU(c->counters.alloc(256));
+    // level order for the debug executor
+    {
+        const int64_t nt = (int64_t)G.tasks.size();
+        c->level_ptr.assign(G.n_levels + 1, 0);
+        for (int64_t t = 0; t < nt; t++) c->level_ptr[G.tasks[t].level + 1]++;
+        for (int l = 0; l < G.n_levels; l++) c->level_ptr[l + 1] += c->level_ptr[l];
+        c->level_order.resize(nt);
+        std::vector<int64_t> pos(c->level_ptr.begin(), c->level_ptr.end() - 1);
+        for (int64_t t = 0; t < nt; t++) c->level_order[pos[G.tasks[t].level]++] = (int32_t)t;
+    }
+    // triangular-solve structures
+    if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, false, false, c->l_ptr, c->l_col, c->l_slot, c->l_diag, c->nL_off))) return rc;
+    if (c->symmetric) {
+        if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, true, true, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->nU_off))) return rc;
+    } else {
+        if ((rc = build_tri(c, c->U_ids, c->U_brow, c->U_bcol, true, false, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->nU_off))) return rc;
+    }
+    const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
+    CU(c->d_b.alloc(next)); CU(c->d_y.alloc(next)); CU(c->d_x.alloc(next));
+    CU(c->flags.alloc((size_t)c->n_block_rows * 2 * sizeof(int32_t)));
+    c->compiled = true;
+    return pack_pending_inputs(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+int soglu_create(soglu_ctx** out, int n_gpus, const int* device_ids) {
+    if (!out) return fail(SOGLU_ERR_ARG, "null output pointer");
+    *out = nullptr;
+    if (n_gpus != 1) return fail(SOGLU_ERR_ARG, "this build shards over one GPU per context (n_gpus must be 1)");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SOGLU_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                             " (soglu-b200 has no CPU fallback)");
+    int dev = device_ids ? device_ids[0] : 0;
+    if (dev < 0 || dev >= count) return fail(SOGLU_ERR_ARG, "device id out of range");
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(SOGLU_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100 class; kernels are built for sm_100a only");
+    soglu_ctx* c = new soglu_ctx();
+    c->device = dev;
+    c->sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+        cudaEventCreate(&c->ev1) != cudaSuccess) {
+        delete c;
+        return fail(SOGLU_ERR_CUDA, "stream/event creation failed");
+    }
+    c->exec_grid = executor_max_grid(dev);
+    c->trsv_grid = trsv_max_grid(dev);
+    if (c->exec_grid <= 0 || c->trsv_grid <= 0) {
+        std::string m = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(cudaGetLastError());
+        soglu_destroy(c);
+        return fail(SOGLU_ERR_CUDA, m);
+    }
+    *out = c;
+    return SOGLU_OK;
+}
+
+void soglu_destroy(soglu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (DevBuf* b : {&c->in_dense, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->counters, &c->initial,
+                      &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->d_b, &c->d_y, &c->d_x, &c->flags})
+        b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
+    if (!c || !key) return fail(SOGLU_ERR_ARG, "bad argument");
+    std::string k(key);
+    if (k == "exec_mode") c->opt_exec_mode = value;
+    else if (k == "fuse_sub") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_sub must be set before the first factor"); c->opt_fuse_sub = value; }
+    else if (k == "grid") c->opt_grid = value;
+    else return fail(SOGLU_ERR_ARG, "unknown option " + k);
+    return SOGLU_OK;
+}
+
+int soglu_set_blocks(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, const double* dense) {
+    if (!c || n_block_ids < 1 || n_input < 0 || (n_input > 0 && (!input_ids || !dense))) return fail(SOGLU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (c->compiled) {
+        // refactorisation with new values on the same pattern
+        if (n_block_ids != c->n_ids || n_input != c->n_input || std::memcmp(input_ids, c->input_ids.data(), n_input * sizeof(int32_t)) != 0)
+            return fail(SOGLU_ERR_ARG, "soglu_set_blocks after compilation must keep the block pattern");
+    } else {
+        c->n_ids = n_block_ids;
+        c->n_input = n_input;
+        c->input_ids.assign(input_ids, input_ids + n_input);
+    }
+    const size_t bytes = (size_t)n_input * BLK * BLK * sizeof(double);
+    CU(c->in_dense.alloc(bytes));
+    if (bytes) CU(cudaMemcpyAsync(c->in_dense.p, dense, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->h2d += (double)bytes;
+    c->inputs_pending = true;
+    c->have_blocks = true;
+    c->factored = false;
+    return SOGLU_OK;
+}
+
+int soglu_set_graph(soglu_ctx* c, int64_t n_ops, const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,
+                    const int32_t* result2, const int32_t* stage, const int32_t* block_row, const int32_t* block_col) {
+    (void)stage; (void)block_row; (void)block_col;
+    if (!c || n_ops < 0 || (n_ops > 0 && (!src || !src2 || !op || !result || !result2))) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (c->compiled) return fail(SOGLU_ERR_ARG, "graph already compiled; create a new context for a new pattern");
+    c->n_ops = n_ops;
+    c->src.assign(src, src + n_ops); c->src2.assign(src2, src2 + n_ops);
+    c->result.assign(result, result + n_ops); c->result2.assign(result2, result2 + n_ops);
+    c->op.assign(op, op + n_ops);
+    c->have_graph = true;
+    return SOGLU_OK;
+}
+
+int soglu_set_factors(soglu_ctx* c, int64_t nL, const int32_t* L_ids, const int32_t* L_brow, const int32_t* L_bcol, int64_t nU,
+                      const int32_t* U_ids, const int32_t* U_brow, const int32_t* U_bcol, int32_t n_block_rows, int symmetric) {
+    if (!c || nL <= 0 || !L_ids || !L_brow || !L_bcol || n_block_rows <= 0) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!symmetric && (nU <= 0 || !U_ids || !U_brow || !U_bcol)) return fail(SOGLU_ERR_ARG, "U factor missing");
+    if (c->compiled) return fail(SOGLU_ERR_ARG, "graph already compiled; create a new context for a new pattern");
+    c->L_ids.assign(L_ids, L_ids + nL); c->L_brow.assign(L_brow, L_brow + nL); c->L_bcol.assign(L_bcol, L_bcol + nL);
+    if (!symmetric) { c->U_ids.assign(U_ids, U_ids + nU); c->U_brow.assign(U_brow, U_brow + nU); c->U_bcol.assign(U_bcol, U_bcol + nU); }
+    c->n_block_rows = n_block_rows;
+    c->symmetric = symmetric ? 1 : 0;
+    c->have_factors = true;
+    return SOGLU_OK;
+}
+
+int soglu_factor(soglu_ctx* c, soglu_stats* out) {
+    if (!c) return fail(SOGLU_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    const int64_t launches0 = c->launches;
+    int rc = finalize(c);
+    if (rc) return rc;
+    TaskGraph& G = c->G;
+    const int32_t nt = (int32_t)G.tasks.size();
+    int grid = c->exec_grid;
+    if (c->opt_grid > 0 && c->opt_grid < grid) grid = (int)c->opt_grid;
+    ExecParams P;
+    P.pool = c->pool.as<double>();
+    P.tasks = c->tasks.as<Task>();
+    P.pairs = c->pairs.as<Pair>();
+    P.succ = c->succ.as<int32_t>();
+    P.dep = c->dep.as<int32_t>();
+    P.ready = c->ready.as<int32_t>();
+    P.head = c->counters.as<int32_t>();
+    P.tail = c->counters.as<int32_t>() + 32;   // separate 128-byte lines
+    CU(cudaEventRecord(c->ev0, c->stream));
+    if (nt > 0) {
+        if (c->opt_exec_mode == 0) {
+            CU(cudaMemcpyAsync(c->dep.p, c->dep0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaMemsetAsync(c->ready.p, 0xff, (size_t)nt * 4, c->stream));
+            CU(cudaMemcpyAsync(c->ready.p, c->initial.p, G.initial.size() * 4, cudaMemcpyDeviceToDevice, c->stream));
+            int32_t ht[64] = {0};
+            ht[32] = (int32_t)G.initial.size();
+            CU(cudaMemcpyAsync(c->counters.p, ht, sizeof ht, cudaMemcpyHostToDevice, c->stream));
+            P.n_tasks = nt;
+            P.signal = 1;
+            CU(launch_executor(P, grid, c->stream));
+            c->launches++;
+        } else {
+            // debug: one launch per dependency level, no in-kernel signalling
+            for (int l = 0; l < G.n_levels; l++) {
+                const int64_t b = c->level_ptr[l], e = c->level_ptr[l + 1];
+                CU(cudaMemcpyAsync(c->ready.p, c->level_order.data() + b, (size_t)(e - b) * 4, cudaMemcpyHostToDevice, c->stream));
+                CU(cudaMemsetAsync(c->counters.p, 0, 256, c->stream));
+                P.n_tasks = (int32_t)(e - b);
+                P.signal = 0;
+                CU(launch_executor(P, (int)std::min<int64_t>(grid, e - b), c->stream));
+                c->launches++;
+            }
+        }
+    }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->factored = true;
+    if (out) {
+        std::memset(out, 0, sizeof *out);
+        out->seconds = ms * 1e-3;
+        out->flops = G.flops;
+        out->bytes = 0;
+        out->kernel_launches = c->launches - launches0;
+        out->tasks = nt;
+        out->pool_blocks = G.n_slots;
+        out->h2d_bytes = c->h2d;
+        out->d2h_bytes = c->d2h;
+    }
+    return SOGLU_OK;
+}
+
+int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* out) {
+    if (!c || !b_ext || !x_ext) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->factored) return fail(SOGLU_ERR_ARG, "soglu_factor must precede soglu_solve");
+    CU(cudaSetDevice(c->device));
+    const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
+    CU(cudaMemcpyAsync(c->d_b.p, b_ext, next, cudaMemcpyHostToDevice, c->stream));
+    TrsvParams P;
+    P.pool = c->pool.as<double>();
+    P.l_ptr = c->l_ptr.as<int64_t>(); P.l_col = c->l_col.as<int32_t>(); P.l_slot = c->l_slot.as<int32_t>(); P.l_diag = c->l_diag.as<int32_t>();
+    P.u_ptr = c->u_ptr.as<int64_t>(); P.u_col = c->u_col.as<int32_t>(); P.u_slot = c->u_slot.as<int32_t>(); P.u_diag = c->u_diag.as<int32_t>();
+    P.n_rows = c->n_block_rows;
+    P.b = c->d_b.as<double>(); P.y = c->d_y.as<double>(); P.x = c->d_x.as<double>();
+    P.done_l = c->flags.as<int32_t>(); P.done_u = c->flags.as<int32_t>() + c->n_block_rows;
+    P.symmetric = c->symmetric;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    CU(cudaMemsetAsync(c->flags.p, 0, (size_t)c->n_block_rows * 2 * sizeof(int32_t), c->stream));
+    CU(launch_trsv(P, std::min(c->trsv_grid, c->n_block_rows), c->stream));
+    c->launches++;
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaMemcpyAsync(x_ext, c->d_x.p, next, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->h2d += (double)next;
+    c->d2h += (double)next;
+    if (out) {
+        std::memset(out, 0, sizeof *out);
+        out->seconds = ms * 1e-3;
+        const double nblk = (double)(c->nL_off + c->nU_off + 2.0 * c->n_block_rows);
+        out->flops = 2.0 * 4096.0 * nblk;
+        out->bytes = (double)BLK * BLK * 8.0 * nblk + 8.0 * 3.0 * c->n_block_rows * BLK;
+        out->kernel_launches = 1;
+        out->tasks = 2 * (int64_t)c->n_block_rows;
+        out->pool_blocks = c->G.n_slots;
+        out->h2d_bytes = (double)next;
+        out->d2h_bytes = (double)next;
+    }
+    return SOGLU_OK;
+}
+
+int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {
+    if (!c || !out_64x64) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled yet");
+    if (id <= 0 || id >= c->n_ids) return fail(SOGLU_ERR_ARG, "block id out of range");
+    const int32_t slot = c->G.slot_of[id];
+    if (slot <= 0) return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " has no storage (never produced, or folded into a fused task)");
+    CU(cudaSetDevice(c->device));
+    DevBuf tmp;
+    CU(tmp.alloc(BLK * BLK * sizeof(double)));
+    CU(launch_unpack_block(c->pool.as<double>(), slot, tmp.as<double>(), c->stream));
+    c->launches++;
+    CU(cudaMemcpyAsync(out_64x64, tmp.p, BLK * BLK * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    tmp.release();
+    return SOGLU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+// Host-side compilation of the reference's flat operation list into the task graph of the
+// persistent executor.
+//
+// The reference executes the list stage by stage and relies on "all writers of one result
+// sit in one stage and one stream" for race freedom (BlockPlanner.cpp:270-276, 399-416).
+// Here every RESULT block becomes one task that applies all of its pending updates
+// (one CTA owns one target block, SURVEY.md App. E invariants), and dependencies are the
+// true producer -> consumer edges on block ids, so stages are not needed at run time.
+//
+// Fusions (results unchanged, op list stays the bit-exact input):
+//   * `sub` whose subtrahend is a mul/mulneg/mult chain read by nobody else is folded into
+//     that chain: R = S2 -/+ sum A*B   (removes one level of the critical path
+//     lu -> inv -> mul -> mul -> sub -> lu and one block write + two block reads).
+#include "tasks.h"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace soglu {
+namespace {
+enum : uint8_t { OP_LU = 1, OP_LOWERINV = 2, OP_UPPERINV = 3, OP_SUB = 4, OP_MUL = 8, OP_MULNEG = 9, OP_LLT = 10, OP_MULT = 11 };
+
+struct IdInfo {
+    int64_t first_writer = -1;  // op index
+    int32_t n_writers = 0;
+    int32_t n_readers = 0;      // ops reading the id
+    uint8_t kind = 0xff;        // op code of the writers
+    bool is_input = false;
+    bool keep = false;
+    bool fused_away = false;    // product folded into its single `sub` reader
+};
+}  // namespace
+
+std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_ids, int64_t n_ops,
+                          const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,
+                          const int32_t* result2, const std::vector<int32_t>& keep_ids, const CompileOptions& opt,
+                          TaskGraph& G) {
+    G = TaskGraph();
+    char msg[256];
+    if (n_ids < 1) return "n_block_ids must be >= 1";
+    std::vector<IdInfo> info(n_ids);
+    for (int64_t k = 0; k < n_input; k++) {
+        int32_t id = input_ids[k];
+        if (id <= 0 || id >= n_ids) return "input block id out of range";
+        info[id].is_input = true;
+    }
+    for (int32_t id : keep_ids)
+        if (id > 0 && id < n_ids) info[id].keep = true;
+
+    auto bad_id = [&](int32_t id) { return id < 0 || id >= n_ids; };
+    for (int64_t i = 0; i < n_ops; i++) {
+        uint8_t o = op[i];
+        if (!(o == OP_LU || o == OP_LOWERINV || o == OP_UPPERINV || o == OP_SUB || o == OP_MUL || o == OP_MULNEG || o == OP_LLT || o == OP_MULT)) {
+            snprintf(msg, sizeof msg, "op %lld: unsupported op code %d", (long long)i, (int)o);
+            return msg;
+        }
+        if (bad_id(src[i]) || bad_id(src2[i]) || bad_id(result[i]) || bad_id(result2[i]) || result[i] <= 0) {
+            snprintf(msg, sizeof msg, "op %lld: block id out of range", (long long)i);
+            return msg;
+        }
+        if (o == OP_LU && result2[i] <= 0) return "lu without second result";
+        if (src[i] == result[i] || src2[i] == result[i] || (result2[i] > 0 && (src[i] == result2[i] || result2[i] == result[i]))) {
+            snprintf(msg, sizeof msg, "op %lld reads its own result", (long long)i);
+            return msg;
+        }
+        int32_t rs[2] = {result[i], o == OP_LU ? result2[i] : 0};
+        for (int32_t r : rs) {
+            if (r <= 0) continue;
+            IdInfo& w = info[r];
+            if (w.is_input) { snprintf(msg, sizeof msg, "op %lld writes input block %d", (long long)i, r); return msg; }
+            if (w.n_writers == 0) { w.first_writer = i; w.kind = o; }
+            else {
+                bool acc = (o == OP_MUL || o == OP_MULNEG || o == OP_MULT);
+                if (w.kind != o || !acc) {
+                    snprintf(msg, sizeof msg, "block %d has writers of mixed or non-accumulating kinds", r);
+                    return msg;
+                }
+            }
+            w.n_writers++;
+        }
+        if (src[i] > 0) info[src[i]].n_readers++;
+        if (src2[i] > 0 && src2[i] != src[i]) info[src2[i]].n_readers++;
+    }
+
+    // ---- fusion decisions ------------------------------------------------------------
+    std::vector<int64_t> fused_sub_of(opt.fuse_sub ? n_ids : 0, -1);  // product id -> index of the sub op
+    if (opt.fuse_sub) {
+        for (int64_t i = 0; i < n_ops; i++) {
+            if (op[i] != OP_SUB) continue;
+            int32_t p = src[i];
+            if (p <= 0) continue;
+            IdInfo& w = info[p];
+            if (w.is_input || w.keep || w.n_writers == 0 || w.n_readers != 1) continue;
+            if (!(w.kind == OP_MUL || w.kind == OP_MULNEG || w.kind == OP_MULT)) continue;
+            if (src2[i] == p) continue;
+            w.fused_away = true;
+            fused_sub_of[p] = i;
+            G.fused_subs++;
+        }
+    }
+
+    // ---- one task per produced block (lu: one task, two blocks) -------------------------
+    // task order = order of the first contributing op, i.e. the reference's stage order
+    G.task_of.assign(n_ids, -1);
+    G.slot_of.assign(n_ids, 0);
+    std::vector<int64_t> pair_count;  // per task
+    for (int64_t i = 0; i < n_ops; i++) {
+        int32_t r = result[i];
+        IdInfo& w = info[r];
+        if (w.first_writer != i) continue;     // only the first writer opens a task
+        if (w.fused_away) continue;            // opened by its sub instead
+        Task t = {};
+        t.out = r;                              // block ids for now; slots are patched below
+        t.n_pairs = 1;
+        switch (op[i]) {
+            case OP_LU: t.type = T_LU; t.out2 = result2[i]; break;
+            case OP_LLT: t.type = T_LLT; break;
+            case OP_LOWERINV: t.type = T_LOWERINV; break;
+            case OP_UPPERINV: t.type = T_UPPERINV; break;
+            case OP_MUL: t.type = T_GEMM; t.n_pairs = w.n_writers; break;
+            case OP_MULNEG: t.type = T_GEMM; t.flags = TF_NEGATE; t.n_pairs = w.n_writers; break;
+            case OP_MULT: t.type = T_GEMM; t.flags = TF_TRANSB; t.n_pairs = w.n_writers; break;
+            case OP_SUB: {
+                int32_t p = src[i];
+                if (p > 0 && info[p].fused_away && fused_sub_of[p] == i) {
+                    const IdInfo& pw = info[p];
+                    t.type = T_GEMM;
+                    t.n_pairs = pw.n_writers;
+                    t.flags = (pw.kind == OP_MULNEG ? 0 : TF_NEGATE) | (pw.kind == OP_MULT ? TF_TRANSB : 0);
+                    if (src2[i] > 0) { t.flags |= TF_INIT; t.init = src2[i]; }
+                } else {
+                    t.type = T_SUB;
+                }
+                break;
+            }
+        }
+        int32_t tid = (int32_t)G.tasks.size();
+        G.task_of[r] = tid;
+        if (t.type == T_LU) G.task_of[t.out2] = tid;
+        G.tasks.push_back(t);
+    }
+    const int64_t nt = (int64_t)G.tasks.size();
+    // redirect fused products to the task of their sub's result
+    if (opt.fuse_sub)
+        for (int64_t id = 1; id < n_ids; id++)
+            if (info[id].fused_away) G.task_of[id] = G.task_of[result[fused_sub_of[id]]];
+
+    // ---- pool slots: inputs and every block a task writes; slot 0 = zero block ----------
+    {
+        int64_t s = 1;
+        for (int64_t id = 1; id < n_ids; id++) {
+            const IdInfo& w = info[id];
+            if (w.is_input || (w.n_writers > 0 && !w.fused_away)) G.slot_of[id] = (int32_t)s++;
+        }
+        G.n_slots = s;
+    }
+
+    // ---- pairs ------------------------------------------------------------------------------
+    {
+        int64_t total = 0;
+        for (Task& t : G.tasks) { t.pair_begin = (int32_t)total; total += t.n_pairs; }
+        if (total > 0x7fffffff) return "too many operand pairs";
+        G.pairs.assign(total, Pair{0, 0});
+        std::vector<int32_t> fill(nt, 0);
+        for (int64_t i = 0; i < n_ops; i++) {
+            int32_t r = result[i];
+            uint8_t o = op[i];
+            int32_t tid;
+            if (o == OP_MUL || o == OP_MULNEG || o == OP_MULT) {
+                tid = G.task_of[r];   // own task, or the fused sub's task
+                Task& t = G.tasks[tid];
+                G.pairs[t.pair_begin + fill[tid]++] = Pair{src[i], src2[i]};
+                G.flops += 524288.0;
+                G.n_gemm_pairs++;
+            } else if (o == OP_SUB) {
+                tid = G.task_of[r];
+                Task& t = G.tasks[tid];
+                G.flops += 4096.0;
+                if (t.type == T_SUB) G.pairs[t.pair_begin] = Pair{src2[i], src[i]};   // a = S2, b = S1
+            } else {
+                tid = G.task_of[r];
+                G.pairs[G.tasks[tid].pair_begin] = Pair{src[i], 0};
+                G.flops += (o == OP_LU) ? 174763.0 : 87381.0;
+            }
+        }
+        for (int64_t t = 0; t < nt; t++)
+            if (G.tasks[t].type == T_GEMM && fill[t] != G.tasks[t].n_pairs) return "internal: pair count mismatch";
+    }
+
+    // ---- dependencies: distinct producer tasks of every source ------------------------------
+    std::vector<std::vector<int32_t>> preds(nt);
+    {
+        auto add = [&](int32_t tid, int32_t id) {
+            if (id <= 0) return;
+            int32_t p = G.task_of[id];
+            if (p >= 0 && p != tid) preds[tid].push_back(p);
+        };
+        for (int64_t t = 0; t < nt; t++) {
+            const Task& T = G.tasks[t];
+            for (int32_t k = 0; k < T.n_pairs; k++) {
+                add((int32_t)t, G.pairs[T.pair_begin + k].a);
+                add((int32_t)t, G.pairs[T.pair_begin + k].b);
+            }
+            if (T.flags & TF_INIT) add((int32_t)t, T.init);
+        }
+        int64_t nsucc = 0;
+        for (int64_t t = 0; t < nt; t++) {
+            auto& v = preds[t];
+            std::sort(v.begin(), v.end());
+            v.erase(std::unique(v.begin(), v.end()), v.end());
+            G.tasks[t].n_deps = (int32_t)v.size();
+            nsucc += (int64_t)v.size();
+        }
+        if (nsucc > 0x7fffffff) return "too many dependency edges";
+        std::vector<int32_t> cnt(nt + 1, 0);
+        for (int64_t t = 0; t < nt; t++)
+            for (int32_t p : preds[t]) cnt[p + 1]++;
+        for (int64_t t = 0; t < nt; t++) cnt[t + 1] += cnt[t];
+        G.succ.assign(nsucc, 0);
+        std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+        for (int64_t t = 0; t < nt; t++)
+            for (int32_t p : preds[t]) G.succ[pos[p]++] = (int32_t)t;
+        for (int64_t t = 0; t < nt; t++) { G.tasks[t].succ_begin = cnt[t]; G.tasks[t].succ_end = cnt[t + 1]; }
+    }
+    // ---- levels (Kahn) + cycle check -----------------------------------------------------------
+    {
+        std::vector<int32_t> deg(nt);
+        std::vector<int32_t> queue;
+        queue.reserve(nt);
+        for (int64_t t = 0; t < nt; t++) {
+            deg[t] = G.tasks[t].n_deps;
+            if (deg[t] == 0) { queue.push_back((int32_t)t); G.tasks[t].level = 0; }
+        }
+        G.initial = queue;
+        size_t head = 0;
+        int32_t maxlev = 0;
+        while (head < queue.size()) {
+            int32_t t = queue[head++];
+            int32_t lv = G.tasks[t].level;
+            maxlev = std::max(maxlev, lv);
+            for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
+                int32_t s = G.succ[e];
+                G.tasks[s].level = std::max(G.tasks[s].level, lv + 1);
+                if (--deg[s] == 0) queue.push_back(s);
+            }
+        }
+        if ((int64_t)queue.size() != nt) return "operation list has a dependency cycle";
+        G.n_levels = nt ? maxlev + 1 : 0;
+    }
+    // ---- patch block ids -> pool slots ---------------------------------------------------------
+    for (Task& t : G.tasks) {
+        t.out = G.slot_of[t.out];
+        if (t.type == T_LU) t.out2 = G.slot_of[t.out2];
+        if (t.flags & TF_INIT) t.init = G.slot_of[t.init];
+    }
+    for (Pair& p : G.pairs) { p.a = G.slot_of[p.a]; p.b = G.slot_of[p.b]; }
+    return "";
+}
+
+}  // namespace soglu

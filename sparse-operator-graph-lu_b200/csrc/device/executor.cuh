@@ -1,0 +1,49 @@
+// Launch interface of the device kernels (implemented in executor.cu / trsv.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "tasks.h"
+
+namespace soglu {
+
+struct ExecParams {
+    double* pool;          // block pool, slot s at pool + s*BLK_ELEMS
+    const Task* tasks;
+    const Pair* pairs;
+    const int32_t* succ;
+    int32_t* dep;          // live dependency counters (reset before every run)
+    int32_t* ready;        // ready queue, n_tasks entries, -1 = not yet published
+    int32_t* head;         // next queue slot to claim
+    int32_t* tail;         // next queue slot to publish
+    int32_t n_tasks;       // queue length for this launch
+    int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
+};
+
+// persistent dependency-counted executor; grid = resident CTAs (1 per SM)
+cudaError_t launch_executor(const ExecParams& p, int grid, cudaStream_t stream);
+int executor_max_grid(int device);        // co-resident CTAs for the executor kernel
+size_t executor_smem_bytes();
+
+// scatter dense 64x64 blocks (row-major, ld 64) into pool slots (ld 68) and back
+cudaError_t launch_pack_blocks(double* pool, const double* dense, const int32_t* slots, int64_t n, cudaStream_t stream);
+cudaError_t launch_unpack_block(const double* pool, int32_t slot, double* dense, cudaStream_t stream);
+
+// ---- block triangular solve -----------------------------------------------------------
+struct TrsvParams {
+    const double* pool;
+    // CSR by block row over off-diagonal factor blocks, columns ascending
+    const int64_t* l_ptr; const int32_t* l_col; const int32_t* l_slot; const int32_t* l_diag;
+    const int64_t* u_ptr; const int32_t* u_col; const int32_t* u_slot; const int32_t* u_diag;
+    int32_t n_rows;        // block rows
+    const double* b;       // n_rows*64
+    double* y;             // forward result
+    double* x;             // backward result
+    int32_t* done_l;       // per block row flags (0 -> 1)
+    int32_t* done_u;
+    int32_t symmetric;     // U = L^T: backward sweep reads L blocks transposed (CSC of L passed in u_*)
+};
+cudaError_t launch_trsv(const TrsvParams& p, int grid, cudaStream_t stream);
+int trsv_max_grid(int device);
+
+}  // namespace soglu

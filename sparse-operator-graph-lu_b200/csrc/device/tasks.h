@@ -1,0 +1,76 @@
+// Device data model of the factorisation: block layout in HBM and the task graph the
+// persistent executor consumes.  Built on the host by compile_tasks() from the reference's
+// flat operation list (struct operation, operation.h:37-52).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace soglu {
+
+// ---- block layout in HBM ---------------------------------------------------------------
+// A block is 64x64 FP64 stored row-major with a leading dimension of 68 doubles
+// (34 816 B).  The 4 pad doubles shift consecutive rows by 8 shared-memory banks, which
+// makes BOTH m8n8k4 DMMA fragment patterns (8 rows x 4 cols for the left operand, 4 rows
+// x 8 cols for the right one) hit every bank exactly twice = the 2-wavefront minimum of a
+// 256-byte warp load, after ONE contiguous cp.async.bulk of the block into shared memory.
+constexpr int BLK = 64;
+constexpr int BLK_LD = 68;
+constexpr int BLK_ELEMS = BLK * BLK_LD;                  // 4352 doubles
+constexpr int BLK_BYTES = BLK_ELEMS * (int)sizeof(double);  // 34816
+
+enum TaskType : int32_t {
+    T_GEMM = 0,      // out = init +/- sum_p A_p * B_p   (mul / mulneg / mult chains, optional fused sub)
+    T_SUB = 1,       // out = S2 - S1                   (missing source = zero block)
+    T_LU = 2,        // (out, out2) = LU(src), no pivoting, |u_ii| < 1e-9 clamped
+    T_LLT = 3,       // out = chol(src), pivot < 1e-20 clamped
+    T_LOWERINV = 4,  // out = src^-1, src lower triangular
+    T_UPPERINV = 5,  // out = src^-1, src upper triangular
+    T_EXIT = 99
+};
+enum TaskFlags : int32_t {
+    TF_NEGATE = 1,   // GEMM: subtract the product sum
+    TF_TRANSB = 2,   // GEMM: use B^T (mult)
+    TF_INIT = 4      // GEMM: start from block `init` instead of zero (fused sub)
+};
+
+struct Task {          // 48 bytes
+    int32_t type;
+    int32_t flags;
+    int32_t n_pairs;     // GEMM: number of (A,B) pairs; others: 1
+    int32_t pair_begin;  // index into the pair array
+    int32_t out;         // pool slot of the result
+    int32_t out2;        // LU: slot of U
+    int32_t init;        // GEMM + TF_INIT: slot of the initial value
+    int32_t succ_begin, succ_end;  // successor task ids (CSR)
+    int32_t n_deps;      // initial dependency counter
+    int32_t level;       // ASAP level (0 = ready at start)
+    int32_t pad;
+};
+struct Pair { int32_t a, b; };   // pool slots; non-GEMM: a = src (or S2), b = S1 / unused
+
+struct TaskGraph {
+    std::vector<Task> tasks;
+    std::vector<Pair> pairs;
+    std::vector<int32_t> succ;
+    std::vector<int32_t> initial;       // tasks with n_deps == 0, in task order
+    std::vector<int32_t> slot_of;       // block id -> pool slot (0 = zero block / none)
+    std::vector<int32_t> task_of;       // block id -> producing task (-1 = input / none)
+    int64_t n_slots = 1;                // slot 0 is the all-zero block
+    int32_t n_levels = 0;
+    double flops = 0;                   // dense-block convention, SURVEY.md 8(d)
+    int64_t n_gemm_pairs = 0;
+    int64_t fused_subs = 0;
+};
+
+struct CompileOptions {
+    bool fuse_sub = true;   // fold `sub` into the producing mul chain when it is the only reader
+};
+
+// Returns "" on success, otherwise the violated invariant.
+std::string compile_tasks(int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, int64_t n_ops,
+                          const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,
+                          const int32_t* result2, const std::vector<int32_t>& keep_ids, const CompileOptions& opt,
+                          TaskGraph& out);
+
+}  // namespace soglu

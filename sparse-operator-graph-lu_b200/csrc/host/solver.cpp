@@ -1,0 +1,100 @@
+// Driver: the reference's SOGLU::solveLU / decompose_solveLU (solver.cpp:50-184) on top of
+// the C ABI of include/soglu.h.  The host does ordering + planning (bit-exact integer
+// work), the GPU does BlockPlanner::calculate and BlockPlanner::solve.
+#include "solver.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "problem.h"
+
+using soglu::Problem;
+
+extern "C" {
+
+int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
+    const Problem* p = reinterpret_cast<const Problem*>(pp);
+    if (!ctx || !p) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
+    const soglu::Plan& pl = p->plan;
+    // input blocks: ids are 1..n_input in allocation order and input_vals is indexed by id-1
+    const int64_t n_in = (int64_t)pl.inputs.size();
+    std::vector<int32_t> in_ids(n_in);
+    for (int64_t k = 0; k < n_in; k++) in_ids[k] = (int32_t)(k + 1);
+    int rc = soglu_set_blocks(ctx, pl.storage, n_in, in_ids.data(), pl.input_vals.data());
+    if (rc) return rc;
+    const int64_t n = (int64_t)pl.ops.size();
+    std::vector<int32_t> src(n), src2(n), res(n), res2(n), stg(n);
+    std::vector<uint8_t> op(n);
+    for (int64_t k = 0; k < n; k++) {
+        const soglu::Op& o = pl.ops[k];
+        src[k] = o.src; src2[k] = o.src2; res[k] = o.result; res2[k] = o.result2; stg[k] = o.stage; op[k] = o.op;
+    }
+    rc = soglu_set_graph(ctx, n, src.data(), src2.data(), op.data(), res.data(), res2.data(), stg.data(), pl.brow.data(), pl.bcol.data());
+    if (rc) return rc;
+    auto split = [](const std::vector<soglu::BlockRef>& v, std::vector<int32_t>& id, std::vector<int32_t>& r, std::vector<int32_t>& c) {
+        id.resize(v.size()); r.resize(v.size()); c.resize(v.size());
+        for (size_t k = 0; k < v.size(); k++) { id[k] = v[k].id; r[k] = v[k].brow; c[k] = v[k].bcol; }
+    };
+    std::vector<int32_t> li, lr, lc, ui, ur, uc;
+    split(pl.L, li, lr, lc);
+    split(pl.U, ui, ur, uc);
+    return soglu_set_factors(ctx, (int64_t)li.size(), li.data(), lr.data(), lc.data(), (int64_t)ui.size(), ui.data(), ur.data(), uc.data(),
+                             p->cfg.blockRows, p->symmetric ? 1 : 0);
+}
+
+int soglu_solve_problem(soglu_ctx* ctx, const soglu_problem* pp, const double* b, double* x, int refine, soglu_stats* out) {
+    const Problem* p = reinterpret_cast<const Problem*>(pp);
+    if (!ctx || !p || !x) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
+    if (refine != 0) { soglu::set_error("iterative refinement is not available in this build"); return SOGLU_ERR_ARG; }
+    std::vector<double> bext;
+    const double* bp = p->b_perm.data();
+    if (b) {   // permute + pad a caller-supplied rhs exactly like the problem's own (GPSOrder.cpp:435-447)
+        bext.assign(p->n_ext, 1.0);
+        for (int i = 0; i < p->dim; i++) bext[i] = b[p->ord.newOrder[i]];
+        bp = bext.data();
+    }
+    std::vector<double> xext(p->n_ext);
+    int rc = soglu_solve(ctx, bp, xext.data(), out);
+    if (rc) return rc;
+    // un-permute (GOrder::reOrderResult, GPSOrder.cpp:41-53)
+    for (int i = 0; i < p->dim; i++) x[i] = xext[p->ord.reverseOrder[i]];
+    return SOGLU_OK;
+}
+
+double* soglu_solveLU(int dim, int valcount, int symmetric, const int* index_i, const int* index_j, const double* vals, const double* b) {
+    soglu_problem* prob = nullptr;
+    if (soglu_problem_from_coo(dim, valcount, symmetric, index_i, index_j, vals, b, &prob)) return nullptr;
+    const Problem* p = reinterpret_cast<const Problem*>(prob);
+    std::cout << p->log;
+    soglu_ctx* ctx = nullptr;
+    double* x = nullptr;
+    soglu_stats fs, ss;
+    do {
+        if (soglu_create(&ctx, 1, nullptr)) break;
+        if (soglu_load_problem(ctx, prob)) break;
+        if (soglu_factor(ctx, &fs)) break;
+        std::cout << "kernel time: " << fs.seconds << "  (" << fs.flops / fs.seconds * 1e-9 << " GFLOP/s, " << fs.tasks << " tasks)\n";
+        x = (double*)std::malloc(sizeof(double) * dim);
+        if (soglu_solve_problem(ctx, prob, nullptr, x, 0, &ss)) { std::free(x); x = nullptr; break; }
+        std::cout << "solve triangled :" << ss.seconds << "  (" << ss.bytes / ss.seconds * 1e-9 << " GB/s)\n";
+        int nan = 0;
+        for (int i = 0; i < dim; i++) nan += (x[i] != x[i]);
+        if (nan) std::cout << "found NaN:  " << nan << std::endl;
+    } while (0);
+    if (!x) std::cout << "soglu error: " << soglu_last_error() << std::endl;
+    if (ctx) soglu_destroy(ctx);
+    soglu_problem_free(prob);
+    return x;
+}
+
+}  // extern "C"
+
+namespace SOGLU {
+int iniData() { return 0; }
+double* solveLU(int dim, int valcount, bool symmetric, int* index_i, int* index_j, double* vals, double* b) {
+    return soglu_solveLU(dim, valcount, symmetric ? 1 : 0, index_i, index_j, vals, b);
+}
+}  // namespace SOGLU
