@@ -46,7 +46,10 @@ struct soglu_ctx {
     // options
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
+    int64_t opt_fuse_inv = 1;
     int64_t opt_grid = 0;          // override CTA count (0 = all resident)
+    int64_t opt_trace = 0;         // record per-task timestamps (debug; adds overhead)
+    DevBuf trace;
 
     // host-side description (borrowed arrays are copied)
     int64_t n_ids = 0, n_input = 0;
@@ -170,6 +173,7 @@ int finalize(soglu_ctx* c) {
     keep.insert(keep.end(), c->U_ids.begin(), c->U_ids.end());
     CompileOptions co;
     co.fuse_sub = c->opt_fuse_sub != 0;
+    co.fuse_inv = c->opt_fuse_inv != 0;
     std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
                                     c->result.data(), c->result2.data(), keep, co, c->G);
     if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
@@ -282,7 +286,9 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     std::string k(key);
     if (k == "exec_mode") c->opt_exec_mode = value;
     else if (k == "fuse_sub") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_sub must be set before the first factor"); c->opt_fuse_sub = value; }
+    else if (k == "fuse_inv") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_inv must be set before the first factor"); c->opt_fuse_inv = value; }
     else if (k == "grid") c->opt_grid = value;
+    else if (k == "trace") c->opt_trace = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
     return SOGLU_OK;
 }
@@ -355,6 +361,12 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     P.ready = c->ready.as<int32_t>();
     P.head = c->counters.as<int32_t>();
     P.tail = c->counters.as<int32_t>() + 32;   // separate 128-byte lines
+    P.trace = nullptr;
+    if (c->opt_trace && nt > 0) {
+        if (!c->trace.p) CU(c->trace.alloc((size_t)nt * 6 * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->trace.p, 0, (size_t)nt * 6 * sizeof(unsigned long long), c->stream));
+        P.trace = c->trace.as<unsigned long long>();
+    }
     CU(cudaEventRecord(c->ev0, c->stream));
     if (nt > 0) {
         if (c->opt_exec_mode == 0) {
@@ -438,6 +450,40 @@ int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* o
         out->d2h_bytes = (double)next;
     }
     return SOGLU_OK;
+}
+
+// debug: cycles of lu / write-out / inverses / total for one diagonal block (slot 1 = first input)
+int soglu_debug_diag_bench(soglu_ctx* c, int iters, long long* cycles4) {
+    if (!c || !c->compiled || c->G.n_slots < 8) return fail(SOGLU_ERR_ARG, "need a compiled problem");
+    DevBuf d;
+    CU(d.alloc(64));
+    CU(launch_diag_bench(c->pool.as<double>(), iters, d.as<long long>(), c->stream));
+    CU(cudaMemcpyAsync(cycles4, d.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    d.release();
+    return SOGLU_OK;
+}
+
+// debug: copy the per-task trace (6 x u64 per task) and the task table (type, n_pairs, level,
+// n_deps per task) of the last traced soglu_factor; returns the number of tasks
+int64_t soglu_debug_trace(soglu_ctx* c, unsigned long long* trace_out, int32_t* task_info_out, int32_t* succ_ptr_out, int32_t* succ_out) {
+    if (!c || !c->compiled) return -1;
+    const int64_t nt = (int64_t)c->G.tasks.size();
+    if (trace_out) {
+        if (!c->trace.p) return -1;
+        if (cudaMemcpy(trace_out, c->trace.p, (size_t)nt * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    }
+    if (task_info_out)
+        for (int64_t t = 0; t < nt; t++) {
+            const Task& T = c->G.tasks[t];
+            task_info_out[4 * t] = T.type; task_info_out[4 * t + 1] = T.n_pairs; task_info_out[4 * t + 2] = T.level; task_info_out[4 * t + 3] = T.n_deps;
+        }
+    if (succ_ptr_out) {
+        for (int64_t t = 0; t < nt; t++) succ_ptr_out[t] = c->G.tasks[t].succ_begin;
+        succ_ptr_out[nt] = (int32_t)c->G.succ.size();
+    }
+    if (succ_out) std::memcpy(succ_out, c->G.succ.data(), c->G.succ.size() * sizeof(int32_t));
+    return nt;
 }
 
 int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {

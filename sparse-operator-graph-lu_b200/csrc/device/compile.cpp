@@ -99,6 +99,36 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         }
     }
 
+    // Inverses: (a) every further lowerInv / upperInv of a block that already has one is the
+    // same computation on the same input -> its result id aliases the first one's block
+    // (the planner re-derives bottom-right inverses at every recursion level, BlockPlanner.cpp:
+    // 1035-1036, 1081-1082); (b) the first inverse of an lu factor is folded into the lu task.
+    std::vector<char> op_fused(n_ops, 0);                 // 1 = folded into an lu task, 2 = alias
+    std::vector<int32_t> alias_to(n_ids, 0);              // result id -> canonical result id
+    std::vector<int64_t> inv_of(n_ids, -1);               // source id -> first inverse op
+    for (int64_t i = 0; i < n_ops; i++) {
+        if (op[i] != OP_LOWERINV && op[i] != OP_UPPERINV) continue;
+        const int32_t f = src[i];
+        if (f <= 0) continue;
+        if (inv_of[f] >= 0) {
+            if (op[inv_of[f]] == op[i] && opt.fuse_inv && !info[result[i]].keep) {
+                alias_to[result[i]] = result[inv_of[f]];
+                op_fused[i] = 2;
+                G.aliased_invs++;
+            }
+            continue;
+        }
+        inv_of[f] = i;
+        if (!opt.fuse_inv) continue;
+        const IdInfo& w = info[f];
+        if (w.n_writers != 1 || w.kind != OP_LU) continue;
+        const int64_t lu_i = w.first_writer;
+        // lowerInv must read the L result, upperInv the U result of that lu
+        if (op[i] == OP_LOWERINV ? (result[lu_i] != f) : (result2[lu_i] != f)) continue;
+        op_fused[i] = 1;
+        G.fused_invs++;
+    }
+
     // ---- one task per produced block (lu: one task, two blocks) -------------------------
     // task order = order of the first contributing op, i.e. the reference's stage order
     G.task_of.assign(n_ids, -1);
@@ -109,11 +139,17 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         IdInfo& w = info[r];
         if (w.first_writer != i) continue;     // only the first writer opens a task
         if (w.fused_away) continue;            // opened by its sub instead
+        if (op_fused[i]) continue;             // inverse folded into its lu task
         Task t = {};
         t.out = r;                              // block ids for now; slots are patched below
         t.n_pairs = 1;
         switch (op[i]) {
-            case OP_LU: t.type = T_LU; t.out2 = result2[i]; break;
+            case OP_LU:
+                t.type = T_LU;
+                t.out2 = result2[i];
+                if (inv_of[r] >= 0 && op_fused[inv_of[r]] == 1) { t.flags |= TF_LINV; t.init = result[inv_of[r]]; }
+                if (inv_of[result2[i]] >= 0 && op_fused[inv_of[result2[i]]] == 1) { t.flags |= TF_UINV; t.out4 = result[inv_of[result2[i]]]; }
+                break;
             case OP_LLT: t.type = T_LLT; break;
             case OP_LOWERINV: t.type = T_LOWERINV; break;
             case OP_UPPERINV: t.type = T_UPPERINV; break;
@@ -136,7 +172,11 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         }
         int32_t tid = (int32_t)G.tasks.size();
         G.task_of[r] = tid;
-        if (t.type == T_LU) G.task_of[t.out2] = tid;
+        if (t.type == T_LU) {
+            G.task_of[t.out2] = tid;
+            if (t.flags & TF_LINV) G.task_of[t.init] = tid;
+            if (t.flags & TF_UINV) G.task_of[t.out4] = tid;
+        }
         G.tasks.push_back(t);
     }
     const int64_t nt = (int64_t)G.tasks.size();
@@ -150,9 +190,11 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         int64_t s = 1;
         for (int64_t id = 1; id < n_ids; id++) {
             const IdInfo& w = info[id];
-            if (w.is_input || (w.n_writers > 0 && !w.fused_away)) G.slot_of[id] = (int32_t)s++;
+            if (w.is_input || (w.n_writers > 0 && !w.fused_away && !alias_to[id])) G.slot_of[id] = (int32_t)s++;
         }
         G.n_slots = s;
+        for (int64_t id = 1; id < n_ids; id++)
+            if (alias_to[id]) { G.slot_of[id] = G.slot_of[alias_to[id]]; G.task_of[id] = G.task_of[alias_to[id]]; }
     }
 
     // ---- pairs ------------------------------------------------------------------------------
@@ -179,7 +221,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                 if (t.type == T_SUB) G.pairs[t.pair_begin] = Pair{src2[i], src[i]};   // a = S2, b = S1
             } else {
                 tid = G.task_of[r];
-                G.pairs[G.tasks[tid].pair_begin] = Pair{src[i], 0};
+                if (!op_fused[i]) G.pairs[G.tasks[tid].pair_begin] = Pair{src[i], 0};
                 G.flops += (o == OP_LU) ? 174763.0 : 87381.0;
             }
         }
@@ -251,7 +293,8 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     for (Task& t : G.tasks) {
         t.out = G.slot_of[t.out];
         if (t.type == T_LU) t.out2 = G.slot_of[t.out2];
-        if (t.flags & TF_INIT) t.init = G.slot_of[t.init];
+        if (t.flags & (TF_INIT | TF_LINV)) t.init = G.slot_of[t.init];
+        if (t.flags & TF_UINV) t.out4 = G.slot_of[t.out4];
     }
     for (Pair& p : G.pairs) { p.a = G.slot_of[p.a]; p.b = G.slot_of[p.b]; }
     return "";

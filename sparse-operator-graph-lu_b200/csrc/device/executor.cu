@@ -32,14 +32,26 @@ constexpr int N_THREADS = N_MATH + 32;             // + producer warp
 constexpr int STAGE_BYTES = 2 * BLK_BYTES;         // A and B
 constexpr int BAR_MATH = 1;                        // named barrier id for the math warps
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+    return r;
+}
+
 struct StageDesc {
-    int32_t type, flags, task, out, out2, init, first, last;
+    int32_t type, flags, task, out, out2, init, out4, first_last;   // first_last: bit0 first, bit1 last
 };
 
 struct __align__(16) SmemCtl {
     uint64_t full[N_STAGES];
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
+    double scratch[576];   // pivot row/column exchange buffers of the register-resident diag kernels
 };
 
 constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
@@ -55,39 +67,192 @@ __device__ __forceinline__ void store_block(double* __restrict__ g, const double
     for (int i = ct; i < BLK_ELEMS / 2; i += N_MATH) g2[i] = s2[i];
 }
 
-// (L, U) = LU(A) without pivoting, unit-diagonal L, |u_kk| < 1e-9 clamped sign-preserving
-// (ludcmpSimple, MatrixStdDouble.cpp:2711-2784; plain FP64 instead of x87 long double).
-// Right-looking elimination, one barrier per column; A is overwritten with U, L goes to Lb.
-__device__ void lu_block(double* __restrict__ A, double* __restrict__ Lb, int ct) {
+// ---- diagonal-block kernels, register resident ---------------------------------------------
+// Thread (ty, tx) of the 16x16 grid of math threads owns the 16 elements (ty+16r, tx+16c) of
+// every 64x64 matrix involved.  Per pivot only the pivot row / column travel through shared
+// memory (double-buffered, ONE barrier per pivot); the loop over 16-pivot groups is unrolled
+// so finished row / column groups drop out statically, and the body is branch-free so that
+// all shared-memory loads of a pivot are in flight together.
+//
+// lu3_reg: (L, U) = LU(A) without pivoting, unit-diagonal L, |u_kk| < 1e-9 clamped
+// sign-preserving (ludcmpSimple, MatrixStdDouble.cpp:2711-2784; plain FP64 instead of x87 long
+// double) and, in the SAME 64-pivot loop, both triangular inverses (inv_lower / inv_upper,
+// MatrixStdDouble.cpp:2787-2802, 2829-2866):
+//   L^-1:  forward elimination W_i -= l_ik * W_k  -- column k of L is exactly the multiplier
+//          column the LU step has just formed;
+//   U^-1:  (U^T)^-1 by the same forward elimination with multipliers u_ki / u_kk taken from
+//          the pivot row, scaled by 1/u_ii at the end and written back transposed.
+// So the fused lu + lowerInv + upperInv task costs one elimination sweep instead of three.
+template <bool WITH_INV>
+__device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* __restrict__ xbuf, double (&a)[4][4], double (&wl)[4][4],
+                                        double (&wu)[4][4], int ct) {
     const int ty = ct >> 4, tx = ct & 15;
-    for (int i = ct; i < BLK_ELEMS; i += N_MATH) Lb[i] = 0.0;
-    math_sync();
-    if (ct < BLK) Lb[ct * BLK_LD + ct] = 1.0;
-    for (int k = 0; k < BLK; k++) {
-        double p = A[k * BLK_LD + k];
-        if (p < 1e-9 && p > -1e-9) p = (p < 0) ? -1e-9 : 1e-9;
-        const double ip = 1.0 / p;
+    double* rowbuf = xbuf;         // [2][64] pivot row of A
+    double* colbuf = xbuf + 128;   // [2][64] pivot column of A
+    double* wlbuf = xbuf + 256;    // [2][64] row k of W_L
+    double* wubuf = xbuf + 384;    // [2][64] row k of W_U
+    double* ipbuf = xbuf + 512;    // [64]    1 / u_kk
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            a[r][c] = As[(ty + 16 * r) * BLK_LD + tx + 16 * c];
+            if (WITH_INV) wl[r][c] = wu[r][c] = (r == c && ty == tx) ? 1.0 : 0.0;
+        }
+#pragma unroll
+    for (int kr = 0; kr < 4; kr++) {
+#pragma unroll 1
+        for (int ko = 0; ko < 16; ko++) {
+            const int k = 16 * kr + ko;
+            const int pb = (k & 1) * 64;
+            if (ty == ko) {
+#pragma unroll
+                for (int c = kr; c < 4; c++) rowbuf[pb + tx + 16 * c] = a[kr][c];
+                if (WITH_INV) {
+#pragma unroll
+                    for (int c = 0; c <= kr; c++) { wlbuf[pb + tx + 16 * c] = wl[kr][c]; wubuf[pb + tx + 16 * c] = wu[kr][c]; }
+                }
+            }
+            if (tx == ko) {
+#pragma unroll
+                for (int r = kr; r < 4; r++) colbuf[pb + ty + 16 * r] = a[r][kr];
+            }
+            math_sync();
+            double p = rowbuf[pb + k];
+            double cbv[4], rbv[4], rbi[4], wlv[4], wuv[4];
+#pragma unroll
+            for (int r = kr; r < 4; r++) { cbv[r] = colbuf[pb + ty + 16 * r]; if (WITH_INV) rbi[r] = rowbuf[pb + ty + 16 * r]; }
+#pragma unroll
+            for (int c = kr; c < 4; c++) rbv[c] = rowbuf[pb + tx + 16 * c];
+            if (WITH_INV) {
+#pragma unroll
+                for (int c = 0; c <= kr; c++) { wlv[c] = wlbuf[pb + tx + 16 * c]; wuv[c] = wubuf[pb + tx + 16 * c]; }
+            }
+            if (p < 1e-9 && p > -1e-9) p = (p < 0) ? -1e-9 : 1e-9;
+            if (ty == ko && tx == ko) a[kr][kr] = p;
+            const double ip = 1.0 / p;
+            if (WITH_INV && ct == 0) ipbuf[k] = ip;
+            // Finished rows / columns are switched off by zeroing their multiplier / pivot-row
+            // entry (a few selects per pivot) instead of predicating every update.
+            const bool cedge = tx > ko, wedge = tx <= ko;
+            rbv[kr] = cedge ? rbv[kr] : 0.0;
+            if (WITH_INV) { wlv[kr] = wedge ? wlv[kr] : 0.0; wuv[kr] = wedge ? wuv[kr] : 0.0; }
+#pragma unroll
+            for (int r = kr; r < 4; r++) {
+                const bool ract = (r > kr) || (ty > ko);
+                const double l = ract ? cbv[r] * ip : 0.0;
+#pragma unroll
+                for (int c = kr; c < 4; c++) a[r][c] = fma(-l, rbv[c], a[r][c]);
+                if (ract && tx == ko) a[r][kr] = l;
+                if (WITH_INV) {
+                    const double m = ract ? rbi[r] * ip : 0.0;
+#pragma unroll
+                    for (int c = 0; c <= kr; c++) {
+                        wl[r][c] = fma(-l, wlv[c], wl[r][c]);
+                        wu[r][c] = fma(-m, wuv[c], wu[r][c]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void lu_task(const double* __restrict__ As, double* __restrict__ xbuf, double* __restrict__ pool, const StageDesc& d, int ct) {
+    const int ty = ct >> 4, tx = ct & 15;
+    double a[4][4], wl[4][4], wu[4][4];
+    const bool inv = d.flags & (TF_LINV | TF_UINV);
+    if (inv) lu3_reg<true>(As, xbuf, a, wl, wu, ct);
+    else lu3_reg<false>(As, xbuf, a, wl, wu, ct);
+    double* gL = pool + (size_t)d.out * BLK_ELEMS;
+    double* gU = pool + (size_t)d.out2 * BLK_ELEMS;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int i = ty + 16 * r, j = tx + 16 * c, o = i * BLK_LD + j;
+            const double v = a[r][c];
+            gL[o] = (j < i) ? v : (j == i ? 1.0 : 0.0);
+            gU[o] = (j >= i) ? v : 0.0;
+        }
+    if (!inv) return;
+    math_sync();   // ipbuf complete
+    if (d.flags & TF_LINV) {
+        double* g = pool + (size_t)d.init * BLK_ELEMS;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) g[(ty + 16 * r) * BLK_LD + tx + 16 * c] = wl[r][c];
+    }
+    if (d.flags & TF_UINV) {
+        double* g = pool + (size_t)d.out4 * BLK_ELEMS;
+        const double* ipbuf = xbuf + 512;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const int i = ty + 16 * r;
-            if (i <= k) continue;
-            const double lik = A[i * BLK_LD + k] * ip;
+            const double di = ipbuf[ty + 16 * r];
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int j = tx + 16 * c;
-                if (j > k) A[i * BLK_LD + j] -= lik * A[k * BLK_LD + j];
-            }
-            if (tx == (k & 15)) Lb[i * BLK_LD + k] = lik;
+            for (int c = 0; c < 4; c++) g[(tx + 16 * c) * BLK_LD + ty + 16 * r] = wu[r][c] * di;   // transposed
         }
-        if (ct == 0) A[k * BLK_LD + k] = p;
-        math_sync();
     }
-    // strict lower part of A still holds unscaled column values: U is upper triangular
-    for (int idx = ct; idx < BLK * BLK; idx += N_MATH) {
-        const int i = idx >> 6, j = idx & 63;
-        if (j < i) A[i * BLK_LD + j] = 0.0;
-    }
+}
+
+// Y = T^-1 for a triangular block T in shared memory, general diagonal (standalone lowerInv /
+// upperInv tasks).  Forward elimination on W = unscaled rows of the inverse; TRANS inverts an
+// upper-triangular T through its transpose (multipliers read from row k, result written back
+// transposed).  Multipliers depend only on T, so they are fetched one pivot ahead.
+template <bool TRANS>
+__device__ __forceinline__ void tri_inv_task(const double* __restrict__ Tm, double* __restrict__ xbuf, double* __restrict__ gout, int ct) {
+    const int ty = ct >> 4, tx = ct & 15;
+    double* wbuf = xbuf;          // [2][64]
+    double* dinv = xbuf + 128;    // [64]
+    double w[4][4];
+    if (ct < BLK) dinv[ct] = 1.0 / Tm[ct * BLK_LD + ct];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) w[r][c] = (r == c && ty == tx) ? 1.0 : 0.0;
     math_sync();
+    double f[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) f[r] = (TRANS ? Tm[ty + 16 * r] : Tm[(ty + 16 * r) * BLK_LD]) * dinv[0];
+#pragma unroll
+    for (int kr = 0; kr < 4; kr++) {
+#pragma unroll 1
+        for (int ko = 0; ko < 16; ko++) {
+            const int k = 16 * kr + ko;
+            const int pb = (k & 1) * 64;
+            if (ty == ko) {
+#pragma unroll
+                for (int c = 0; c <= kr; c++) wbuf[pb + tx + 16 * c] = w[kr][c];
+            }
+            math_sync();
+            double wv[4], fn[4];
+#pragma unroll
+            for (int c = 0; c <= kr; c++) wv[c] = wbuf[pb + tx + 16 * c];
+            const int kn = (k + 1) & 63;
+            const double dn = dinv[kn];
+#pragma unroll
+            for (int r = 0; r < 4; r++) fn[r] = (TRANS ? Tm[kn * BLK_LD + ty + 16 * r] : Tm[(ty + 16 * r) * BLK_LD + kn]) * dn;
+            wv[kr] = (tx <= ko) ? wv[kr] : 0.0;
+#pragma unroll
+            for (int r = kr; r < 4; r++) {
+                const double fr = ((r > kr) || (ty > ko)) ? f[r] : 0.0;
+#pragma unroll
+                for (int c = 0; c <= kr; c++) w[r][c] = fma(-fr, wv[c], w[r][c]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) f[r] = fn[r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const double di = dinv[ty + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double v = w[r][c] * di;
+            if (TRANS) gout[(tx + 16 * c) * BLK_LD + ty + 16 * r] = v;
+            else gout[(ty + 16 * r) * BLK_LD + tx + 16 * c] = v;
+        }
+    }
 }
 
 // L = chol(A) reading the lower triangle, pivot < 1e-20 clamped (lltdcmpSimple,
@@ -116,65 +281,6 @@ __device__ void llt_block(double* __restrict__ A, double* __restrict__ Lb, int c
         if (ct == 0) Lb[k * BLK_LD + k] = lkk;
         math_sync();
     }
-}
-
-// Y = L^-1 for lower-triangular L with general diagonal (inv_lower, MatrixStdDouble.cpp:
-// 2787-2802).  Row-oriented elimination on W = unscaled rows: W_i -= L_ik/L_kk * W_k.
-__device__ void inv_lower_block(const double* __restrict__ L, double* __restrict__ Y, int ct) {
-    const int ty = ct >> 4, tx = ct & 15;
-    for (int i = ct; i < BLK_ELEMS; i += N_MATH) Y[i] = 0.0;
-    math_sync();
-    if (ct < BLK) Y[ct * BLK_LD + ct] = 1.0;
-    math_sync();
-    for (int k = 0; k < BLK - 1; k++) {
-        const double dk = 1.0 / L[k * BLK_LD + k];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int i = ty + 16 * r;
-            if (i <= k) continue;
-            const double f = L[i * BLK_LD + k] * dk;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int j = tx + 16 * c;
-                if (j <= k) Y[i * BLK_LD + j] -= f * Y[k * BLK_LD + j];
-            }
-        }
-        math_sync();
-    }
-    for (int idx = ct; idx < BLK * BLK; idx += N_MATH) {
-        const int i = idx >> 6, j = idx & 63;
-        if (j <= i) Y[i * BLK_LD + j] *= 1.0 / L[i * BLK_LD + i];
-    }
-    math_sync();
-}
-
-// Y = U^-1 for upper-triangular U (inv_upper, MatrixStdDouble.cpp:2829-2866).
-__device__ void inv_upper_block(const double* __restrict__ U, double* __restrict__ Y, int ct) {
-    const int ty = ct >> 4, tx = ct & 15;
-    for (int i = ct; i < BLK_ELEMS; i += N_MATH) Y[i] = 0.0;
-    math_sync();
-    if (ct < BLK) Y[ct * BLK_LD + ct] = 1.0;
-    math_sync();
-    for (int k = BLK - 1; k > 0; k--) {
-        const double dk = 1.0 / U[k * BLK_LD + k];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int i = ty + 16 * r;
-            if (i >= k) continue;
-            const double f = U[i * BLK_LD + k] * dk;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int j = tx + 16 * c;
-                if (j >= k) Y[i * BLK_LD + j] -= f * Y[k * BLK_LD + j];
-            }
-        }
-        math_sync();
-    }
-    for (int idx = ct; idx < BLK * BLK; idx += N_MATH) {
-        const int i = idx >> 6, j = idx & 63;
-        if (j >= i) Y[i * BLK_LD + j] *= 1.0 / U[i * BLK_LD + i];
-    }
-    math_sync();
 }
 
 // ---- Schur update: acc(32x16 per warp) += A(64x64) * B(64x64) from shared memory -------
@@ -231,6 +337,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     ptx::mbar_arrive(&ctl->full[s]);
                     break;
                 }
+                if (P.trace) { P.trace[6 * (size_t)t + 1] = gtime(); P.trace[6 * (size_t)t + 5] = smid(); }
                 const Task T = P.tasks[t];
                 ptx::fence_proxy_async();
                 const int nst = (T.type == T_GEMM) ? T.n_pairs : 1;
@@ -239,8 +346,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     const int s = it % N_STAGES;
                     ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);
                     StageDesc d;
-                    d.type = T.type; d.flags = T.flags; d.task = t; d.out = T.out; d.out2 = T.out2; d.init = T.init;
-                    d.first = (p == 0); d.last = (p == nst - 1);
+                    d.type = T.type; d.flags = T.flags; d.task = t; d.out = T.out; d.out2 = T.out2; d.init = T.init; d.out4 = T.out4;
+                    d.first_last = (p == 0 ? 1 : 0) | (p == nst - 1 ? 2 : 0);
                     ctl->desc[s] = d;
                     const Pair pr = P.pairs[T.pair_begin + p];
                     double* As = stage_base + (size_t)s * (STAGE_BYTES / 8);
@@ -265,8 +372,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
         double* As = stage_base + (size_t)s * (STAGE_BYTES / 8);
         double* Bs = As + BLK_ELEMS;
 
+        if (P.trace && (d.first_last & 1) && ct == 0) P.trace[6 * (size_t)d.task + 2] = gtime();
         if (d.type == T_GEMM) {
-            if (d.first) {
+            if (d.first_last & 1) {
 #pragma unroll
                 for (int mi = 0; mi < 4; mi++)
 #pragma unroll
@@ -276,7 +384,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
             else mma_block<false>(As, Bs, acc, mw, lane);
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&ctl->empty[s]);
-            if (!d.last) continue;
+            if (!(d.first_last & 2)) continue;
             // epilogue: out = init -/+ acc, 16-byte stores straight from the accumulators
             const int g = lane >> 2, t = lane & 3;
             double* out = P.pool + (size_t)d.out * BLK_ELEMS;
@@ -311,21 +419,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     break;
                 }
                 case T_LU:
-                    lu_block(As, Bs, ct);
-                    store_block(out, Bs, ct);
-                    store_block(P.pool + (size_t)d.out2 * BLK_ELEMS, As, ct);
+                    lu_task(As, ctl->scratch, P.pool, d, ct);
                     break;
                 case T_LLT:
                     llt_block(As, Bs, ct);
                     store_block(out, Bs, ct);
                     break;
                 case T_LOWERINV:
-                    inv_lower_block(As, Bs, ct);
-                    store_block(out, Bs, ct);
+                    tri_inv_task<false>(As, ctl->scratch, out, ct);
                     break;
                 case T_UPPERINV:
-                    inv_upper_block(As, Bs, ct);
-                    store_block(out, Bs, ct);
+                    tri_inv_task<true>(As, ctl->scratch, out, ct);
                     break;
                 default: break;
             }
@@ -335,6 +439,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
         if (d.type != T_GEMM) {
             if (lane == 0) ptx::mbar_arrive(&ctl->empty[s]);
         }
+        if (P.trace && ct == 0) P.trace[6 * (size_t)d.task + 3] = gtime();
         if (P.signal) {
             const Task* T = P.tasks + d.task;
             const int sb = T->succ_begin, se = T->succ_end;
@@ -345,12 +450,56 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     if (atomicSub(P.dep + nx, 1) == 1) {
                         __threadfence();
                         const int pos = atomicAdd(P.tail, 1);
+                        if (P.trace) P.trace[6 * (size_t)nx + 0] = gtime();
                         ptx::st_release(P.ready + pos, nx);
                     }
                 }
             }
+            if (P.trace) {
+                math_sync();
+                if (ct == 0) P.trace[6 * (size_t)d.task + 4] = gtime();
+            }
         }
     }
+}
+
+// debug micro-benchmark: cycle counts of the diagonal-block kernels in isolation (1 CTA)
+__global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, int iters, long long* cycles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (size_t)N_STAGES * STAGE_BYTES);
+    if (threadIdx.x < 32) return;
+    const int ct = threadIdx.x - 32;
+    long long t_lu3 = 0, t_lu = 0, t_invl = 0, t_invu = 0;
+    for (int it = 0; it < iters; it++) {
+        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
+        math_sync();
+        StageDesc d = {};
+        d.out = 2; d.out2 = 3; d.init = 4; d.out4 = 5;
+        d.flags = TF_LINV | TF_UINV;
+        long long c0 = clock64();
+        lu_task(As, ctl->scratch, pool, d, ct);
+        math_sync();
+        long long c1 = clock64();
+        d.flags = 0;
+        lu_task(As, ctl->scratch, pool, d, ct);
+        math_sync();
+        long long c2 = clock64();
+        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[2 * BLK_ELEMS + i];
+        math_sync();
+        long long c3 = clock64();
+        tri_inv_task<false>(As, ctl->scratch, pool + 6 * (size_t)BLK_ELEMS, ct);
+        math_sync();
+        long long c4 = clock64();
+        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[3 * BLK_ELEMS + i];
+        math_sync();
+        long long c5 = clock64();
+        tri_inv_task<true>(As, ctl->scratch, pool + 7 * (size_t)BLK_ELEMS, ct);
+        math_sync();
+        long long c6 = clock64();
+        t_lu3 += c1 - c0; t_lu += c2 - c1; t_invl += c4 - c3; t_invu += c6 - c5;
+    }
+    if (ct == 0) { cycles[0] = t_lu3 / iters; cycles[1] = t_lu / iters; cycles[2] = t_invl / iters; cycles[3] = t_invu / iters; }
 }
 
 __global__ void pack_blocks_kernel(double* __restrict__ pool, const double* __restrict__ dense, const int32_t* __restrict__ slots, int64_t n) {
@@ -388,6 +537,13 @@ cudaError_t launch_executor(const ExecParams& p, int grid, cudaStream_t stream) 
     // cooperative launch: the runtime guarantees that all CTAs are co-resident, which the
     // claim-then-wait ready queue relies on
     return cudaLaunchCooperativeKernel((const void*)executor_kernel, dim3(grid), dim3(N_THREADS), args, SMEM_BYTES, stream);
+}
+
+cudaError_t launch_diag_bench(double* pool, int iters, long long* cycles, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(diag_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    diag_bench_kernel<<<1, N_THREADS, SMEM_BYTES, stream>>>(pool, iters, cycles);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_pack_blocks(double* pool, const double* dense, const int32_t* slots, int64_t n, cudaStream_t stream) {

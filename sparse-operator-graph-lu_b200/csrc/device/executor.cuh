@@ -18,12 +18,15 @@ struct ExecParams {
     int32_t* tail;         // next queue slot to publish
     int32_t n_tasks;       // queue length for this launch
     int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
+    unsigned long long* trace;   // optional: 6 x u64 per task (published, claimed, loaded, computed, signalled, smid)
 };
 
 // persistent dependency-counted executor; grid = resident CTAs (1 per SM)
 cudaError_t launch_executor(const ExecParams& p, int grid, cudaStream_t stream);
 int executor_max_grid(int device);        // co-resident CTAs for the executor kernel
 size_t executor_smem_bytes();
+
+cudaError_t launch_diag_bench(double* pool, int iters, long long* cycles, cudaStream_t stream);
 
 // scatter dense 64x64 blocks (row-major, ld 64) into pool slots (ld 68) and back
 cudaError_t launch_pack_blocks(double* pool, const double* dense, const int32_t* slots, int64_t n, cudaStream_t stream);

@@ -71,6 +71,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// x = fma(-a, b, x) executed under a predicate (a predicated DFMA: no select, no branch)
+__device__ __forceinline__ void pfnma(double& x, double a, double b, bool pred) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}" : "+d"(x) : "d"(-a), "d"(b), "r"((int)pred));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 }  // namespace ptx

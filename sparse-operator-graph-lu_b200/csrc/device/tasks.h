@@ -31,7 +31,9 @@ enum TaskType : int32_t {
 enum TaskFlags : int32_t {
     TF_NEGATE = 1,   // GEMM: subtract the product sum
     TF_TRANSB = 2,   // GEMM: use B^T (mult)
-    TF_INIT = 4      // GEMM: start from block `init` instead of zero (fused sub)
+    TF_INIT = 4,     // GEMM: start from block `init` instead of zero (fused sub)
+    TF_LINV = 8,     // LU/LLT: also produce out3 = L^-1 (fused lowerInv)
+    TF_UINV = 16     // LU: also produce out4 = U^-1 (fused upperInv)
 };
 
 struct Task {          // 48 bytes
@@ -41,11 +43,11 @@ struct Task {          // 48 bytes
     int32_t pair_begin;  // index into the pair array
     int32_t out;         // pool slot of the result
     int32_t out2;        // LU: slot of U
-    int32_t init;        // GEMM + TF_INIT: slot of the initial value
+    int32_t init;        // GEMM + TF_INIT: slot of the initial value; LU + TF_LINV: slot of L^-1 (out3)
     int32_t succ_begin, succ_end;  // successor task ids (CSR)
     int32_t n_deps;      // initial dependency counter
     int32_t level;       // ASAP level (0 = ready at start)
-    int32_t pad;
+    int32_t out4;        // LU + TF_UINV: slot of U^-1
 };
 struct Pair { int32_t a, b; };   // pool slots; non-GEMM: a = src (or S2), b = S1 / unused
 
@@ -61,10 +63,13 @@ struct TaskGraph {
     double flops = 0;                   // dense-block convention, SURVEY.md 8(d)
     int64_t n_gemm_pairs = 0;
     int64_t fused_subs = 0;
+    int64_t fused_invs = 0;
+    int64_t aliased_invs = 0;
 };
 
 struct CompileOptions {
     bool fuse_sub = true;   // fold `sub` into the producing mul chain when it is the only reader
+    bool fuse_inv = true;   // fold the first lowerInv / upperInv of an lu's factors into the lu task
 };
 
 // Returns "" on success, otherwise the violated invariant.

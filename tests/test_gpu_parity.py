@@ -1,0 +1,203 @@
+"""GPU parity: the CUDA hot path through the C ABI versus (a) golden x recorded from the
+unmodified reference, (b) the oracle port on the same inputs, block by block for the factors,
+and (c) size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): relative solution difference <= 1e-10; residual
+||Ax-b||/||b|| <= 1e-12 on the well-conditioned 3D cases."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden, ref_harness_path, unpermute, write_case_mtx
+
+pytestmark = pytest.mark.gpu
+TOL_X = 1e-10
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_solution_matches_reference_golden(sg, tmp_path, name):
+    g = load_golden(name)
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    ctx = sg.Context(0)
+    ctx.load(p)
+    fs = ctx.factor()
+    x, ss = ctx.solve(p)
+    assert fs["kernel_launches"] >= 1 and ss["kernel_launches"] >= 1
+    assert not np.isnan(x).any()
+    assert _rel(x, g["x"]) <= TOL_X
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["lap2d_64", "lap3d_13x11x9", "banded_3000", "lap3d_16_sym", "lap2d_64_sym"])
+def test_factor_blocks_match_oracle(sg, oracle, tmp_path, name):
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    x_ext_o, h = oracle.run(p)
+    worst = 0.0
+    for what in ("L", "U"):
+        ids = p.i32(what)
+        for k in range(len(ids)):
+            mine = ctx.get_block(ids[k, 0])
+            ref = oracle.block(h, ids[k, 0])
+            worst = max(worst, np.abs(mine - ref).max() / max(1.0, np.abs(ref).max()))
+    oracle.free(h)
+    assert worst <= 1e-12, worst
+    x_ext, _ = ctx.solve_ext(p.f64("b_perm"))
+    assert _rel(x_ext, x_ext_o) <= TOL_X
+    ctx.close()
+
+
+@pytest.mark.parametrize("fuse_sub,fuse_inv", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_executor_modes_agree(sg, tmp_path, fuse_sub, fuse_inv):
+    """Persistent DAG executor vs one-launch-per-level debug executor, with and without the
+    task fusions: same kernels, so the results agree to rounding of the fused epilogues."""
+    g = load_golden("lap3d_24")
+    p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
+    xs = []
+    for mode in (0, 1):
+        ctx = sg.Context(0)
+        ctx.set_option("exec_mode", mode)
+        ctx.set_option("fuse_sub", fuse_sub)
+        ctx.set_option("fuse_inv", fuse_inv)
+        ctx.load(p)
+        fs = ctx.factor()
+        if mode == 1:
+            assert fs["kernel_launches"] > 100      # one launch per dependency level
+        x, _ = ctx.solve(p)
+        xs.append(x)
+        ctx.close()
+    assert _rel(xs[0], xs[1]) <= 1e-13
+    assert _rel(xs[0], g["x"]) <= TOL_X
+
+
+def test_refactor_and_multiple_rhs(sg, tmp_path):
+    """Factor twice (same pattern), solve several right-hand sides: idempotence + linearity."""
+    import gen_mtx
+    n, r, c, v = gen_mtx.generate("lap3d", 14)
+    b1 = gen_mtx.rhs(n)
+    p = sg.Problem.from_coo(n, r, c, v, b1)
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    x1, _ = ctx.solve(p)
+    ctx.factor()
+    x1b, _ = ctx.solve(p)
+    np.testing.assert_array_equal(x1, x1b)          # deterministic re-factorisation
+    rng = np.random.default_rng(3)
+    b2 = rng.standard_normal(n)
+    x2, _ = ctx.solve(p, b2)
+    x12, _ = ctx.solve(p, b1 + 2.0 * b2)
+    assert _rel(x12, x1 + 2.0 * x2) <= 1e-12          # linearity of the solve
+    ax = np.zeros(n)
+    np.add.at(ax, r, v * x2[c])
+    assert np.linalg.norm(ax - b2) / np.linalg.norm(b2) <= 1e-12
+    ctx.close()
+
+
+def test_array_abi_without_problem_helper(sg, tmp_path):
+    """Drive soglu_set_blocks / set_graph / set_factors directly with plain arrays (what a
+    reference-side binding would pass), not through soglu_load_problem."""
+    g = load_golden("lap2d_50x37")
+    p = sg.Problem.from_mtx(write_case_mtx("lap2d_50x37", tmp_path))
+    ops = p.i32("ops")
+    ctx = sg.Context(0)
+    n_in = p.size("n_input")
+    ctx.set_blocks(p.size("storage"), np.arange(1, n_in + 1, dtype=np.int32), p.f64("input_vals"))
+    ctx.set_graph({"op": ops[:, 0], "src": ops[:, 1], "src2": ops[:, 2], "result": ops[:, 3], "result2": ops[:, 4]}, stage=ops[:, 5])
+    ctx.set_factors(p.i32("L"), p.i32("U"), p.size("block_rows"))
+    ctx.factor()
+    x_ext, _ = ctx.solve_ext(p.f64("b_perm"))
+    assert _rel(unpermute(p, x_ext), g["x"]) <= TOL_X
+    ctx.close()
+
+
+def test_error_paths(sg):
+    ctx = sg.Context(0)
+    with pytest.raises(sg.SogluError):
+        ctx.factor()                                   # nothing loaded
+    # an op list that writes an input block violates the invariants -> SOGLU_ERR_GRAPH
+    ctx.set_blocks(4, np.array([1], dtype=np.int32), np.eye(64).reshape(1, -1))
+    ctx.set_graph({"op": [4], "src": [0], "src2": [2], "result": [1], "result2": [0]})
+    ctx.set_factors(np.array([[1, 0, 0]], dtype=np.int32), np.array([[1, 0, 0]], dtype=np.int32), 1)
+    with pytest.raises(sg.SogluError) as e:
+        ctx.factor()
+    assert "writes input block" in str(e.value)
+    ctx.close()
+
+
+def test_solve_cli(sg, tmp_path):
+    """./solve <file.mtx>: reference console lines + a correct <base>_x.mtx."""
+    g = load_golden("lap3d_13x11x9")
+    path = write_case_mtx("lap3d_13x11x9", tmp_path)
+    out = subprocess.run([sg.SOLVE_PATH, path], capture_output=True, text=True, check=True).stdout
+    for token in ("GGPS reorder: levels:", "re Order time:", "reduced ops to:", "plan time:", "kernel time:", "solve triangled", "max rhs error:"):
+        assert token in out, out
+    err = float(out.split("max rhs error:")[1].split()[0])
+    assert err <= 1e-11
+    xs = [float(t) for t in open(path.replace(".mtx", "_x.mtx")).read().split("\n")[2:] if t.strip()]
+    assert _rel(np.array(xs), g["x"]) <= TOL_X
+
+
+def test_solve_lu_dropin(sg):
+    import gen_mtx
+    n, r, c, v = gen_mtx.generate("lap2d", 40, 33)
+    b = gen_mtx.rhs(n)
+    x = sg.solve_lu(n, r, c, v, b)
+    ax = np.zeros(n)
+    np.add.at(ax, r, v * x[c])
+    assert np.linalg.norm(ax - b) / np.linalg.norm(b) <= 1e-11
+
+
+def test_midsize_against_live_reference(sg, tmp_path):
+    """3D 40^3 (n=64 000, 340 k ops): GPU x vs the unmodified reference run on the host."""
+    harness = ref_harness_path()
+    if harness is None:
+        pytest.skip("oracle/_ref not present on this box")
+    path = str(tmp_path / "l3d40.mtx")
+    sg.write_stencil_mtx("lap3d", path, 40)
+    out = tmp_path / "ref"
+    out.mkdir()
+    subprocess.run([harness, path, str(out)], check=True, capture_output=True, env=dict(os.environ, OMP_NUM_THREADS="16"))
+    xref = np.fromfile(out / "x.f64")
+    p = sg.Problem.from_mtx(path)
+    np.testing.assert_array_equal(p.i32("ops"), np.fromfile(out / "ops_fine.i32", dtype=np.int32).reshape(-1, 8))
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    x, _ = ctx.solve(p)
+    assert _rel(x, xref) <= TOL_X
+    ctx.close()
+
+
+def test_config2_properties(sg, tmp_path):
+    """BASELINE config 2 (3D 7-pt 64^3, n = 262 144, 7.1 M ops) at full size: residual gate,
+    padding rows, and agreement with a second factorisation."""
+    path = str(tmp_path / "l3d64.mtx")
+    sg.write_stencil_mtx("lap3d", path, 64)
+    p = sg.Problem.from_mtx(path)
+    assert p.size("n_ops") == 7106089 and p.size("storage") == 1529367
+    ctx = sg.Context(0)
+    ctx.load(p)
+    fs = ctx.factor()
+    x, ss = ctx.solve(p)
+    n = p.size("dim")
+    # 7-point Laplacian residual without materialising A on the host twice
+    X = x.reshape(64, 64, 64)
+    ax = 6.0 * X
+    ax[1:, :, :] -= X[:-1, :, :]; ax[:-1, :, :] -= X[1:, :, :]
+    ax[:, 1:, :] -= X[:, :-1, :]; ax[:, :-1, :] -= X[:, 1:, :]
+    ax[:, :, 1:] -= X[:, :, :-1]; ax[:, :, :-1] -= X[:, :, 1:]
+    b = 1.0 + 0.25 * (np.arange(n) % 7)
+    res = np.linalg.norm(ax.ravel() - b) / np.linalg.norm(b)
+    assert res <= 1e-12, res
+    assert abs(x[0] - 1.0377) < 1e-4 and abs(x[1] - 1.74207) < 1e-4 and abs(x[2] - 2.25873) < 1e-4
+    assert fs["flops"] > 3.5e12
+    ctx.close()
