@@ -41,6 +41,7 @@ WORKLOADS = {
     "nine2d_1024": ("nine2d", (1024, 1024, 0), "configs[3]: 2D 9-point stencil 1024x1024 (n=1,048,576)"),
     "lap3d_100": ("lap3d", (100, 100, 100), "configs[4]: 3D 7-point Laplacian 100^3 (n=1,000,000)"),
     "lap3d_24": ("lap3d", (24, 24, 24), "smoke-sized 3D 7-point Laplacian 24^3"),
+    "lap3d_40": ("lap3d", (40, 40, 40), "profiling-sized 3D 7-point Laplacian 40^3 (n=64,000)"),
 }
 FP64_PEAK_FALLBACK_TFLOPS = 36.98   # tools/fp64_peak.cu (DMMA m8n8k4) on this pool, profiles/r01_fp64_peak.txt
 
