@@ -47,6 +47,7 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
+    int64_t opt_split = 1;
     int64_t opt_grid = 0;          // override CTA count (0 = all resident)
     int64_t opt_trace = 0;         // record per-task timestamps (debug; adds overhead)
     DevBuf trace;
@@ -72,7 +73,7 @@ struct soglu_ctx {
     std::vector<int64_t> level_ptr;
     DevBuf pool, tasks, pairs, succ, dep0, dep, ready, counters, initial;
     // solve structures
-    DevBuf l_ptr, l_col, l_slot, l_diag, u_ptr, u_col, u_slot, u_diag, d_b, d_y, d_x, flags;
+    DevBuf l_ptr, l_col, l_slot, l_diag, l_dinv, u_ptr, u_col, u_slot, u_diag, u_dinv, d_b, d_y, d_x;
     int64_t nL_off = 0, nU_off = 0;
     int64_t launches = 0;
     double h2d = 0, d2h = 0;
@@ -102,7 +103,7 @@ int upload(DevBuf& b, const std::vector<T>& v, soglu_ctx* c) {
 // CSR over off-diagonal factor blocks of one triangle; lower: cols < row, upper: cols > row.
 // transpose = true builds the structure of the transposed factor (CSC of L for L^T).
 int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<int32_t>& br, const std::vector<int32_t>& bc,
-              bool upper, bool transpose, DevBuf& dptr, DevBuf& dcol, DevBuf& dslot, DevBuf& ddiag, int64_t& n_off) {
+              bool upper, bool transpose, DevBuf& dptr, DevBuf& dcol, DevBuf& dslot, DevBuf& ddiag, DevBuf& ddinv, int64_t& n_off) {
     const int n = c->n_block_rows;
     std::vector<int64_t> ptr(n + 1, 0);
     std::vector<int32_t> diag(n, -1);
@@ -144,6 +145,16 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
     if ((rc = upload(dcol, col, c))) return rc;
     if ((rc = upload(dslot, slot, c))) return rc;
     if ((rc = upload(ddiag, diag, c))) return rc;
+    // explicit inverses of the diagonal blocks, where the factorisation produced them (fused lu tasks)
+    std::vector<int32_t> inv_of_slot(c->G.n_slots, 0);
+    for (const Task& T : c->G.tasks)
+        if (T.type == T_LU) {
+            if (T.flags & TF_LINV) inv_of_slot[T.out] = T.init;
+            if (T.flags & TF_UINV) inv_of_slot[T.out2] = T.out4;
+        }
+    std::vector<int32_t> dinv(n, 0);
+    for (int r = 0; r < n; r++) dinv[r] = inv_of_slot[diag[r]];
+    if ((rc = upload(ddinv, dinv, c))) return rc;
     return SOGLU_OK;
 }
 
@@ -174,6 +185,8 @@ int finalize(soglu_ctx* c) {
     CompileOptions co;
     co.fuse_sub = c->opt_fuse_sub != 0;
     co.fuse_inv = c->opt_fuse_inv != 0;
+    co.split_narrow = (int)c->opt_split;
+    co.n_sms = c->sms;
     std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
                                     c->result.data(), c->result2.data(), keep, co, c->G);
     if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
@@ -218,15 +231,14 @@ int finalize(soglu_ctx* c) {
         for (int64_t t = 0; t < nt; t++) c->level_order[pos[G.tasks[t].level]++] = (int32_t)t;
     }
     // triangular-solve structures
-    if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, false, false, c->l_ptr, c->l_col, c->l_slot, c->l_diag, c->nL_off))) return rc;
+    if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, false, false, c->l_ptr, c->l_col, c->l_slot, c->l_diag, c->l_dinv, c->nL_off))) return rc;
     if (c->symmetric) {
-        if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, true, true, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->nU_off))) return rc;
+        if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, true, true, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->u_dinv, c->nU_off))) return rc;
     } else {
-        if ((rc = build_tri(c, c->U_ids, c->U_brow, c->U_bcol, true, false, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->nU_off))) return rc;
+        if ((rc = build_tri(c, c->U_ids, c->U_brow, c->U_bcol, true, false, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->u_dinv, c->nU_off))) return rc;
     }
     const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
     CU(c->d_b.alloc(next)); CU(c->d_y.alloc(next)); CU(c->d_x.alloc(next));
-    CU(c->flags.alloc((size_t)c->n_block_rows * 2 * sizeof(int32_t)));
     c->compiled = true;
     return pack_pending_inputs(c);
 }
@@ -273,7 +285,7 @@ void soglu_destroy(soglu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (DevBuf* b : {&c->in_dense, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->counters, &c->initial,
-                      &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->d_b, &c->d_y, &c->d_x, &c->flags})
+                      &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->d_y, &c->d_x, &c->trace})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -287,6 +299,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     if (k == "exec_mode") c->opt_exec_mode = value;
     else if (k == "fuse_sub") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_sub must be set before the first factor"); c->opt_fuse_sub = value; }
     else if (k == "fuse_inv") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_inv must be set before the first factor"); c->opt_fuse_inv = value; }
+    else if (k == "split") { if (c->compiled) return fail(SOGLU_ERR_ARG, "split must be set before the first factor"); c->opt_split = value; }
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
@@ -421,15 +434,15 @@ int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* o
     TrsvParams P;
     P.pool = c->pool.as<double>();
     P.l_ptr = c->l_ptr.as<int64_t>(); P.l_col = c->l_col.as<int32_t>(); P.l_slot = c->l_slot.as<int32_t>(); P.l_diag = c->l_diag.as<int32_t>();
+    P.l_dinv = c->l_dinv.as<int32_t>();
     P.u_ptr = c->u_ptr.as<int64_t>(); P.u_col = c->u_col.as<int32_t>(); P.u_slot = c->u_slot.as<int32_t>(); P.u_diag = c->u_diag.as<int32_t>();
+    P.u_dinv = c->u_dinv.as<int32_t>();
     P.n_rows = c->n_block_rows;
     P.b = c->d_b.as<double>(); P.y = c->d_y.as<double>(); P.x = c->d_x.as<double>();
-    P.done_l = c->flags.as<int32_t>(); P.done_u = c->flags.as<int32_t>() + c->n_block_rows;
     P.symmetric = c->symmetric;
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(cudaMemsetAsync(c->flags.p, 0, (size_t)c->n_block_rows * 2 * sizeof(int32_t), c->stream));
     CU(launch_trsv(P, std::min(c->trsv_grid, c->n_block_rows), c->stream));
-    c->launches++;
+    c->launches += 2;   // sentinel fill + solve kernel
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaMemcpyAsync(x_ext, c->d_x.p, next, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -443,7 +456,7 @@ int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* o
         const double nblk = (double)(c->nL_off + c->nU_off + 2.0 * c->n_block_rows);
         out->flops = 2.0 * 4096.0 * nblk;
         out->bytes = (double)BLK * BLK * 8.0 * nblk + 8.0 * 3.0 * c->n_block_rows * BLK;
-        out->kernel_launches = 1;
+        out->kernel_launches = 2;
         out->tasks = 2 * (int64_t)c->n_block_rows;
         out->pool_blocks = c->G.n_slots;
         out->h2d_bytes = (double)next;
@@ -456,9 +469,9 @@ int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* o
 int soglu_debug_diag_bench(soglu_ctx* c, int iters, long long* cycles4) {
     if (!c || !c->compiled || c->G.n_slots < 8) return fail(SOGLU_ERR_ARG, "need a compiled problem");
     DevBuf d;
-    CU(d.alloc(64));
+    CU(d.alloc(128));
     CU(launch_diag_bench(c->pool.as<double>(), iters, d.as<long long>(), c->stream));
-    CU(cudaMemcpyAsync(cycles4, d.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(cycles4, d.p, 80, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     d.release();
     return SOGLU_OK;

@@ -289,6 +289,68 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         if ((int64_t)queue.size() != nt) return "operation list has a dependency cycle";
         G.n_levels = nt ? maxlev + 1 : 0;
     }
+    // ---- row split of GEMM tasks in narrow levels -------------------------------------------------
+    // In a level with fewer GEMM tasks than SMs the factorisation is latency-bound: one 64x64x64
+    // product occupies one SM for ~2.4 us per pair while the others idle.  Such tasks are split
+    // into 2 or 4 row slices (each slice loads its rows of A and all of B); consumers depend on
+    // every slice.  Wide levels stay whole (no extra operand traffic where throughput matters).
+    for (Task& t : G.tasks)
+        if (t.type == T_GEMM) t.flags |= (4 << TF_NROWS_SHIFT);
+    if (opt.split_narrow && nt > 0) {
+        std::vector<int32_t> level_gemms(G.n_levels, 0);
+        for (const Task& t : G.tasks)
+            if (t.type == T_GEMM) level_gemms[t.level]++;
+        std::vector<int32_t> split(nt, 1), base(nt + 1, 0);
+        for (int64_t t = 0; t < nt; t++) {
+            const Task& T = G.tasks[t];
+            if (T.type == T_GEMM) {
+                const int w = level_gemms[T.level];
+                if (4 * w <= opt.n_sms) split[t] = 4;
+                else if (2 * w <= opt.n_sms) split[t] = 2;
+            }
+            base[t + 1] = base[t] + split[t];
+            if (split[t] > 1) G.split_tasks++;
+        }
+        if (G.split_tasks > 0) {
+            const int64_t nt2 = base[nt];
+            std::vector<Task> tasks2(nt2);
+            int64_t nsucc2 = 0;
+            for (int64_t t = 0; t < nt; t++) {
+                int64_t fan = 0;
+                for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) fan += split[G.succ[e]];
+                nsucc2 += fan * split[t];
+            }
+            if (nsucc2 > 0x7fffffff) return "too many dependency edges after row split";
+            std::vector<int32_t> succ2(nsucc2);
+            std::vector<int32_t> deps2(nt2, 0);
+            int64_t pos = 0;
+            for (int64_t t = 0; t < nt; t++) {
+                const Task& T = G.tasks[t];
+                for (int s = 0; s < split[t]; s++) {
+                    Task N = T;
+                    if (split[t] > 1) {
+                        const int rows16 = 4 / split[t];
+                        N.flags = (T.flags & 0xff) | ((s * rows16) << TF_ROW0_SHIFT) | (rows16 << TF_NROWS_SHIFT);
+                    }
+                    N.succ_begin = (int32_t)pos;
+                    for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+                        const int32_t d = G.succ[e];
+                        for (int q = 0; q < split[d]; q++) { succ2[pos++] = base[d] + q; deps2[base[d] + q]++; }
+                    }
+                    N.succ_end = (int32_t)pos;
+                    tasks2[base[t] + s] = N;
+                }
+            }
+            for (int64_t t = 0; t < nt2; t++) tasks2[t].n_deps = deps2[t];
+            G.tasks.swap(tasks2);
+            G.succ.swap(succ2);
+            G.initial.clear();
+            for (int64_t t = 0; t < nt2; t++)
+                if (G.tasks[t].n_deps == 0) G.initial.push_back((int32_t)t);
+            for (int32_t& x : G.task_of)
+                if (x >= 0) x = base[x];
+        }
+    }
     // ---- patch block ids -> pool slots ---------------------------------------------------------
     for (Task& t : G.tasks) {
         t.out = G.slot_of[t.out];
@@ -297,6 +359,8 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         if (t.flags & TF_UINV) t.out4 = G.slot_of[t.out4];
     }
     for (Pair& p : G.pairs) { p.a = G.slot_of[p.a]; p.b = G.slot_of[p.b]; }
+    for (Task& t : G.tasks)
+        for (int k = 0; k < 2; k++) t.first[k] = (k < t.n_pairs) ? G.pairs[t.pair_begin + k] : Pair{0, 0};
     return "";
 }
 

@@ -51,7 +51,7 @@ struct __align__(16) SmemCtl {
     uint64_t full[N_STAGES];
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
-    double scratch[576];   // pivot row/column exchange buffers of the register-resident diag kernels
+    double scratch[584];   // pivot row/column exchange buffers of the register-resident diag kernels
 };
 
 constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
@@ -83,7 +83,7 @@ __device__ __forceinline__ void store_block(double* __restrict__ g, const double
 //   U^-1:  (U^T)^-1 by the same forward elimination with multipliers u_ki / u_kk taken from
 //          the pivot row, scaled by 1/u_ii at the end and written back transposed.
 // So the fused lu + lowerInv + upperInv task costs one elimination sweep instead of three.
-template <bool WITH_INV>
+template <bool WITH_INV, int DBG = 0>
 __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* __restrict__ xbuf, double (&a)[4][4], double (&wl)[4][4],
                                         double (&wu)[4][4], int ct) {
     const int ty = ct >> 4, tx = ct & 15;
@@ -92,6 +92,7 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
     double* wlbuf = xbuf + 256;    // [2][64] row k of W_L
     double* wubuf = xbuf + 384;    // [2][64] row k of W_U
     double* ipbuf = xbuf + 512;    // [64]    1 / u_kk
+    double* ipnext = xbuf + 576;   // [2]     1 / u_kk of the pivot about to be used (double-buffered)
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -99,6 +100,17 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
             a[r][c] = As[(ty + 16 * r) * BLK_LD + tx + 16 * c];
             if (WITH_INV) wl[r][c] = wu[r][c] = (r == c && ty == tx) ? 1.0 : 0.0;
         }
+    // The reciprocal of pivot k+1 is formed by the warp that owns element (k+1,k+1) as soon as
+    // pivot k has updated it, and published with the pivot row: the other warps' updates of
+    // pivot k overlap that division instead of every thread waiting for 1/p after the barrier.
+    if (ct == 0) {
+        double p = a[0][0];
+        if (p < 1e-9 && p > -1e-9) p = (p < 0) ? -1e-9 : 1e-9;
+        a[0][0] = p;
+        const double ip0 = ptx::fast_rcp(p);
+        ipnext[0] = ip0;
+        if (WITH_INV) ipbuf[0] = ip0;
+    }
 #pragma unroll
     for (int kr = 0; kr < 4; kr++) {
 #pragma unroll 1
@@ -117,8 +129,28 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
 #pragma unroll
                 for (int r = kr; r < 4; r++) colbuf[pb + ty + 16 * r] = a[r][kr];
             }
-            math_sync();
-            double p = rowbuf[pb + k];
+            if (!(DBG & 1)) math_sync();
+            const double ip = (DBG & 2) ? 1.0 : ipnext[k & 1];
+            // Next pivot first: the warp owning element (k+1,k+1) applies pivot k to that one element,
+            // clamps it and forms its reciprocal BEFORE its share of the trailing update, so the
+            // division overlaps the other warps' updates (warp-uniform branch, no divergence).
+            bool own_next = false;
+            double p_next = 0.0;
+            {
+                const int k1 = k + 1, ko1 = k1 & 15;
+                if (!(DBG & 2) && k1 < BLK && (ty >> 1) == (ko1 >> 1)) {
+                    own_next = (ty == ko1) && (tx == ko1);
+                    const double a_sel = (ko != 15) ? a[kr][kr] : a[kr < 3 ? kr + 1 : 3][kr < 3 ? kr + 1 : 3];
+                    double p = fma(-(colbuf[pb + k1] * ip), rowbuf[pb + k1], a_sel);
+                    if (p < 1e-9 && p > -1e-9) p = (p < 0) ? -1e-9 : 1e-9;
+                    const double ipn = ptx::fast_rcp(p);
+                    p_next = p;
+                    if (own_next) {
+                        ipnext[k1 & 1] = ipn;
+                        if (WITH_INV) ipbuf[k1] = ipn;
+                    }
+                }
+            }
             double cbv[4], rbv[4], rbi[4], wlv[4], wuv[4];
 #pragma unroll
             for (int r = kr; r < 4; r++) { cbv[r] = colbuf[pb + ty + 16 * r]; if (WITH_INV) rbi[r] = rowbuf[pb + ty + 16 * r]; }
@@ -128,10 +160,6 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
 #pragma unroll
                 for (int c = 0; c <= kr; c++) { wlv[c] = wlbuf[pb + tx + 16 * c]; wuv[c] = wubuf[pb + tx + 16 * c]; }
             }
-            if (p < 1e-9 && p > -1e-9) p = (p < 0) ? -1e-9 : 1e-9;
-            if (ty == ko && tx == ko) a[kr][kr] = p;
-            const double ip = 1.0 / p;
-            if (WITH_INV && ct == 0) ipbuf[k] = ip;
             // Finished rows / columns are switched off by zeroing their multiplier / pivot-row
             // entry (a few selects per pivot) instead of predicating every update.
             const bool cedge = tx > ko, wedge = tx <= ko;
@@ -141,8 +169,10 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
             for (int r = kr; r < 4; r++) {
                 const bool ract = (r > kr) || (ty > ko);
                 const double l = ract ? cbv[r] * ip : 0.0;
+                if (!(DBG & 4)) {
 #pragma unroll
-                for (int c = kr; c < 4; c++) a[r][c] = fma(-l, rbv[c], a[r][c]);
+                    for (int c = kr; c < 4; c++) a[r][c] = fma(-l, rbv[c], a[r][c]);
+                }
                 if (ract && tx == ko) a[r][kr] = l;
                 if (WITH_INV) {
                     const double m = ract ? rbi[r] * ip : 0.0;
@@ -152,6 +182,9 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
                         wu[r][c] = fma(-m, wuv[c], wu[r][c]);
                     }
                 }
+            }
+            if (own_next) {   // the loops above produced the unclamped value; keep the clamped pivot
+                if (ko != 15) a[kr][kr] = p_next; else a[kr < 3 ? kr + 1 : 3][kr < 3 ? kr + 1 : 3] = p_next;
             }
         }
     }
@@ -283,26 +316,46 @@ __device__ void llt_block(double* __restrict__ A, double* __restrict__ Lb, int c
     }
 }
 
-// ---- Schur update: acc(32x16 per warp) += A(64x64) * B(64x64) from shared memory -------
-// warp w: rows 32*(w>>2) .. +31, cols 16*(w&3) .. +15; 4 x 2 DMMA tiles, 16 k-steps of 4.
-template <bool TRANSB>
+// ---- Schur update: acc += A(rows) * B(64x64) from shared memory, FP64 tensor cores ------------
+// A warp owns MT x NT DMMA tiles (8x8 each) starting at (row_base, col_base); 16 k-steps of 4.
+// Whole block (64 rows): 8 warps x (4 x 2 tiles); half (32 rows): 8 x (2 x 2); quarter: 8 x (2 x 1).
+template <bool TRANSB, int MT, int NT>
 __device__ __forceinline__ void mma_block(const double* __restrict__ As, const double* __restrict__ Bs, double (&acc)[4][2][2],
-                                          int warp, int lane) {
+                                          int row_base, int col_base, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    const double* a0 = As + (32 * (warp >> 2) + g) * BLK_LD + t;
-    const double* b0 = TRANSB ? Bs + (16 * (warp & 3) + g) * BLK_LD + t : Bs + t * BLK_LD + 16 * (warp & 3) + g;
+    const double* a0 = As + (row_base + g) * BLK_LD + t;
+    const double* b0 = TRANSB ? Bs + (col_base + g) * BLK_LD + t : Bs + t * BLK_LD + col_base + g;
 #pragma unroll
     for (int k0 = 0; k0 < BLK; k0 += 4) {
-        double a[4], b[2];
+        double a[MT], b[NT];
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++) a[mi] = a0[mi * 8 * BLK_LD + k0];
+        for (int mi = 0; mi < MT; mi++) a[mi] = a0[mi * 8 * BLK_LD + k0];
 #pragma unroll
-        for (int ni = 0; ni < 2; ni++) b[ni] = TRANSB ? b0[ni * 8 * BLK_LD + k0] : b0[k0 * BLK_LD + ni * 8];
+        for (int ni = 0; ni < NT; ni++) b[ni] = TRANSB ? b0[ni * 8 * BLK_LD + k0] : b0[k0 * BLK_LD + ni * 8];
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++)
+        for (int mi = 0; mi < MT; mi++)
 #pragma unroll
-            for (int ni = 0; ni < 2; ni++) ptx::dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            for (int ni = 0; ni < NT; ni++) ptx::dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const double* __restrict__ ini, const double (&acc)[4][2][2],
+                                              int row_base, int col_base, int lane, bool neg, bool has_init) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NT; ni++) {
+            const int off = (row_base + 8 * mi + g) * BLK_LD + col_base + 8 * ni + 2 * t;
+            double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            if (neg) { v.x = -v.x; v.y = -v.y; }
+            if (has_init) {
+                const double2 c0 = ptx::ld_cg_f64x2(ini + off);
+                v.x += c0.x; v.y += c0.y;
+            }
+            *reinterpret_cast<double2*>(out + off) = v;
+        }
 }
 
 __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
@@ -328,7 +381,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 const int slot = atomicAdd(P.head, 1);
                 int t = -1;
                 if (slot < P.n_tasks) {
-                    while ((t = ptx::ld_acquire(P.ready + slot)) < 0) __nanosleep(64);
+                    while ((t = ptx::ld_acquire(P.ready + slot)) < 0) {}
                 }
                 if (t < 0) {
                     const int s = it % N_STAGES;
@@ -349,10 +402,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     d.type = T.type; d.flags = T.flags; d.task = t; d.out = T.out; d.out2 = T.out2; d.init = T.init; d.out4 = T.out4;
                     d.first_last = (p == 0 ? 1 : 0) | (p == nst - 1 ? 2 : 0);
                     ctl->desc[s] = d;
-                    const Pair pr = P.pairs[T.pair_begin + p];
+                    const Pair pr = (p == 0) ? T.first[0] : ((p == 1) ? T.first[1] : P.pairs[T.pair_begin + p]);
                     double* As = stage_base + (size_t)s * (STAGE_BYTES / 8);
-                    ptx::mbar_arrive_expect_tx(&ctl->full[s], two ? 2 * BLK_BYTES : BLK_BYTES);
-                    ptx::bulk_g2s(As, P.pool + (size_t)pr.a * BLK_ELEMS, BLK_BYTES, &ctl->full[s]);
+                    // GEMM row slice: only rows [16*row0, 16*(row0+nrows)) of A are needed (same place in smem)
+                    const int a_off = (T.type == T_GEMM) ? ((T.flags >> TF_ROW0_SHIFT) & 3) * 16 * BLK_LD : 0;
+                    const uint32_t a_bytes = (T.type == T_GEMM) ? (uint32_t)((T.flags >> TF_NROWS_SHIFT) & 7) * 16 * BLK_LD * 8 : (uint32_t)BLK_BYTES;
+                    ptx::mbar_arrive_expect_tx(&ctl->full[s], two ? a_bytes + BLK_BYTES : a_bytes);
+                    ptx::bulk_g2s(As + a_off, P.pool + (size_t)pr.a * BLK_ELEMS + a_off, a_bytes, &ctl->full[s]);
                     if (two) ptx::bulk_g2s(As + BLK_ELEMS, P.pool + (size_t)pr.b * BLK_ELEMS, BLK_BYTES, &ctl->full[s]);
                 }
             }
@@ -380,29 +436,29 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
 #pragma unroll
                     for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             }
-            if (d.flags & TF_TRANSB) mma_block<true>(As, Bs, acc, mw, lane);
-            else mma_block<false>(As, Bs, acc, mw, lane);
+            const int nrows16 = (d.flags >> TF_NROWS_SHIFT) & 7, row0 = ((d.flags >> TF_ROW0_SHIFT) & 3) * 16;
+            const bool tb = d.flags & TF_TRANSB;
+            int rb, cb;
+            if (nrows16 == 4) {
+                rb = 32 * (mw >> 2); cb = 16 * (mw & 3);
+                if (tb) mma_block<true, 4, 2>(As, Bs, acc, rb, cb, lane); else mma_block<false, 4, 2>(As, Bs, acc, rb, cb, lane);
+            } else if (nrows16 == 2) {
+                rb = row0 + 16 * (mw >> 2); cb = 16 * (mw & 3);
+                if (tb) mma_block<true, 2, 2>(As, Bs, acc, rb, cb, lane); else mma_block<false, 2, 2>(As, Bs, acc, rb, cb, lane);
+            } else {
+                rb = row0; cb = 8 * mw;
+                if (tb) mma_block<true, 2, 1>(As, Bs, acc, rb, cb, lane); else mma_block<false, 2, 1>(As, Bs, acc, rb, cb, lane);
+            }
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&ctl->empty[s]);
             if (!(d.first_last & 2)) continue;
             // epilogue: out = init -/+ acc, 16-byte stores straight from the accumulators
-            const int g = lane >> 2, t = lane & 3;
             double* out = P.pool + (size_t)d.out * BLK_ELEMS;
             const double* ini = P.pool + (size_t)d.init * BLK_ELEMS;
             const bool neg = d.flags & TF_NEGATE, has_init = d.flags & TF_INIT;
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 2; ni++) {
-                    const int off = (32 * (mw >> 2) + 8 * mi + g) * BLK_LD + 16 * (mw & 3) + 8 * ni + 2 * t;
-                    double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-                    if (neg) { v.x = -v.x; v.y = -v.y; }
-                    if (has_init) {
-                        const double2 c0 = ptx::ld_cg_f64x2(ini + off);
-                        v.x += c0.x; v.y += c0.y;
-                    }
-                    *reinterpret_cast<double2*>(out + off) = v;
-                }
+            if (nrows16 == 4) gemm_epilogue<4, 2>(out, ini, acc, rb, cb, lane, neg, has_init);
+            else if (nrows16 == 2) gemm_epilogue<2, 2>(out, ini, acc, rb, cb, lane, neg, has_init);
+            else gemm_epilogue<2, 1>(out, ini, acc, rb, cb, lane, neg, has_init);
         } else {
             double* out = P.pool + (size_t)d.out * BLK_ELEMS;
             switch (d.type) {
@@ -485,6 +541,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
         lu_task(As, ctl->scratch, pool, d, ct);
         math_sync();
         long long c2 = clock64();
+        {
+            double a[4][4], wl[4][4], wu[4][4];
+            long long e0 = clock64();
+            lu3_reg<false, 1>(As, ctl->scratch, a, wl, wu, ct); math_sync();
+            long long e1 = clock64();
+            lu3_reg<false, 2>(As, ctl->scratch, a, wl, wu, ct); math_sync();
+            long long e2 = clock64();
+            lu3_reg<false, 4>(As, ctl->scratch, a, wl, wu, ct); math_sync();
+            long long e3 = clock64();
+            lu3_reg<false, 6>(As, ctl->scratch, a, wl, wu, ct); math_sync();
+            long long e4 = clock64();
+            lu3_reg<false, 7>(As, ctl->scratch, a, wl, wu, ct); math_sync();
+            long long e5 = clock64();
+            lu3_reg<false, 0>(As, ctl->scratch, a, wl, wu, ct); math_sync();
+            long long e6 = clock64();
+            if (ct == 0 && it == iters - 1) { cycles[4] = e1 - e0; cycles[5] = e2 - e1; cycles[6] = e3 - e2; cycles[7] = e4 - e3; cycles[8] = e5 - e4; cycles[9] = e6 - e5; }
+            if (a[0][0] == 1.2345e-300) pool[0] = a[1][1] + a[2][2] + a[3][3];
+        }
         for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[2 * BLK_ELEMS + i];
         math_sync();
         long long c3 = clock64();

@@ -36,14 +36,12 @@ cudaError_t launch_unpack_block(const double* pool, int32_t slot, double* dense,
 struct TrsvParams {
     const double* pool;
     // CSR by block row over off-diagonal factor blocks, columns ascending
-    const int64_t* l_ptr; const int32_t* l_col; const int32_t* l_slot; const int32_t* l_diag;
-    const int64_t* u_ptr; const int32_t* u_col; const int32_t* u_slot; const int32_t* u_diag;
+    const int64_t* l_ptr; const int32_t* l_col; const int32_t* l_slot; const int32_t* l_diag; const int32_t* l_dinv;
+    const int64_t* u_ptr; const int32_t* u_col; const int32_t* u_slot; const int32_t* u_diag; const int32_t* u_dinv;
     int32_t n_rows;        // block rows
     const double* b;       // n_rows*64
-    double* y;             // forward result
-    double* x;             // backward result
-    int32_t* done_l;       // per block row flags (0 -> 1)
-    int32_t* done_u;
+    double* y;             // forward result  (pre-filled with the NaN sentinel by launch_trsv)
+    double* x;             // backward result (idem)
     int32_t symmetric;     // U = L^T: backward sweep reads L blocks transposed (CSC of L passed in u_*)
 };
 cudaError_t launch_trsv(const TrsvParams& p, int grid, cudaStream_t stream);

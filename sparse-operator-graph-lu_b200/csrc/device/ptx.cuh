@@ -76,6 +76,18 @@ __device__ __forceinline__ void pfnma(double& x, double a, double b, bool pred) 
     asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}" : "+d"(x) : "d"(-a), "d"(b), "r"((int)pred));
 }
 
+// 1/x for finite |x| >= 1e-9: hardware seed (MUFU.RCP64H) + two Newton steps, branch-free
+// (error <= ~1 ulp; the IEEE-rounded 1.0/x would add a special-case call on the pivot chain)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 }  // namespace ptx

@@ -33,10 +33,15 @@ enum TaskFlags : int32_t {
     TF_TRANSB = 2,   // GEMM: use B^T (mult)
     TF_INIT = 4,     // GEMM: start from block `init` instead of zero (fused sub)
     TF_LINV = 8,     // LU/LLT: also produce out3 = L^-1 (fused lowerInv)
-    TF_UINV = 16     // LU: also produce out4 = U^-1 (fused upperInv)
+    TF_UINV = 16,    // LU: also produce out4 = U^-1 (fused upperInv)
+    // GEMM row split: the task computes rows [16*row0, 16*row0 + 16*nrows) of the target block
+    TF_ROW0_SHIFT = 8,    // 2 bits: first row / 16
+    TF_NROWS_SHIFT = 12   // 3 bits: rows / 16 (4 = whole block, 2 = half, 1 = quarter)
 };
 
-struct Task {          // 48 bytes
+struct Pair { int32_t a, b; };   // pool slots; non-GEMM: a = src (or S2), b = S1 / unused
+
+struct Task {          // 64 bytes = one 64-byte line: the scheduler needs ONE load per task
     int32_t type;
     int32_t flags;
     int32_t n_pairs;     // GEMM: number of (A,B) pairs; others: 1
@@ -48,8 +53,8 @@ struct Task {          // 48 bytes
     int32_t n_deps;      // initial dependency counter
     int32_t level;       // ASAP level (0 = ready at start)
     int32_t out4;        // LU + TF_UINV: slot of U^-1
+    Pair first[2];       // copy of the first two operand pairs (saves a dependent fetch)
 };
-struct Pair { int32_t a, b; };   // pool slots; non-GEMM: a = src (or S2), b = S1 / unused
 
 struct TaskGraph {
     std::vector<Task> tasks;
@@ -65,11 +70,14 @@ struct TaskGraph {
     int64_t fused_subs = 0;
     int64_t fused_invs = 0;
     int64_t aliased_invs = 0;
+    int64_t split_tasks = 0;   // GEMM tasks that were row-split
 };
 
 struct CompileOptions {
     bool fuse_sub = true;   // fold `sub` into the producing mul chain when it is the only reader
     bool fuse_inv = true;   // fold the first lowerInv / upperInv of an lu's factors into the lu task
+    int split_narrow = 1;   // split GEMM tasks of narrow dependency levels by output rows (latency-bound phases)
+    int n_sms = 148;        // width against which a level counts as narrow
 };
 
 // Returns "" on success, otherwise the violated invariant.

@@ -3,18 +3,22 @@
 // BlockPlanner.cpp:669-862).
 //
 // After GPS ordering the factors are banded, so at block granularity the solve is a chain:
-// block row i needs block row i-1.  One persistent kernel walks that
-// chain as a software pipeline: block row i belongs to CTA (i mod grid); the CTA consumes
-// the off-diagonal blocks of its row in ascending column order, each as soon as the
-// producing row has published its segment (per-row flag, release/acquire at gpu scope),
-// so everything except the last dependency is already folded in when row i-1 finishes.
-// The forward (L) and backward (U) sweeps run in the same launch; row i of the backward
-// sweep additionally waits for y_i of the forward sweep.
+// block row i needs block row i-1.  One persistent kernel walks that chain
+// as a software pipeline: block row i belongs to CTA (i mod grid).  Per row the CTA
+//   * starts two TMA bulk copies at once: the NEAREST off-diagonal block (the one that
+//     multiplies the segment produced last, i.e. the chain-critical one) and the diagonal
+//     operator -- the explicit 64x64 inverse of the diagonal block when the factorisation
+//     produced one (fused lu task), else the diagonal block itself;
+//   * folds in all other off-diagonal blocks in ascending distance from the critical one,
+//     each a 64x64 GEMV streamed from HBM/L2 with the next block's loads already in flight;
+//   * waits for the last segment, applies the staged block and the diagonal operator from
+//     shared memory, and publishes its 64 values.
+// Segments are SELF-VALIDATING: y and x are pre-filled with a NaN sentinel, each consumer
+// thread spins on exactly the 8-byte word it needs, so the chain has no flag, no fence and a
+// single L2 round trip per hop.  Forward (L) and backward (U or L^T) sweeps share one launch.
 //
-// Work per off-diagonal block: a 64x64 GEMV straight from HBM/L2 (each factor block is read
-// exactly once per sweep -> HBM-bound per block, latency-bound along the chain).
-// The diagonal 64x64 triangular solve is done by one warp with the block staged in shared
-// memory (divides by the stored diagonal like lowerSolver/upperSolver, 757 / 821).
+// Per factor block 32 768 B are read once per sweep (HBM-bound per block); the chain of
+// 2 x n_block_rows dependent hops bounds the total (reported with the number in bench.py).
 #include "executor.cuh"
 #include "ptx.cuh"
 
@@ -22,16 +26,36 @@ namespace soglu {
 namespace {
 
 constexpr int TR_THREADS = 256;
+constexpr unsigned long long SENTINEL = 0xFFF8DEADFFF8DEADull;   // a NaN no arithmetic produces
 
-__device__ __forceinline__ void wait_flag(const int32_t* f) {
-    while (ptx::ld_acquire(f) == 0) __nanosleep(32);
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const double* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double poll_value(const double* p) {
+    unsigned long long v;
+    while ((v = ld_volatile_u64(p)) == SENTINEL) {}
+    return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ void publish_value(double* p, double x) {
+    unsigned long long v = (unsigned long long)__double_as_longlong(x);
+    if (v == SENTINEL) v = 0x7FF8000000000000ull;   // never publish the sentinel itself
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// r[0..63] -= M * v  (or M^T * v), M a pool block (ld 68), 256 threads: 4 threads per row
+struct __align__(16) TrsvSmem {
+    double last[BLK_ELEMS];   // nearest off-diagonal block of the row
+    double diag[BLK_ELEMS];   // diagonal block or its explicit inverse
+    double r[BLK];            // running right-hand side segment
+    double v[BLK];            // source segment of the block being applied
+    double t[BLK];            // r after the off-diagonal part (input of the diagonal operator)
+    uint64_t bar;
+};
+
+// 4 threads per row: racc[row] -= sum_c M[row][c] * v[c]  (or M^T), M in global memory
 template <bool TRANS>
-__device__ __forceinline__ void gemv_sub(const double* __restrict__ M, const double* __restrict__ v, double* __restrict__ racc, int tid) {
-    // thread (row = tid>>2, part = tid&3) handles 16 interleaved double2 chunks of its row
-    const int row = tid >> 2, part = tid & 3;
+__device__ __forceinline__ double gemv_part_global(const double* __restrict__ M, const double* __restrict__ v, int row, int part) {
     double s = 0.0;
     if (!TRANS) {
         const double* m = M + row * BLK_LD;
@@ -39,114 +63,164 @@ __device__ __forceinline__ void gemv_sub(const double* __restrict__ M, const dou
         for (int c = 0; c < 8; c++) {
             const int col = (c * 4 + part) * 2;
             const double2 a = ptx::ld_cg_f64x2(m + col);
-            s += a.x * v[col] + a.y * v[col + 1];
+            s = fma(a.x, v[col], s);
+            s = fma(a.y, v[col + 1], s);
         }
     } else {
-        // (M^T v)[row] = sum_k M[k][row] v[k]; part splits k
 #pragma unroll 4
-        for (int k = part; k < BLK; k += 4) s += ptx::ld_cg_f64(M + k * BLK_LD + row) * v[k];
+        for (int k = part; k < BLK; k += 4) s = fma(ptx::ld_cg_f64(M + k * BLK_LD + row), v[k], s);
     }
+    return s;
+}
+template <bool TRANS>
+__device__ __forceinline__ double gemv_part_smem(const double* __restrict__ M, const double* __restrict__ v, int row, int part) {
+    double s = 0.0;
+    if (!TRANS) {
+        const double* m = M + row * BLK_LD;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int col = (c * 4 + part) * 2;
+            const double2 a = *reinterpret_cast<const double2*>(m + col);
+            s = fma(a.x, v[col], s);
+            s = fma(a.y, v[col + 1], s);
+        }
+    } else {
+#pragma unroll 4
+        for (int k = part; k < BLK; k += 4) s = fma(M[k * BLK_LD + row], v[k], s);
+    }
+    return s;
+}
+__device__ __forceinline__ double quad_sum(double s) {
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (part == 0) racc[row] -= s;
+    return s;
 }
 
-// one sweep over one block row: rhs segment -> solution segment
+// One block row of one sweep.  UPPER: backward sweep (columns > row); TRANS: apply blocks transposed.
 template <bool UPPER, bool TRANS>
 __device__ void solve_row(const double* __restrict__ pool, int row, const int64_t* __restrict__ ptr, const int32_t* __restrict__ col,
-                          const int32_t* __restrict__ slot, const int32_t* __restrict__ diag, const double* __restrict__ rhs,
-                          double* __restrict__ sol, int32_t* __restrict__ done, const int32_t* __restrict__ also_wait,
-                          double* sD, double* sR, double* sV, int tid) {
-    if (also_wait) {
-        if (tid == 0) wait_flag(also_wait + row);
-    }
-    __syncthreads();
-    if (tid < BLK) sR[tid] = ptx::ld_cg_f64(rhs + (size_t)row * BLK + tid);
-    // stage the diagonal block while waiting for dependencies
-    {
-        const double* D = pool + (size_t)diag[row] * BLK_ELEMS;
-        for (int i = tid; i < BLK_ELEMS / 2; i += TR_THREADS) reinterpret_cast<double2*>(sD)[i] = ptx::ld_cg_f64x2(D + 2 * i);
-    }
-    __syncthreads();
+                          const int32_t* __restrict__ slot, const int32_t* __restrict__ diag, const int32_t* __restrict__ dinv,
+                          const double* __restrict__ rhs, bool rhs_is_computed, double* __restrict__ sol, TrsvSmem& S,
+                          uint32_t& phase, int tid) {
     const int64_t b = ptr[row], e = ptr[row + 1];
-    // forward: ascending columns; backward: descending columns (nearest dependency last)
-    for (int64_t q = 0; q < e - b; q++) {
-        const int64_t k = UPPER ? (e - 1 - q) : (b + q);
-        const int c = col[k];
-        if (tid == 0) wait_flag(done + c);
-        __syncthreads();
-        if (tid < BLK) sV[tid] = ptx::ld_cg_f64(sol + (size_t)c * BLK + tid);
-        __syncthreads();
-        gemv_sub<TRANS>(pool + (size_t)slot[k] * BLK_ELEMS, sV, sR, tid);
-        __syncthreads();
+    const int nb = (int)(e - b);
+    // chain-critical block: forward = largest column (< row), backward = smallest column (> row)
+    const int64_t kcrit = UPPER ? b : e - 1;
+    const int inv_slot = dinv[row];
+    if (tid == 0) {
+        const uint32_t bytes = (nb > 0 ? 2u : 1u) * BLK_BYTES;
+        ptx::mbar_arrive_expect_tx(&S.bar, bytes);
+        ptx::bulk_g2s(S.diag, pool + (size_t)(inv_slot > 0 ? inv_slot : diag[row]) * BLK_ELEMS, BLK_BYTES, &S.bar);
+        if (nb > 0) ptx::bulk_g2s(S.last, pool + (size_t)slot[kcrit] * BLK_ELEMS, BLK_BYTES, &S.bar);
     }
-    // diagonal solve by warp 0: lane owns rows lane and lane+32
-    if (tid < 32) {
+    if (tid < BLK) S.r[tid] = rhs_is_computed ? poll_value(rhs + (size_t)row * BLK + tid) : rhs[(size_t)row * BLK + tid];
+    const int rrow = tid >> 2, part = tid & 3;
+    // non-critical blocks, far to near
+    for (int q = 0; q < nb - 1; q++) {
+        const int64_t k = UPPER ? (e - 1 - q) : (b + q);
+        __syncthreads();
+        if (tid < BLK) S.v[tid] = poll_value(sol + (size_t)col[k] * BLK + tid);
+        __syncthreads();
+        const double s = quad_sum(gemv_part_global<TRANS>(pool + (size_t)slot[k] * BLK_ELEMS, S.v, rrow, part));
+        if (part == 0) S.r[rrow] -= s;
+    }
+    __syncthreads();
+    // critical block from shared memory
+    ptx::mbar_wait(&S.bar, phase);
+    phase ^= 1;
+    if (nb > 0) {
+        if (tid < BLK) S.v[tid] = poll_value(sol + (size_t)col[kcrit] * BLK + tid);
+        __syncthreads();
+        const double s = quad_sum(gemv_part_smem<TRANS>(S.last, S.v, rrow, part));
+        if (part == 0) S.t[rrow] = S.r[rrow] - s;
+    } else if (tid < BLK) {
+        S.t[tid] = S.r[tid];
+    }
+    __syncthreads();
+    if (inv_slot > 0) {
+        // x = D^-1 t with the explicit inverse (a GEMV instead of a 64-step substitution)
+        const double s = quad_sum(gemv_part_smem<TRANS>(S.diag, S.t, rrow, part));
+        if (part == 0) publish_value(sol + (size_t)row * BLK + rrow, s);
+    } else if (tid < 32) {
+        // substitution with the stored diagonal (lowerSolver / upperSolver, BlockPlanner.cpp:757, 821)
         const int lane = tid;
-        double r0 = sR[lane], r1 = sR[lane + 32];
+        const double* D = S.diag;
+        double r0 = S.t[lane], r1 = S.t[lane + 32];
         if (!UPPER) {
             for (int k = 0; k < BLK; k++) {
-                const double dkk = sD[k * BLK_LD + k];
-                double xk = (k < 32 ? r0 : r1) / dkk;
+                double xk = (k < 32 ? r0 : r1) / D[k * BLK_LD + k];
                 xk = __shfl_sync(0xffffffffu, xk, k & 31);
                 if (lane == (k & 31)) { if (k < 32) r0 = xk; else r1 = xk; }
-                // element (i,k) of the triangular matrix: D[i][k], or D[k][i] when transposed
-                if (lane > k) r0 -= (TRANS ? sD[k * BLK_LD + lane] : sD[lane * BLK_LD + k]) * xk;
-                if (lane + 32 > k) r1 -= (TRANS ? sD[k * BLK_LD + lane + 32] : sD[(lane + 32) * BLK_LD + k]) * xk;
+                if (lane > k) r0 -= (TRANS ? D[k * BLK_LD + lane] : D[lane * BLK_LD + k]) * xk;
+                if (lane + 32 > k) r1 -= (TRANS ? D[k * BLK_LD + lane + 32] : D[(lane + 32) * BLK_LD + k]) * xk;
             }
         } else {
             for (int k = BLK - 1; k >= 0; k--) {
-                const double dkk = sD[k * BLK_LD + k];
-                double xk = (k < 32 ? r0 : r1) / dkk;
+                double xk = (k < 32 ? r0 : r1) / D[k * BLK_LD + k];
                 xk = __shfl_sync(0xffffffffu, xk, k & 31);
                 if (lane == (k & 31)) { if (k < 32) r0 = xk; else r1 = xk; }
-                if (lane < k) r0 -= (TRANS ? sD[k * BLK_LD + lane] : sD[lane * BLK_LD + k]) * xk;
-                if (lane + 32 < k) r1 -= (TRANS ? sD[k * BLK_LD + lane + 32] : sD[(lane + 32) * BLK_LD + k]) * xk;
+                if (lane < k) r0 -= (TRANS ? D[k * BLK_LD + lane] : D[lane * BLK_LD + k]) * xk;
+                if (lane + 32 < k) r1 -= (TRANS ? D[k * BLK_LD + lane + 32] : D[(lane + 32) * BLK_LD + k]) * xk;
             }
         }
-        sol[(size_t)row * BLK + lane] = r0;
-        sol[(size_t)row * BLK + lane + 32] = r1;
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            ptx::st_release(done + row, 1);
-        }
+        publish_value(sol + (size_t)row * BLK + lane, r0);
+        publish_value(sol + (size_t)row * BLK + lane + 32, r1);
     }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(TR_THREADS) trsv_kernel(TrsvParams P) {
-    __shared__ __align__(16) double sD[BLK_ELEMS];
-    __shared__ double sR[BLK];
-    __shared__ double sV[BLK];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TrsvSmem& S = *reinterpret_cast<TrsvSmem*>(smem_raw);
     const int tid = threadIdx.x;
     const int G = gridDim.x;
+    if (tid == 0) {
+        ptx::mbar_init(&S.bar, 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
     // forward sweep: L y = b
     for (int row = blockIdx.x; row < P.n_rows; row += G)
-        solve_row<false, false>(P.pool, row, P.l_ptr, P.l_col, P.l_slot, P.l_diag, P.b, P.y, P.done_l, nullptr, sD, sR, sV, tid);
-    // backward sweep: U x = y (or L^T x = y)
+        solve_row<false, false>(P.pool, row, P.l_ptr, P.l_col, P.l_slot, P.l_diag, P.l_dinv, P.b, false, P.y, S, phase, tid);
+    // backward sweep: U x = y (or L^T x = y); its right-hand side is the forward result
     for (int r = blockIdx.x; r < P.n_rows; r += G) {
         const int row = P.n_rows - 1 - r;
         if (P.symmetric)
-            solve_row<true, true>(P.pool, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.y, P.x, P.done_u, P.done_l, sD, sR, sV, tid);
+            solve_row<true, true>(P.pool, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, tid);
         else
-            solve_row<true, false>(P.pool, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.y, P.x, P.done_u, P.done_l, sD, sR, sV, tid);
+            solve_row<true, false>(P.pool, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, tid);
+    }
+}
+
+__global__ void fill_sentinel_kernel(double* __restrict__ a, double* __restrict__ b, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        reinterpret_cast<unsigned long long*>(a)[i] = SENTINEL;
+        reinterpret_cast<unsigned long long*>(b)[i] = SENTINEL;
     }
 }
 
 }  // namespace
 
 int trsv_max_grid(int device) {
+    cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsvSmem));
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_kernel, TR_THREADS, 0) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_kernel, TR_THREADS, sizeof(TrsvSmem)) != cudaSuccess) return 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
 
 cudaError_t launch_trsv(const TrsvParams& p, int grid, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsvSmem));
+    if (e != cudaSuccess) return e;
+    const int64_t n = (int64_t)p.n_rows * BLK;
+    fill_sentinel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p.y, p.x, n);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     TrsvParams pp = p;
     void* args[] = {&pp};
-    return cudaLaunchCooperativeKernel((const void*)trsv_kernel, dim3(grid), dim3(TR_THREADS), args, 0, stream);
+    return cudaLaunchCooperativeKernel((const void*)trsv_kernel, dim3(grid), dim3(TR_THREADS), args, sizeof(TrsvSmem), stream);
 }
 
 }  // namespace soglu
