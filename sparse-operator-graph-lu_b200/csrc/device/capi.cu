@@ -71,7 +71,8 @@ struct soglu_ctx {
     TaskGraph G;
     std::vector<int32_t> level_order;   // tasks sorted by level (debug executor)
     std::vector<int64_t> level_ptr;
-    DevBuf pool, tasks, pairs, succ, dep0, dep, ready, counters, initial;
+    DevBuf pool, tasks, pairs, succ, dep0, dep, ready, ready0, counters, counters0;
+    int64_t opt_max_slots = 0;     // debug: cap the block pool (forces segments + slot recycling)
     // solve structures
     DevBuf l_ptr, l_col, l_slot, l_diag, l_dinv, u_ptr, u_col, u_slot, u_diag, u_dinv, d_b, d_y, d_x;
     int64_t nL_off = 0, nU_off = 0;
@@ -187,6 +188,16 @@ int finalize(soglu_ctx* c) {
     co.fuse_inv = c->opt_fuse_inv != 0;
     co.split_narrow = (int)c->opt_split;
     co.n_sms = c->sms;
+    {
+        // pool capacity: what is free now minus the graph arrays (estimated from the op count) and a margin
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const double graph_est = (double)c->n_ops * 40.0 + (double)c->n_block_rows * 64 * 8 * 4 + 1.5e9;
+        double cap = ((double)free_b - graph_est) / (double)BLK_BYTES;
+        if (cap < 16) cap = 16;
+        co.max_slots = (int64_t)cap;
+        if (c->opt_max_slots > 0 && c->opt_max_slots < co.max_slots) co.max_slots = c->opt_max_slots;
+    }
     std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
                                     c->result.data(), c->result2.data(), keep, co, c->G);
     if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
@@ -216,10 +227,22 @@ int finalize(soglu_ctx* c) {
         for (size_t t = 0; t < G.tasks.size(); t++) d0[t] = G.tasks[t].n_deps;
         if ((rc = upload(c->dep0, d0, c))) return rc;
     }
-    if ((rc = upload(c->initial, G.initial, c))) return rc;
+    {
+        // ready queue image: per segment slice, the initially ready tasks first, -1 elsewhere;
+        // counter image: per segment one 256-byte record {head = 0, ..., tail = #initial at int 32}
+        const int nseg = (int)G.seg_begin.size() - 1;
+        std::vector<int32_t> r0(std::max<size_t>(G.tasks.size(), 1), -1), c0((size_t)std::max(nseg, 1) * 64, 0);
+        for (int sg = 0; sg < nseg; sg++) {
+            const int32_t nb = G.seg_init[sg + 1] - G.seg_init[sg];
+            for (int32_t k = 0; k < nb; k++) r0[G.seg_begin[sg] + k] = G.initial[G.seg_init[sg] + k];
+            c0[(size_t)sg * 64 + 32] = nb;
+        }
+        if ((rc = upload(c->ready0, r0, c))) return rc;
+        if ((rc = upload(c->counters0, c0, c))) return rc;
+        CU(c->counters.alloc(c0.size() * 4));
+    }
     CU(c->dep.alloc(std::max<size_t>(G.tasks.size(), 1) * 4));
     CU(c->ready.alloc(std::max<size_t>(G.tasks.size(), 1) * 4));
-    CU(c->counters.alloc(256));
     // level order for the debug executor
     {
         const int64_t nt = (int64_t)G.tasks.size();
@@ -284,7 +307,7 @@ int soglu_create(soglu_ctx** out, int n_gpus, const int* device_ids) {
 void soglu_destroy(soglu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (DevBuf* b : {&c->in_dense, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->counters, &c->initial,
+    for (DevBuf* b : {&c->in_dense, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
                       &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->d_y, &c->d_x, &c->trace})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -300,6 +323,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "fuse_sub") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_sub must be set before the first factor"); c->opt_fuse_sub = value; }
     else if (k == "fuse_inv") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_inv must be set before the first factor"); c->opt_fuse_inv = value; }
     else if (k == "split") { if (c->compiled) return fail(SOGLU_ERR_ARG, "split must be set before the first factor"); c->opt_split = value; }
+    else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
@@ -383,22 +407,30 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     CU(cudaEventRecord(c->ev0, c->stream));
     if (nt > 0) {
         if (c->opt_exec_mode == 0) {
+            const int nseg = (int)G.seg_begin.size() - 1;
             CU(cudaMemcpyAsync(c->dep.p, c->dep0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
-            CU(cudaMemsetAsync(c->ready.p, 0xff, (size_t)nt * 4, c->stream));
-            CU(cudaMemcpyAsync(c->ready.p, c->initial.p, G.initial.size() * 4, cudaMemcpyDeviceToDevice, c->stream));
-            int32_t ht[64] = {0};
-            ht[32] = (int32_t)G.initial.size();
-            CU(cudaMemcpyAsync(c->counters.p, ht, sizeof ht, cudaMemcpyHostToDevice, c->stream));
-            P.n_tasks = nt;
+            CU(cudaMemcpyAsync(c->ready.p, c->ready0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->counters.p, c->counters0.p, (size_t)nseg * 256, cudaMemcpyDeviceToDevice, c->stream));
             P.signal = 1;
-            CU(launch_executor(P, grid, c->stream));
-            c->launches++;
+            // one persistent launch per segment (a single one unless the pool forces slot recycling)
+            for (int sg = 0; sg < nseg; sg++) {
+                P.ready = c->ready.as<int32_t>() + G.seg_begin[sg];
+                P.head = c->counters.as<int32_t>() + (size_t)sg * 64;
+                P.tail = P.head + 32;
+                P.n_tasks = G.seg_begin[sg + 1] - G.seg_begin[sg];
+                if (P.n_tasks == 0) continue;
+                CU(launch_executor(P, grid, c->stream));
+                c->launches++;
+            }
         } else {
             // debug: one launch per dependency level, no in-kernel signalling
             for (int l = 0; l < G.n_levels; l++) {
                 const int64_t b = c->level_ptr[l], e = c->level_ptr[l + 1];
                 CU(cudaMemcpyAsync(c->ready.p, c->level_order.data() + b, (size_t)(e - b) * 4, cudaMemcpyHostToDevice, c->stream));
                 CU(cudaMemsetAsync(c->counters.p, 0, 256, c->stream));
+                P.ready = c->ready.as<int32_t>();
+                P.head = c->counters.as<int32_t>();
+                P.tail = P.head + 32;
                 P.n_tasks = (int32_t)(e - b);
                 P.signal = 0;
                 CU(launch_executor(P, (int)std::min<int64_t>(grid, e - b), c->stream));
@@ -504,6 +536,7 @@ int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {
     if (!c->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled yet");
     if (id <= 0 || id >= c->n_ids) return fail(SOGLU_ERR_ARG, "block id out of range");
     const int32_t slot = c->G.slot_of[id];
+    if (c->G.recycled[id]) return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " was recycled (its pool slot was reused after its last reader)");
     if (slot <= 0) return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " has no storage (never produced, or folded into a fused task)");
     CU(cudaSetDevice(c->device));
     DevBuf tmp;

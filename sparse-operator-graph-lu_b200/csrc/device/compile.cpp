@@ -185,17 +185,9 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         for (int64_t id = 1; id < n_ids; id++)
             if (info[id].fused_away) G.task_of[id] = G.task_of[result[fused_sub_of[id]]];
 
-    // ---- pool slots: inputs and every block a task writes; slot 0 = zero block ----------
-    {
-        int64_t s = 1;
-        for (int64_t id = 1; id < n_ids; id++) {
-            const IdInfo& w = info[id];
-            if (w.is_input || (w.n_writers > 0 && !w.fused_away && !alias_to[id])) G.slot_of[id] = (int32_t)s++;
-        }
-        G.n_slots = s;
-        for (int64_t id = 1; id < n_ids; id++)
-            if (alias_to[id]) { G.slot_of[id] = G.slot_of[alias_to[id]]; G.task_of[id] = G.task_of[alias_to[id]]; }
-    }
+    // (pool slots are assigned after the pairs are known: recycling needs every block's last reader)
+    for (int64_t id = 1; id < n_ids; id++)
+        if (alias_to[id]) G.task_of[id] = G.task_of[alias_to[id]];
 
     // ---- pairs ------------------------------------------------------------------------------
     {
@@ -229,13 +221,104 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             if (G.tasks[t].type == T_GEMM && fill[t] != G.tasks[t].n_pairs) return "internal: pair count mismatch";
     }
 
-    // ---- dependencies: distinct producer tasks of every source ------------------------------
+    // ---- pool slots and segments -------------------------------------------------------------------
+    // Unlimited pool: every input / produced block gets its own slot, one segment.  Limited pool
+    // (opt.max_slots): walk the tasks in order (a topological order: the op list is stage-sorted),
+    // hand out free slots, and when none is left close the segment there; at a segment boundary
+    // every block whose producer and readers all lie before it is dead and its slot returns to the
+    // free list.  Inputs, kept blocks (L, U) and the diagonal inverses the solve uses are pinned.
+    auto canon = [&](int32_t id) { return alias_to[id] ? alias_to[id] : id; };
+    std::vector<int32_t> seg_of(nt, 0);
+    G.recycled.assign(n_ids, 0);
+    G.seg_begin.assign(1, 0);
+    {
+        auto needs_slot = [&](int64_t id) { const IdInfo& w = info[id]; return w.is_input || (w.n_writers > 0 && !w.fused_away && !alias_to[id]); };
+        int64_t need = 1, n_in = 0;
+        for (int64_t id = 1; id < n_ids; id++) { if (needs_slot(id)) need++; if (info[id].is_input) n_in++; }
+        if (opt.max_slots <= 0 || need <= opt.max_slots) {
+            int64_t s = 1;
+            for (int64_t id = 1; id < n_ids; id++)
+                if (needs_slot(id)) G.slot_of[id] = (int32_t)s++;
+            G.n_slots = s;
+        } else {
+            if (opt.max_slots <= n_in + 8) return "block pool too small even for the input blocks";
+            // last task that touches each block (producer or reader)
+            std::vector<int32_t> last_touch(n_ids, -1);
+            std::vector<char> pinned(n_ids, 0);
+            for (int64_t id = 1; id < n_ids; id++) pinned[id] = info[id].is_input || info[id].keep;
+            for (int64_t t = 0; t < nt; t++) {
+                const Task& T = G.tasks[t];
+                auto touch = [&](int32_t id) { if (id > 0) { id = canon(id); if (last_touch[id] < t) last_touch[id] = (int32_t)t; } };
+                touch(T.out);
+                if (T.type == T_LU) {
+                    touch(T.out2);
+                    if (T.flags & TF_LINV) { touch(T.init); pinned[canon(T.init)] = 1; }
+                    if (T.flags & TF_UINV) { touch(T.out4); pinned[canon(T.out4)] = 1; }
+                }
+                if (T.flags & TF_INIT) touch(T.init);
+                for (int32_t k = 0; k < T.n_pairs; k++) { touch(G.pairs[T.pair_begin + k].a); touch(G.pairs[T.pair_begin + k].b); }
+            }
+            // blocks ordered by last touch, for the release sweep at boundaries
+            std::vector<int32_t> by_touch;
+            for (int64_t id = 1; id < n_ids; id++)
+                if (needs_slot(id) && !pinned[id]) by_touch.push_back((int32_t)id);
+            std::sort(by_touch.begin(), by_touch.end(), [&](int32_t x, int32_t y) { return last_touch[x] < last_touch[y]; });
+            size_t rel = 0;
+            std::vector<int32_t> freelist;
+            int64_t next_fresh = 1;
+            for (int64_t id = 1; id < n_ids; id++)
+                if (info[id].is_input) G.slot_of[id] = (int32_t)next_fresh++;
+            auto take = [&]() -> int32_t {
+                if (!freelist.empty()) { int32_t s = freelist.back(); freelist.pop_back(); return s; }
+                if (next_fresh < opt.max_slots) return (int32_t)next_fresh++;
+                return -1;
+            };
+            int32_t cur_seg = 0;
+            for (int64_t t = 0; t < nt; t++) {
+                const Task& T = G.tasks[t];
+                int32_t outs[4] = {T.out, 0, 0, 0};
+                int no = 1;
+                if (T.type == T_LU) {
+                    outs[no++] = T.out2;
+                    if (T.flags & TF_LINV) outs[no++] = T.init;
+                    if (T.flags & TF_UINV) outs[no++] = T.out4;
+                }
+                for (int k = 0; k < no; k++) {
+                    const int32_t id = outs[k];
+                    if (alias_to[id] || G.slot_of[id] > 0) continue;
+                    int32_t sl = take();
+                    if (sl < 0) {
+                        // close the segment before task t and release everything dead by then
+                        if (G.seg_begin.back() == (int32_t)t) return "block pool too small: a single task's live set does not fit";
+                        G.seg_begin.push_back((int32_t)t);
+                        cur_seg++;
+                        while (rel < by_touch.size() && last_touch[by_touch[rel]] < t) {
+                            const int32_t dead = by_touch[rel++];
+                            if (G.slot_of[dead] > 0) { freelist.push_back(G.slot_of[dead]); G.recycled[dead] = 1; }
+                        }
+                        sl = take();
+                        if (sl < 0) return "block pool too small for the live set of the factorisation";
+                    }
+                    G.slot_of[id] = sl;
+                }
+                seg_of[t] = cur_seg;
+            }
+            G.n_slots = next_fresh;
+        }
+        for (int64_t id = 1; id < n_ids; id++)
+            if (alias_to[id]) { G.slot_of[id] = G.slot_of[alias_to[id]]; G.recycled[id] = G.recycled[alias_to[id]]; }
+        G.seg_begin.push_back((int32_t)nt);
+    }
+
+    // ---- dependencies: distinct producer tasks of every source, inside the same segment ----------
+    // (producers in earlier segments have finished before the launch starts)
     std::vector<std::vector<int32_t>> preds(nt);
     {
         auto add = [&](int32_t tid, int32_t id) {
             if (id <= 0) return;
             int32_t p = G.task_of[id];
-            if (p >= 0 && p != tid) preds[tid].push_back(p);
+            if (p >= 0 && p != tid && seg_of[p] == seg_of[tid]) preds[tid].push_back(p);
+            if (p > tid) preds[tid].push_back(-1);   // marker: op list is not topologically ordered
         };
         for (int64_t t = 0; t < nt; t++) {
             const Task& T = G.tasks[t];
@@ -244,6 +327,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                 add((int32_t)t, G.pairs[T.pair_begin + k].b);
             }
             if (T.flags & TF_INIT) add((int32_t)t, T.init);
+            for (int32_t p : preds[t]) if (p < 0) return "operation list is not in dependency order (a block is read before its producer's first op)";
         }
         int64_t nsucc = 0;
         for (int64_t t = 0; t < nt; t++) {
@@ -287,6 +371,15 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             }
         }
         if ((int64_t)queue.size() != nt) return "operation list has a dependency cycle";
+        // levels restart in every segment: make them globally increasing (segment order)
+        const int nseg = (int)G.seg_begin.size() - 1;
+        if (nseg > 1) {
+            std::vector<int32_t> segmax(nseg, 0), off(nseg + 1, 0);
+            for (int64_t t = 0; t < nt; t++) segmax[seg_of[t]] = std::max(segmax[seg_of[t]], G.tasks[t].level);
+            for (int sg = 0; sg < nseg; sg++) off[sg + 1] = off[sg] + segmax[sg] + 1;
+            for (int64_t t = 0; t < nt; t++) G.tasks[t].level += off[seg_of[t]];
+            maxlev = off[nseg] - 1;
+        }
         G.n_levels = nt ? maxlev + 1 : 0;
     }
     // ---- row split of GEMM tasks in narrow levels -------------------------------------------------
@@ -344,11 +437,20 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             for (int64_t t = 0; t < nt2; t++) tasks2[t].n_deps = deps2[t];
             G.tasks.swap(tasks2);
             G.succ.swap(succ2);
-            G.initial.clear();
-            for (int64_t t = 0; t < nt2; t++)
-                if (G.tasks[t].n_deps == 0) G.initial.push_back((int32_t)t);
             for (int32_t& x : G.task_of)
                 if (x >= 0) x = base[x];
+            for (int32_t& b : G.seg_begin) b = base[b];
+        }
+    }
+    // per-segment lists of initially ready tasks
+    {
+        const int nseg = (int)G.seg_begin.size() - 1;
+        G.initial.clear();
+        G.seg_init.assign(1, 0);
+        for (int sg = 0; sg < nseg; sg++) {
+            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
+                if (G.tasks[t].n_deps == 0) G.initial.push_back(t);
+            G.seg_init.push_back((int32_t)G.initial.size());
         }
     }
     // ---- patch block ids -> pool slots ---------------------------------------------------------

@@ -64,6 +64,12 @@ struct TaskGraph {
     std::vector<int32_t> slot_of;       // block id -> pool slot (0 = zero block / none)
     std::vector<int32_t> task_of;       // block id -> producing task (-1 = input / none)
     int64_t n_slots = 1;                // slot 0 is the all-zero block
+    // Segments: contiguous task ranges executed by one executor launch each.  A single segment
+    // unless the block pool is smaller than the number of blocks; then slots are recycled at
+    // segment boundaries (every reader of the previous occupant finished with the launch).
+    std::vector<int32_t> seg_begin;     // n_segments + 1 task indices
+    std::vector<int32_t> seg_init;      // n_segments + 1 offsets into `initial`
+    std::vector<uint8_t> recycled;      // block id -> its slot is reused later (contents do not survive)
     int32_t n_levels = 0;
     double flops = 0;                   // dense-block convention, SURVEY.md 8(d)
     int64_t n_gemm_pairs = 0;
@@ -78,6 +84,7 @@ struct CompileOptions {
     bool fuse_inv = true;   // fold the first lowerInv / upperInv of an lu's factors into the lu task
     int split_narrow = 1;   // split GEMM tasks of narrow dependency levels by output rows (latency-bound phases)
     int n_sms = 148;        // width against which a level counts as narrow
+    int64_t max_slots = 0;  // block-pool capacity in slots (0 = unlimited: no recycling)
 };
 
 // Returns "" on success, otherwise the violated invariant.

@@ -201,3 +201,47 @@ def test_config2_properties(sg, tmp_path):
     assert abs(x[0] - 1.0377) < 1e-4 and abs(x[1] - 1.74207) < 1e-4 and abs(x[2] - 2.25873) < 1e-4
     assert fs["flops"] > 3.5e12
     ctx.close()
+
+
+@pytest.mark.parametrize("name,max_slots", [("lap3d_24", 5200), ("lap3d_24", 7000), ("lap2d_64", 800), ("banded_3000", 1670)])
+def test_pool_recycling_segments(sg, tmp_path, name, max_slots):
+    """A block pool smaller than the number of blocks: the factorisation runs as several executor
+    launches with slots recycled at the boundaries; results are unchanged."""
+    g = load_golden(name)
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    ref = sg.Context(0)
+    ref.load(p)
+    f0 = ref.factor()
+    x0, _ = ref.solve(p)
+    assert f0["pool_blocks"] > max_slots           # the cap really binds
+    ctx = sg.Context(0)
+    ctx.set_option("max_slots", max_slots)
+    ctx.load(p)
+    fs = ctx.factor()
+    assert fs["pool_blocks"] <= max_slots
+    assert fs["kernel_launches"] >= 2              # more than one segment (+ input packing)
+    x, _ = ctx.solve(p)
+    np.testing.assert_array_equal(x, x0)           # same kernels, same order of accumulation
+    assert _rel(x, g["x"]) <= TOL_X
+    fs2 = ctx.factor()                             # re-factorisation reuses the recycled pool correctly
+    x2, _ = ctx.solve(p)
+    np.testing.assert_array_equal(x2, x0)
+    # L/U survive, temporaries do not
+    ctx.get_block(p.i32("L")[0, 0])
+    ops = p.i32("ops")
+    with pytest.raises(sg.SogluError):
+        for o in ops[ops[:, 0] == 4][:200]:        # some early `sub` results must have been recycled
+            ctx.get_block(o[3])
+    ctx.close()
+    ref.close()
+
+
+def test_pool_too_small_is_an_error(sg, tmp_path):
+    p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
+    ctx = sg.Context(0)
+    ctx.set_option("max_slots", 2000)              # below inputs + factors
+    ctx.load(p)
+    with pytest.raises(sg.SogluError) as e:
+        ctx.factor()
+    assert "pool too small" in str(e.value)
+    ctx.close()
