@@ -52,6 +52,14 @@ struct soglu_ctx {
     int64_t opt_trace = 0;         // record per-task timestamps (debug; adds overhead)
     DevBuf trace;
 
+    // multi-GPU (one process per GPU): process grid, localized task graph, peer mappings
+    bool dist = false;
+    int rank = 0, world = 1, pr = 1, pc = 1;
+    DistLayout D;
+    std::vector<int32_t> brow, bcol;      // per block id (ownership)
+    bool peers_ready = false;
+    void* peer_pool[MAX_GPUS] = {}, *peer_dep[MAX_GPUS] = {}, *peer_ready[MAX_GPUS] = {}, *peer_counters[MAX_GPUS] = {};
+
     // host-side description (borrowed arrays are copied)
     int64_t n_ids = 0, n_input = 0;
     std::vector<int32_t> input_ids;
@@ -101,6 +109,9 @@ int upload(DevBuf& b, const std::vector<T>& v, soglu_ctx* c) {
     return SOGLU_OK;
 }
 
+// global pool slot -> block reference used by the kernels (owner-encoded in multi-GPU mode)
+int32_t slot_ref(const soglu_ctx* c, int32_t global_slot) { return c->dist ? c->D.slot_ref[global_slot] : global_slot; }
+
 // CSR over off-diagonal factor blocks of one triangle; lower: cols < row, upper: cols > row.
 // transpose = true builds the structure of the transposed factor (CSC of L for L^T).
 int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<int32_t>& br, const std::vector<int32_t>& bc,
@@ -113,12 +124,12 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
         int r = transpose ? bc[k] : br[k], cc = transpose ? br[k] : bc[k];
         if (r < 0 || r >= n || cc < 0 || cc >= n) return fail(SOGLU_ERR_ARG, "factor block coordinate out of range");
         if (ids[k] <= 0 || ids[k] >= c->n_ids) return fail(SOGLU_ERR_ARG, "factor block id out of range");
-        if (r == cc) { diag[r] = c->G.slot_of[ids[k]]; continue; }
+        if (r == cc) { diag[r] = slot_ref(c, c->G.slot_of[ids[k]]); continue; }
         if (upper ? (cc < r) : (cc > r)) return fail(SOGLU_ERR_ARG, "factor block on the wrong side of the diagonal");
         ptr[r + 1]++;
     }
     for (int r = 0; r < n; r++) {
-        if (diag[r] <= 0) return fail(SOGLU_ERR_GRAPH, "factor has no diagonal block in block row " + std::to_string(r));
+        if (diag[r] == -1 || diag[r] == slot_ref(c, 0)) return fail(SOGLU_ERR_GRAPH, "factor has no diagonal block in block row " + std::to_string(r));
         ptr[r + 1] += ptr[r];
     }
     n_off = ptr[n];
@@ -128,7 +139,7 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
         int r = transpose ? bc[k] : br[k], cc = transpose ? br[k] : bc[k];
         if (r == cc) continue;
         col[pos[r]] = cc;
-        slot[pos[r]] = c->G.slot_of[ids[k]];
+        slot[pos[r]] = slot_ref(c, c->G.slot_of[ids[k]]);
         pos[r]++;
     }
     // ascending columns inside each row
@@ -140,21 +151,26 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
         for (int64_t q = ptr[r]; q < ptr[r + 1]; q++) { col[q] = tmp[q - ptr[r]].first; slot[q] = tmp[q - ptr[r]].second; }
     }
     for (int64_t q = 0; q < n_off; q++)
-        if (slot[q] <= 0) return fail(SOGLU_ERR_GRAPH, "factor block is never produced by the operation list");
+        if (slot[q] == slot_ref(c, 0)) return fail(SOGLU_ERR_GRAPH, "factor block is never produced by the operation list");
     int rc;
     if ((rc = upload(dptr, ptr, c))) return rc;
     if ((rc = upload(dcol, col, c))) return rc;
     if ((rc = upload(dslot, slot, c))) return rc;
     if ((rc = upload(ddiag, diag, c))) return rc;
     // explicit inverses of the diagonal blocks, where the factorisation produced them (fused lu tasks)
-    std::vector<int32_t> inv_of_slot(c->G.n_slots, 0);
+    std::vector<int32_t> inv_of_slot(c->G.n_slots, 0);   // global slot -> global slot of its inverse
     for (const Task& T : c->G.tasks)
         if (T.type == T_LU) {
             if (T.flags & TF_LINV) inv_of_slot[T.out] = T.init;
             if (T.flags & TF_UINV) inv_of_slot[T.out2] = T.out4;
         }
     std::vector<int32_t> dinv(n, 0);
-    for (int r = 0; r < n; r++) dinv[r] = inv_of_slot[diag[r]];
+    for (size_t k = 0; k < m; k++) {
+        const int r = transpose ? bc[k] : br[k], cc = transpose ? br[k] : bc[k];
+        if (r != cc) continue;
+        const int32_t inv = inv_of_slot[c->G.slot_of[ids[k]]];
+        dinv[r] = inv > 0 ? slot_ref(c, inv) : 0;
+    }
     if ((rc = upload(ddinv, dinv, c))) return rc;
     return SOGLU_OK;
 }
@@ -162,7 +178,12 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
 int pack_pending_inputs(soglu_ctx* c) {
     if (!c->inputs_pending) return SOGLU_OK;
     std::vector<int32_t> slots(c->n_input);
-    for (int64_t k = 0; k < c->n_input; k++) slots[k] = c->G.slot_of[c->input_ids[k]];
+    for (int64_t k = 0; k < c->n_input; k++) {
+        const int32_t g = c->G.slot_of[c->input_ids[k]];
+        if (!c->dist) { slots[k] = g; continue; }
+        const int32_t ref = c->D.slot_ref[g];
+        slots[k] = ((int)((uint32_t)ref >> REF_SHIFT) == c->rank) ? (ref & REF_MASK) : -1;   // other GPUs' inputs are skipped
+    }
     DevBuf dslots;
     int rc = upload(dslots, slots, c);
     if (rc) return rc;
@@ -197,11 +218,17 @@ int finalize(soglu_ctx* c) {
         if (cap < 16) cap = 16;
         co.max_slots = (int64_t)cap;
         if (c->opt_max_slots > 0 && c->opt_max_slots < co.max_slots) co.max_slots = c->opt_max_slots;
+        if (c->dist) co.max_slots = 0;   // sharded: every GPU holds only its share; checked after localisation
     }
     std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
                                     c->result.data(), c->result2.data(), keep, co, c->G);
     if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
     TaskGraph& G = c->G;
+    if (c->dist) {
+        err = localize_tasks(G, c->n_ids, c->brow.empty() ? nullptr : c->brow.data(), c->bcol.empty() ? nullptr : c->bcol.data(), c->rank,
+                             c->world, c->pr, c->pc, c->D);
+        if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
+    }
     // the op arrays are no longer needed on the host
     std::vector<int32_t>().swap(c->src); std::vector<int32_t>().swap(c->src2);
     std::vector<int32_t>().swap(c->result); std::vector<int32_t>().swap(c->result2);
@@ -209,8 +236,11 @@ int finalize(soglu_ctx* c) {
 
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const size_t pool_bytes = (size_t)G.n_slots * BLK_BYTES;
-    const size_t aux = G.tasks.size() * (sizeof(Task) + 12) + G.pairs.size() * sizeof(Pair) + G.succ.size() * 4 + (256u << 20);
+    const std::vector<Task>& tasks_up = c->dist ? c->D.tasks : G.tasks;
+    const std::vector<Pair>& pairs_up = c->dist ? c->D.pairs : G.pairs;
+    const std::vector<int32_t>& succ_up = c->dist ? c->D.succ : G.succ;
+    const size_t pool_bytes = (size_t)(c->dist ? c->D.slots_per_rank[c->rank] : G.n_slots) * BLK_BYTES;
+    const size_t aux = tasks_up.size() * (sizeof(Task) + 12) + pairs_up.size() * sizeof(Pair) + succ_up.size() * 4 + (256u << 20);
     if (pool_bytes + aux > free_b) {
         char m[256];
         snprintf(m, sizeof m, "block pool needs %.1f GB (+%.1f GB graph) but only %.1f GB of HBM are free", pool_bytes * 1e-9, aux * 1e-9, free_b * 1e-9);
@@ -219,30 +249,35 @@ int finalize(soglu_ctx* c) {
     CU(c->pool.alloc(pool_bytes));
     CU(cudaMemsetAsync(c->pool.p, 0, pool_bytes, c->stream));
     int rc;
-    if ((rc = upload(c->tasks, G.tasks, c))) return rc;
-    if ((rc = upload(c->pairs, G.pairs, c))) return rc;
-    if ((rc = upload(c->succ, G.succ, c))) return rc;
+    if ((rc = upload(c->tasks, tasks_up, c))) return rc;
+    if ((rc = upload(c->pairs, pairs_up, c))) return rc;
+    if ((rc = upload(c->succ, succ_up, c))) return rc;
     {
-        std::vector<int32_t> d0(G.tasks.size());
-        for (size_t t = 0; t < G.tasks.size(); t++) d0[t] = G.tasks[t].n_deps;
+        std::vector<int32_t> d0(tasks_up.size());
+        for (size_t t = 0; t < tasks_up.size(); t++) d0[t] = tasks_up[t].n_deps;
         if ((rc = upload(c->dep0, d0, c))) return rc;
     }
     {
         // ready queue image: per segment slice, the initially ready tasks first, -1 elsewhere;
         // counter image: per segment one 256-byte record {head = 0, ..., tail = #initial at int 32}
         const int nseg = (int)G.seg_begin.size() - 1;
-        std::vector<int32_t> r0(std::max<size_t>(G.tasks.size(), 1), -1), c0((size_t)std::max(nseg, 1) * 64, 0);
-        for (int sg = 0; sg < nseg; sg++) {
-            const int32_t nb = G.seg_init[sg + 1] - G.seg_init[sg];
-            for (int32_t k = 0; k < nb; k++) r0[G.seg_begin[sg] + k] = G.initial[G.seg_init[sg] + k];
-            c0[(size_t)sg * 64 + 32] = nb;
+        std::vector<int32_t> r0(std::max<size_t>(tasks_up.size(), 1), -1), c0((size_t)std::max(nseg, 1) * 64, 0);
+        if (c->dist) {   // one segment, this GPU's tasks only
+            for (size_t k = 0; k < c->D.initial.size(); k++) r0[k] = c->D.initial[k];
+            c0[32] = (int32_t)c->D.initial.size();
+        } else {
+            for (int sg = 0; sg < nseg; sg++) {
+                const int32_t nb = G.seg_init[sg + 1] - G.seg_init[sg];
+                for (int32_t k = 0; k < nb; k++) r0[G.seg_begin[sg] + k] = G.initial[G.seg_init[sg] + k];
+                c0[(size_t)sg * 64 + 32] = nb;
+            }
         }
         if ((rc = upload(c->ready0, r0, c))) return rc;
         if ((rc = upload(c->counters0, c0, c))) return rc;
         CU(c->counters.alloc(c0.size() * 4));
     }
-    CU(c->dep.alloc(std::max<size_t>(G.tasks.size(), 1) * 4));
-    CU(c->ready.alloc(std::max<size_t>(G.tasks.size(), 1) * 4));
+    CU(c->dep.alloc(std::max<size_t>(tasks_up.size(), 1) * 4));
+    CU(c->ready.alloc(std::max<size_t>(tasks_up.size(), 1) * 4));
     // level order for the debug executor
     {
         const int64_t nt = (int64_t)G.tasks.size();
@@ -355,13 +390,18 @@ int soglu_set_blocks(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const i
 
 int soglu_set_graph(soglu_ctx* c, int64_t n_ops, const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,
                     const int32_t* result2, const int32_t* stage, const int32_t* block_row, const int32_t* block_col) {
-    (void)stage; (void)block_row; (void)block_col;
+    (void)stage;
     if (!c || n_ops < 0 || (n_ops > 0 && (!src || !src2 || !op || !result || !result2))) return fail(SOGLU_ERR_ARG, "bad argument");
     if (c->compiled) return fail(SOGLU_ERR_ARG, "graph already compiled; create a new context for a new pattern");
     c->n_ops = n_ops;
     c->src.assign(src, src + n_ops); c->src2.assign(src2, src2 + n_ops);
     c->result.assign(result, result + n_ops); c->result2.assign(result2, result2 + n_ops);
     c->op.assign(op, op + n_ops);
+    if (block_row && block_col) {
+        if (!c->have_blocks) return fail(SOGLU_ERR_ARG, "soglu_set_blocks must precede soglu_set_graph when block coordinates are passed");
+        c->brow.assign(block_row, block_row + c->n_ids);
+        c->bcol.assign(block_col, block_col + c->n_ids);
+    }
     c->have_graph = true;
     return SOGLU_OK;
 }

@@ -466,4 +466,72 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     return "";
 }
 
+
+std::string localize_tasks(const TaskGraph& G, int64_t n_ids, const int32_t* brow, const int32_t* bcol, int rank, int world, int pr,
+                           int pc, DistLayout& D) {
+    D = DistLayout();
+    D.rank = rank; D.world = world; D.pr = pr; D.pc = pc;
+    if (world < 1 || world > MAX_GPUS || pr * pc != world || rank < 0 || rank >= world) return "bad process grid";
+    if (G.seg_begin.size() > 2) return "multi-GPU sharding with a recycling block pool is not supported yet (the blocks of one GPU's share must fit its HBM)";
+    const int64_t nt = (int64_t)G.tasks.size();
+    // slot owners from the block coordinates
+    std::vector<int8_t> slot_owner(G.n_slots, -1);
+    for (int64_t id = 1; id < n_ids; id++) {
+        const int32_t sl = G.slot_of[id];
+        if (sl <= 0) continue;
+        int o = 0;
+        if (brow && bcol && brow[id] >= 0 && bcol[id] >= 0) o = (brow[id] % pr) * pc + (bcol[id] % pc);
+        if (slot_owner[sl] >= 0 && slot_owner[sl] != o) return "aliased blocks with different owners";
+        slot_owner[sl] = (int8_t)o;
+    }
+    D.slots_per_rank.assign(world, 1);   // local slot 0 = zero block everywhere
+    D.slot_ref.assign(G.n_slots, 0);
+    D.slot_ref[0] = make_ref(rank, 0);
+    for (int64_t sl = 1; sl < G.n_slots; sl++) {
+        const int o = slot_owner[sl] < 0 ? 0 : slot_owner[sl];
+        if (D.slots_per_rank[o] > REF_MASK) return "too many blocks per GPU";
+        D.slot_ref[sl] = make_ref(o, (int32_t)D.slots_per_rank[o]++);
+    }
+    D.task_owner.resize(nt);
+    D.task_local.resize(nt);
+    D.tasks_per_rank.assign(world, 0);
+    for (int64_t t = 0; t < nt; t++) {
+        const int o = (int)((uint32_t)D.slot_ref[G.tasks[t].out] >> REF_SHIFT);
+        D.task_owner[t] = (int8_t)o;
+        D.task_local[t] = (int32_t)D.tasks_per_rank[o]++;
+    }
+    auto ref = [&](int32_t slot) { return D.slot_ref[slot]; };
+    auto remote = [&](int32_t r) { return (int)((uint32_t)r >> REF_SHIFT) != rank; };
+    for (int64_t t = 0; t < nt; t++) {
+        if (D.task_owner[t] != rank) continue;
+        Task T = G.tasks[t];
+        const int32_t pb = (int32_t)D.pairs.size();
+        for (int32_t k = 0; k < T.n_pairs; k++) {
+            const Pair& p = G.pairs[T.pair_begin + k];
+            Pair q{ref(p.a), ref(p.b)};
+            D.remote_operands += (p.a > 0 && remote(q.a)) + (p.b > 0 && remote(q.b));
+            D.pairs.push_back(q);
+        }
+        T.pair_begin = pb;
+        T.out = ref(T.out);
+        if (T.type == T_LU) T.out2 = ref(T.out2);
+        if (T.flags & (TF_INIT | TF_LINV)) T.init = ref(T.init);
+        if (T.flags & TF_UINV) T.out4 = ref(T.out4);
+        if (T.type == T_LU && (remote(T.out2) || ((T.flags & TF_LINV) && remote(T.init)) || ((T.flags & TF_UINV) && remote(T.out4))))
+            return "lu outputs with different owners";
+        const int32_t sb = (int32_t)D.succ.size();
+        for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+            const int32_t s = G.succ[e];
+            D.succ.push_back(make_ref(D.task_owner[s], D.task_local[s]));
+            D.remote_edges += D.task_owner[s] != rank;
+        }
+        T.succ_begin = sb;
+        T.succ_end = (int32_t)D.succ.size();
+        for (int k = 0; k < 2; k++) T.first[k] = (k < T.n_pairs) ? D.pairs[pb + k] : Pair{make_ref(rank, 0), make_ref(rank, 0)};
+        if (T.n_deps == 0) D.initial.push_back((int32_t)D.tasks.size());
+        D.tasks.push_back(T);
+    }
+    return "";
+}
+
 }  // namespace soglu

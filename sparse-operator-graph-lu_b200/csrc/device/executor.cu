@@ -43,6 +43,11 @@ __device__ __forceinline__ unsigned smid() {
     return r;
 }
 
+// block reference -> address (owner in the top 3 bits; owner 0 / world 1 on a single GPU)
+__device__ __forceinline__ double* blk_ptr(const ExecParams& P, int32_t ref) {
+    return P.pools[(uint32_t)ref >> REF_SHIFT] + (size_t)(ref & REF_MASK) * BLK_ELEMS;
+}
+
 struct StageDesc {
     int32_t type, flags, task, out, out2, init, out4, first_last;   // first_last: bit0 first, bit1 last
 };
@@ -190,14 +195,14 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
     }
 }
 
-__device__ __forceinline__ void lu_task(const double* __restrict__ As, double* __restrict__ xbuf, double* __restrict__ pool, const StageDesc& d, int ct) {
+__device__ __forceinline__ void lu_task(const double* __restrict__ As, double* __restrict__ xbuf, const ExecParams& P, const StageDesc& d, int ct) {
     const int ty = ct >> 4, tx = ct & 15;
     double a[4][4], wl[4][4], wu[4][4];
     const bool inv = d.flags & (TF_LINV | TF_UINV);
     if (inv) lu3_reg<true>(As, xbuf, a, wl, wu, ct);
     else lu3_reg<false>(As, xbuf, a, wl, wu, ct);
-    double* gL = pool + (size_t)d.out * BLK_ELEMS;
-    double* gU = pool + (size_t)d.out2 * BLK_ELEMS;
+    double* gL = blk_ptr(P, d.out);
+    double* gU = blk_ptr(P, d.out2);
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -210,14 +215,14 @@ __device__ __forceinline__ void lu_task(const double* __restrict__ As, double* _
     if (!inv) return;
     math_sync();   // ipbuf complete
     if (d.flags & TF_LINV) {
-        double* g = pool + (size_t)d.init * BLK_ELEMS;
+        double* g = blk_ptr(P, d.init);
 #pragma unroll
         for (int r = 0; r < 4; r++)
 #pragma unroll
             for (int c = 0; c < 4; c++) g[(ty + 16 * r) * BLK_LD + tx + 16 * c] = wl[r][c];
     }
     if (d.flags & TF_UINV) {
-        double* g = pool + (size_t)d.out4 * BLK_ELEMS;
+        double* g = blk_ptr(P, d.out4);
         const double* ipbuf = xbuf + 512;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
@@ -381,7 +386,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 const int slot = atomicAdd(P.head, 1);
                 int t = -1;
                 if (slot < P.n_tasks) {
-                    while ((t = ptx::ld_acquire(P.ready + slot)) < 0) {}
+                    if (P.world > 1) { while ((t = ptx::ld_acquire_sys(P.ready + slot)) < 0) {} }
+                    else { while ((t = ptx::ld_acquire(P.ready + slot)) < 0) {} }
                 }
                 if (t < 0) {
                     const int s = it % N_STAGES;
@@ -408,8 +414,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     const int a_off = (T.type == T_GEMM) ? ((T.flags >> TF_ROW0_SHIFT) & 3) * 16 * BLK_LD : 0;
                     const uint32_t a_bytes = (T.type == T_GEMM) ? (uint32_t)((T.flags >> TF_NROWS_SHIFT) & 7) * 16 * BLK_LD * 8 : (uint32_t)BLK_BYTES;
                     ptx::mbar_arrive_expect_tx(&ctl->full[s], two ? a_bytes + BLK_BYTES : a_bytes);
-                    ptx::bulk_g2s(As + a_off, P.pool + (size_t)pr.a * BLK_ELEMS + a_off, a_bytes, &ctl->full[s]);
-                    if (two) ptx::bulk_g2s(As + BLK_ELEMS, P.pool + (size_t)pr.b * BLK_ELEMS, BLK_BYTES, &ctl->full[s]);
+                    ptx::bulk_g2s(As + a_off, blk_ptr(P, pr.a) + a_off, a_bytes, &ctl->full[s]);
+                    if (two) ptx::bulk_g2s(As + BLK_ELEMS, blk_ptr(P, pr.b), BLK_BYTES, &ctl->full[s]);
                 }
             }
         }
@@ -453,14 +459,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
             if (lane == 0) ptx::mbar_arrive(&ctl->empty[s]);
             if (!(d.first_last & 2)) continue;
             // epilogue: out = init -/+ acc, 16-byte stores straight from the accumulators
-            double* out = P.pool + (size_t)d.out * BLK_ELEMS;
-            const double* ini = P.pool + (size_t)d.init * BLK_ELEMS;
+            double* out = blk_ptr(P, d.out);
+            const double* ini = blk_ptr(P, d.init);
             const bool neg = d.flags & TF_NEGATE, has_init = d.flags & TF_INIT;
             if (nrows16 == 4) gemm_epilogue<4, 2>(out, ini, acc, rb, cb, lane, neg, has_init);
             else if (nrows16 == 2) gemm_epilogue<2, 2>(out, ini, acc, rb, cb, lane, neg, has_init);
             else gemm_epilogue<2, 1>(out, ini, acc, rb, cb, lane, neg, has_init);
         } else {
-            double* out = P.pool + (size_t)d.out * BLK_ELEMS;
+            double* out = blk_ptr(P, d.out);
             switch (d.type) {
                 case T_SUB: {
                     // R = S2 - S1 (mat_sub / mat_copy / mat_neg, MatrixStdDouble.cpp:2948-3121);
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     break;
                 }
                 case T_LU:
-                    lu_task(As, ctl->scratch, P.pool, d, ct);
+                    lu_task(As, ctl->scratch, P, d, ct);
                     break;
                 case T_LLT:
                     llt_block(As, Bs, ct);
@@ -500,14 +506,28 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
             const Task* T = P.tasks + d.task;
             const int sb = T->succ_begin, se = T->succ_end;
             if (sb + ct < se) {
-                __threadfence();
-                for (int e = sb + ct; e < se; e += N_MATH) {
-                    const int nx = P.succ[e];
-                    if (atomicSub(P.dep + nx, 1) == 1) {
-                        __threadfence();
-                        const int pos = atomicAdd(P.tail, 1);
-                        if (P.trace) P.trace[6 * (size_t)nx + 0] = gtime();
-                        ptx::st_release(P.ready + pos, nx);
+                if (P.world > 1) {
+                    // successors may live on peer GPUs: system-scope fences and atomics over NVLink
+                    __threadfence_system();
+                    for (int e = sb + ct; e < se; e += N_MATH) {
+                        const int32_t ref = P.succ[e];
+                        const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & REF_MASK;
+                        if (atomicSub_system(P.deps[o] + nx, 1) == 1) {
+                            __threadfence_system();
+                            const int pos = atomicAdd_system(P.tails[o], 1);
+                            ptx::st_release_sys(P.readys[o] + pos, nx);
+                        }
+                    }
+                } else {
+                    __threadfence();
+                    for (int e = sb + ct; e < se; e += N_MATH) {
+                        const int nx = P.succ[e];
+                        if (atomicSub(P.dep + nx, 1) == 1) {
+                            __threadfence();
+                            const int pos = atomicAdd(P.tail, 1);
+                            if (P.trace) P.trace[6 * (size_t)nx + 0] = gtime();
+                            ptx::st_release(P.ready + pos, nx);
+                        }
                     }
                 }
             }
@@ -526,6 +546,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (size_t)N_STAGES * STAGE_BYTES);
     if (threadIdx.x < 32) return;
     const int ct = threadIdx.x - 32;
+    ExecParams BP = {};
+    BP.pools[0] = pool; BP.pool = pool; BP.world = 1;
     long long t_lu3 = 0, t_lu = 0, t_invl = 0, t_invu = 0;
     for (int it = 0; it < iters; it++) {
         for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
@@ -534,11 +556,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
         d.out = 2; d.out2 = 3; d.init = 4; d.out4 = 5;
         d.flags = TF_LINV | TF_UINV;
         long long c0 = clock64();
-        lu_task(As, ctl->scratch, pool, d, ct);
+        lu_task(As, ctl->scratch, BP, d, ct);
         math_sync();
         long long c1 = clock64();
         d.flags = 0;
-        lu_task(As, ctl->scratch, pool, d, ct);
+        lu_task(As, ctl->scratch, BP, d, ct);
         math_sync();
         long long c2 = clock64();
         {

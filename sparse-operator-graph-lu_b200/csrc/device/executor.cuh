@@ -8,7 +8,14 @@
 namespace soglu {
 
 struct ExecParams {
-    double* pool;          // block pool, slot s at pool + s*BLK_ELEMS
+    // Multi-GPU: per-owner base pointers (peer-mapped through CUDA IPC); block / task references carry
+    // the owner in their top 3 bits (tasks.h make_ref).  Single GPU: world = 1, index 0 only.
+    double* pools[MAX_GPUS];
+    int32_t* deps[MAX_GPUS];
+    int32_t* readys[MAX_GPUS];
+    int32_t* tails[MAX_GPUS];
+    int32_t world, rank;
+    double* pool;          // this GPU's block pool, slot s at pool + s*BLK_ELEMS
     const Task* tasks;
     const Pair* pairs;
     const int32_t* succ;
@@ -34,6 +41,7 @@ cudaError_t launch_unpack_block(const double* pool, int32_t slot, double* dense,
 
 // ---- block triangular solve -----------------------------------------------------------
 struct TrsvParams {
+    const double* pools[MAX_GPUS];   // factor blocks may live on peer GPUs (references as in ExecParams)
     const double* pool;
     // CSR by block row over off-diagonal factor blocks, columns ascending
     const int64_t* l_ptr; const int32_t* l_col; const int32_t* l_slot; const int32_t* l_diag; const int32_t* l_dinv;

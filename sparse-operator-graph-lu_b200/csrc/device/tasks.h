@@ -87,6 +87,32 @@ struct CompileOptions {
     int64_t max_slots = 0;  // block-pool capacity in slots (0 = unlimited: no recycling)
 };
 
+// ---- multi-GPU: 2D block-cyclic owner-computes sharding -------------------------------------------
+// Block (brow, bcol) lives on GPU (brow mod pr) * pc + (bcol mod pc); a task runs where its
+// result lives and pulls remote operands over NVLink.  References to blocks and tasks on other
+// GPUs are 32-bit: owner in the top 3 bits, local index in the low 29.
+constexpr int REF_SHIFT = 29;
+constexpr int32_t REF_MASK = (1 << REF_SHIFT) - 1;
+constexpr int MAX_GPUS = 8;
+inline int32_t make_ref(int owner, int32_t local) { return (int32_t)(((uint32_t)owner << REF_SHIFT) | (uint32_t)local); }
+
+struct DistLayout {
+    int rank = 0, world = 1, pr = 1, pc = 1;
+    std::vector<int8_t> task_owner;      // global task -> owner
+    std::vector<int32_t> task_local;     // global task -> index in the owner's task array
+    std::vector<int32_t> slot_ref;       // global slot -> reference (slot 0 -> this rank's zero block)
+    std::vector<int64_t> tasks_per_rank, slots_per_rank;
+    // this rank's share, references already encoded
+    std::vector<Task> tasks;
+    std::vector<Pair> pairs;
+    std::vector<int32_t> succ;
+    std::vector<int32_t> initial;
+    int64_t remote_edges = 0, remote_operands = 0;
+};
+// brow/bcol: per block id (may be null -> everything on rank 0)
+std::string localize_tasks(const TaskGraph& G, int64_t n_ids, const int32_t* brow, const int32_t* bcol, int rank, int world, int pr,
+                           int pc, DistLayout& out);
+
 // Returns "" on success, otherwise the violated invariant.
 std::string compile_tasks(int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, int64_t n_ops,
                           const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,

@@ -44,6 +44,10 @@ __device__ __forceinline__ void publish_value(double* p, double x) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ const double* blk_ptr(const TrsvParams& P, int32_t ref) {
+    return P.pools[(uint32_t)ref >> REF_SHIFT] + (size_t)(ref & REF_MASK) * BLK_ELEMS;
+}
+
 struct __align__(16) TrsvSmem {
     double last[BLK_ELEMS];   // nearest off-diagonal block of the row
     double diag[BLK_ELEMS];   // diagonal block or its explicit inverse
@@ -98,7 +102,7 @@ __device__ __forceinline__ double quad_sum(double s) {
 
 // One block row of one sweep.  UPPER: backward sweep (columns > row); TRANS: apply blocks transposed.
 template <bool UPPER, bool TRANS>
-__device__ void solve_row(const double* __restrict__ pool, int row, const int64_t* __restrict__ ptr, const int32_t* __restrict__ col,
+__device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restrict__ ptr, const int32_t* __restrict__ col,
                           const int32_t* __restrict__ slot, const int32_t* __restrict__ diag, const int32_t* __restrict__ dinv,
                           const double* __restrict__ rhs, bool rhs_is_computed, double* __restrict__ sol, TrsvSmem& S,
                           uint32_t& phase, int tid) {
@@ -110,8 +114,8 @@ __device__ void solve_row(const double* __restrict__ pool, int row, const int64_
     if (tid == 0) {
         const uint32_t bytes = (nb > 0 ? 2u : 1u) * BLK_BYTES;
         ptx::mbar_arrive_expect_tx(&S.bar, bytes);
-        ptx::bulk_g2s(S.diag, pool + (size_t)(inv_slot > 0 ? inv_slot : diag[row]) * BLK_ELEMS, BLK_BYTES, &S.bar);
-        if (nb > 0) ptx::bulk_g2s(S.last, pool + (size_t)slot[kcrit] * BLK_ELEMS, BLK_BYTES, &S.bar);
+        ptx::bulk_g2s(S.diag, blk_ptr(P, inv_slot != 0 ? inv_slot : diag[row]), BLK_BYTES, &S.bar);
+        if (nb > 0) ptx::bulk_g2s(S.last, blk_ptr(P, slot[kcrit]), BLK_BYTES, &S.bar);
     }
     if (tid < BLK) S.r[tid] = rhs_is_computed ? poll_value(rhs + (size_t)row * BLK + tid) : rhs[(size_t)row * BLK + tid];
     const int rrow = tid >> 2, part = tid & 3;
@@ -121,7 +125,7 @@ __device__ void solve_row(const double* __restrict__ pool, int row, const int64_
         __syncthreads();
         if (tid < BLK) S.v[tid] = poll_value(sol + (size_t)col[k] * BLK + tid);
         __syncthreads();
-        const double s = quad_sum(gemv_part_global<TRANS>(pool + (size_t)slot[k] * BLK_ELEMS, S.v, rrow, part));
+        const double s = quad_sum(gemv_part_global<TRANS>(blk_ptr(P, slot[k]), S.v, rrow, part));
         if (part == 0) S.r[rrow] -= s;
     }
     __syncthreads();
@@ -137,7 +141,7 @@ __device__ void solve_row(const double* __restrict__ pool, int row, const int64_
         S.t[tid] = S.r[tid];
     }
     __syncthreads();
-    if (inv_slot > 0) {
+    if (inv_slot != 0) {
         // x = D^-1 t with the explicit inverse (a GEMV instead of a 64-step substitution)
         const double s = quad_sum(gemv_part_smem<TRANS>(S.diag, S.t, rrow, part));
         if (part == 0) publish_value(sol + (size_t)row * BLK + rrow, s);
@@ -182,14 +186,14 @@ __global__ void __launch_bounds__(TR_THREADS) trsv_kernel(TrsvParams P) {
     uint32_t phase = 0;
     // forward sweep: L y = b
     for (int row = blockIdx.x; row < P.n_rows; row += G)
-        solve_row<false, false>(P.pool, row, P.l_ptr, P.l_col, P.l_slot, P.l_diag, P.l_dinv, P.b, false, P.y, S, phase, tid);
+        solve_row<false, false>(P, row, P.l_ptr, P.l_col, P.l_slot, P.l_diag, P.l_dinv, P.b, false, P.y, S, phase, tid);
     // backward sweep: U x = y (or L^T x = y); its right-hand side is the forward result
     for (int r = blockIdx.x; r < P.n_rows; r += G) {
         const int row = P.n_rows - 1 - r;
         if (P.symmetric)
-            solve_row<true, true>(P.pool, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, tid);
+            solve_row<true, true>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, tid);
         else
-            solve_row<true, false>(P.pool, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, tid);
+            solve_row<true, false>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, tid);
     }
 }
 

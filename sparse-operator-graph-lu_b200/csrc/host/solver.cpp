@@ -98,3 +98,38 @@ double* solveLU(int dim, int valcount, bool symmetric, int* index_i, int* index_
     return soglu_solveLU(dim, valcount, symmetric ? 1 : 0, index_i, index_j, vals, b);
 }
 }  // namespace SOGLU
+
+// ---- host-only view of the task compiler (no GPU needed): used by the CPU tests -------------------
+#include "../device/tasks.h"
+#include <chrono>
+extern "C" int soglu_debug_compile(const soglu_problem* pp, int fuse_sub, int fuse_inv, int split, int64_t max_slots, int64_t* out, int n_out) {
+    const Problem* p = reinterpret_cast<const Problem*>(pp);
+    if (!p || !out || n_out < 16) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
+    const soglu::Plan& pl = p->plan;
+    const int64_t n = (int64_t)pl.ops.size();
+    std::vector<int32_t> src(n), src2(n), res(n), res2(n);
+    std::vector<uint8_t> op(n);
+    for (int64_t k = 0; k < n; k++) { const soglu::Op& o = pl.ops[k]; src[k] = o.src; src2[k] = o.src2; res[k] = o.result; res2[k] = o.result2; op[k] = o.op; }
+    std::vector<int32_t> in_ids(pl.inputs.size()), keep;
+    for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = (int32_t)(k + 1);
+    for (const auto& r : pl.L) keep.push_back(r.id);
+    for (const auto& r : pl.U) keep.push_back(r.id);
+    soglu::CompileOptions co;
+    co.fuse_sub = fuse_sub != 0; co.fuse_inv = fuse_inv != 0; co.split_narrow = split; co.max_slots = max_slots;
+    soglu::TaskGraph G;
+    auto t0 = std::chrono::steady_clock::now();
+    std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
+    int64_t deps = 0, maxdeps = 0, gemm = 0, lu = 0, subs = 0;
+    for (const soglu::Task& t : G.tasks) {
+        deps += t.n_deps; maxdeps = std::max<int64_t>(maxdeps, t.n_deps);
+        gemm += t.type == soglu::T_GEMM; lu += t.type == soglu::T_LU; subs += t.type == soglu::T_SUB;
+    }
+    int64_t v[16] = {(int64_t)G.tasks.size(), (int64_t)G.pairs.size(), (int64_t)G.succ.size(), (int64_t)G.initial.size(), G.n_slots, G.n_levels,
+                     G.fused_subs, G.fused_invs, G.aliased_invs, G.split_tasks, (int64_t)G.seg_begin.size() - 1, deps, maxdeps, gemm, lu,
+                     (int64_t)(dt * 1e6)};
+    for (int i = 0; i < 16; i++) out[i] = v[i];
+    (void)subs;
+    return SOGLU_OK;
+}

@@ -1,0 +1,68 @@
+"""Task compiler (op list -> task graph of the persistent executor) on the host, no GPU:
+fusion / aliasing / row-split / segment bookkeeping must stay consistent."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import write_case_mtx
+
+NAMES = "tasks pairs succ initial slots levels fused_subs fused_invs aliased_invs split_tasks segments deps maxdeps gemm lu usec".split()
+
+
+def compile_stats(sg, p, fuse_sub=1, fuse_inv=1, split=1, max_slots=0):
+    L = sg.lib()
+    L.soglu_debug_compile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]
+    out = (ctypes.c_int64 * 16)()
+    rc = L.soglu_debug_compile(p.h, fuse_sub, fuse_inv, split, max_slots, out, 16)
+    if rc:
+        raise sg.SogluError(L.soglu_last_error().decode())
+    return dict(zip(NAMES, list(out)))
+
+
+@pytest.fixture(scope="module")
+def prob(sg, tmp_path_factory):
+    return sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path_factory.mktemp("c")))
+
+
+def test_plain_compile_counts(sg, prob):
+    ops = prob.i32("ops")
+    s = compile_stats(sg, prob, 0, 0, 0)
+    n_results = len(np.unique(ops[:, 3]))               # one task per result block (lu: two blocks, one task)
+    assert s["tasks"] == n_results
+    assert s["pairs"] == (np.isin(ops[:, 0], (8, 9, 11))).sum() + (~np.isin(ops[:, 0], (8, 9, 11))).sum()
+    assert s["deps"] == s["succ"] and s["segments"] == 1
+    assert s["lu"] == (ops[:, 0] == 1).sum()
+    assert s["slots"] == 1 + prob.size("n_input") + len(np.unique(np.concatenate([ops[:, 3], ops[ops[:, 0] == 1, 4]])))
+    assert s["levels"] == 1422                           # true dependency depth, SURVEY.md Appendix E
+
+
+def test_fusions_reduce_tasks_and_depth(sg, prob):
+    base = compile_stats(sg, prob, 0, 0, 0)
+    fs = compile_stats(sg, prob, 1, 0, 0)
+    fi = compile_stats(sg, prob, 0, 1, 0)
+    both = compile_stats(sg, prob, 1, 1, 0)
+    assert fs["fused_subs"] > 0 and fs["tasks"] == base["tasks"] - fs["fused_subs"]
+    assert fi["fused_invs"] > 0 and fi["tasks"] == base["tasks"] - fi["fused_invs"] - fi["aliased_invs"]
+    assert both["levels"] < fs["levels"] < base["levels"]
+    assert both["slots"] < base["slots"]                 # folded products and aliased inverses need no storage
+
+
+def test_row_split_bookkeeping(sg, prob):
+    a = compile_stats(sg, prob, 1, 1, 0)
+    b = compile_stats(sg, prob, 1, 1, 1)
+    assert b["split_tasks"] > 0 and b["tasks"] > a["tasks"]
+    assert b["deps"] == b["succ"] and b["pairs"] == a["pairs"] and b["slots"] == a["slots"]
+    assert b["levels"] == a["levels"]
+
+
+def test_segments_when_pool_is_small(sg, prob):
+    full = compile_stats(sg, prob)
+    assert full["segments"] == 1
+    small = compile_stats(sg, prob, max_slots=5200)
+    assert small["segments"] > 1 and small["slots"] <= 5200
+    assert small["succ"] < full["succ"]                  # cross-segment edges are dropped
+    tiny = compile_stats(sg, prob, max_slots=4600)
+    assert tiny["segments"] >= small["segments"]
+    with pytest.raises(sg.SogluError):
+        compile_stats(sg, prob, max_slots=1500)          # below inputs + factors
