@@ -104,6 +104,30 @@ int soglu_get_block(soglu_ctx* ctx, int32_t id, double* out_64x64);
  * the persistent executor (debug / cross-check path; same kernels' math). */
 int soglu_set_option(soglu_ctx* ctx, const char* key, int64_t value);
 
+/* ---------------- A2. multi-GPU: one process per GPU, 2D block-cyclic block ownership -------
+ * Block (brow, bcol) lives on GPU (brow mod grid_rows) * grid_cols + (bcol mod grid_cols); an
+ * operation runs where its result lives and pulls remote operands over NVLink (peer memory
+ * mapped through CUDA IPC); dependency counters and ready queues of peers are updated with
+ * system-scope atomics.  The reference has no multi-device path; this extends
+ * BlockPlanner::calculate (BlockPlanner.cpp:376-651).  Call order on EVERY rank:
+ *   soglu_create_dist -> soglu_set_blocks / soglu_set_graph (with block_row / block_col) /
+ *   soglu_set_factors (the same full problem on every rank) -> soglu_dist_export ->
+ *   [all-gather the blobs] -> soglu_dist_import -> per factorisation: soglu_dist_reset ->
+ *   [barrier] -> soglu_factor -> [barrier] -> soglu_solve on rank 0 -> [barrier]. */
+int soglu_create_dist(soglu_ctx** out, int device, int rank, int world, int grid_rows, int grid_cols);
+int64_t soglu_dist_blob_bytes(void);
+int soglu_dist_export(soglu_ctx* ctx, void* blob);
+int soglu_dist_import(soglu_ctx* ctx, const void* all_blobs_in_rank_order);
+int soglu_dist_reset(soglu_ctx* ctx);
+/* When one GPU's share does not fit its HBM the factorisation runs as several launches ("segments") with
+ * pool slots recycled in between: for seg in 0..soglu_dist_segments-1: soglu_dist_set_segment(seg) ->
+ * soglu_factor -> [barrier].  One segment: soglu_factor alone. */
+int soglu_dist_segments(soglu_ctx* ctx);
+int soglu_dist_set_segment(soglu_ctx* ctx, int segment);
+/* out5: tasks run here (incl. fetch tasks), pool slots (owned + mirrors), dependency edges to other GPUs,
+ * operand block reads from other GPUs, remote blocks mirrored locally */
+int soglu_dist_info(soglu_ctx* ctx, int64_t* out5);
+
 /* ---------------- B. host front-end (bit-exact integer planning) ------------------------ */
 
 typedef struct soglu_problem soglu_problem;

@@ -19,6 +19,8 @@ ABI_SYMBOLS = [
     "soglu_set_factors", "soglu_factor", "soglu_solve", "soglu_get_block", "soglu_set_option", "soglu_problem_from_mtx",
     "soglu_problem_from_coo", "soglu_problem_free", "soglu_problem_size", "soglu_problem_get_i32", "soglu_problem_get_f64",
     "soglu_problem_log", "soglu_load_problem", "soglu_solve_problem", "soglu_solveLU", "soglu_free", "soglu_write_stencil_mtx",
+    "soglu_create_dist", "soglu_dist_blob_bytes", "soglu_dist_export", "soglu_dist_import", "soglu_dist_reset", "soglu_dist_info",
+    "soglu_dist_segments", "soglu_dist_set_segment",
 ]
 
 OP_NAMES = {1: "lu", 2: "lowerInv", 3: "upperInv", 4: "sub", 8: "mul", 9: "mulneg", 10: "llt", 11: "mult"}
@@ -76,6 +78,14 @@ def lib():
     L.soglu_free.argtypes = [vp]
     L.soglu_free.restype = None
     L.soglu_write_stencil_mtx.argtypes = [cp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, cp]
+    L.soglu_create_dist.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.soglu_dist_blob_bytes.restype = i64
+    L.soglu_dist_export.argtypes = [vp, vp]
+    L.soglu_dist_import.argtypes = [vp, vp]
+    L.soglu_dist_reset.argtypes = [vp]
+    L.soglu_dist_info.argtypes = [vp, vp]
+    L.soglu_dist_segments.argtypes = [vp]
+    L.soglu_dist_set_segment.argtypes = [vp, ctypes.c_int]
     _lib = L
     return L
 
@@ -153,10 +163,51 @@ class Problem:
 class Context:
     """One GPU context: block pool + compiled task graph + factor/solve."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, rank=0, world=1, grid=None):
+        """world > 1: this process drives one GPU of a 2D block-cyclic process grid (rows, cols)."""
         self.h = ctypes.c_void_p()
-        dev = (ctypes.c_int * 1)(device)
-        _check(lib().soglu_create(ctypes.byref(self.h), 1, dev))
+        self.rank, self.world = rank, world
+        if world == 1:
+            dev = (ctypes.c_int * 1)(device)
+            _check(lib().soglu_create(ctypes.byref(self.h), 1, dev))
+        else:
+            pr, pc = grid if grid else default_grid(world)
+            _check(lib().soglu_create_dist(ctypes.byref(self.h), device, rank, world, pr, pc))
+
+    # ---- multi-GPU plumbing: the caller moves the blobs between ranks (torch.distributed) ----
+    def dist_export(self):
+        n = int(lib().soglu_dist_blob_bytes())
+        blob = np.zeros(n, dtype=np.uint8)
+        _check(lib().soglu_dist_export(self.h, _ptr(blob)))
+        return blob
+
+    def dist_import(self, all_blobs):
+        all_blobs = np.ascontiguousarray(all_blobs, dtype=np.uint8)
+        _check(lib().soglu_dist_import(self.h, _ptr(all_blobs)))
+
+    def dist_reset(self):
+        _check(lib().soglu_dist_reset(self.h))
+
+    def factor_dist(self, barrier):
+        """One sharded factorisation: reset, then every segment on all ranks with `barrier()` in between.
+        Returns the stats of the last segment with `seconds` summed over segments."""
+        self.dist_reset()
+        barrier()
+        nseg = int(lib().soglu_dist_segments(self.h))
+        total, st = 0.0, None
+        for sg in range(nseg):
+            _check(lib().soglu_dist_set_segment(self.h, sg))
+            st = self.factor()
+            total += st["seconds"]
+            barrier()
+        st["seconds"] = total
+        st["segments"] = nseg
+        return st
+
+    def dist_info(self):
+        out = np.zeros(5, dtype=np.int64)
+        _check(lib().soglu_dist_info(self.h, _ptr(out)))
+        return dict(zip(("tasks", "slots", "remote_edges", "remote_operands", "mirrored"), out.tolist()))
 
     def set_option(self, key, value):
         _check(lib().soglu_set_option(self.h, key.encode(), int(value)))
@@ -222,6 +273,16 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def default_grid(world):
+    """process grid (rows, cols) of the 2D block-cyclic ownership: 1->1x1, 2->1x2, 4->2x2, 8->2x4"""
+    pr = 1
+    while pr * pr * 2 <= world:
+        pr *= 2
+    if world % pr:
+        pr = 1
+    return pr, world // pr
 
 
 def write_stencil_mtx(kind, path, nx, ny=0, nz=0, symmetric=False):

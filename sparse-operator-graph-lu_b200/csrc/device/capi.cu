@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -47,6 +48,8 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
+    int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
+    int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;
     int64_t opt_grid = 0;          // override CTA count (0 = all resident)
     int64_t opt_trace = 0;         // record per-task timestamps (debug; adds overhead)
@@ -58,6 +61,7 @@ struct soglu_ctx {
     DistLayout D;
     std::vector<int32_t> brow, bcol;      // per block id (ownership)
     bool peers_ready = false;
+    int dist_segment = 0;               // segment the next soglu_factor call runs (multi-GPU)
     void* peer_pool[MAX_GPUS] = {}, *peer_dep[MAX_GPUS] = {}, *peer_ready[MAX_GPUS] = {}, *peer_counters[MAX_GPUS] = {};
 
     // host-side description (borrowed arrays are copied)
@@ -109,8 +113,11 @@ int upload(DevBuf& b, const std::vector<T>& v, soglu_ctx* c) {
     return SOGLU_OK;
 }
 
-// global pool slot -> block reference used by the kernels (owner-encoded in multi-GPU mode)
-int32_t slot_ref(const soglu_ctx* c, int32_t global_slot) { return c->dist ? c->D.slot_ref[global_slot] : global_slot; }
+// block id -> block reference used by the kernels (owner in the top bits; plain slot on one GPU)
+int32_t id_ref(const soglu_ctx* c, int32_t id) {
+    const int32_t sl = c->G.slot_of[id];
+    return sl > 0 ? make_ref(c->G.owner_of[id], sl) : 0;
+}
 
 // CSR over off-diagonal factor blocks of one triangle; lower: cols < row, upper: cols > row.
 // transpose = true builds the structure of the transposed factor (CSC of L for L^T).
@@ -124,12 +131,12 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
         int r = transpose ? bc[k] : br[k], cc = transpose ? br[k] : bc[k];
         if (r < 0 || r >= n || cc < 0 || cc >= n) return fail(SOGLU_ERR_ARG, "factor block coordinate out of range");
         if (ids[k] <= 0 || ids[k] >= c->n_ids) return fail(SOGLU_ERR_ARG, "factor block id out of range");
-        if (r == cc) { diag[r] = slot_ref(c, c->G.slot_of[ids[k]]); continue; }
+        if (r == cc) { diag[r] = id_ref(c, ids[k]); continue; }
         if (upper ? (cc < r) : (cc > r)) return fail(SOGLU_ERR_ARG, "factor block on the wrong side of the diagonal");
         ptr[r + 1]++;
     }
     for (int r = 0; r < n; r++) {
-        if (diag[r] == -1 || diag[r] == slot_ref(c, 0)) return fail(SOGLU_ERR_GRAPH, "factor has no diagonal block in block row " + std::to_string(r));
+        if (diag[r] == -1 || diag[r] == 0) return fail(SOGLU_ERR_GRAPH, "factor has no diagonal block in block row " + std::to_string(r));
         ptr[r + 1] += ptr[r];
     }
     n_off = ptr[n];
@@ -139,7 +146,7 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
         int r = transpose ? bc[k] : br[k], cc = transpose ? br[k] : bc[k];
         if (r == cc) continue;
         col[pos[r]] = cc;
-        slot[pos[r]] = slot_ref(c, c->G.slot_of[ids[k]]);
+        slot[pos[r]] = id_ref(c, ids[k]);
         pos[r]++;
     }
     // ascending columns inside each row
@@ -151,25 +158,23 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
         for (int64_t q = ptr[r]; q < ptr[r + 1]; q++) { col[q] = tmp[q - ptr[r]].first; slot[q] = tmp[q - ptr[r]].second; }
     }
     for (int64_t q = 0; q < n_off; q++)
-        if (slot[q] == slot_ref(c, 0)) return fail(SOGLU_ERR_GRAPH, "factor block is never produced by the operation list");
+        if (slot[q] == 0) return fail(SOGLU_ERR_GRAPH, "factor block is never produced by the operation list");
     int rc;
     if ((rc = upload(dptr, ptr, c))) return rc;
     if ((rc = upload(dcol, col, c))) return rc;
     if ((rc = upload(dslot, slot, c))) return rc;
     if ((rc = upload(ddiag, diag, c))) return rc;
     // explicit inverses of the diagonal blocks, where the factorisation produced them (fused lu tasks)
-    std::vector<int32_t> inv_of_slot(c->G.n_slots, 0);   // global slot -> global slot of its inverse
+    std::unordered_map<int32_t, int32_t> inv_of_ref;   // reference of a diagonal factor block -> reference of its inverse
     for (const Task& T : c->G.tasks)
         if (T.type == T_LU) {
-            if (T.flags & TF_LINV) inv_of_slot[T.out] = T.init;
-            if (T.flags & TF_UINV) inv_of_slot[T.out2] = T.out4;
+            if (T.flags & TF_LINV) inv_of_ref[T.out] = T.init;
+            if (T.flags & TF_UINV) inv_of_ref[T.out2] = T.out4;
         }
     std::vector<int32_t> dinv(n, 0);
-    for (size_t k = 0; k < m; k++) {
-        const int r = transpose ? bc[k] : br[k], cc = transpose ? br[k] : bc[k];
-        if (r != cc) continue;
-        const int32_t inv = inv_of_slot[c->G.slot_of[ids[k]]];
-        dinv[r] = inv > 0 ? slot_ref(c, inv) : 0;
+    for (int r = 0; r < n; r++) {
+        auto it = inv_of_ref.find(diag[r]);
+        if (it != inv_of_ref.end()) dinv[r] = it->second;
     }
     if ((rc = upload(ddinv, dinv, c))) return rc;
     return SOGLU_OK;
@@ -179,10 +184,8 @@ int pack_pending_inputs(soglu_ctx* c) {
     if (!c->inputs_pending) return SOGLU_OK;
     std::vector<int32_t> slots(c->n_input);
     for (int64_t k = 0; k < c->n_input; k++) {
-        const int32_t g = c->G.slot_of[c->input_ids[k]];
-        if (!c->dist) { slots[k] = g; continue; }
-        const int32_t ref = c->D.slot_ref[g];
-        slots[k] = ((int)((uint32_t)ref >> REF_SHIFT) == c->rank) ? (ref & REF_MASK) : -1;   // other GPUs' inputs are skipped
+        const int32_t id = c->input_ids[k];
+        slots[k] = (!c->dist || c->G.owner_of[id] == c->rank) ? c->G.slot_of[id] : -1;   // other GPUs' inputs are skipped
     }
     DevBuf dslots;
     int rc = upload(dslots, slots, c);
@@ -218,15 +221,26 @@ int finalize(soglu_ctx* c) {
         if (cap < 16) cap = 16;
         co.max_slots = (int64_t)cap;
         if (c->opt_max_slots > 0 && c->opt_max_slots < co.max_slots) co.max_slots = c->opt_max_slots;
-        if (c->dist) co.max_slots = 0;   // sharded: every GPU holds only its share; checked after localisation
+
+    }
+    std::vector<int8_t> owners;
+    if (c->dist) {
+        // 2D block-cyclic ownership over nb x nb squares of blocks (coordinates from soglu_set_graph)
+        if (c->brow.empty()) return fail(SOGLU_ERR_ARG, "multi-GPU context: soglu_set_graph needs block_row / block_col");
+        const int nb = (int)std::max<int64_t>(1, c->opt_dist_nb);
+        owners.assign(c->n_ids, 0);
+        for (int64_t id = 1; id < c->n_ids; id++)
+            if (c->brow[id] >= 0 && c->bcol[id] >= 0) owners[id] = (int8_t)(((c->brow[id] / nb) % c->pr) * c->pc + ((c->bcol[id] / nb) % c->pc));
+        co.owner_of_id = owners.data();
+        co.n_owners = c->world;
+        co.mirror_min = (int)std::max<int64_t>(1, c->opt_mirror_min);
     }
     std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
                                     c->result.data(), c->result2.data(), keep, co, c->G);
     if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
     TaskGraph& G = c->G;
     if (c->dist) {
-        err = localize_tasks(G, c->n_ids, c->brow.empty() ? nullptr : c->brow.data(), c->bcol.empty() ? nullptr : c->bcol.data(), c->rank,
-                             c->world, c->pr, c->pc, c->D);
+        err = localize_tasks(G, c->rank, c->D);
         if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
     }
     // the op arrays are no longer needed on the host
@@ -239,7 +253,7 @@ int finalize(soglu_ctx* c) {
     const std::vector<Task>& tasks_up = c->dist ? c->D.tasks : G.tasks;
     const std::vector<Pair>& pairs_up = c->dist ? c->D.pairs : G.pairs;
     const std::vector<int32_t>& succ_up = c->dist ? c->D.succ : G.succ;
-    const size_t pool_bytes = (size_t)(c->dist ? c->D.slots_per_rank[c->rank] : G.n_slots) * BLK_BYTES;
+    const size_t pool_bytes = (size_t)G.slots_per_owner[c->dist ? c->rank : 0] * BLK_BYTES;
     const size_t aux = tasks_up.size() * (sizeof(Task) + 12) + pairs_up.size() * sizeof(Pair) + succ_up.size() * 4 + (256u << 20);
     if (pool_bytes + aux > free_b) {
         char m[256];
@@ -260,17 +274,15 @@ int finalize(soglu_ctx* c) {
     {
         // ready queue image: per segment slice, the initially ready tasks first, -1 elsewhere;
         // counter image: per segment one 256-byte record {head = 0, ..., tail = #initial at int 32}
-        const int nseg = (int)G.seg_begin.size() - 1;
+        const std::vector<int32_t>& sb = c->dist ? c->D.seg_begin : G.seg_begin;
+        const std::vector<int32_t>& si = c->dist ? c->D.seg_init : G.seg_init;
+        const std::vector<int32_t>& ini = c->dist ? c->D.initial : G.initial;
+        const int nseg = (int)sb.size() - 1;
         std::vector<int32_t> r0(std::max<size_t>(tasks_up.size(), 1), -1), c0((size_t)std::max(nseg, 1) * 64, 0);
-        if (c->dist) {   // one segment, this GPU's tasks only
-            for (size_t k = 0; k < c->D.initial.size(); k++) r0[k] = c->D.initial[k];
-            c0[32] = (int32_t)c->D.initial.size();
-        } else {
-            for (int sg = 0; sg < nseg; sg++) {
-                const int32_t nb = G.seg_init[sg + 1] - G.seg_init[sg];
-                for (int32_t k = 0; k < nb; k++) r0[G.seg_begin[sg] + k] = G.initial[G.seg_init[sg] + k];
-                c0[(size_t)sg * 64 + 32] = nb;
-            }
+        for (int sg = 0; sg < nseg; sg++) {
+            const int32_t nb = si[sg + 1] - si[sg];
+            for (int32_t k = 0; k < nb; k++) r0[sb[sg] + k] = ini[si[sg] + k];
+            c0[(size_t)sg * 64 + 32] = nb;
         }
         if ((rc = upload(c->ready0, r0, c))) return rc;
         if ((rc = upload(c->counters0, c0, c))) return rc;
@@ -339,9 +351,113 @@ int soglu_create(soglu_ctx** out, int n_gpus, const int* device_ids) {
     return SOGLU_OK;
 }
 
+// ---- multi-GPU: one process per GPU, peers mapped through CUDA IPC -------------------------------
+struct DistBlob { cudaIpcMemHandle_t pool, dep, ready, counters; int32_t rank, valid; };
+
+int soglu_create_dist(soglu_ctx** out, int device, int rank, int world, int grid_rows, int grid_cols) {
+    if (world < 1 || world > MAX_GPUS || grid_rows * grid_cols != world || rank < 0 || rank >= world)
+        return fail(SOGLU_ERR_ARG, "bad process grid (world <= 8, grid_rows * grid_cols == world)");
+    int dev[1] = {device};
+    int rc = soglu_create(out, 1, dev);
+    if (rc) return rc;
+    soglu_ctx* c = *out;
+    c->dist = world > 1;
+    c->rank = rank; c->world = world; c->pr = grid_rows; c->pc = grid_cols;
+    return SOGLU_OK;
+}
+
+int64_t soglu_dist_blob_bytes(void) { return (int64_t)sizeof(DistBlob); }
+
+// compile + allocate this GPU's share, then write the IPC handles of its pool / counters / queue
+int soglu_dist_export(soglu_ctx* c, void* blob) {
+    if (!c || !blob) return fail(SOGLU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    int rc = finalize(c);
+    if (rc) return rc;
+    DistBlob b;
+    std::memset(&b, 0, sizeof b);
+    b.rank = c->rank; b.valid = 1;
+    if (c->dist) {
+        CU(cudaIpcGetMemHandle(&b.pool, c->pool.p));
+        CU(cudaIpcGetMemHandle(&b.dep, c->dep.p));
+        CU(cudaIpcGetMemHandle(&b.ready, c->ready.p));
+        CU(cudaIpcGetMemHandle(&b.counters, c->counters.p));
+    }
+    std::memcpy(blob, &b, sizeof b);
+    return SOGLU_OK;
+}
+
+// all_blobs: world blobs in rank order (gathered by the caller, e.g. torch.distributed.all_gather)
+int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
+    if (!c || !all_blobs) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->compiled) return fail(SOGLU_ERR_ARG, "soglu_dist_export must precede soglu_dist_import");
+    CU(cudaSetDevice(c->device));
+    const DistBlob* bl = reinterpret_cast<const DistBlob*>(all_blobs);
+    for (int g = 0; g < c->world; g++) {
+        if (g == c->rank || !c->dist) {
+            c->peer_pool[g] = c->pool.p; c->peer_dep[g] = c->dep.p; c->peer_ready[g] = c->ready.p; c->peer_counters[g] = c->counters.p;
+            continue;
+        }
+        if (!bl[g].valid || bl[g].rank != g) return fail(SOGLU_ERR_ARG, "peer handle blob " + std::to_string(g) + " is missing or out of order");
+        CU(cudaIpcOpenMemHandle(&c->peer_pool[g], bl[g].pool, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&c->peer_dep[g], bl[g].dep, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&c->peer_ready[g], bl[g].ready, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&c->peer_counters[g], bl[g].counters, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->peers_ready = true;
+    return SOGLU_OK;
+}
+
+// reset this GPU's dependency counters and ready queue; the caller must put a barrier across all
+// ranks between soglu_dist_reset and soglu_factor, and another one after soglu_factor
+int soglu_dist_reset(soglu_ctx* c) {
+    if (!c || !c->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled");
+    CU(cudaSetDevice(c->device));
+    int rc = pack_pending_inputs(c);
+    if (rc) return rc;
+    const size_t nt = c->dist ? c->D.tasks.size() : c->G.tasks.size();
+    if (nt) {
+        CU(cudaMemcpyAsync(c->dep.p, c->dep0.p, nt * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->ready.p, c->ready0.p, nt * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(c->counters.p, c->counters0.p, c->counters0.bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->dist_segment = 0;
+    return SOGLU_OK;
+}
+
+// number of executor launches (segments) one factorisation needs; > 1 when the pools recycle slots
+int soglu_dist_segments(soglu_ctx* c) {
+    if (!c || !c->compiled) return -1;
+    return (int)((c->dist ? c->D.seg_begin.size() : c->G.seg_begin.size()) - 1);
+}
+// select the segment the next soglu_factor call runs (all ranks the same one, barrier in between)
+int soglu_dist_set_segment(soglu_ctx* c, int seg) {
+    if (!c || !c->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled");
+    c->dist_segment = seg;
+    return SOGLU_OK;
+}
+
+// owned tasks / blocks / remote edges / remote operand reads of this rank
+int soglu_dist_info(soglu_ctx* c, int64_t* out4) {
+    if (!c || !out4 || !c->compiled) return fail(SOGLU_ERR_ARG, "bad argument");
+    out4[0] = (int64_t)(c->dist ? c->D.tasks.size() : c->G.tasks.size());
+    out4[1] = c->G.slots_per_owner[c->dist ? c->rank : 0];
+    out4[2] = c->dist ? c->D.remote_edges : 0;
+    out4[3] = c->dist ? c->D.remote_operands : 0;
+    out4[4] = c->dist ? c->D.mirrored : 0;
+    return SOGLU_OK;
+}
+
 void soglu_destroy(soglu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->dist)
+        for (int g = 0; g < c->world; g++) {
+            if (g == c->rank) continue;
+            for (void* p : {c->peer_pool[g], c->peer_dep[g], c->peer_ready[g], c->peer_counters[g]})
+                if (p) cudaIpcCloseMemHandle(p);
+        }
     for (DevBuf* b : {&c->in_dense, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
                       &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->d_y, &c->d_x, &c->trace})
         b->release();
@@ -359,6 +475,8 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "fuse_inv") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_inv must be set before the first factor"); c->opt_fuse_inv = value; }
     else if (k == "split") { if (c->compiled) return fail(SOGLU_ERR_ARG, "split must be set before the first factor"); c->opt_split = value; }
     else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
+    else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
+    else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
@@ -426,11 +544,21 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     int rc = finalize(c);
     if (rc) return rc;
     TaskGraph& G = c->G;
-    const int32_t nt = (int32_t)G.tasks.size();
+    const int32_t nt = (int32_t)(c->dist ? c->D.tasks.size() : G.tasks.size());
     int grid = c->exec_grid;
     if (c->opt_grid > 0 && c->opt_grid < grid) grid = (int)c->opt_grid;
-    ExecParams P;
+    ExecParams P = {};
     P.pool = c->pool.as<double>();
+    P.world = c->world; P.rank = c->rank;
+    if (c->dist) {
+        if (!c->peers_ready) return fail(SOGLU_ERR_ARG, "multi-GPU context: exchange peer handles (soglu_dist_export / soglu_dist_import) and call soglu_dist_reset before soglu_factor");
+        for (int g = 0; g < c->world; g++) {
+            P.pools[g] = (double*)c->peer_pool[g]; P.deps[g] = (int32_t*)c->peer_dep[g];
+            P.readys[g] = (int32_t*)c->peer_ready[g]; P.tails[g] = (int32_t*)c->peer_counters[g] + 32;
+        }
+    } else {
+        P.pools[0] = c->pool.as<double>();
+    }
     P.tasks = c->tasks.as<Task>();
     P.pairs = c->pairs.as<Pair>();
     P.succ = c->succ.as<int32_t>();
@@ -446,7 +574,26 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     }
     CU(cudaEventRecord(c->ev0, c->stream));
     if (nt > 0) {
-        if (c->opt_exec_mode == 0) {
+        if (c->dist) {
+            // counters / queues were reset by soglu_dist_reset (all ranks, then a barrier) -- a late
+            // reset here could wipe a signal a faster peer has already delivered
+            const int nseg = (int)c->D.seg_begin.size() - 1;
+            const int sg = c->dist_segment;
+            if (sg < 0 || sg >= nseg) return fail(SOGLU_ERR_ARG, "segment out of range");
+            for (int g = 0; g < c->world; g++) {
+                P.readys[g] = (int32_t*)c->peer_ready[g] + c->D.seg_begin_all[g][sg];
+                P.tails[g] = (int32_t*)c->peer_counters[g] + (size_t)sg * 64 + 32;
+            }
+            P.ready = c->ready.as<int32_t>() + c->D.seg_begin[sg];
+            P.head = c->counters.as<int32_t>() + (size_t)sg * 64;
+            P.tail = P.head + 32;
+            P.signal = 1;
+            P.n_tasks = c->D.seg_begin[sg + 1] - c->D.seg_begin[sg];
+            if (P.n_tasks > 0) {
+                CU(launch_executor(P, grid, c->stream));
+                c->launches++;
+            }
+        } else if (c->opt_exec_mode == 0) {
             const int nseg = (int)G.seg_begin.size() - 1;
             CU(cudaMemcpyAsync(c->dep.p, c->dep0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
             CU(cudaMemcpyAsync(c->ready.p, c->ready0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -490,7 +637,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
         out->bytes = 0;
         out->kernel_launches = c->launches - launches0;
         out->tasks = nt;
-        out->pool_blocks = G.n_slots;
+        out->pool_blocks = G.slots_per_owner[c->dist ? c->rank : 0];
         out->h2d_bytes = c->h2d;
         out->d2h_bytes = c->d2h;
     }
@@ -503,8 +650,11 @@ int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* o
     CU(cudaSetDevice(c->device));
     const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
     CU(cudaMemcpyAsync(c->d_b.p, b_ext, next, cudaMemcpyHostToDevice, c->stream));
-    TrsvParams P;
+    if (c->dist && c->rank != 0) return fail(SOGLU_ERR_ARG, "multi-GPU context: the triangular solve runs on rank 0 (it reads the peers' factor blocks over NVLink)");
+    TrsvParams P = {};
     P.pool = c->pool.as<double>();
+    if (c->dist) { for (int g = 0; g < c->world; g++) P.pools[g] = (const double*)c->peer_pool[g]; }
+    else P.pools[0] = c->pool.as<double>();
     P.l_ptr = c->l_ptr.as<int64_t>(); P.l_col = c->l_col.as<int32_t>(); P.l_slot = c->l_slot.as<int32_t>(); P.l_diag = c->l_diag.as<int32_t>();
     P.l_dinv = c->l_dinv.as<int32_t>();
     P.u_ptr = c->u_ptr.as<int64_t>(); P.u_col = c->u_col.as<int32_t>(); P.u_slot = c->u_slot.as<int32_t>(); P.u_diag = c->u_diag.as<int32_t>();
@@ -581,7 +731,9 @@ int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {
     CU(cudaSetDevice(c->device));
     DevBuf tmp;
     CU(tmp.alloc(BLK * BLK * sizeof(double)));
-    CU(launch_unpack_block(c->pool.as<double>(), slot, tmp.as<double>(), c->stream));
+    const int32_t local = slot;
+    if (c->dist && c->G.owner_of[id] != c->rank) { tmp.release(); return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " lives on another GPU"); }
+    CU(launch_unpack_block(c->pool.as<double>(), local, tmp.as<double>(), c->stream));
     c->launches++;
     CU(cudaMemcpyAsync(out_64x64, tmp.p, BLK * BLK * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -179,7 +179,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         }
         G.tasks.push_back(t);
     }
-    const int64_t nt = (int64_t)G.tasks.size();
+    int64_t nt = (int64_t)G.tasks.size();
     // redirect fused products to the task of their sub's result
     if (opt.fuse_sub)
         for (int64_t id = 1; id < n_ids; id++)
@@ -221,6 +221,112 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             if (G.tasks[t].type == T_GEMM && fill[t] != G.tasks[t].n_pairs) return "internal: pair count mismatch";
     }
 
+    // ---- multi-GPU: owners, mirrors of remote blocks and their fetch tasks ---------------------------
+    // A task runs on the GPU that owns its result block.  A produced block that a GPU reads at least
+    // mirror_min times from a peer is MIRRORED there: a fetch task (a T_SUB "copy": out = remote - 0)
+    // owned by the reader copies it once over NVLink as soon as it is complete, and the reader's
+    // tasks use the copy (the panel broadcast of the north star, pulled by the consumer).  Mirrors
+    // are ordinary blocks (ids appended after the caller's) so slot recycling and segments cover them.
+    int64_t nid = n_ids;                       // block ids including mirrors
+    const int nown = std::max(1, opt.n_owners);
+    G.n_owners = nown;
+    G.owner_of.assign(n_ids, 0);
+    if (nown > 1) {
+        if (nown > MAX_GPUS) return "too many GPUs";
+        if (opt.owner_of_id)
+            for (int64_t id = 1; id < n_ids; id++) {
+                if (opt.owner_of_id[id] < 0 || opt.owner_of_id[id] >= nown) return "block owner out of range";
+                G.owner_of[id] = opt.owner_of_id[id];
+            }
+        for (int64_t id = 1; id < n_ids; id++)
+            if (alias_to[id]) G.owner_of[id] = G.owner_of[alias_to[id]];
+        auto cn = [&](int32_t id) { return alias_to[id] ? alias_to[id] : id; };
+        std::vector<int8_t> town(nt);
+        for (int64_t t = 0; t < nt; t++) town[t] = G.owner_of[cn(G.tasks[t].out)];
+        for (int64_t t = 0; t < nt; t++) {
+            const Task& T = G.tasks[t];
+            if (T.type == T_LU && (G.owner_of[T.out2] != town[t] || ((T.flags & TF_LINV) && G.owner_of[cn(T.init)] != town[t]) ||
+                                   ((T.flags & TF_UINV) && G.owner_of[cn(T.out4)] != town[t])))
+                return "lu outputs with different owners";
+        }
+        auto for_src = [&](Task& T, auto&& fn) {
+            for (int32_t k = 0; k < T.n_pairs; k++) { fn(G.pairs[T.pair_begin + k].a); fn(G.pairs[T.pair_begin + k].b); }
+            if (T.flags & TF_INIT) fn(T.init);
+        };
+        std::vector<uint8_t> reads((size_t)nown * n_ids, 0);
+        for (int64_t t = 0; t < nt; t++) {
+            const int r = town[t];
+            for_src(G.tasks[t], [&](int32_t& sid) {
+                if (sid <= 0) return;
+                const int32_t c = cn(sid);
+                if (G.owner_of[c] != r && G.task_of[c] >= 0) { uint8_t& n = reads[(size_t)r * n_ids + c]; if (n < 255) n++; }
+            });
+        }
+        // fetch tasks, grouped behind the task that completes the block they copy
+        std::vector<int32_t> mirror_id((size_t)nown * n_ids, 0);
+        std::vector<std::vector<std::pair<int32_t, int8_t>>> fetch_after(nt);   // producer task -> (block id, reader)
+        G.mirrors_per_owner.assign(nown, 0);
+        for (int r = 0; r < nown; r++)
+            for (int64_t id = 1; id < n_ids; id++)
+                if (reads[(size_t)r * n_ids + id] >= opt.mirror_min) {
+                    mirror_id[(size_t)r * n_ids + id] = (int32_t)nid++;
+                    fetch_after[G.task_of[id]].push_back({(int32_t)id, (int8_t)r});
+                    G.mirrors_per_owner[r]++;
+                }
+        std::vector<uint8_t>().swap(reads);
+        if (nid > n_ids) {
+            if (nid > 0x7fffffff) return "too many block ids";
+            info.resize(nid);
+            alias_to.resize(nid, 0);
+            G.task_of.resize(nid, -1);
+            G.slot_of.resize(nid, 0);
+            G.owner_of.resize(nid, 0);
+            // operands of every task: remote mirrored sources -> the reader's mirror id
+            for (int64_t t = 0; t < nt; t++) {
+                const int r = town[t];
+                for_src(G.tasks[t], [&](int32_t& sid) {
+                    if (sid <= 0) return;
+                    const int32_t c = cn(sid);
+                    if (c < n_ids && G.owner_of[c] != r) { const int32_t m = mirror_id[(size_t)r * n_ids + c]; if (m) sid = m; }
+                });
+            }
+            // merged task order: every task followed by the fetch tasks of the blocks it completes
+            std::vector<Task> merged;
+            merged.reserve(nt + (nid - n_ids));
+            std::vector<int32_t> new_index(nt);
+            std::vector<int8_t> town2;
+            town2.reserve(nt + (nid - n_ids));
+            for (int64_t t = 0; t < nt; t++) {
+                new_index[t] = (int32_t)merged.size();
+                merged.push_back(G.tasks[t]);
+                town2.push_back(town[t]);
+                for (const auto& f : fetch_after[t]) {
+                    const int32_t m = mirror_id[(size_t)f.second * n_ids + f.first];
+                    Task F = {};
+                    F.type = T_SUB;                      // out = a - b with b = zero block: a copy
+                    F.n_pairs = 1;
+                    F.pair_begin = (int32_t)G.pairs.size();
+                    G.pairs.push_back(Pair{f.first, 0});
+                    F.out = m;
+                    IdInfo& w = info[m];
+                    w.n_writers = 1; w.kind = OP_SUB; w.first_writer = -1;
+                    G.owner_of[m] = f.second;
+                    G.task_of[m] = (int32_t)merged.size();
+                    merged.push_back(F);
+                    town2.push_back(f.second);
+                }
+            }
+            for (int64_t id = 1; id < n_ids; id++)
+                if (G.task_of[id] >= 0) G.task_of[id] = new_index[G.task_of[id]];
+            G.tasks.swap(merged);
+            town.swap(town2);
+            nt = (int64_t)G.tasks.size();
+        }
+        G.task_owner = town;
+    } else {
+        G.task_owner.assign(nt, 0);
+    }
+
     // ---- pool slots and segments -------------------------------------------------------------------
     // Unlimited pool: every input / produced block gets its own slot, one segment.  Limited pool
     // (opt.max_slots): walk the tasks in order (a topological order: the op list is stage-sorted),
@@ -229,23 +335,25 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     // free list.  Inputs, kept blocks (L, U) and the diagonal inverses the solve uses are pinned.
     auto canon = [&](int32_t id) { return alias_to[id] ? alias_to[id] : id; };
     std::vector<int32_t> seg_of(nt, 0);
-    G.recycled.assign(n_ids, 0);
+    G.recycled.assign(nid, 0);
     G.seg_begin.assign(1, 0);
+    G.slots_per_owner.assign(nown, 1);          // local slot 0 of every GPU is its all-zero block
     {
         auto needs_slot = [&](int64_t id) { const IdInfo& w = info[id]; return w.is_input || (w.n_writers > 0 && !w.fused_away && !alias_to[id]); };
-        int64_t need = 1, n_in = 0;
-        for (int64_t id = 1; id < n_ids; id++) { if (needs_slot(id)) need++; if (info[id].is_input) n_in++; }
-        if (opt.max_slots <= 0 || need <= opt.max_slots) {
-            int64_t s = 1;
-            for (int64_t id = 1; id < n_ids; id++)
-                if (needs_slot(id)) G.slot_of[id] = (int32_t)s++;
-            G.n_slots = s;
+        std::vector<int64_t> need(nown, 1), n_in(nown, 0);
+        for (int64_t id = 1; id < nid; id++) { if (needs_slot(id)) need[G.owner_of[id]]++; if (info[id].is_input) n_in[G.owner_of[id]]++; }
+        bool fits = true;
+        for (int o = 0; o < nown; o++) fits = fits && (opt.max_slots <= 0 || need[o] <= opt.max_slots);
+        if (fits) {
+            for (int64_t id = 1; id < nid; id++)
+                if (needs_slot(id)) G.slot_of[id] = (int32_t)G.slots_per_owner[G.owner_of[id]]++;
         } else {
-            if (opt.max_slots <= n_in + 8) return "block pool too small even for the input blocks";
+            for (int o = 0; o < nown; o++)
+                if (opt.max_slots <= n_in[o] + 8) return "block pool too small even for the input blocks";
             // last task that touches each block (producer or reader)
-            std::vector<int32_t> last_touch(n_ids, -1);
-            std::vector<char> pinned(n_ids, 0);
-            for (int64_t id = 1; id < n_ids; id++) pinned[id] = info[id].is_input || info[id].keep;
+            std::vector<int32_t> last_touch(nid, -1);
+            std::vector<char> pinned(nid, 0);
+            for (int64_t id = 1; id < nid; id++) pinned[id] = info[id].is_input || info[id].keep;
             for (int64_t t = 0; t < nt; t++) {
                 const Task& T = G.tasks[t];
                 auto touch = [&](int32_t id) { if (id > 0) { id = canon(id); if (last_touch[id] < t) last_touch[id] = (int32_t)t; } };
@@ -260,17 +368,16 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             }
             // blocks ordered by last touch, for the release sweep at boundaries
             std::vector<int32_t> by_touch;
-            for (int64_t id = 1; id < n_ids; id++)
+            for (int64_t id = 1; id < nid; id++)
                 if (needs_slot(id) && !pinned[id]) by_touch.push_back((int32_t)id);
             std::sort(by_touch.begin(), by_touch.end(), [&](int32_t x, int32_t y) { return last_touch[x] < last_touch[y]; });
             size_t rel = 0;
-            std::vector<int32_t> freelist;
-            int64_t next_fresh = 1;
-            for (int64_t id = 1; id < n_ids; id++)
-                if (info[id].is_input) G.slot_of[id] = (int32_t)next_fresh++;
-            auto take = [&]() -> int32_t {
-                if (!freelist.empty()) { int32_t s = freelist.back(); freelist.pop_back(); return s; }
-                if (next_fresh < opt.max_slots) return (int32_t)next_fresh++;
+            std::vector<std::vector<int32_t>> freelist(nown);
+            for (int64_t id = 1; id < nid; id++)
+                if (info[id].is_input) G.slot_of[id] = (int32_t)G.slots_per_owner[G.owner_of[id]]++;
+            auto take = [&](int o) -> int32_t {
+                if (!freelist[o].empty()) { int32_t sl = freelist[o].back(); freelist[o].pop_back(); return sl; }
+                if (G.slots_per_owner[o] < opt.max_slots) return (int32_t)G.slots_per_owner[o]++;
                 return -1;
             };
             int32_t cur_seg = 0;
@@ -286,27 +393,28 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                 for (int k = 0; k < no; k++) {
                     const int32_t id = outs[k];
                     if (alias_to[id] || G.slot_of[id] > 0) continue;
-                    int32_t sl = take();
+                    const int o = G.owner_of[id];
+                    int32_t sl = take(o);
                     if (sl < 0) {
-                        // close the segment before task t and release everything dead by then
+                        // close the segment before task t and release everything dead by then (all GPUs)
                         if (G.seg_begin.back() == (int32_t)t) return "block pool too small: a single task's live set does not fit";
                         G.seg_begin.push_back((int32_t)t);
                         cur_seg++;
                         while (rel < by_touch.size() && last_touch[by_touch[rel]] < t) {
                             const int32_t dead = by_touch[rel++];
-                            if (G.slot_of[dead] > 0) { freelist.push_back(G.slot_of[dead]); G.recycled[dead] = 1; }
+                            if (G.slot_of[dead] > 0) { freelist[G.owner_of[dead]].push_back(G.slot_of[dead]); G.recycled[dead] = 1; }
                         }
-                        sl = take();
+                        sl = take(o);
                         if (sl < 0) return "block pool too small for the live set of the factorisation";
                     }
                     G.slot_of[id] = sl;
                 }
                 seg_of[t] = cur_seg;
             }
-            G.n_slots = next_fresh;
         }
-        for (int64_t id = 1; id < n_ids; id++)
+        for (int64_t id = 1; id < nid; id++)
             if (alias_to[id]) { G.slot_of[id] = G.slot_of[alias_to[id]]; G.recycled[id] = G.recycled[alias_to[id]]; }
+        G.n_slots = G.slots_per_owner[0];
         G.seg_begin.push_back((int32_t)nt);
     }
 
@@ -435,6 +543,12 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                 }
             }
             for (int64_t t = 0; t < nt2; t++) tasks2[t].n_deps = deps2[t];
+            {
+                std::vector<int8_t> own2(nt2);
+                for (int64_t t = 0; t < nt; t++)
+                    for (int q = 0; q < split[t]; q++) own2[base[t] + q] = G.task_owner[t];
+                G.task_owner.swap(own2);
+            }
             G.tasks.swap(tasks2);
             G.succ.swap(succ2);
             for (int32_t& x : G.task_of)
@@ -453,83 +567,81 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             G.seg_init.push_back((int32_t)G.initial.size());
         }
     }
-    // ---- patch block ids -> pool slots ---------------------------------------------------------
-    for (Task& t : G.tasks) {
-        t.out = G.slot_of[t.out];
-        if (t.type == T_LU) t.out2 = G.slot_of[t.out2];
-        if (t.flags & (TF_INIT | TF_LINV)) t.init = G.slot_of[t.init];
-        if (t.flags & TF_UINV) t.out4 = G.slot_of[t.out4];
+    // ---- patch block ids -> block references (owner in the top bits; plain slots on one GPU) --------
+    {
+        auto ref = [&](int32_t id, int reader) -> int32_t {
+            if (id <= 0 || G.slot_of[id] <= 0) return make_ref(reader, 0);     // the reader's own zero block
+            return make_ref(G.owner_of[id], G.slot_of[id]);
+        };
+        // pairs are shared by the row slices of one task: patch them once, per first slice
+        std::vector<char> pdone(G.pairs.size(), 0);
+        for (size_t t = 0; t < G.tasks.size(); t++) {
+            Task& T = G.tasks[t];
+            const int o = G.task_owner[t];
+            T.out = ref(T.out, o);
+            if (T.type == T_LU) T.out2 = ref(T.out2, o);
+            if (T.flags & (TF_INIT | TF_LINV)) T.init = ref(T.init, o);
+            if (T.flags & TF_UINV) T.out4 = ref(T.out4, o);
+            for (int32_t k = 0; k < T.n_pairs; k++) {
+                const size_t q = (size_t)T.pair_begin + k;
+                if (pdone[q]) continue;
+                pdone[q] = 1;
+                G.pairs[q].a = ref(G.pairs[q].a, o);
+                G.pairs[q].b = ref(G.pairs[q].b, o);
+            }
+        }
+        for (Task& T : G.tasks)
+            for (int k = 0; k < 2; k++) T.first[k] = (k < T.n_pairs) ? G.pairs[T.pair_begin + k] : Pair{0, 0};
     }
-    for (Pair& p : G.pairs) { p.a = G.slot_of[p.a]; p.b = G.slot_of[p.b]; }
-    for (Task& t : G.tasks)
-        for (int k = 0; k < 2; k++) t.first[k] = (k < t.n_pairs) ? G.pairs[t.pair_begin + k] : Pair{0, 0};
     return "";
 }
 
 
-std::string localize_tasks(const TaskGraph& G, int64_t n_ids, const int32_t* brow, const int32_t* bcol, int rank, int world, int pr,
-                           int pc, DistLayout& D) {
+std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {
+    // The graph was compiled with owners: tasks, block references and mirrors are already per GPU.
+    // A rank keeps its tasks (renumbered in order) and rewrites successor ids to (owner, local).
     D = DistLayout();
-    D.rank = rank; D.world = world; D.pr = pr; D.pc = pc;
-    if (world < 1 || world > MAX_GPUS || pr * pc != world || rank < 0 || rank >= world) return "bad process grid";
-    if (G.seg_begin.size() > 2) return "multi-GPU sharding with a recycling block pool is not supported yet (the blocks of one GPU's share must fit its HBM)";
+    D.rank = rank; D.world = G.n_owners;
+    if (rank < 0 || rank >= G.n_owners) return "bad rank";
     const int64_t nt = (int64_t)G.tasks.size();
-    // slot owners from the block coordinates
-    std::vector<int8_t> slot_owner(G.n_slots, -1);
-    for (int64_t id = 1; id < n_ids; id++) {
-        const int32_t sl = G.slot_of[id];
-        if (sl <= 0) continue;
-        int o = 0;
-        if (brow && bcol && brow[id] >= 0 && bcol[id] >= 0) o = (brow[id] % pr) * pc + (bcol[id] % pc);
-        if (slot_owner[sl] >= 0 && slot_owner[sl] != o) return "aliased blocks with different owners";
-        slot_owner[sl] = (int8_t)o;
-    }
-    D.slots_per_rank.assign(world, 1);   // local slot 0 = zero block everywhere
-    D.slot_ref.assign(G.n_slots, 0);
-    D.slot_ref[0] = make_ref(rank, 0);
-    for (int64_t sl = 1; sl < G.n_slots; sl++) {
-        const int o = slot_owner[sl] < 0 ? 0 : slot_owner[sl];
-        if (D.slots_per_rank[o] > REF_MASK) return "too many blocks per GPU";
-        D.slot_ref[sl] = make_ref(o, (int32_t)D.slots_per_rank[o]++);
-    }
-    D.task_owner.resize(nt);
+    D.task_owner = G.task_owner;
     D.task_local.resize(nt);
-    D.tasks_per_rank.assign(world, 0);
-    for (int64_t t = 0; t < nt; t++) {
-        const int o = (int)((uint32_t)D.slot_ref[G.tasks[t].out] >> REF_SHIFT);
-        D.task_owner[t] = (int8_t)o;
-        D.task_local[t] = (int32_t)D.tasks_per_rank[o]++;
+    D.tasks_per_rank.assign(G.n_owners, 0);
+    for (int64_t t = 0; t < nt; t++) D.task_local[t] = (int32_t)D.tasks_per_rank[G.task_owner[t]]++;
+    D.slots_per_rank = G.slots_per_owner;
+    D.mirrored = G.mirrors_per_owner.empty() ? 0 : G.mirrors_per_owner[rank];
+    const int nseg = (int)G.seg_begin.size() - 1;
+    D.seg_begin.assign(1, 0);
+    D.seg_init.assign(1, 0);
+    D.seg_begin_all.assign(G.n_owners, std::vector<int32_t>(nseg + 1, 0));
+    for (int sg = 0; sg < nseg; sg++) {
+        for (int o = 0; o < G.n_owners; o++) D.seg_begin_all[o][sg + 1] = D.seg_begin_all[o][sg];
+        for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) D.seg_begin_all[G.task_owner[t]][sg + 1]++;
     }
-    auto ref = [&](int32_t slot) { return D.slot_ref[slot]; };
-    auto remote = [&](int32_t r) { return (int)((uint32_t)r >> REF_SHIFT) != rank; };
-    for (int64_t t = 0; t < nt; t++) {
-        if (D.task_owner[t] != rank) continue;
-        Task T = G.tasks[t];
-        const int32_t pb = (int32_t)D.pairs.size();
-        for (int32_t k = 0; k < T.n_pairs; k++) {
-            const Pair& p = G.pairs[T.pair_begin + k];
-            Pair q{ref(p.a), ref(p.b)};
-            D.remote_operands += (p.a > 0 && remote(q.a)) + (p.b > 0 && remote(q.b));
-            D.pairs.push_back(q);
+    for (int sg = 0; sg < nseg; sg++) {
+        for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
+            if (G.task_owner[t] != rank) continue;
+            Task T = G.tasks[t];
+            const int32_t pb = (int32_t)D.pairs.size();
+            for (int32_t k = 0; k < T.n_pairs; k++) {
+                const Pair& p = G.pairs[T.pair_begin + k];
+                D.remote_operands += ((int)((uint32_t)p.a >> REF_SHIFT) != rank) + ((int)((uint32_t)p.b >> REF_SHIFT) != rank);
+                D.pairs.push_back(p);
+            }
+            T.pair_begin = pb;
+            const int32_t sb = (int32_t)D.succ.size();
+            for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+                const int32_t s2 = G.succ[e];
+                D.succ.push_back(make_ref(G.task_owner[s2], D.task_local[s2]));
+                D.remote_edges += G.task_owner[s2] != rank;
+            }
+            T.succ_begin = sb;
+            T.succ_end = (int32_t)D.succ.size();
+            if (T.n_deps == 0) D.initial.push_back((int32_t)D.tasks.size());
+            D.tasks.push_back(T);
         }
-        T.pair_begin = pb;
-        T.out = ref(T.out);
-        if (T.type == T_LU) T.out2 = ref(T.out2);
-        if (T.flags & (TF_INIT | TF_LINV)) T.init = ref(T.init);
-        if (T.flags & TF_UINV) T.out4 = ref(T.out4);
-        if (T.type == T_LU && (remote(T.out2) || ((T.flags & TF_LINV) && remote(T.init)) || ((T.flags & TF_UINV) && remote(T.out4))))
-            return "lu outputs with different owners";
-        const int32_t sb = (int32_t)D.succ.size();
-        for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
-            const int32_t s = G.succ[e];
-            D.succ.push_back(make_ref(D.task_owner[s], D.task_local[s]));
-            D.remote_edges += D.task_owner[s] != rank;
-        }
-        T.succ_begin = sb;
-        T.succ_end = (int32_t)D.succ.size();
-        for (int k = 0; k < 2; k++) T.first[k] = (k < T.n_pairs) ? D.pairs[pb + k] : Pair{make_ref(rank, 0), make_ref(rank, 0)};
-        if (T.n_deps == 0) D.initial.push_back((int32_t)D.tasks.size());
-        D.tasks.push_back(T);
+        D.seg_begin.push_back((int32_t)D.tasks.size());
+        D.seg_init.push_back((int32_t)D.initial.size());
     }
     return "";
 }

@@ -600,6 +600,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
 
 __global__ void pack_blocks_kernel(double* __restrict__ pool, const double* __restrict__ dense, const int32_t* __restrict__ slots, int64_t n) {
     for (int64_t b = blockIdx.x; b < n; b += gridDim.x) {
+        if (slots[b] < 0) continue;   // block owned by another GPU
         double* dst = pool + (size_t)slots[b] * BLK_ELEMS;
         const double* src = dense + (size_t)b * BLK * BLK;
         for (int i = threadIdx.x; i < BLK_ELEMS; i += blockDim.x) {

@@ -19,6 +19,12 @@ constexpr int BLK_LD = 68;
 constexpr int BLK_ELEMS = BLK * BLK_LD;                  // 4352 doubles
 constexpr int BLK_BYTES = BLK_ELEMS * (int)sizeof(double);  // 34816
 
+// references to blocks / tasks on other GPUs: owner in the top 3 bits, local index in the low 29
+constexpr int REF_SHIFT = 29;
+constexpr int32_t REF_MASK = (1 << REF_SHIFT) - 1;
+constexpr int MAX_GPUS = 8;
+inline int32_t make_ref(int owner, int32_t local) { return (int32_t)(((uint32_t)owner << REF_SHIFT) | (uint32_t)local); }
+
 enum TaskType : int32_t {
     T_GEMM = 0,      // out = init +/- sum_p A_p * B_p   (mul / mulneg / mult chains, optional fused sub)
     T_SUB = 1,       // out = S2 - S1                   (missing source = zero block)
@@ -70,6 +76,13 @@ struct TaskGraph {
     std::vector<int32_t> seg_begin;     // n_segments + 1 task indices
     std::vector<int32_t> seg_init;      // n_segments + 1 offsets into `initial`
     std::vector<uint8_t> recycled;      // block id -> its slot is reused later (contents do not survive)
+    // multi-GPU (n_owners > 1): slots are numbered per owner and every block / zero-block reference in
+    // tasks and pairs carries its owner (make_ref); slot_of[] stays the owner-local slot
+    int n_owners = 1;
+    std::vector<int8_t> owner_of;       // block id (incl. mirror ids appended after the caller's ids) -> owner
+    std::vector<int8_t> task_owner;     // task -> GPU that runs it
+    std::vector<int64_t> slots_per_owner;
+    std::vector<int64_t> mirrors_per_owner;
     int32_t n_levels = 0;
     double flops = 0;                   // dense-block convention, SURVEY.md 8(d)
     int64_t n_gemm_pairs = 0;
@@ -84,34 +97,31 @@ struct CompileOptions {
     bool fuse_inv = true;   // fold the first lowerInv / upperInv of an lu's factors into the lu task
     int split_narrow = 1;   // split GEMM tasks of narrow dependency levels by output rows (latency-bound phases)
     int n_sms = 148;        // width against which a level counts as narrow
-    int64_t max_slots = 0;  // block-pool capacity in slots (0 = unlimited: no recycling)
+    int64_t max_slots = 0;  // block-pool capacity in slots PER GPU (0 = unlimited: no recycling)
+    // multi-GPU: owner GPU of every block id (nullptr: everything on GPU 0).  Blocks a GPU reads at
+    // least `mirror_min` times from a peer get a local mirror filled by a fetch task.
+    const int8_t* owner_of_id = nullptr;
+    int n_owners = 1;
+    int mirror_min = 1;
 };
 
 // ---- multi-GPU: 2D block-cyclic owner-computes sharding -------------------------------------------
-// Block (brow, bcol) lives on GPU (brow mod pr) * pc + (bcol mod pc); a task runs where its
-// result lives and pulls remote operands over NVLink.  References to blocks and tasks on other
-// GPUs are 32-bit: owner in the top 3 bits, local index in the low 29.
-constexpr int REF_SHIFT = 29;
-constexpr int32_t REF_MASK = (1 << REF_SHIFT) - 1;
-constexpr int MAX_GPUS = 8;
-inline int32_t make_ref(int owner, int32_t local) { return (int32_t)(((uint32_t)owner << REF_SHIFT) | (uint32_t)local); }
-
-struct DistLayout {
-    int rank = 0, world = 1, pr = 1, pc = 1;
+// Block (brow, bcol) lives on GPU ((brow/nb) mod pr) * pc + ((bcol/nb) mod pc); a task runs where its
+// result lives and pulls remote operands over NVLink (directly, or once into a local mirror).
+struct DistLayout {     // one GPU's share of an owner-compiled TaskGraph
+    int rank = 0, world = 1;
     std::vector<int8_t> task_owner;      // global task -> owner
     std::vector<int32_t> task_local;     // global task -> index in the owner's task array
-    std::vector<int32_t> slot_ref;       // global slot -> reference (slot 0 -> this rank's zero block)
     std::vector<int64_t> tasks_per_rank, slots_per_rank;
-    // this rank's share, references already encoded
-    std::vector<Task> tasks;
+    std::vector<Task> tasks;             // successor ids rewritten to make_ref(owner, local task)
     std::vector<Pair> pairs;
     std::vector<int32_t> succ;
-    std::vector<int32_t> initial;
-    int64_t remote_edges = 0, remote_operands = 0;
+    std::vector<int32_t> initial;        // local task ids, grouped by segment
+    std::vector<int32_t> seg_begin, seg_init;
+    std::vector<std::vector<int32_t>> seg_begin_all;   // [owner][segment] first local task (peers' queue slices)
+    int64_t remote_edges = 0, remote_operands = 0, mirrored = 0;
 };
-// brow/bcol: per block id (may be null -> everything on rank 0)
-std::string localize_tasks(const TaskGraph& G, int64_t n_ids, const int32_t* brow, const int32_t* bcol, int rank, int world, int pr,
-                           int pc, DistLayout& out);
+std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& out);
 
 // Returns "" on success, otherwise the violated invariant.
 std::string compile_tasks(int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, int64_t n_ops,

@@ -102,6 +102,46 @@ double* solveLU(int dim, int valcount, bool symmetric, int* index_i, int* index_
 // ---- host-only view of the task compiler (no GPU needed): used by the CPU tests -------------------
 #include "../device/tasks.h"
 #include <chrono>
+extern "C" int soglu_debug_compile(const soglu_problem* pp, int fuse_sub, int fuse_inv, int split, int64_t max_slots, int64_t* out, int n_out);
+// same with a process grid: out[16..] = per-owner {tasks, slots, mirrors} triples
+extern "C" int soglu_debug_compile_dist(const soglu_problem* pp, int64_t max_slots, int pr, int pc, int nb, int64_t* out, int n_out) {
+    const Problem* p = reinterpret_cast<const Problem*>(pp);
+    const int world = pr * pc;
+    if (!p || !out || n_out < 16 + 3 * world) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
+    const soglu::Plan& pl = p->plan;
+    const int64_t n = (int64_t)pl.ops.size();
+    std::vector<int32_t> src(n), src2(n), res(n), res2(n);
+    std::vector<uint8_t> op(n);
+    for (int64_t k = 0; k < n; k++) { const soglu::Op& o = pl.ops[k]; src[k] = o.src; src2[k] = o.src2; res[k] = o.result; res2[k] = o.result2; op[k] = o.op; }
+    std::vector<int32_t> in_ids(pl.inputs.size()), keep;
+    for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = (int32_t)(k + 1);
+    for (const auto& r : pl.L) keep.push_back(r.id);
+    for (const auto& r : pl.U) keep.push_back(r.id);
+    std::vector<int8_t> owners(pl.storage, 0);
+    for (int64_t id = 1; id < pl.storage; id++)
+        if (pl.brow[id] >= 0 && pl.bcol[id] >= 0) owners[id] = (int8_t)(((pl.brow[id] / nb) % pr) * pc + ((pl.bcol[id] / nb) % pc));
+    soglu::CompileOptions co;
+    co.max_slots = max_slots; co.owner_of_id = owners.data(); co.n_owners = world;
+    soglu::TaskGraph G;
+    std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
+    if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
+    int64_t deps = 0;
+    for (const soglu::Task& t : G.tasks) deps += t.n_deps;
+    int64_t v[16] = {(int64_t)G.tasks.size(), (int64_t)G.pairs.size(), (int64_t)G.succ.size(), (int64_t)G.initial.size(), G.n_slots, G.n_levels,
+                     G.fused_subs, G.fused_invs, G.aliased_invs, G.split_tasks, (int64_t)G.seg_begin.size() - 1, deps, 0, 0, 0, (int64_t)(G.flops * 1e-6)};
+    for (int i = 0; i < 16; i++) out[i] = v[i];
+    int64_t remote_edges = 0;
+    for (int r = 0; r < world; r++) {
+        soglu::DistLayout D;
+        err = soglu::localize_tasks(G, r, D);
+        if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
+        out[16 + 3 * r] = (int64_t)D.tasks.size(); out[17 + 3 * r] = G.slots_per_owner[r]; out[18 + 3 * r] = D.mirrored;
+        remote_edges += D.remote_edges;
+        int64_t dd = 0; for (const soglu::Task& t : D.tasks) dd += t.n_deps;
+        out[12] += dd; out[13] += (int64_t)D.succ.size(); out[14] += D.remote_operands;
+    }
+    return SOGLU_OK;
+}
 extern "C" int soglu_debug_compile(const soglu_problem* pp, int fuse_sub, int fuse_inv, int split, int64_t max_slots, int64_t* out, int n_out) {
     const Problem* p = reinterpret_cast<const Problem*>(pp);
     if (!p || !out || n_out < 16) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }

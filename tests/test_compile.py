@@ -66,3 +66,47 @@ def test_segments_when_pool_is_small(sg, prob):
     assert tiny["segments"] >= small["segments"]
     with pytest.raises(sg.SogluError):
         compile_stats(sg, prob, max_slots=1500)          # below inputs + factors
+
+
+def compile_dist(sg, p, pr, pc, nb=1, max_slots=0):
+    L = sg.lib()
+    L.soglu_debug_compile_dist.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    n = 16 + 3 * pr * pc
+    out = (ctypes.c_int64 * n)()
+    rc = L.soglu_debug_compile_dist(p.h, max_slots, pr, pc, nb, out, n)
+    if rc:
+        raise sg.SogluError(L.soglu_last_error().decode())
+    v = list(out)
+    d = dict(zip(NAMES, v[:16]))
+    d["local_deps"], d["local_succ"], d["remote_operands"] = v[12], v[13], v[14]
+    d["per_rank"] = [tuple(v[16 + 3 * r: 19 + 3 * r]) for r in range(pr * pc)]   # (tasks, slots, mirrors)
+    return d
+
+
+@pytest.mark.parametrize("pr,pc,nb", [(1, 2, 1), (2, 2, 1), (2, 2, 4), (2, 4, 2)])
+def test_multi_gpu_sharding_bookkeeping(sg, prob, pr, pc, nb):
+    """2D block-cyclic owner-computes sharding: every task lands on exactly one GPU, mirrors add one
+    fetch task each, and the per-GPU pieces add up to the global graph."""
+    one = compile_stats(sg, prob)
+    d = compile_dist(sg, prob, pr, pc, nb)
+    world = pr * pc
+    mirrors = sum(m for _, _, m in d["per_rank"])
+    assert mirrors > 0
+    assert sum(t for t, _, _ in d["per_rank"]) == d["tasks"]           # partition of the tasks
+    assert d["local_deps"] == d["deps"] == d["local_succ"] == d["succ"]  # every edge kept exactly once
+    assert d["pairs"] == one["pairs"] + mirrors                           # one operand pair per fetch task
+    assert d["segments"] == 1
+    slots = sum(s for _, s, _ in d["per_rank"])
+    assert slots == one["slots"] + mirrors + (world - 1)                  # + a zero block per extra GPU
+    assert max(s for _, s, _ in d["per_rank"]) < one["slots"]             # the share of one GPU is smaller
+    # mirrored blocks are read locally: far fewer remote operand reads than remote blocks read directly
+    assert d["remote_operands"] <= mirrors + 2 * prob.size("n_input")  # only fetch tasks (and reads of remote inputs) cross GPUs
+
+
+def test_multi_gpu_with_small_pools_uses_segments(sg, prob):
+    d = compile_dist(sg, prob, 1, 2, 1)
+    cap = max(s for _, s, _ in d["per_rank"]) - 400
+    e = compile_dist(sg, prob, 1, 2, 1, max_slots=cap)
+    assert e["segments"] > 1
+    assert all(s <= cap for _, s, _ in e["per_rank"])
+    assert sum(t for t, _, _ in e["per_rank"]) == e["tasks"]
