@@ -13,8 +13,10 @@ value  = algorithmic GFLOP/s (dense-block convention of SURVEY.md 8d, from the o
          the wall time of K steps, bracketed by barrier + cuda synchronize, max over ranks.
 e2e    = same metric through the C ABI from HOST buffers: every step re-uploads the dense input
          blocks and the right-hand side (H2D) and reads x back (D2H) inside the timed region.
-N > 1  = N independent replicas, one per GPU (the 2D block-cyclic sharding of the north star is
-         not implemented yet; DESIGN.md says so) -- reported as weak scaling of replicas.
+N > 1  = ONE factorisation sharded over the N GPUs (2D block-cyclic block ownership, owner computes,
+         remote operands pulled over NVLink into local mirrors; one process per GPU, peers mapped with
+         CUDA IPC; NCCL only for bootstrap / barriers); the solve runs on rank 0 over peer memory.
+         Total work is fixed -> "scaling": "strong".  value = op-list FLOPs / max-over-ranks time.
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/ref_harness, its own OpenMP path on
 the host cores, "kernel time" + "solve triangled") on the same workload; if the prebuilt
@@ -33,6 +35,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if "WORLD_SIZE" in os.environ:   # torchrun pins OMP_NUM_THREADS=1; the host planner is OpenMP-parallel
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(1, int(os.environ["WORLD_SIZE"]))))
 
 WORKLOADS = {
     # name: (stencil kind, dims, BASELINE.json config)
@@ -256,12 +260,6 @@ def main():
     sflops, sbytes = solve_flops_bytes(prob)
 
     dev = local_rank if use_dist else 0
-    ctx = sg.Context(dev)
-    t0 = time.perf_counter()
-    ctx.load(prob)
-    first = ctx.factor()                       # includes the one-time task-graph compilation + upload
-    t_first = time.perf_counter() - t0
-    x, _ = ctx.solve(prob)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -269,18 +267,42 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    ctx = sg.Context(dev, rank, world)
+    t0 = time.perf_counter()
+    ctx.load(prob)
+    if use_dist:
+        blob = torch.from_numpy(ctx.dist_export()).cuda()          # compiles + allocates this GPU's share
+        allb = [torch.empty_like(blob) for _ in range(world)]
+        dist.all_gather(allb, blob)
+        ctx.dist_import(torch.stack(allb).cpu().numpy())
+        factor = lambda: ctx.factor_dist(barrier)
+    else:
+        factor = ctx.factor
+    first = factor()                           # includes the one-time task-graph compilation + upload
+    t_first = time.perf_counter() - t0
+    x = None
+    if rank == 0:
+        x, _ = ctx.solve(prob)
+    barrier()
+
     # ---- device-resident steps ---------------------------------------------------------------
+    def step():
+        fs = factor()
+        ss = {"kernel_launches": 0, "seconds": 0.0}
+        if rank == 0:
+            _, ss = ctx.solve(prob)
+        if use_dist:
+            barrier()                           # peers keep their factor blocks mapped until rank 0 has solved
+        return fs, ss
     for _ in range(max(args.warmup, 3)):
-        ctx.factor()
-        ctx.solve(prob)
+        step()
     sampler = ClockSampler(dev) if rank == 0 else None
     barrier()
     t0 = time.perf_counter()
     launches, f_dev, s_dev = 0, [], []
     for _ in range(args.steps):
-        fs = ctx.factor()
-        xx, ss = ctx.solve(prob)
-        launches += fs["kernel_launches"] + ss["kernel_launches"]
+        fs, ss = step()
+        launches += fs["kernel_launches"] * fs.get("segments", 1) + ss["kernel_launches"]
         f_dev.append(fs["seconds"])
         s_dev.append(ss["seconds"])
     barrier()
@@ -288,7 +310,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     elapsed = reduce_max(elapsed, "cuda" if use_dist else None)
     step_s = elapsed / args.steps
-    value = aggregate_gflops(flops + sflops, step_s, world)
+    value = aggregate_gflops(flops + sflops, step_s, 1 if use_dist else world)   # sharded: the work is done once
 
     # ---- end to end from host buffers (pinned), H2D + D2H inside the timed region ---------------
     n_in = prob.size("n_input")
@@ -302,10 +324,13 @@ def main():
     st = sg.Stats()
 
     def e2e_step():
-        ctx.set_blocks(prob.size("storage"), ids, vals_np)                                 # H2D: dense input blocks
-        ctx.factor()
-        rc = L.soglu_solve(ctx.h, b_np.ctypes.data_as(ctypes.c_void_p), x_np.ctypes.data_as(ctypes.c_void_p), ctypes.byref(st))  # H2D b, D2H x
-        assert rc == 0
+        ctx.set_blocks(prob.size("storage"), ids, vals_np)                                 # H2D: dense input blocks (every rank: it keeps its share)
+        factor()
+        if rank == 0:
+            rc = L.soglu_solve(ctx.h, b_np.ctypes.data_as(ctypes.c_void_p), x_np.ctypes.data_as(ctypes.c_void_p), ctypes.byref(st))  # H2D b, D2H x
+            assert rc == 0
+        if use_dist:
+            barrier()
     for _ in range(2):
         e2e_step()
     barrier()
@@ -319,8 +344,9 @@ def main():
     h2d = float(vals_np.nbytes + b_np.nbytes)
     d2h = float(x_np.nbytes)
     # the e2e result must be the same solution
-    x_e2e = x_np[prob.i32("perm_old2new")]
-    assert np.array_equal(x_e2e, x), "end-to-end path produced a different solution"
+    if rank == 0:
+        x_e2e = x_np[prob.i32("perm_old2new")]
+        assert np.array_equal(x_e2e, x), "end-to-end path produced a different solution"
 
     if rank == 0:
         peak, peak_how = measure_fp64_peak()
@@ -366,15 +392,16 @@ def main():
         # residual of the benchmarked solution (7-point / 5-point / 9-point stencils): report, do not hide
         line = {
             "metric": "fp64_lu_factor_solve_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong" if use_dist else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][2], "name": args.workload, "n": prob.size("dim"), "ops": prob.size("n_ops"),
                        "tasks": int(first["tasks"]), "pool_blocks": int(first["pool_blocks"]),
-                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (block-cyclic sharding not implemented)" % world,
+                       "parallelism": "1 GPU" if world == 1 else "one factorisation sharded over %d GPUs: 2D block-cyclic (%dx%d grid, 16x16-block squares), owner computes, NVLink peer pulls; solve on rank 0" % ((world,) + sg.default_grid(world)),
+                       "segments": int(first.get("segments", 1)),
                        "l2": "inputs_exceed_l2 (block pool %.1f GB >> 126 MB L2)" % (first["pool_blocks"] * 34816 * 1e-9),
                        "factor_ms": t_factor * 1e3, "solve_ms": t_solve * 1e3, "factor_gflops": flops / t_factor * 1e-9,
                        "solve_gbs": sbytes / t_solve * 1e-9, "host_plan_s": t_plan, "first_call_s": t_first},
-            "e2e": {"value": aggregate_gflops(flops + sflops, e2e_s, world), "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": aggregate_gflops(flops + sflops, e2e_s, 1 if use_dist else world), "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,

@@ -245,3 +245,23 @@ def test_pool_too_small_is_an_error(sg, tmp_path):
         ctx.factor()
     assert "pool too small" in str(e.value)
     ctx.close()
+
+
+def test_two_gpu_sharded_factorisation():
+    """One factorisation sharded over 2 GPUs (one process per GPU, CUDA IPC peer pools, NVLink pulls):
+    bitwise equal to the single-GPU result, with and without slot recycling (segments)."""
+    import json
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import ROOT
+    for extra, port in (([], 29541), (["max_slots=4000"], 29542), (["dist_nb=1", "mirror_min=2"], 29543)):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.join(ROOT, "tests", "_dist_worker.py"), "lap3d", "24"] + extra
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert out.returncode == 0, out.stderr[-3000:]
+        rec = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+        assert rec["world"] == 2 and rec["bitwise_equal"], rec
+        assert all(r["tasks"] > 0 for r in rec["per_rank"])
+        assert sum(r["mirrored"] for r in rec["per_rank"]) > 0
