@@ -389,7 +389,20 @@ def main():
                 dt = time.perf_counter() - t0
                 f2 = float(p2.f64("flops")[0]) + solve_flops_bytes(p2)[0]
                 cpu = {"value": f2 / dt * 1e-9, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": "oracle port (scalar C) on lap3d_24; oracle/_ref unusable on this host"}
-        # residual of the benchmarked solution (7-point / 5-point / 9-point stencils): report, do not hide
+        # accuracy of the benchmarked solution: raw and after one device-side refinement step (not timed)
+        accuracy = None
+        if WORKLOADS[args.workload][0] == "lap3d":
+            nx, ny, nz = WORKLOADS[args.workload][1]
+            bb = 1.0 + 0.25 * (np.arange(prob.size("dim")) % 7)
+
+            def resid(xv):
+                X = xv.reshape(nz, ny, nx)
+                ax = 6.0 * X
+                ax[1:] -= X[:-1]; ax[:-1] -= X[1:]; ax[:, 1:] -= X[:, :-1]; ax[:, :-1] -= X[:, 1:]; ax[:, :, 1:] -= X[:, :, :-1]; ax[:, :, :-1] -= X[:, :, 1:]
+                return float(np.linalg.norm(ax.ravel() - bb) / np.linalg.norm(bb))
+            xr, _ = ctx.solve(prob, refine=1)
+            accuracy = {"residual_rel": resid(x), "residual_rel_after_1_refinement": resid(xr), "nan": int(np.isnan(x).sum()),
+                        "note": "||Ax-b||/||b||, north-star gate 1e-12; refinement = FP64 residual + re-solve on the device"}
         line = {
             "metric": "fp64_lu_factor_solve_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong" if use_dist else "weak", "vs_baseline": None,
@@ -407,6 +420,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "executor_kernel (whole factorisation DAG, one persistent launch per step)", "peak_source": peak_how},
             "cpu_baseline": cpu,
+            "accuracy": accuracy,
             "clocks": clocks,
         }
         print(json.dumps(line))

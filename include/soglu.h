@@ -97,6 +97,12 @@ int soglu_factor(soglu_ctx* ctx, soglu_stats* out);
  * (NOT overwritten, unlike the reference); x_ext receives n_block_rows*64 values. */
 int soglu_solve(soglu_ctx* ctx, const double* b_ext, double* x_ext, soglu_stats* out);
 
+/* Iterative refinement on the device (the reference has none): soglu_set_matrix takes the
+ * CSR of the permuted system padded with the identity to n_block_rows*64 rows; soglu_solve_refined does
+ * solve + `steps` x (r = b - A x in FP64, solve, x += d) and returns the refined x_ext. */
+int soglu_set_matrix(soglu_ctx* ctx, int64_t n_ext, int64_t nnz, const int64_t* row_ptr, const int32_t* col, const double* val);
+int soglu_solve_refined(soglu_ctx* ctx, const double* b_ext, double* x_ext, int steps, soglu_stats* out);
+
 /* parity helpers: read back one block (dense 64x64) after soglu_factor; error if the block
  * was recycled (only inputs of later ops, L and U are guaranteed to survive). */
 int soglu_get_block(soglu_ctx* ctx, int32_t id, double* out_64x64);

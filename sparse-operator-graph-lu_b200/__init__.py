@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "soglu_problem_from_coo", "soglu_problem_free", "soglu_problem_size", "soglu_problem_get_i32", "soglu_problem_get_f64",
     "soglu_problem_log", "soglu_load_problem", "soglu_solve_problem", "soglu_solveLU", "soglu_free", "soglu_write_stencil_mtx",
     "soglu_create_dist", "soglu_dist_blob_bytes", "soglu_dist_export", "soglu_dist_import", "soglu_dist_reset", "soglu_dist_info",
-    "soglu_dist_segments", "soglu_dist_set_segment",
+    "soglu_dist_segments", "soglu_dist_set_segment", "soglu_set_matrix", "soglu_solve_refined",
 ]
 
 OP_NAMES = {1: "lu", 2: "lowerInv", 3: "upperInv", 4: "sub", 8: "mul", 9: "mulneg", 10: "llt", 11: "mult"}
@@ -251,11 +251,12 @@ class Context:
         _check(lib().soglu_solve(self.h, _ptr(b_ext), _ptr(x), ctypes.byref(st)))
         return x, st.as_dict()
 
-    def solve(self, problem, b=None):
+    def solve(self, problem, b=None, refine=0):
+        """x in the original ordering; refine > 0 adds that many device-side iterative-refinement steps."""
         x = np.empty(problem.size("dim"), dtype=np.float64)
         b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
         st = Stats()
-        _check(lib().soglu_solve_problem(self.h, problem.h, _ptr(b), _ptr(x), 0, ctypes.byref(st)))
+        _check(lib().soglu_solve_problem(self.h, problem.h, _ptr(b), _ptr(x), int(refine), ctypes.byref(st)))
         return x, st.as_dict()
 
     def get_block(self, block_id):

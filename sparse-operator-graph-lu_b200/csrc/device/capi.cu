@@ -88,6 +88,8 @@ struct soglu_ctx {
     // solve structures
     DevBuf l_ptr, l_col, l_slot, l_diag, l_dinv, u_ptr, u_col, u_slot, u_diag, u_dinv, d_b, d_y, d_x;
     int64_t nL_off = 0, nU_off = 0;
+    DevBuf m_rp, m_ci, m_v, d_r, d_xacc;   // CSR of the permuted padded matrix (iterative refinement)
+    int64_t m_n = 0, m_nnz = 0;
     int64_t launches = 0;
     double h2d = 0, d2h = 0;
 };
@@ -459,7 +461,7 @@ void soglu_destroy(soglu_ctx* c) {
                 if (p) cudaIpcCloseMemHandle(p);
         }
     for (DevBuf* b : {&c->in_dense, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
-                      &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->d_y, &c->d_x, &c->trace})
+                      &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->d_y, &c->d_x, &c->trace, &c->m_rp, &c->m_ci, &c->m_v, &c->d_r, &c->d_xacc})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -644,13 +646,8 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     return SOGLU_OK;
 }
 
-int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* out) {
-    if (!c || !b_ext || !x_ext) return fail(SOGLU_ERR_ARG, "bad argument");
-    if (!c->factored) return fail(SOGLU_ERR_ARG, "soglu_factor must precede soglu_solve");
-    CU(cudaSetDevice(c->device));
-    const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
-    CU(cudaMemcpyAsync(c->d_b.p, b_ext, next, cudaMemcpyHostToDevice, c->stream));
-    if (c->dist && c->rank != 0) return fail(SOGLU_ERR_ARG, "multi-GPU context: the triangular solve runs on rank 0 (it reads the peers' factor blocks over NVLink)");
+// one forward/back substitution on device buffers: rhs (n_ext) -> sol (n_ext)
+static int run_trsv(soglu_ctx* c, const double* d_rhs, double* d_sol) {
     TrsvParams P = {};
     P.pool = c->pool.as<double>();
     if (c->dist) { for (int g = 0; g < c->world; g++) P.pools[g] = (const double*)c->peer_pool[g]; }
@@ -660,13 +657,40 @@ int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* o
     P.u_ptr = c->u_ptr.as<int64_t>(); P.u_col = c->u_col.as<int32_t>(); P.u_slot = c->u_slot.as<int32_t>(); P.u_diag = c->u_diag.as<int32_t>();
     P.u_dinv = c->u_dinv.as<int32_t>();
     P.n_rows = c->n_block_rows;
-    P.b = c->d_b.as<double>(); P.y = c->d_y.as<double>(); P.x = c->d_x.as<double>();
+    P.b = d_rhs; P.y = c->d_y.as<double>(); P.x = d_sol;
     P.symmetric = c->symmetric;
-    CU(cudaEventRecord(c->ev0, c->stream));
     CU(launch_trsv(P, std::min(c->trsv_grid, c->n_block_rows), c->stream));
     c->launches += 2;   // sentinel fill + solve kernel
+    return SOGLU_OK;
+}
+
+static int solve_impl(soglu_ctx* c, const double* b_ext, double* x_ext, int refine, soglu_stats* out) {
+    if (!c || !b_ext || !x_ext) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->factored) return fail(SOGLU_ERR_ARG, "soglu_factor must precede soglu_solve");
+    if (c->dist && c->rank != 0) return fail(SOGLU_ERR_ARG, "multi-GPU context: the triangular solve runs on rank 0 (it reads the peers' factor blocks over NVLink)");
+    if (refine > 0 && c->m_n == 0) return fail(SOGLU_ERR_ARG, "iterative refinement needs the matrix: call soglu_set_matrix first");
+    CU(cudaSetDevice(c->device));
+    const int64_t launches0 = c->launches;
+    const int64_t n = (int64_t)c->n_block_rows * BLK;
+    const size_t next = (size_t)n * sizeof(double);
+    CU(cudaMemcpyAsync(c->d_b.p, b_ext, next, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    int rc = run_trsv(c, c->d_b.as<double>(), c->d_x.as<double>());
+    if (rc) return rc;
+    if (refine > 0) {
+        // x_acc = x; repeat: r = b - A x_acc; solve A d = r; x_acc += d   (all FP64, on the device)
+        if (!c->d_r.p) { CU(c->d_r.alloc(next)); CU(c->d_xacc.alloc(next)); }
+        CU(cudaMemcpyAsync(c->d_xacc.p, c->d_x.p, next, cudaMemcpyDeviceToDevice, c->stream));
+        for (int it = 0; it < refine; it++) {
+            CU(launch_residual(c->m_rp.as<int64_t>(), c->m_ci.as<int32_t>(), c->m_v.as<double>(), c->d_b.as<double>(), c->d_xacc.as<double>(),
+                               c->d_r.as<double>(), n, c->stream));
+            if ((rc = run_trsv(c, c->d_r.as<double>(), c->d_x.as<double>()))) return rc;
+            CU(launch_axpy(c->d_xacc.as<double>(), c->d_x.as<double>(), n, c->stream));
+            c->launches += 2;
+        }
+    }
     CU(cudaEventRecord(c->ev1, c->stream));
-    CU(cudaMemcpyAsync(x_ext, c->d_x.p, next, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(x_ext, refine > 0 ? c->d_xacc.p : c->d_x.p, next, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -675,15 +699,38 @@ int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* o
     if (out) {
         std::memset(out, 0, sizeof *out);
         out->seconds = ms * 1e-3;
-        const double nblk = (double)(c->nL_off + c->nU_off + 2.0 * c->n_block_rows);
+        const double nblk = (double)(c->nL_off + c->nU_off + 2.0 * c->n_block_rows) * (1 + refine);
         out->flops = 2.0 * 4096.0 * nblk;
-        out->bytes = (double)BLK * BLK * 8.0 * nblk + 8.0 * 3.0 * c->n_block_rows * BLK;
-        out->kernel_launches = 2;
-        out->tasks = 2 * (int64_t)c->n_block_rows;
-        out->pool_blocks = c->G.n_slots;
+        out->bytes = (double)BLK * BLK * 8.0 * nblk + 8.0 * 3.0 * c->n_block_rows * BLK * (1 + refine);
+        out->kernel_launches = c->launches - launches0;
+        out->tasks = 2 * (int64_t)c->n_block_rows * (1 + refine);
+        out->pool_blocks = c->G.slots_per_owner[c->dist ? c->rank : 0];
         out->h2d_bytes = (double)next;
         out->d2h_bytes = (double)next;
     }
+    return SOGLU_OK;
+}
+
+int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* out) { return solve_impl(c, b_ext, x_ext, 0, out); }
+
+// solve + `steps` rounds of iterative refinement on the device (needs soglu_set_matrix)
+int soglu_solve_refined(soglu_ctx* c, const double* b_ext, double* x_ext, int steps, soglu_stats* out) {
+    return solve_impl(c, b_ext, x_ext, steps < 0 ? 0 : steps, out);
+}
+
+// CSR of the permuted system padded with the identity to n_block_rows*64 rows (what the factors factorise)
+int soglu_set_matrix(soglu_ctx* c, int64_t n_ext, int64_t nnz, const int64_t* row_ptr, const int32_t* col, const double* val) {
+    if (!c || n_ext <= 0 || nnz < 0 || !row_ptr || (nnz > 0 && (!col || !val))) return fail(SOGLU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(c->m_rp.alloc((size_t)(n_ext + 1) * 8)); CU(c->m_ci.alloc(std::max<size_t>(nnz, 1) * 4)); CU(c->m_v.alloc(std::max<size_t>(nnz, 1) * 8));
+    CU(cudaMemcpyAsync(c->m_rp.p, row_ptr, (size_t)(n_ext + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (nnz) {
+        CU(cudaMemcpyAsync(c->m_ci.p, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->m_v.p, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->m_n = n_ext; c->m_nnz = nnz;
+    c->h2d += (double)((n_ext + 1) * 8 + nnz * 12);
     return SOGLU_OK;
 }
 

@@ -54,5 +54,9 @@ struct TrsvParams {
 };
 cudaError_t launch_trsv(const TrsvParams& p, int grid, cudaStream_t stream);
 int trsv_max_grid(int device);
+// iterative refinement: r = b - A x (CSR of the permuted padded system), x += d
+cudaError_t launch_residual(const int64_t* rp, const int32_t* ci, const double* v, const double* b, const double* x, double* r, int64_t n,
+                            cudaStream_t stream);
+cudaError_t launch_axpy(double* x, const double* d, int64_t n, cudaStream_t stream);
 
 }  // namespace soglu

@@ -205,7 +205,31 @@ __global__ void fill_sentinel_kernel(double* __restrict__ a, double* __restrict_
     }
 }
 
+// ---- iterative refinement helpers: r = b - A x on the permuted, padded system (CSR), x += d ------
+__global__ void residual_kernel(const int64_t* __restrict__ rp, const int32_t* __restrict__ ci, const double* __restrict__ v,
+                                const double* __restrict__ b, const double* __restrict__ x, double* __restrict__ r, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = b[i];
+    for (int64_t k = rp[i]; k < rp[i + 1]; k++) s = fma(-v[k], x[ci[k]], s);
+    r[i] = s;
+}
+__global__ void axpy_kernel(double* __restrict__ x, const double* __restrict__ d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += d[i];
+}
+
 }  // namespace
+
+cudaError_t launch_residual(const int64_t* rp, const int32_t* ci, const double* v, const double* b, const double* x, double* r, int64_t n,
+                            cudaStream_t stream) {
+    residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rp, ci, v, b, x, r, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_axpy(double* x, const double* d, int64_t n, cudaStream_t stream) {
+    axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, d, n);
+    return cudaGetLastError();
+}
 
 int trsv_max_grid(int device) {
     cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsvSmem));

@@ -48,7 +48,22 @@ int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
 int soglu_solve_problem(soglu_ctx* ctx, const soglu_problem* pp, const double* b, double* x, int refine, soglu_stats* out) {
     const Problem* p = reinterpret_cast<const Problem*>(pp);
     if (!ctx || !p || !x) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
-    if (refine != 0) { soglu::set_error("iterative refinement is not available in this build"); return SOGLU_ERR_ARG; }
+    if (refine > 0) {
+        // CSR of the permuted matrix, padded with the identity like the planner does (BlockPlanner.cpp:1520-1539);
+        // duplicates keep the last value, as in the block scatter (BlockPlanner.cpp:1510)
+        const int64_t n = p->n_ext, nnz = (int64_t)p->pv.size();
+        std::vector<int64_t> rp(n + 1, 0);
+        for (int64_t k = 0; k < nnz; k++) rp[p->pi[k] + 1]++;
+        for (int64_t i = p->dim; i < n; i++) rp[i + 1]++;
+        for (int64_t i = 0; i < n; i++) rp[i + 1] += rp[i];
+        std::vector<int32_t> ci(rp[n]);
+        std::vector<double> cv(rp[n]);
+        std::vector<int64_t> pos(rp.begin(), rp.end() - 1);
+        for (int64_t k = 0; k < nnz; k++) { ci[pos[p->pi[k]]] = p->pj[k]; cv[pos[p->pi[k]]++] = p->pv[k]; }
+        for (int64_t i = p->dim; i < n; i++) { ci[pos[i]] = (int32_t)i; cv[pos[i]++] = 1.0; }
+        int rcm = soglu_set_matrix(ctx, n, rp[n], rp.data(), ci.data(), cv.data());
+        if (rcm) return rcm;
+    }
     std::vector<double> bext;
     const double* bp = p->b_perm.data();
     if (b) {   // permute + pad a caller-supplied rhs exactly like the problem's own (GPSOrder.cpp:435-447)
@@ -57,7 +72,7 @@ int soglu_solve_problem(soglu_ctx* ctx, const soglu_problem* pp, const double* b
         bp = bext.data();
     }
     std::vector<double> xext(p->n_ext);
-    int rc = soglu_solve(ctx, bp, xext.data(), out);
+    int rc = refine > 0 ? soglu_solve_refined(ctx, bp, xext.data(), refine, out) : soglu_solve(ctx, bp, xext.data(), out);
     if (rc) return rc;
     // un-permute (GOrder::reOrderResult, GPSOrder.cpp:41-53)
     for (int i = 0; i < p->dim; i++) x[i] = xext[p->ord.reverseOrder[i]];

@@ -265,3 +265,38 @@ def test_two_gpu_sharded_factorisation():
         assert rec["world"] == 2 and rec["bitwise_equal"], rec
         assert all(r["tasks"] > 0 for r in rec["per_rank"])
         assert sum(r["mirrored"] for r in rec["per_rank"]) > 0
+
+
+def test_iterative_refinement_lowers_residual(sg, tmp_path):
+    """Device-side refinement (r = b - A x in FP64, re-solve, update) drives the residual to the FP64 floor
+    (SURVEY.md 0.9): on the 2D Laplacian, where the raw solve sits near 1e-12, one step must not be worse
+    and must stay within the solution-parity tolerance of the reference."""
+    g = load_golden("lap2d_64")
+    p = sg.Problem.from_mtx(write_case_mtx("lap2d_64", tmp_path))
+    import gen_mtx
+    n, r, c, v = gen_mtx.generate("lap2d", 64)
+    b = gen_mtx.rhs(n)
+
+    def resid(x):
+        ax = np.zeros(n)
+        np.add.at(ax, r, v * x[c])
+        return np.linalg.norm(ax - b) / np.linalg.norm(b)
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    x0, s0 = ctx.solve(p)
+    x1, s1 = ctx.solve(p, refine=1)
+    x2, _ = ctx.solve(p, refine=2)
+    assert s1["kernel_launches"] > s0["kernel_launches"]
+    assert resid(x1) <= resid(x0) * 1.05 and resid(x2) <= resid(x0) * 1.05
+    assert resid(x1) <= 1e-12
+    assert _rel(x1, g["x"]) <= TOL_X and _rel(x2, g["x"]) <= TOL_X
+    # a perturbed factorisation-free check: refinement must fix a deliberately bad start? (not exposed) -- instead
+    # check a second right-hand side goes through the same path
+    rng = np.random.default_rng(5)
+    b2 = rng.standard_normal(n)
+    y, _ = ctx.solve(p, b2, refine=1)
+    ay = np.zeros(n)
+    np.add.at(ay, r, v * y[c])
+    assert np.linalg.norm(ay - b2) / np.linalg.norm(b2) <= 1e-12
+    ctx.close()

@@ -18,6 +18,7 @@ t = time.time(); ctx.load(p); print("load %.1f s" % (time.time() - t), flush=Tru
 t = time.time(); fs = ctx.factor(); print("first factor wall %.1f s (compile + upload + run)" % (time.time() - t), fs, flush=True)
 fs = ctx.factor(); print("factor %.4f s  %.1f GFLOP/s  launches %d pool %.1f GB" % (fs["seconds"], fs["flops"] / fs["seconds"] * 1e-9, fs["kernel_launches"], fs["pool_blocks"] * 34816e-9), flush=True)
 x, ss = ctx.solve(p); print("solve %.4f s  %.1f GB/s" % (ss["seconds"], ss["bytes"] / ss["seconds"] * 1e-9), flush=True)
+xr, sr = ctx.solve(p, refine=1); print("solve+1 refinement %.4f s" % sr["seconds"], flush=True)
 n = p.size("dim")
 b = 1.0 + 0.25 * (np.arange(n) % 7)
 if kind == "lap3d":
@@ -25,4 +26,7 @@ if kind == "lap3d":
     X = x.reshape(nz, ny, nx); ax = 6.0 * X
     ax[1:] -= X[:-1]; ax[:-1] -= X[1:]; ax[:, 1:] -= X[:, :-1]; ax[:, :-1] -= X[:, 1:]; ax[:, :, 1:] -= X[:, :, :-1]; ax[:, :, :-1] -= X[:, :, 1:]
     print("residual ||Ax-b||/||b|| = %.3e  nan %d  x[0:3] %s" % (np.linalg.norm(ax.ravel() - b) / np.linalg.norm(b), int(np.isnan(x).sum()), x[:3]))
+    X = xr.reshape(nz, ny, nx); ax = 6.0 * X
+    ax[1:] -= X[:-1]; ax[:-1] -= X[1:]; ax[:, 1:] -= X[:, :-1]; ax[:, :-1] -= X[:, 1:]; ax[:, :, 1:] -= X[:, :, :-1]; ax[:, :, :-1] -= X[:, :, 1:]
+    print("residual after 1 refinement step = %.3e   rel change of x %.3e" % (np.linalg.norm(ax.ravel() - b) / np.linalg.norm(b), np.linalg.norm(xr - x) / np.linalg.norm(x)))
 print("host maxrss %.1f GB" % (resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6))
