@@ -57,7 +57,10 @@ struct __align__(16) SmemCtl {
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
     double scratch[584];   // pivot row/column exchange buffers of the register-resident diag kernels
+    int local_task;        // mailbox: a successor the math warps hand straight to this CTA's scheduler (-1 = empty)
+    int polling;           // scheduler is idle, spinning on its claimed queue slot
 };
+constexpr int SLOT_SKIP = -2;   // queue slot of a task that was handed over locally
 
 constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
 
@@ -363,6 +366,20 @@ __device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const do
         }
 }
 
+// Local hand-over: if this CTA's scheduler is idle (spinning on a queue slot nobody has filled yet) the
+// released successor goes straight into its mailbox -- no queue round trip through L2 on the critical
+// chain.  Dekker-style: write the mailbox, then re-check `polling`; the scheduler clears `polling`, then
+// re-checks the mailbox, so at least one side sees the other.  The queue slot is still consumed
+// (SLOT_SKIP) to keep the claim-then-wait accounting exact.
+__device__ __forceinline__ bool hand_over(SmemCtl* ctl, int task) {
+    if (!*(volatile int*)&ctl->polling) return false;
+    if (atomicCAS(&ctl->local_task, -1, task) != -1) return false;
+    __threadfence_block();
+    if (*(volatile int*)&ctl->polling) return true;
+    // the scheduler may have left its polling loop: take the task back unless it already took it
+    return atomicCAS(&ctl->local_task, task, -1) != task;
+}
+
 __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
@@ -374,6 +391,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
             ptx::mbar_init(&ctl->full[s], 1);
             ptx::mbar_init(&ctl->empty[s], N_MATH_WARPS);
         }
+        ctl->local_task = -1;
+        ctl->polling = 0;
         ptx::fence_mbar_init();
     }
     __syncthreads();
@@ -382,20 +401,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
         // ================= scheduler + TMA producer =====================================
         if (lane == 0) {
             uint32_t it = 0;
-            while (true) {
-                const int slot = atomicAdd(P.head, 1);
-                int t = -1;
-                if (slot < P.n_tasks) {
-                    if (P.world > 1) { while ((t = ptx::ld_acquire_sys(P.ready + slot)) < 0) {} }
-                    else { while ((t = ptx::ld_acquire(P.ready + slot)) < 0) {} }
-                }
-                if (t < 0) {
-                    const int s = it % N_STAGES;
-                    ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);
-                    ctl->desc[s].type = T_EXIT;
-                    ptx::mbar_arrive(&ctl->full[s]);
-                    break;
-                }
+            // stream the operand blocks of one ready task into the stage ring
+            auto issue = [&](int t) {
                 if (P.trace) { P.trace[6 * (size_t)t + 1] = gtime(); P.trace[6 * (size_t)t + 5] = smid(); }
                 const Task T = P.tasks[t];
                 ptx::fence_proxy_async();
@@ -417,6 +424,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     ptx::bulk_g2s(As + a_off, blk_ptr(P, pr.a) + a_off, a_bytes, &ctl->full[s]);
                     if (two) ptx::bulk_g2s(As + BLK_ELEMS, blk_ptr(P, pr.b), BLK_BYTES, &ctl->full[s]);
                 }
+            };
+            volatile int* mailbox = &ctl->local_task;
+            volatile int* polling = &ctl->polling;
+            auto take_local = [&]() -> int {     // a task the math warps of THIS CTA just released
+                const int lt = *mailbox;
+                if (lt >= 0) { *mailbox = -1; __threadfence_block(); }
+                return lt;
+            };
+            while (true) {
+                const int slot = atomicAdd(P.head, 1);
+                if (slot >= P.n_tasks) {
+                    // the queue is exhausted; a local hand-over may still arrive while the math warps finish
+                    // their last task, but then its queue slot (SLOT_SKIP) was published before head ran out,
+                    // so nothing can be pending here
+                    const int lt = take_local();
+                    if (lt >= 0) issue(lt);
+                    const int s = it % N_STAGES;
+                    ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);
+                    ctl->desc[s].type = T_EXIT;
+                    ptx::mbar_arrive(&ctl->full[s]);
+                    break;
+                }
+                int t;
+                *polling = 1;
+                __threadfence_block();
+                while (true) {
+                    t = (P.world > 1) ? ptx::ld_acquire_sys(P.ready + slot) : ptx::ld_acquire(P.ready + slot);
+                    if (t != -1) break;
+                    const int lt = take_local();
+                    if (lt >= 0) issue(lt);      // run the local successor now; keep waiting for the claimed slot after
+                }
+                *polling = 0;
+                __threadfence_block();
+                const int lt = take_local();     // hand-over that raced with leaving the polling loop
+                if (lt >= 0) issue(lt);
+                if (t == SLOT_SKIP) continue;     // that task went to its releaser's own scheduler
+                issue(t);
             }
         }
         return;
@@ -514,8 +558,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                         const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & REF_MASK;
                         if (atomicSub_system(P.deps[o] + nx, 1) == 1) {
                             __threadfence_system();
+                            const bool handed = (o == P.rank) && hand_over(ctl, nx);
                             const int pos = atomicAdd_system(P.tails[o], 1);
-                            ptx::st_release_sys(P.readys[o] + pos, nx);
+                            ptx::st_release_sys(P.readys[o] + pos, handed ? SLOT_SKIP : nx);
                         }
                     }
                 } else {
@@ -524,9 +569,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                         const int nx = P.succ[e];
                         if (atomicSub(P.dep + nx, 1) == 1) {
                             __threadfence();
-                            const int pos = atomicAdd(P.tail, 1);
                             if (P.trace) P.trace[6 * (size_t)nx + 0] = gtime();
-                            ptx::st_release(P.ready + pos, nx);
+                            const bool handed = hand_over(ctl, nx);
+                            const int pos = atomicAdd(P.tail, 1);
+                            ptx::st_release(P.ready + pos, handed ? SLOT_SKIP : nx);
                         }
                     }
                 }
