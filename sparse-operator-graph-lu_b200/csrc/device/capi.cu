@@ -48,6 +48,7 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
+    int64_t opt_handover = 0;
     int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
     int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;
@@ -479,6 +480,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
     else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
     else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
+    else if (k == "handover") c->opt_handover = value;
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
@@ -552,6 +554,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     ExecParams P = {};
     P.pool = c->pool.as<double>();
     P.world = c->world; P.rank = c->rank;
+    P.handover = (int32_t)c->opt_handover;
     if (c->dist) {
         if (!c->peers_ready) return fail(SOGLU_ERR_ARG, "multi-GPU context: exchange peer handles (soglu_dist_export / soglu_dist_import) and call soglu_dist_reset before soglu_factor");
         for (int g = 0; g < c->world; g++) {

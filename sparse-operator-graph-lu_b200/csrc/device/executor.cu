@@ -366,7 +366,8 @@ __device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const do
         }
 }
 
-// Local hand-over: if this CTA's scheduler is idle (spinning on a queue slot nobody has filled yet) the
+// Local hand-over (option "handover", off by default: measured 4 % SLOWER at 64^3 -- 289 vs 277 ms -- the
+// skipped queue slots cost idle schedulers a claim round trip each): if this CTA's scheduler is idle (spinning on a queue slot nobody has filled yet) the
 // released successor goes straight into its mailbox -- no queue round trip through L2 on the critical
 // chain.  Dekker-style: write the mailbox, then re-check `polling`; the scheduler clears `polling`, then
 // re-checks the mailbox, so at least one side sees the other.  The queue slot is still consumed
@@ -551,16 +552,32 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
             const int sb = T->succ_begin, se = T->succ_end;
             if (sb + ct < se) {
                 if (P.world > 1) {
-                    // successors may live on peer GPUs: system-scope fences and atomics over NVLink
-                    __threadfence_system();
+                    // Successors on this GPU are released at gpu scope (cheap); only successors on peer GPUs
+                    // pay for system-scope fences and atomics over NVLink.  A counter may be decremented from
+                    // both scopes: the atomics themselves are performed at the owning GPU's L2 either way.
+                    __threadfence();
+                    bool remote = false;
                     for (int e = sb + ct; e < se; e += N_MATH) {
                         const int32_t ref = P.succ[e];
                         const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & REF_MASK;
-                        if (atomicSub_system(P.deps[o] + nx, 1) == 1) {
-                            __threadfence_system();
-                            const bool handed = (o == P.rank) && hand_over(ctl, nx);
-                            const int pos = atomicAdd_system(P.tails[o], 1);
-                            ptx::st_release_sys(P.readys[o] + pos, handed ? SLOT_SKIP : nx);
+                        if (o != P.rank) { remote = true; continue; }
+                        if (atomicSub(P.dep + nx, 1) == 1) {
+                            __threadfence();
+                            const int pos = atomicAdd(P.tail, 1);
+                            ptx::st_release(P.ready + pos, nx);
+                        }
+                    }
+                    if (remote) {
+                        __threadfence_system();
+                        for (int e = sb + ct; e < se; e += N_MATH) {
+                            const int32_t ref = P.succ[e];
+                            const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & REF_MASK;
+                            if (o == P.rank) continue;
+                            if (atomicSub_system(P.deps[o] + nx, 1) == 1) {
+                                __threadfence_system();
+                                const int pos = atomicAdd_system(P.tails[o], 1);
+                                ptx::st_release_sys(P.readys[o] + pos, nx);
+                            }
                         }
                     }
                 } else {
@@ -570,7 +587,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                         if (atomicSub(P.dep + nx, 1) == 1) {
                             __threadfence();
                             if (P.trace) P.trace[6 * (size_t)nx + 0] = gtime();
-                            const bool handed = hand_over(ctl, nx);
+                            const bool handed = P.handover && hand_over(ctl, nx);
                             const int pos = atomicAdd(P.tail, 1);
                             ptx::st_release(P.ready + pos, handed ? SLOT_SKIP : nx);
                         }

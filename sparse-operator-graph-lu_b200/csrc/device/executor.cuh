@@ -15,6 +15,7 @@ struct ExecParams {
     int32_t* readys[MAX_GPUS];
     int32_t* tails[MAX_GPUS];
     int32_t world, rank;
+    int32_t handover;      // hand a released successor to this CTA's own scheduler when it is idle
     double* pool;          // this GPU's block pool, slot s at pool + s*BLK_ELEMS
     const Task* tasks;
     const Pair* pairs;

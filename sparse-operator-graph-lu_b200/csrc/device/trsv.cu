@@ -48,13 +48,17 @@ __device__ __forceinline__ const double* blk_ptr(const TrsvParams& P, int32_t re
     return P.pools[(uint32_t)ref >> REF_SHIFT] + (size_t)(ref & REF_MASK) * BLK_ELEMS;
 }
 
+constexpr int RING = 4;       // off-diagonal blocks in flight per CTA (TMA bulk copies; hides NVLink latency too)
+
 struct __align__(16) TrsvSmem {
-    double last[BLK_ELEMS];   // nearest off-diagonal block of the row
-    double diag[BLK_ELEMS];   // diagonal block or its explicit inverse
-    double r[BLK];            // running right-hand side segment
-    double v[BLK];            // source segment of the block being applied
-    double t[BLK];            // r after the off-diagonal part (input of the diagonal operator)
+    double last[BLK_ELEMS];          // nearest off-diagonal block of the row
+    double diag[BLK_ELEMS];          // diagonal block or its explicit inverse
+    double ring[RING][BLK_ELEMS];    // the other off-diagonal blocks, streamed through shared memory
+    double r[BLK];                   // running right-hand side segment
+    double v[BLK];                   // source segment of the block being applied
+    double t[BLK];                   // r after the off-diagonal part (input of the diagonal operator)
     uint64_t bar;
+    uint64_t ring_bar[RING];
 };
 
 // 4 threads per row: racc[row] -= sum_c M[row][c] * v[c]  (or M^T), M in global memory
@@ -105,7 +109,7 @@ template <bool UPPER, bool TRANS>
 __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restrict__ ptr, const int32_t* __restrict__ col,
                           const int32_t* __restrict__ slot, const int32_t* __restrict__ diag, const int32_t* __restrict__ dinv,
                           const double* __restrict__ rhs, bool rhs_is_computed, double* __restrict__ sol, TrsvSmem& S,
-                          uint32_t& phase, int tid) {
+                          uint32_t& phase, uint32_t& ring_phase, int tid) {
     const int64_t b = ptr[row], e = ptr[row + 1];
     const int nb = (int)(e - b);
     // chain-critical block: forward = largest column (< row), backward = smallest column (> row)
@@ -119,14 +123,29 @@ __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restric
     }
     if (tid < BLK) S.r[tid] = rhs_is_computed ? poll_value(rhs + (size_t)row * BLK + tid) : rhs[(size_t)row * BLK + tid];
     const int rrow = tid >> 2, part = tid & 3;
-    // non-critical blocks, far to near
+    // non-critical blocks, far to near, RING bulk copies in flight
+    auto blk_of = [&](int q) -> int64_t { return UPPER ? (e - 1 - q) : (b + q); };
+    if (tid == 0) {
+        for (int q = 0; q < RING && q < nb - 1; q++) {
+            ptx::mbar_arrive_expect_tx(&S.ring_bar[q], BLK_BYTES);
+            ptx::bulk_g2s(S.ring[q], blk_ptr(P, slot[blk_of(q)]), BLK_BYTES, &S.ring_bar[q]);
+        }
+    }
     for (int q = 0; q < nb - 1; q++) {
-        const int64_t k = UPPER ? (e - 1 - q) : (b + q);
+        const int64_t k = blk_of(q);
+        const int rs = q % RING;
         __syncthreads();
         if (tid < BLK) S.v[tid] = poll_value(sol + (size_t)col[k] * BLK + tid);
+        ptx::mbar_wait(&S.ring_bar[rs], (ring_phase >> rs) & 1);
+        ring_phase ^= 1u << rs;
         __syncthreads();
-        const double s = quad_sum(gemv_part_global<TRANS>(blk_ptr(P, slot[k]), S.v, rrow, part));
+        const double s = quad_sum(gemv_part_smem<TRANS>(S.ring[rs], S.v, rrow, part));
         if (part == 0) S.r[rrow] -= s;
+        __syncthreads();                       // everyone is done with ring[rs]
+        if (tid == 0 && q + RING < nb - 1) {
+            ptx::mbar_arrive_expect_tx(&S.ring_bar[rs], BLK_BYTES);
+            ptx::bulk_g2s(S.ring[rs], blk_ptr(P, slot[blk_of(q + RING)]), BLK_BYTES, &S.ring_bar[rs]);
+        }
     }
     __syncthreads();
     // critical block from shared memory
@@ -180,20 +199,21 @@ __global__ void __launch_bounds__(TR_THREADS) trsv_kernel(TrsvParams P) {
     const int G = gridDim.x;
     if (tid == 0) {
         ptx::mbar_init(&S.bar, 1);
+        for (int q = 0; q < RING; q++) ptx::mbar_init(&S.ring_bar[q], 1);
         ptx::fence_mbar_init();
     }
     __syncthreads();
-    uint32_t phase = 0;
+    uint32_t phase = 0, ring_phase = 0;
     // forward sweep: L y = b
     for (int row = blockIdx.x; row < P.n_rows; row += G)
-        solve_row<false, false>(P, row, P.l_ptr, P.l_col, P.l_slot, P.l_diag, P.l_dinv, P.b, false, P.y, S, phase, tid);
+        solve_row<false, false>(P, row, P.l_ptr, P.l_col, P.l_slot, P.l_diag, P.l_dinv, P.b, false, P.y, S, phase, ring_phase, tid);
     // backward sweep: U x = y (or L^T x = y); its right-hand side is the forward result
     for (int r = blockIdx.x; r < P.n_rows; r += G) {
         const int row = P.n_rows - 1 - r;
         if (P.symmetric)
-            solve_row<true, true>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, tid);
+            solve_row<true, true>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, ring_phase, tid);
         else
-            solve_row<true, false>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, tid);
+            solve_row<true, false>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, ring_phase, tid);
     }
 }
 
