@@ -417,8 +417,11 @@ def main():
             "e2e": {"value": aggregate_gflops(flops + sflops, e2e_s, 1 if use_dist else world), "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "executor_kernel (whole factorisation DAG, one persistent launch per step)", "peak_source": peak_how},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s", "frac": achieved / (peak * world),
+                         "traffic": traffic if world == 1 else None,
+                         "kernel": "executor_kernel (the whole factorisation DAG: %d persistent launch(es) per step per GPU; achieved = op-list FLOPs / "
+                                   "CUDA-event time of those launches, max over ranks)" % int(first.get("segments", 1) if use_dist else max(1, (launches // max(1, args.steps)) - 2)),
+                         "peak_source": peak_how + ("; x %d GPUs" % world if world > 1 else "")},
             "cpu_baseline": cpu,
             "accuracy": accuracy,
             "clocks": clocks,
