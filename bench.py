@@ -309,6 +309,7 @@ def main():
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
     elapsed = reduce_max(elapsed, "cuda" if use_dist else None)
+    t_factor_all = reduce_max(sum(f_dev) / len(f_dev), "cuda" if use_dist else None)   # device time of the executor launches, max over ranks
     step_s = elapsed / args.steps
     value = aggregate_gflops(flops + sflops, step_s, 1 if use_dist else world)   # sharded: the work is done once
 
@@ -350,7 +351,7 @@ def main():
 
     if rank == 0:
         peak, peak_how = measure_fp64_peak()
-        t_factor = sum(f_dev) / len(f_dev)
+        t_factor = t_factor_all
         t_solve = sum(s_dev) / len(s_dev)
         achieved = flops / t_factor * 1e-12
         traffic = None
