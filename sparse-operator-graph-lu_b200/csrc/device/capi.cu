@@ -48,7 +48,7 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
-    int64_t opt_handover = 0;
+    int64_t opt_hi_ctas = 16;      // CTAs dedicated to the high-priority queue (0 = one FIFO queue)
     int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
     int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;
@@ -215,6 +215,7 @@ int finalize(soglu_ctx* c) {
     co.fuse_inv = c->opt_fuse_inv != 0;
     co.split_narrow = (int)c->opt_split;
     co.n_sms = c->sms;
+    co.hi_ctas = (int)std::max<int64_t>(0, std::min<int64_t>(c->opt_hi_ctas, c->exec_grid / 2));
     {
         // pool capacity: what is free now minus the graph arrays (estimated from the op count) and a margin
         size_t free_b = 0, total_b = 0;
@@ -255,7 +256,7 @@ int finalize(soglu_ctx* c) {
     CU(cudaMemGetInfo(&free_b, &total_b));
     const std::vector<Task>& tasks_up = c->dist ? c->D.tasks : G.tasks;
     const std::vector<Pair>& pairs_up = c->dist ? c->D.pairs : G.pairs;
-    const std::vector<int32_t>& succ_up = c->dist ? c->D.succ : G.succ;
+    const std::vector<int32_t>& succ_up = c->dist ? c->D.succ : G.succ_enc;
     const size_t pool_bytes = (size_t)G.slots_per_owner[c->dist ? c->rank : 0] * BLK_BYTES;
     const size_t aux = tasks_up.size() * (sizeof(Task) + 12) + pairs_up.size() * sizeof(Pair) + succ_up.size() * 4 + (256u << 20);
     if (pool_bytes + aux > free_b) {
@@ -277,16 +278,21 @@ int finalize(soglu_ctx* c) {
     {
         // ready queue image: per segment slice, the initially ready tasks first, -1 elsewhere;
         // counter image: per segment one 256-byte record {head = 0, ..., tail = #initial at int 32}
+        // ready-queue image: per segment slice [hi queue | bulk queue], the initially ready tasks first in each,
+        // -1 elsewhere; counter image: per segment one 512-byte record {head_hi @0, tail_hi @32, head_lo @64, tail_lo @96}
         const std::vector<int32_t>& sb = c->dist ? c->D.seg_begin : G.seg_begin;
         const std::vector<int32_t>& si = c->dist ? c->D.seg_init : G.seg_init;
+        const std::vector<int32_t>& nh = c->dist ? c->D.seg_nhi : G.seg_nhi;
         const std::vector<int32_t>& ini = c->dist ? c->D.initial : G.initial;
         const int nseg = (int)sb.size() - 1;
-        std::vector<int32_t> r0(std::max<size_t>(tasks_up.size(), 1), -1), c0((size_t)std::max(nseg, 1) * 64, 0);
-        for (int sg = 0; sg < nseg; sg++) {
-            const int32_t nb = si[sg + 1] - si[sg];
-            for (int32_t k = 0; k < nb; k++) r0[sb[sg] + k] = ini[si[sg] + k];
-            c0[(size_t)sg * 64 + 32] = nb;
-        }
+        std::vector<int32_t> r0(std::max<size_t>(tasks_up.size(), 1), -1), c0((size_t)std::max(nseg, 1) * 128, 0);
+        for (int sg = 0; sg < nseg; sg++)
+            for (int cls = 0; cls < 2; cls++) {
+                const int32_t base = sb[sg] + (cls ? nh[sg] : 0);
+                const int32_t nb = si[2 * sg + cls + 1] - si[2 * sg + cls];
+                for (int32_t k = 0; k < nb; k++) r0[base + k] = ini[si[2 * sg + cls] + k];
+                c0[(size_t)sg * 128 + 32 + 64 * cls] = nb;
+            }
         if ((rc = upload(c->ready0, r0, c))) return rc;
         if ((rc = upload(c->counters0, c0, c))) return rc;
         CU(c->counters.alloc(c0.size() * 4));
@@ -480,7 +486,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
     else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
     else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
-    else if (k == "handover") c->opt_handover = value;
+    else if (k == "hi_ctas") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_ctas must be set before the first factor"); c->opt_hi_ctas = value; }
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
@@ -554,13 +560,9 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     ExecParams P = {};
     P.pool = c->pool.as<double>();
     P.world = c->world; P.rank = c->rank;
-    P.handover = (int32_t)c->opt_handover;
     if (c->dist) {
         if (!c->peers_ready) return fail(SOGLU_ERR_ARG, "multi-GPU context: exchange peer handles (soglu_dist_export / soglu_dist_import) and call soglu_dist_reset before soglu_factor");
-        for (int g = 0; g < c->world; g++) {
-            P.pools[g] = (double*)c->peer_pool[g]; P.deps[g] = (int32_t*)c->peer_dep[g];
-            P.readys[g] = (int32_t*)c->peer_ready[g]; P.tails[g] = (int32_t*)c->peer_counters[g] + 32;
-        }
+        for (int g = 0; g < c->world; g++) { P.pools[g] = (double*)c->peer_pool[g]; P.deps[g] = (int32_t*)c->peer_dep[g]; }
     } else {
         P.pools[0] = c->pool.as<double>();
     }
@@ -568,15 +570,33 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     P.pairs = c->pairs.as<Pair>();
     P.succ = c->succ.as<int32_t>();
     P.dep = c->dep.as<int32_t>();
-    P.ready = c->ready.as<int32_t>();
-    P.head = c->counters.as<int32_t>();
-    P.tail = c->counters.as<int32_t>() + 32;   // separate 128-byte lines
     P.trace = nullptr;
     if (c->opt_trace && nt > 0) {
         if (!c->trace.p) CU(c->trace.alloc((size_t)nt * 6 * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->trace.p, 0, (size_t)nt * 6 * sizeof(unsigned long long), c->stream));
         P.trace = c->trace.as<unsigned long long>();
     }
+    // queue pointers of one segment (this GPU and, sharded, the peers' queues of the same segment)
+    auto set_segment = [&](int sg) {
+        const std::vector<int32_t>& sb = c->dist ? c->D.seg_begin : G.seg_begin;
+        const std::vector<int32_t>& nh = c->dist ? c->D.seg_nhi : G.seg_nhi;
+        int32_t* cnt = c->counters.as<int32_t>() + (size_t)sg * 128;
+        P.ready[0] = c->ready.as<int32_t>() + sb[sg];
+        P.ready[1] = P.ready[0] + nh[sg];
+        P.head[0] = cnt; P.tail[0] = cnt + 32; P.head[1] = cnt + 64; P.tail[1] = cnt + 96;
+        P.n_tasks[0] = nh[sg];
+        P.n_tasks[1] = sb[sg + 1] - sb[sg] - nh[sg];
+        const int32_t want = (sg < (int)G.seg_hi_ctas.size()) ? G.seg_hi_ctas[sg] : (int32_t)c->opt_hi_ctas;
+        P.n_hi_ctas = (P.n_tasks[0] > 0 && P.n_tasks[1] > 0) ? (int32_t)std::min<int64_t>(want, grid / 2) : (P.n_tasks[0] > 0 ? grid : 0);
+        if (c->opt_hi_ctas <= 0) P.n_hi_ctas = 0;
+        if (c->dist)
+            for (int g = 0; g < c->world; g++) {
+                int32_t* rb = (int32_t*)c->peer_ready[g] + c->D.seg_begin_all[g][sg];
+                int32_t* cb = (int32_t*)c->peer_counters[g] + (size_t)sg * 128;
+                P.readys[g][0] = rb; P.readys[g][1] = rb + c->D.seg_nhi_all[g][sg];
+                P.tails[g][0] = cb + 32; P.tails[g][1] = cb + 96;
+            }
+    };
     CU(cudaEventRecord(c->ev0, c->stream));
     if (nt > 0) {
         if (c->dist) {
@@ -585,16 +605,9 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
             const int nseg = (int)c->D.seg_begin.size() - 1;
             const int sg = c->dist_segment;
             if (sg < 0 || sg >= nseg) return fail(SOGLU_ERR_ARG, "segment out of range");
-            for (int g = 0; g < c->world; g++) {
-                P.readys[g] = (int32_t*)c->peer_ready[g] + c->D.seg_begin_all[g][sg];
-                P.tails[g] = (int32_t*)c->peer_counters[g] + (size_t)sg * 64 + 32;
-            }
-            P.ready = c->ready.as<int32_t>() + c->D.seg_begin[sg];
-            P.head = c->counters.as<int32_t>() + (size_t)sg * 64;
-            P.tail = P.head + 32;
+            set_segment(sg);
             P.signal = 1;
-            P.n_tasks = c->D.seg_begin[sg + 1] - c->D.seg_begin[sg];
-            if (P.n_tasks > 0) {
+            if (P.n_tasks[0] + P.n_tasks[1] > 0) {
                 CU(launch_executor(P, grid, c->stream));
                 c->launches++;
             }
@@ -602,15 +615,12 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
             const int nseg = (int)G.seg_begin.size() - 1;
             CU(cudaMemcpyAsync(c->dep.p, c->dep0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
             CU(cudaMemcpyAsync(c->ready.p, c->ready0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
-            CU(cudaMemcpyAsync(c->counters.p, c->counters0.p, (size_t)nseg * 256, cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->counters.p, c->counters0.p, c->counters0.bytes, cudaMemcpyDeviceToDevice, c->stream));
             P.signal = 1;
             // one persistent launch per segment (a single one unless the pool forces slot recycling)
             for (int sg = 0; sg < nseg; sg++) {
-                P.ready = c->ready.as<int32_t>() + G.seg_begin[sg];
-                P.head = c->counters.as<int32_t>() + (size_t)sg * 64;
-                P.tail = P.head + 32;
-                P.n_tasks = G.seg_begin[sg + 1] - G.seg_begin[sg];
-                if (P.n_tasks == 0) continue;
+                set_segment(sg);
+                if (P.n_tasks[0] + P.n_tasks[1] == 0) continue;
                 CU(launch_executor(P, grid, c->stream));
                 c->launches++;
             }
@@ -619,11 +629,13 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
             for (int l = 0; l < G.n_levels; l++) {
                 const int64_t b = c->level_ptr[l], e = c->level_ptr[l + 1];
                 CU(cudaMemcpyAsync(c->ready.p, c->level_order.data() + b, (size_t)(e - b) * 4, cudaMemcpyHostToDevice, c->stream));
-                CU(cudaMemsetAsync(c->counters.p, 0, 256, c->stream));
-                P.ready = c->ready.as<int32_t>();
-                P.head = c->counters.as<int32_t>();
-                P.tail = P.head + 32;
-                P.n_tasks = (int32_t)(e - b);
+                CU(cudaMemsetAsync(c->counters.p, 0, 512, c->stream));
+                int32_t* cnt = c->counters.as<int32_t>();
+                P.ready[0] = P.ready[1] = c->ready.as<int32_t>();
+                P.head[0] = cnt; P.tail[0] = cnt + 32; P.head[1] = cnt + 64; P.tail[1] = cnt + 96;
+                P.n_tasks[0] = 0;
+                P.n_tasks[1] = (int32_t)(e - b);
+                P.n_hi_ctas = 0;
                 P.signal = 0;
                 CU(launch_executor(P, (int)std::min<int64_t>(grid, e - b), c->stream));
                 c->launches++;

@@ -14,6 +14,7 @@
 #include "tasks.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 
 namespace soglu {
@@ -556,15 +557,83 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             for (int32_t& b : G.seg_begin) b = base[b];
         }
     }
-    // per-segment lists of initially ready tasks
+    // ---- priority classes -----------------------------------------------------------------------------
+    // Estimated times (us): slack = critical path of the segment - longest path through the task.  With one
+    // FIFO queue a released critical-chain task waits behind every bulk update published before it (247 us
+    // on average at 100^3), which stretches the chain; the small-slack tasks get their own queue.
+    G.seg_nhi.assign(G.seg_begin.size() - 1, 0);
+    if (opt.hi_ctas > 0 && !G.tasks.empty()) {
+        const int64_t n2 = (int64_t)G.tasks.size();
+        std::vector<float> dur(n2), tl(n2, 0.f), bl(n2, 0.f);
+        for (int64_t t = 0; t < n2; t++) {
+            const Task& T = G.tasks[t];
+            float c = 1.f;
+            switch (T.type) {
+                case T_GEMM: c = 2.1f * T.n_pairs * (((T.flags >> TF_NROWS_SHIFT) & 7) / 4.f); break;
+                case T_LU: c = (T.flags & (TF_LINV | TF_UINV)) ? 20.f : 12.f; break;
+                case T_LLT: c = 15.f; break;
+                case T_LOWERINV: case T_UPPERINV: c = 7.f; break;
+                default: c = 1.f; break;
+            }
+            dur[t] = 6.f + c;
+        }
+        for (int64_t t = 0; t < n2; t++)     // tasks are in topological order
+            for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
+                const int32_t s2 = G.succ[e];
+                tl[s2] = std::max(tl[s2], tl[t] + dur[t]);
+            }
+        for (int64_t t = n2 - 1; t >= 0; t--) {
+            float m = 0.f;
+            for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) m = std::max(m, bl[G.succ[e]]);
+            bl[t] = dur[t] + m;
+        }
+        const int nseg = (int)G.seg_begin.size() - 1;
+        std::vector<float> cp(nseg, 0.f);
+        for (int sg = 0; sg < nseg; sg++)
+            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) cp[sg] = std::max(cp[sg], tl[t] + bl[t]);
+        float theta = 400.f;
+        for (int round = 0; round < 10; round++) {
+            bool ok = true;
+            for (int sg = 0; sg < nseg && ok; sg++) {
+                double busy = 0;
+                for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
+                    if (cp[sg] - (tl[t] + bl[t]) < theta) busy += dur[t];
+                ok = busy <= 0.5 * opt.hi_ctas * std::max(1, G.n_owners) * (double)cp[sg];
+            }
+            if (ok) break;
+            theta *= 0.5f;
+        }
+        G.seg_hi_ctas.assign(nseg, 0);
+        for (int sg = 0; sg < nseg; sg++) {
+            double busy = 0;
+            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
+                if (cp[sg] - (tl[t] + bl[t]) < theta) { G.tasks[t].flags |= TF_HI; G.n_hi++; busy += dur[t]; }
+            G.critical_path_us = std::max(G.critical_path_us, (double)cp[sg]);
+            // dedicated CTAs per GPU for this segment: 4x the average load of the high-priority tasks, at least 4
+            const double avg = busy / std::max(1.0, (double)cp[sg]) / std::max(1, G.n_owners);
+            G.seg_hi_ctas[sg] = (int32_t)std::min<double>(opt.hi_ctas, std::max(4.0, std::ceil(4.0 * avg)));
+        }
+        G.hi_threshold_us = theta;
+    }
+    G.succ_enc.resize(G.succ.size());
+    for (size_t e = 0; e < G.succ.size(); e++) G.succ_enc[e] = G.succ[e] | ((G.tasks[G.succ[e]].flags & TF_HI) ? TASK_HI_BIT : 0);
+    if ((int64_t)G.tasks.size() > TASK_LOCAL_MASK) return "too many tasks";
+
+    // per-segment lists of initially ready tasks, high-priority ones first (single GPU: every task is owned
+    // by GPU 0; the multi-GPU split is redone per rank in localize_tasks)
     {
         const int nseg = (int)G.seg_begin.size() - 1;
         G.initial.clear();
         G.seg_init.assign(1, 0);
         for (int sg = 0; sg < nseg; sg++) {
-            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
-                if (G.tasks[t].n_deps == 0) G.initial.push_back(t);
-            G.seg_init.push_back((int32_t)G.initial.size());
+            for (int cls = 0; cls < 2; cls++) {
+                for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
+                    const bool hi = G.tasks[t].flags & TF_HI;
+                    if (cls == 0 && hi) G.seg_nhi[sg]++;
+                    if (G.tasks[t].n_deps == 0 && hi == (cls == 0)) G.initial.push_back(t);
+                }
+                G.seg_init.push_back((int32_t)G.initial.size());
+            }
         }
     }
     // ---- patch block ids -> block references (owner in the top bits; plain slots on one GPU) --------
@@ -613,12 +682,18 @@ std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {
     const int nseg = (int)G.seg_begin.size() - 1;
     D.seg_begin.assign(1, 0);
     D.seg_init.assign(1, 0);
+    D.seg_nhi.assign(nseg, 0);
     D.seg_begin_all.assign(G.n_owners, std::vector<int32_t>(nseg + 1, 0));
+    D.seg_nhi_all.assign(G.n_owners, std::vector<int32_t>(nseg, 0));
     for (int sg = 0; sg < nseg; sg++) {
         for (int o = 0; o < G.n_owners; o++) D.seg_begin_all[o][sg + 1] = D.seg_begin_all[o][sg];
-        for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) D.seg_begin_all[G.task_owner[t]][sg + 1]++;
+        for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
+            D.seg_begin_all[G.task_owner[t]][sg + 1]++;
+            if (G.tasks[t].flags & TF_HI) D.seg_nhi_all[G.task_owner[t]][sg]++;
+        }
     }
     for (int sg = 0; sg < nseg; sg++) {
+        std::vector<int32_t> init_lo;
         for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
             if (G.task_owner[t] != rank) continue;
             Task T = G.tasks[t];
@@ -632,16 +707,19 @@ std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {
             const int32_t sb = (int32_t)D.succ.size();
             for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
                 const int32_t s2 = G.succ[e];
-                D.succ.push_back(make_ref(G.task_owner[s2], D.task_local[s2]));
+                D.succ.push_back(make_task_ref(G.task_owner[s2], G.tasks[s2].flags & TF_HI, D.task_local[s2]));
                 D.remote_edges += G.task_owner[s2] != rank;
             }
             T.succ_begin = sb;
             T.succ_end = (int32_t)D.succ.size();
-            if (T.n_deps == 0) D.initial.push_back((int32_t)D.tasks.size());
+            if (T.n_deps == 0) { if (T.flags & TF_HI) D.initial.push_back((int32_t)D.tasks.size()); else init_lo.push_back((int32_t)D.tasks.size()); }
+            if (T.flags & TF_HI) D.seg_nhi[sg]++;
             D.tasks.push_back(T);
         }
-        D.seg_begin.push_back((int32_t)D.tasks.size());
         D.seg_init.push_back((int32_t)D.initial.size());
+        D.initial.insert(D.initial.end(), init_lo.begin(), init_lo.end());
+        D.seg_init.push_back((int32_t)D.initial.size());
+        D.seg_begin.push_back((int32_t)D.tasks.size());
     }
     return "";
 }

@@ -57,10 +57,7 @@ struct __align__(16) SmemCtl {
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
     double scratch[584];   // pivot row/column exchange buffers of the register-resident diag kernels
-    int local_task;        // mailbox: a successor the math warps hand straight to this CTA's scheduler (-1 = empty)
-    int polling;           // scheduler is idle, spinning on its claimed queue slot
 };
-constexpr int SLOT_SKIP = -2;   // queue slot of a task that was handed over locally
 
 constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
 
@@ -366,21 +363,6 @@ __device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const do
         }
 }
 
-// Local hand-over (option "handover", off by default: measured 4 % SLOWER at 64^3 -- 289 vs 277 ms -- the
-// skipped queue slots cost idle schedulers a claim round trip each): if this CTA's scheduler is idle (spinning on a queue slot nobody has filled yet) the
-// released successor goes straight into its mailbox -- no queue round trip through L2 on the critical
-// chain.  Dekker-style: write the mailbox, then re-check `polling`; the scheduler clears `polling`, then
-// re-checks the mailbox, so at least one side sees the other.  The queue slot is still consumed
-// (SLOT_SKIP) to keep the claim-then-wait accounting exact.
-__device__ __forceinline__ bool hand_over(SmemCtl* ctl, int task) {
-    if (!*(volatile int*)&ctl->polling) return false;
-    if (atomicCAS(&ctl->local_task, -1, task) != -1) return false;
-    __threadfence_block();
-    if (*(volatile int*)&ctl->polling) return true;
-    // the scheduler may have left its polling loop: take the task back unless it already took it
-    return atomicCAS(&ctl->local_task, task, -1) != task;
-}
-
 __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
@@ -392,8 +374,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
             ptx::mbar_init(&ctl->full[s], 1);
             ptx::mbar_init(&ctl->empty[s], N_MATH_WARPS);
         }
-        ctl->local_task = -1;
-        ctl->polling = 0;
         ptx::fence_mbar_init();
     }
     __syncthreads();
@@ -426,21 +406,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     if (two) ptx::bulk_g2s(As + BLK_ELEMS, blk_ptr(P, pr.b), BLK_BYTES, &ctl->full[s]);
                 }
             };
-            volatile int* mailbox = &ctl->local_task;
-            volatile int* polling = &ctl->polling;
-            auto take_local = [&]() -> int {     // a task the math warps of THIS CTA just released
-                const int lt = *mailbox;
-                if (lt >= 0) { *mailbox = -1; __threadfence_block(); }
-                return lt;
-            };
+            // CTAs 0..n_hi_ctas-1 serve the high-priority queue, the others the bulk queue; each claims the next
+            // slot of its queue and waits until a finishing CTA publishes a task there
+            const int q = (blockIdx.x < (unsigned)P.n_hi_ctas) ? 0 : 1;
             while (true) {
-                const int slot = atomicAdd(P.head, 1);
-                if (slot >= P.n_tasks) {
-                    // the queue is exhausted; a local hand-over may still arrive while the math warps finish
-                    // their last task, but then its queue slot (SLOT_SKIP) was published before head ran out,
-                    // so nothing can be pending here
-                    const int lt = take_local();
-                    if (lt >= 0) issue(lt);
+                const int slot = atomicAdd(P.head[q], 1);
+                if (slot >= P.n_tasks[q]) {
                     const int s = it % N_STAGES;
                     ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);
                     ctl->desc[s].type = T_EXIT;
@@ -448,19 +419,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     break;
                 }
                 int t;
-                *polling = 1;
-                __threadfence_block();
-                while (true) {
-                    t = (P.world > 1) ? ptx::ld_acquire_sys(P.ready + slot) : ptx::ld_acquire(P.ready + slot);
-                    if (t != -1) break;
-                    const int lt = take_local();
-                    if (lt >= 0) issue(lt);      // run the local successor now; keep waiting for the claimed slot after
-                }
-                *polling = 0;
-                __threadfence_block();
-                const int lt = take_local();     // hand-over that raced with leaving the polling loop
-                if (lt >= 0) issue(lt);
-                if (t == SLOT_SKIP) continue;     // that task went to its releaser's own scheduler
+                if (P.world > 1) { while ((t = ptx::ld_acquire_sys(P.ready[q] + slot)) < 0) {} }
+                else { while ((t = ptx::ld_acquire(P.ready[q] + slot)) < 0) {} }
                 issue(t);
             }
         }
@@ -551,45 +511,32 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
             const Task* T = P.tasks + d.task;
             const int sb = T->succ_begin, se = T->succ_end;
             if (sb + ct < se) {
-                if (P.world > 1) {
-                    // Successors on this GPU are released at gpu scope (cheap); only successors on peer GPUs
-                    // pay for system-scope fences and atomics over NVLink.  A counter may be decremented from
-                    // both scopes: the atomics themselves are performed at the owning GPU's L2 either way.
-                    __threadfence();
-                    bool remote = false;
+                // Successors on this GPU are released at gpu scope (cheap); only successors on peer GPUs pay for
+                // system-scope fences and atomics over NVLink.  A counter may be decremented from both scopes:
+                // the atomics themselves are performed at the owning GPU's L2 either way.
+                __threadfence();
+                bool remote = false;
+                for (int e = sb + ct; e < se; e += N_MATH) {
+                    const int32_t ref = P.succ[e];
+                    const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
+                    if (o != P.rank) { remote = true; continue; }
+                    if (atomicSub(P.dep + nx, 1) == 1) {
+                        __threadfence();
+                        const int pos = atomicAdd(P.tail[qq], 1);
+                        if (P.trace) P.trace[6 * (size_t)nx + 0] = gtime();
+                        ptx::st_release(P.ready[qq] + pos, nx);
+                    }
+                }
+                if (remote) {
+                    __threadfence_system();
                     for (int e = sb + ct; e < se; e += N_MATH) {
                         const int32_t ref = P.succ[e];
-                        const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & REF_MASK;
-                        if (o != P.rank) { remote = true; continue; }
-                        if (atomicSub(P.dep + nx, 1) == 1) {
-                            __threadfence();
-                            const int pos = atomicAdd(P.tail, 1);
-                            ptx::st_release(P.ready + pos, nx);
-                        }
-                    }
-                    if (remote) {
-                        __threadfence_system();
-                        for (int e = sb + ct; e < se; e += N_MATH) {
-                            const int32_t ref = P.succ[e];
-                            const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & REF_MASK;
-                            if (o == P.rank) continue;
-                            if (atomicSub_system(P.deps[o] + nx, 1) == 1) {
-                                __threadfence_system();
-                                const int pos = atomicAdd_system(P.tails[o], 1);
-                                ptx::st_release_sys(P.readys[o] + pos, nx);
-                            }
-                        }
-                    }
-                } else {
-                    __threadfence();
-                    for (int e = sb + ct; e < se; e += N_MATH) {
-                        const int nx = P.succ[e];
-                        if (atomicSub(P.dep + nx, 1) == 1) {
-                            __threadfence();
-                            if (P.trace) P.trace[6 * (size_t)nx + 0] = gtime();
-                            const bool handed = P.handover && hand_over(ctl, nx);
-                            const int pos = atomicAdd(P.tail, 1);
-                            ptx::st_release(P.ready + pos, handed ? SLOT_SKIP : nx);
+                        const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
+                        if (o == P.rank) continue;
+                        if (atomicSub_system(P.deps[o] + nx, 1) == 1) {
+                            __threadfence_system();
+                            const int pos = atomicAdd_system(P.tails[o][qq], 1);
+                            ptx::st_release_sys(P.readys[o][qq] + pos, nx);
                         }
                     }
                 }

@@ -10,21 +10,23 @@ namespace soglu {
 struct ExecParams {
     // Multi-GPU: per-owner base pointers (peer-mapped through CUDA IPC); block / task references carry
     // the owner in their top 3 bits (tasks.h make_ref).  Single GPU: world = 1, index 0 only.
+    // Two ready queues per GPU: [0] high priority (small-slack tasks, served by CTAs 0..n_hi_ctas-1),
+    // [1] everything else (served by the remaining CTAs).
     double* pools[MAX_GPUS];
     int32_t* deps[MAX_GPUS];
-    int32_t* readys[MAX_GPUS];
-    int32_t* tails[MAX_GPUS];
+    int32_t* readys[MAX_GPUS][2];
+    int32_t* tails[MAX_GPUS][2];
     int32_t world, rank;
-    int32_t handover;      // hand a released successor to this CTA's own scheduler when it is idle
     double* pool;          // this GPU's block pool, slot s at pool + s*BLK_ELEMS
     const Task* tasks;
     const Pair* pairs;
-    const int32_t* succ;
+    const int32_t* succ;   // task references: owner | priority bit | local id
     int32_t* dep;          // live dependency counters (reset before every run)
-    int32_t* ready;        // ready queue, n_tasks entries, -1 = not yet published
-    int32_t* head;         // next queue slot to claim
-    int32_t* tail;         // next queue slot to publish
-    int32_t n_tasks;       // queue length for this launch
+    int32_t* ready[2];     // ready queues of this launch, -1 = not yet published
+    int32_t* head[2];      // next queue slot to claim
+    int32_t* tail[2];      // next queue slot to publish
+    int32_t n_tasks[2];    // queue lengths for this launch
+    int32_t n_hi_ctas;     // CTAs dedicated to queue 0
     int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
     unsigned long long* trace;   // optional: 6 x u64 per task (published, claimed, loaded, computed, signalled, smid)
 };

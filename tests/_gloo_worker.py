@@ -16,5 +16,8 @@ mine = 0.25 * (rank + 1)                      # rank 1 is the slow one
 tmax = bench.reduce_max(mine)
 val = bench.aggregate_gflops(1e9, tmax, world)
 dist.barrier()
-print(json.dumps({"rank": rank, "local_rank": local_rank, "world": world, "tmax": tmax, "value": val}))
+for r in range(world):          # one rank at a time so the lines never interleave
+    if r == rank:
+        print(json.dumps({"rank": rank, "local_rank": local_rank, "world": world, "tmax": tmax, "value": val}), flush=True)
+    dist.barrier()
 dist.destroy_process_group()
