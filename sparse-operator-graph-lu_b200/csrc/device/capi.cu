@@ -48,7 +48,8 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
-    int64_t opt_hi_ctas = 16;      // CTAs dedicated to the high-priority queue (0 = one FIFO queue)
+    int64_t opt_hi_ctas = 0;       // CTAs dedicated to a high-priority queue of small-slack tasks; 0 (default) = one FIFO
+                                   // queue: measured SLOWER with 16 (100^3: 2.58 -> 2.73 s on 1 GPU, 1.64 -> 1.91 s on 4)
     int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
     int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;

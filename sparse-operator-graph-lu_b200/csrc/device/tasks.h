@@ -117,7 +117,7 @@ struct CompileOptions {
     // priority scheduling: tasks whose estimated slack (critical path - longest path through the task) is below a
     // threshold go to a separate queue served by `hi_ctas` dedicated CTAs; the threshold shrinks until those
     // CTAs are at most half busy.  0 = one FIFO queue.
-    int hi_ctas = 16;
+    int hi_ctas = 0;
 };
 
 // ---- multi-GPU: 2D block-cyclic owner-computes sharding -------------------------------------------
