@@ -411,7 +411,7 @@ def main():
             "config": {"workload": WORKLOADS[args.workload][2], "name": args.workload, "n": prob.size("dim"), "ops": prob.size("n_ops"),
                        "tasks": int(first["tasks"]), "pool_blocks": int(first["pool_blocks"]),
                        "parallelism": "1 GPU" if world == 1 else "one factorisation sharded over %d GPUs: 2D block-cyclic (%dx%d grid, 16x16-block squares), owner computes, NVLink peer pulls; solve on rank 0" % ((world,) + sg.default_grid(world)),
-                       "segments": int(first.get("segments", 1)),
+                       "segments": int(first.get("segments", 1) if use_dist else first["kernel_launches"]),   # executor launches per factorisation (pool recycling)
                        "l2": "inputs_exceed_l2 (block pool %.1f GB >> 126 MB L2)" % (first["pool_blocks"] * 34816 * 1e-9),
                        "factor_ms": t_factor * 1e3, "solve_ms": t_solve * 1e3, "factor_gflops": flops / t_factor * 1e-9,
                        "solve_gbs": sbytes / t_solve * 1e-9, "host_plan_s": t_plan, "first_call_s": t_first},

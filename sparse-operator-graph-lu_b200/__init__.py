@@ -277,7 +277,7 @@ class Context:
 
 
 def default_grid(world):
-    """process grid (rows, cols) of the 2D block-cyclic ownership: 1->1x1, 2->1x2, 4->2x2, 8->2x4"""
+    """process grid (rows, cols) of the 2D block-cyclic ownership: 1->1x1, 2->2x1, 4->2x2, 8->4x2 (the grids the scaling numbers were measured with)"""
     pr = 1
     while pr * pr * 2 <= world:
         pr *= 2

@@ -58,3 +58,7 @@ def test_too_small_matrix_is_rejected(sg):
         assert "not supported" in str(e)
     else:
         raise AssertionError("dim < 64 must be rejected")
+
+
+def test_default_process_grids(sg):
+    assert [sg.default_grid(n) for n in (1, 2, 4, 8)] == [(1, 1), (2, 1), (2, 2), (4, 2)]
