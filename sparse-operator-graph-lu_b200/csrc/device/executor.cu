@@ -508,18 +508,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
         }
         if (P.trace && ct == 0) P.trace[6 * (size_t)d.task + 3] = gtime();
         if (P.signal) {
-            // Only the LAST math warp releases the successors; the other seven go straight on to the MMAs of the
-            // next task (its operands are already staged), so the fence + atomics overlap tensor work.  Its
-            // fence is cumulative over the stores the whole CTA issued before the barrier above.
             const Task* T = P.tasks + d.task;
             const int sb = T->succ_begin, se = T->succ_end;
-            if (mw == N_MATH_WARPS - 1 && sb + lane < se) {
+            if (sb + ct < se) {
                 // Successors on this GPU are released at gpu scope (cheap); only successors on peer GPUs pay for
                 // system-scope fences and atomics over NVLink.  A counter may be decremented from both scopes:
                 // the atomics themselves are performed at the owning GPU's L2 either way.
                 __threadfence();
                 bool remote = false;
-                for (int e = sb + lane; e < se; e += 32) {
+                for (int e = sb + ct; e < se; e += N_MATH) {
                     const int32_t ref = P.succ[e];
                     const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
                     if (o != P.rank) { remote = true; continue; }
@@ -532,7 +529,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 }
                 if (remote) {
                     __threadfence_system();
-                    for (int e = sb + lane; e < se; e += 32) {
+                    for (int e = sb + ct; e < se; e += N_MATH) {
                         const int32_t ref = P.succ[e];
                         const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
                         if (o == P.rank) continue;
