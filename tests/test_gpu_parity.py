@@ -300,3 +300,43 @@ def test_iterative_refinement_lowers_residual(sg, tmp_path):
     np.add.at(ay, r, v * y[c])
     assert np.linalg.norm(ay - b2) / np.linalg.norm(b2) <= 1e-12
     ctx.close()
+
+
+@pytest.mark.parametrize("n,w,k,seed", [(64, 8, 3, 1), (65, 10, 4, 2), (129, 40, 6, 5), (200, 199, 9, 6), (513, 25, 3, 8)])
+def test_edge_sizes_match_oracle(sg, oracle, n, w, k, seed):
+    """One block row, just over one, nearly dense band: CUDA path vs the oracle on the same planned problem."""
+    import gen_mtx
+    n, r, c, v = gen_mtx.banded(n, w, k, seed=seed)
+    p = sg.Problem.from_coo(n, r, c, v, gen_mtx.rhs(n))
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    x_ext, _ = ctx.solve_ext(p.f64("b_perm"))
+    xo, h = oracle.run(p)
+    oracle.free(h)
+    assert _rel(x_ext, xo) <= TOL_X
+    ctx.close()
+
+
+def test_symmetric_disconnected_matrix(sg, oracle):
+    """LL^T path (llt, mult, transposed back-substitution) on a matrix with two connected components."""
+    import gen_mtx
+    n1, r1, c1, v1 = gen_mtx.generate("lap2d", 9, 8)
+    n2, r2, c2, v2 = gen_mtx.generate("lap2d", 7, 6)
+    n = n1 + n2
+    r = np.concatenate([r1, r2 + n1]); c = np.concatenate([c1, c2 + n1]); v = np.concatenate([v1, v2])
+    keep = r >= c
+    p = sg.Problem.from_coo(n, r[keep], c[keep], v[keep], gen_mtx.rhs(n), symmetric=True)
+    assert p.size("n_U") == 0
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    x, _ = ctx.solve(p)
+    xo, h = oracle.run(p)
+    oracle.free(h)
+    assert _rel(x, unpermute(p, xo)) <= TOL_X
+    ax = np.zeros(n)
+    np.add.at(ax, r, v * x[c])
+    b = gen_mtx.rhs(n)
+    assert np.linalg.norm(ax - b) / np.linalg.norm(b) <= 1e-12
+    ctx.close()

@@ -64,3 +64,54 @@ def test_oracle_vs_live_reference(sg, oracle, tmp_path):
         mine = oracle.block(h, L[k, 0])
         assert np.abs(mine - Lv[k]).max() <= 1e-12 * max(1.0, np.abs(Lv[k]).max())
     oracle.free(h)
+
+
+@pytest.mark.parametrize("n,w,k,seed", [(64, 8, 3, 1), (65, 10, 4, 2), (127, 20, 5, 3), (128, 30, 5, 4), (129, 40, 6, 5),
+                                         (200, 199, 9, 6), (511, 60, 7, 7), (513, 25, 3, 8), (1000, 300, 9, 9)])
+def test_planner_bit_exact_on_random_matrices(sg, tmp_path, n, w, k, seed):
+    """Edge sizes (one block, just over one block, powers of two +-1, nearly dense band): reader + GPS ordering +
+    planner versus a LIVE run of the unmodified reference -- permutation, op list, stages and block ids bit-exact."""
+    harness = ref_harness_path()
+    if harness is None:
+        pytest.skip("oracle/_ref not built (or host CPU lacks AVX-512)")
+    import gen_mtx
+    n, r, c, v = gen_mtx.banded(n, w, k, seed=seed)
+    path = str(tmp_path / "m.mtx")
+    gen_mtx.write_mtx(path, n, r, c, v)
+    out = tmp_path / "ref"
+    out.mkdir()
+    subprocess.run([harness, path, str(out)], check=True, capture_output=True, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    p = sg.Problem.from_mtx(path)
+    rd = lambda f, dt: np.fromfile(out / f, dtype=dt)
+    np.testing.assert_array_equal(p.i32("perm_new2old"), rd("perm_new2old.i32", np.int32))
+    np.testing.assert_array_equal(p.i32("coarse_ops"), rd("ops_coarse.i32", np.int32).reshape(-1, 8))
+    np.testing.assert_array_equal(p.i32("ops"), rd("ops_fine.i32", np.int32).reshape(-1, 8))
+    np.testing.assert_array_equal(p.i32("laststage"), rd("laststage.i32", np.int32))
+    np.testing.assert_array_equal(p.i32("L"), rd("L.i32", np.int32).reshape(-1, 3))
+    np.testing.assert_array_equal(p.i32("U"), rd("U.i32", np.int32).reshape(-1, 3))
+    np.testing.assert_array_equal(p.f64("b_perm"), rd("b_perm.f64", np.float64))
+
+
+def test_symmetric_and_disconnected_inputs_vs_live_reference(sg, oracle, tmp_path):
+    """A block-diagonal (two disconnected components) symmetric matrix: exercises addMissing (GPSOrder.cpp:251-277)
+    and the LL^T path end to end against the reference's x."""
+    harness = ref_harness_path()
+    if harness is None:
+        pytest.skip("oracle/_ref not built (or host CPU lacks AVX-512)")
+    import gen_mtx
+    n1, r1, c1, v1 = gen_mtx.generate("lap2d", 9, 8)
+    n2, r2, c2, v2 = gen_mtx.generate("lap2d", 7, 6)
+    n = n1 + n2
+    r = np.concatenate([r1, r2 + n1]); c = np.concatenate([c1, c2 + n1]); v = np.concatenate([v1, v2])
+    path = str(tmp_path / "two.mtx")
+    gen_mtx.write_mtx(path, n, r, c, v, symmetric=True)
+    out = tmp_path / "ref"
+    out.mkdir()
+    subprocess.run([harness, path, str(out)], check=True, capture_output=True, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    p = sg.Problem.from_mtx(path)
+    np.testing.assert_array_equal(p.i32("perm_new2old"), np.fromfile(out / "perm_new2old.i32", dtype=np.int32))
+    np.testing.assert_array_equal(p.i32("ops"), np.fromfile(out / "ops_fine.i32", dtype=np.int32).reshape(-1, 8))
+    x_ext, h = oracle.run(p)
+    oracle.free(h)
+    xref = np.fromfile(out / "x.f64")
+    assert np.linalg.norm(unpermute(p, x_ext) - xref) / np.linalg.norm(xref) <= 1e-12
