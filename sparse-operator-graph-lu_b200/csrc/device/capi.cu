@@ -776,11 +776,21 @@ int64_t soglu_debug_trace(soglu_ctx* c, unsigned long long* trace_out, int32_t* 
             const Task& T = c->G.tasks[t];
             task_info_out[4 * t] = T.type; task_info_out[4 * t + 1] = T.n_pairs; task_info_out[4 * t + 2] = T.level; task_info_out[4 * t + 3] = T.n_deps;
         }
-    if (succ_ptr_out) {
-        for (int64_t t = 0; t < nt; t++) succ_ptr_out[t] = c->G.tasks[t].succ_begin;
-        succ_ptr_out[nt] = (int32_t)c->G.succ.size();
+    // successor lists name group leaders and are shared by the slices of a task: export them expanded to
+    // one plain CSR (every slice -> every slice of every successor) for the analysis scripts
+    if (succ_ptr_out || succ_out) {
+        int64_t pos = 0;
+        for (int64_t t = 0; t < nt; t++) {
+            const Task& T = c->G.tasks[t];
+            if (succ_ptr_out) succ_ptr_out[t] = (int32_t)pos;
+            for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+                const int32_t s2 = c->G.succ[e];
+                for (int q = 0, g = task_group_size(c->G.tasks[s2]); q < g; q++, pos++)
+                    if (succ_out) succ_out[pos] = s2 + q;
+            }
+        }
+        if (succ_ptr_out) succ_ptr_out[nt] = (int32_t)pos;
     }
-    if (succ_out) std::memcpy(succ_out, c->G.succ.data(), c->G.succ.size() * sizeof(int32_t));
     return nt;
 }
 

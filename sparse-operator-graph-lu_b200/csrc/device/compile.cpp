@@ -15,7 +15,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 
 namespace soglu {
 namespace {
@@ -38,6 +40,15 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                           TaskGraph& G) {
     G = TaskGraph();
     char msg[256];
+    // SOGLU_TIMING=1 prints the phase times to stderr (diagnostics only)
+    const bool timing = std::getenv("SOGLU_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[compile] %-25s %8.3f s\n", what, std::chrono::duration<double>(t1 - t_last).count());
+        t_last = t1;
+    };
     if (n_ids < 1) return "n_block_ids must be >= 1";
     std::vector<IdInfo> info(n_ids);
     for (int64_t k = 0; k < n_input; k++) {
@@ -83,6 +94,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         if (src2[i] > 0 && src2[i] != src[i]) info[src2[i]].n_readers++;
     }
 
+    lap("validate + id info");
     // ---- fusion decisions ------------------------------------------------------------
     std::vector<int64_t> fused_sub_of(opt.fuse_sub ? n_ids : 0, -1);  // product id -> index of the sub op
     if (opt.fuse_sub) {
@@ -130,6 +142,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         G.fused_invs++;
     }
 
+    lap("fusion decisions");
     // ---- one task per produced block (lu: one task, two blocks) -------------------------
     // task order = order of the first contributing op, i.e. the reference's stage order
     G.task_of.assign(n_ids, -1);
@@ -190,6 +203,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     for (int64_t id = 1; id < n_ids; id++)
         if (alias_to[id]) G.task_of[id] = G.task_of[alias_to[id]];
 
+    lap("tasks");
     // ---- pairs ------------------------------------------------------------------------------
     {
         int64_t total = 0;
@@ -222,6 +236,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             if (G.tasks[t].type == T_GEMM && fill[t] != G.tasks[t].n_pairs) return "internal: pair count mismatch";
     }
 
+    lap("pairs");
     // ---- multi-GPU: owners, mirrors of remote blocks and their fetch tasks ---------------------------
     // A task runs on the GPU that owns its result block.  A produced block that a GPU reads at least
     // mirror_min times from a peer is MIRRORED there: a fetch task (a T_SUB "copy": out = remote - 0)
@@ -328,6 +343,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         G.task_owner.assign(nt, 0);
     }
 
+    lap("owners + mirrors");
     // ---- pool slots and segments -------------------------------------------------------------------
     // Unlimited pool: every input / produced block gets its own slot, one segment.  Limited pool
     // (opt.max_slots): walk the tasks in order (a topological order: the op list is stage-sorted),
@@ -419,44 +435,57 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         G.seg_begin.push_back((int32_t)nt);
     }
 
+    lap("slots + segments");
     // ---- dependencies: distinct producer tasks of every source, inside the same segment ----------
     // (producers in earlier segments have finished before the launch starts)
-    std::vector<std::vector<int32_t>> preds(nt);
+    // predecessor lists in one flat array (capacity = operand count per task), sorted and made unique per task
+    std::vector<int64_t> poff(nt + 1, 0);
+    for (int64_t t = 0; t < nt; t++) poff[t + 1] = poff[t] + 2 * (int64_t)G.tasks[t].n_pairs + ((G.tasks[t].flags & TF_INIT) ? 1 : 0);
+    std::vector<int32_t> pflat(poff[nt]);
+    std::vector<int32_t> pcnt(nt, 0);
     {
-        auto add = [&](int32_t tid, int32_t id) {
-            if (id <= 0) return;
-            int32_t p = G.task_of[id];
-            if (p >= 0 && p != tid && seg_of[p] == seg_of[tid]) preds[tid].push_back(p);
-            if (p > tid) preds[tid].push_back(-1);   // marker: op list is not topologically ordered
-        };
+        int order_error = 0;
+#pragma omp parallel for schedule(dynamic, 2048) reduction(| : order_error)
         for (int64_t t = 0; t < nt; t++) {
             const Task& T = G.tasks[t];
+            int32_t* v = pflat.data() + poff[t];
+            int32_t n = 0;
+            auto add = [&](int32_t id) {
+                if (id <= 0) return;
+                const int32_t p = G.task_of[id];
+                if (p > t) order_error = 1;   // the op list is not topologically ordered
+                if (p >= 0 && p != t && seg_of[p] == seg_of[t]) v[n++] = p;
+            };
             for (int32_t k = 0; k < T.n_pairs; k++) {
-                add((int32_t)t, G.pairs[T.pair_begin + k].a);
-                add((int32_t)t, G.pairs[T.pair_begin + k].b);
+                add(G.pairs[T.pair_begin + k].a);
+                add(G.pairs[T.pair_begin + k].b);
             }
-            if (T.flags & TF_INIT) add((int32_t)t, T.init);
-            for (int32_t p : preds[t]) if (p < 0) return "operation list is not in dependency order (a block is read before its producer's first op)";
+            if (T.flags & TF_INIT) add(T.init);
+            if (n > 1) {
+                std::sort(v, v + n);
+                n = (int32_t)(std::unique(v, v + n) - v);
+            }
+            pcnt[t] = n;
         }
+        if (order_error) return "operation list is not in dependency order (a block is read before its producer's first op)";
         int64_t nsucc = 0;
-        for (int64_t t = 0; t < nt; t++) {
-            auto& v = preds[t];
-            std::sort(v.begin(), v.end());
-            v.erase(std::unique(v.begin(), v.end()), v.end());
-            G.tasks[t].n_deps = (int32_t)v.size();
-            nsucc += (int64_t)v.size();
-        }
+        for (int64_t t = 0; t < nt; t++) { G.tasks[t].n_deps = pcnt[t]; nsucc += pcnt[t]; }
         if (nsucc > 0x7fffffff) return "too many dependency edges";
         std::vector<int32_t> cnt(nt + 1, 0);
-        for (int64_t t = 0; t < nt; t++)
-            for (int32_t p : preds[t]) cnt[p + 1]++;
+        for (int64_t t = 0; t < nt; t++) {
+            const int32_t* v = pflat.data() + poff[t];
+            for (int32_t k = 0; k < pcnt[t]; k++) cnt[v[k] + 1]++;
+        }
         for (int64_t t = 0; t < nt; t++) cnt[t + 1] += cnt[t];
         G.succ.assign(nsucc, 0);
         std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
-        for (int64_t t = 0; t < nt; t++)
-            for (int32_t p : preds[t]) G.succ[pos[p]++] = (int32_t)t;
+        for (int64_t t = 0; t < nt; t++) {
+            const int32_t* v = pflat.data() + poff[t];
+            for (int32_t k = 0; k < pcnt[t]; k++) G.succ[pos[v[k]]++] = (int32_t)t;
+        }
         for (int64_t t = 0; t < nt; t++) { G.tasks[t].succ_begin = cnt[t]; G.tasks[t].succ_end = cnt[t + 1]; }
     }
+    lap("dependencies");
     // ---- levels (Kahn) + cycle check -----------------------------------------------------------
     {
         std::vector<int32_t> deg(nt);
@@ -491,6 +520,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         }
         G.n_levels = nt ? maxlev + 1 : 0;
     }
+    lap("levels");
     // ---- row split of GEMM tasks in narrow levels -------------------------------------------------
     // In a level with fewer GEMM tasks than SMs the factorisation is latency-bound: one 64x64x64
     // product occupies one SM for ~2.4 us per pair while the others idle.  Such tasks are split
@@ -514,36 +544,29 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             if (split[t] > 1) G.split_tasks++;
         }
         if (G.split_tasks > 0) {
+            // The slices of one task form a group with ONE dependency counter (the leader's): a finishing slice
+            // decrements each successor group once, so a group waits for every slice of every predecessor, and the
+            // slices share their task's successor list (no edge multiplication).
             const int64_t nt2 = base[nt];
             std::vector<Task> tasks2(nt2);
-            int64_t nsucc2 = 0;
-            for (int64_t t = 0; t < nt; t++) {
-                int64_t fan = 0;
-                for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) fan += split[G.succ[e]];
-                nsucc2 += fan * split[t];
-            }
-            if (nsucc2 > 0x7fffffff) return "too many dependency edges after row split";
-            std::vector<int32_t> succ2(nsucc2);
-            std::vector<int32_t> deps2(nt2, 0);
-            int64_t pos = 0;
+#pragma omp parallel for schedule(static)
             for (int64_t t = 0; t < nt; t++) {
                 const Task& T = G.tasks[t];
+                int32_t nd = 0;
+                const int32_t* v = pflat.data() + poff[t];
+                for (int32_t k = 0; k < pcnt[t]; k++) nd += split[v[k]];
                 for (int s = 0; s < split[t]; s++) {
                     Task N = T;
                     if (split[t] > 1) {
                         const int rows16 = 4 / split[t];
                         N.flags = (T.flags & 0xff) | ((s * rows16) << TF_ROW0_SHIFT) | (rows16 << TF_NROWS_SHIFT);
                     }
-                    N.succ_begin = (int32_t)pos;
-                    for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
-                        const int32_t d = G.succ[e];
-                        for (int q = 0; q < split[d]; q++) { succ2[pos++] = base[d] + q; deps2[base[d] + q]++; }
-                    }
-                    N.succ_end = (int32_t)pos;
+                    N.n_deps = nd;
                     tasks2[base[t] + s] = N;
                 }
             }
-            for (int64_t t = 0; t < nt2; t++) tasks2[t].n_deps = deps2[t];
+#pragma omp parallel for schedule(static)
+            for (int64_t e = 0; e < (int64_t)G.succ.size(); e++) G.succ[e] = base[G.succ[e]];
             {
                 std::vector<int8_t> own2(nt2);
                 for (int64_t t = 0; t < nt; t++)
@@ -551,12 +574,12 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                 G.task_owner.swap(own2);
             }
             G.tasks.swap(tasks2);
-            G.succ.swap(succ2);
             for (int32_t& x : G.task_of)
                 if (x >= 0) x = base[x];
             for (int32_t& b : G.seg_begin) b = base[b];
         }
     }
+    lap("row split");
     // ---- priority classes -----------------------------------------------------------------------------
     // Estimated times (us): slack = critical path of the segment - longest path through the task.  With one
     // FIFO queue a released critical-chain task waits behind every bulk update published before it (247 us
@@ -577,14 +600,14 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             }
             dur[t] = 6.f + c;
         }
-        for (int64_t t = 0; t < n2; t++)     // tasks are in topological order
+        for (int64_t t = 0; t < n2; t++)     // tasks are in topological order; successors are group leaders
             for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
                 const int32_t s2 = G.succ[e];
-                tl[s2] = std::max(tl[s2], tl[t] + dur[t]);
+                for (int q = 0, g = task_group_size(G.tasks[s2]); q < g; q++) tl[s2 + q] = std::max(tl[s2 + q], tl[t] + dur[t]);
             }
         for (int64_t t = n2 - 1; t >= 0; t--) {
             float m = 0.f;
-            for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) m = std::max(m, bl[G.succ[e]]);
+            for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) m = std::max(m, bl[G.succ[e]]);   // slices are alike
             bl[t] = dur[t] + m;
         }
         const int nseg = (int)G.seg_begin.size() - 1;
@@ -608,6 +631,13 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             double busy = 0;
             for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
                 if (cp[sg] - (tl[t] + bl[t]) < theta) { G.tasks[t].flags |= TF_HI; G.n_hi++; busy += dur[t]; }
+            // one class per group: the slices follow their leader
+            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
+                if (!task_is_leader(G.tasks[t])) {
+                    const int32_t lead = t - ((G.tasks[t].flags >> TF_ROW0_SHIFT) & 3) / std::max(1, (G.tasks[t].flags >> TF_NROWS_SHIFT) & 7);
+                    const bool hi = G.tasks[lead].flags & TF_HI, mine = G.tasks[t].flags & TF_HI;
+                    if (hi != mine) { G.tasks[t].flags ^= TF_HI; G.n_hi += hi ? 1 : -1; }
+                }
             G.critical_path_us = std::max(G.critical_path_us, (double)cp[sg]);
             // dedicated CTAs per GPU for this segment: 4x the average load of the high-priority tasks, at least 4
             const double avg = busy / std::max(1.0, (double)cp[sg]) / std::max(1, G.n_owners);
@@ -616,7 +646,11 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         G.hi_threshold_us = theta;
     }
     G.succ_enc.resize(G.succ.size());
-    for (size_t e = 0; e < G.succ.size(); e++) G.succ_enc[e] = G.succ[e] | ((G.tasks[G.succ[e]].flags & TF_HI) ? TASK_HI_BIT : 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < (int64_t)G.succ.size(); e++) {
+        const Task& S = G.tasks[G.succ[e]];
+        G.succ_enc[e] = make_task_ref(0, S.flags & TF_HI, task_log2_slices(S), G.succ[e]);
+    }
     if ((int64_t)G.tasks.size() > TASK_LOCAL_MASK) return "too many tasks";
 
     // per-segment lists of initially ready tasks, high-priority ones first (single GPU: every task is owned
@@ -636,6 +670,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             }
         }
     }
+    lap("priority + initial");
     // ---- patch block ids -> block references (owner in the top bits; plain slots on one GPU) --------
     {
         auto ref = [&](int32_t id, int reader) -> int32_t {
@@ -662,6 +697,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         for (Task& T : G.tasks)
             for (int k = 0; k < 2; k++) T.first[k] = (k < T.n_pairs) ? G.pairs[T.pair_begin + k] : Pair{0, 0};
     }
+    lap("patch refs");
     return "";
 }
 
@@ -692,6 +728,7 @@ std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {
             if (G.tasks[t].flags & TF_HI) D.seg_nhi_all[G.task_owner[t]][sg]++;
         }
     }
+    int32_t shared_from = -1, shared_begin = 0, shared_end = 0;
     for (int sg = 0; sg < nseg; sg++) {
         std::vector<int32_t> init_lo;
         for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
@@ -704,14 +741,18 @@ std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {
                 D.pairs.push_back(p);
             }
             T.pair_begin = pb;
-            const int32_t sb = (int32_t)D.succ.size();
-            for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
-                const int32_t s2 = G.succ[e];
-                D.succ.push_back(make_task_ref(G.task_owner[s2], G.tasks[s2].flags & TF_HI, D.task_local[s2]));
-                D.remote_edges += G.task_owner[s2] != rank;
+            if (T.succ_begin != shared_from || T.succ_end - T.succ_begin != shared_end - shared_begin) {   // slices share one list
+                shared_from = T.succ_begin;
+                shared_begin = (int32_t)D.succ.size();
+                for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+                    const int32_t s2 = G.succ[e];
+                    D.succ.push_back(make_task_ref(G.task_owner[s2], G.tasks[s2].flags & TF_HI, task_log2_slices(G.tasks[s2]), D.task_local[s2]));
+                }
+                shared_end = (int32_t)D.succ.size();
             }
-            T.succ_begin = sb;
-            T.succ_end = (int32_t)D.succ.size();
+            for (int32_t e = T.succ_begin; e < T.succ_end; e++) D.remote_edges += G.task_owner[G.succ[e]] != rank;
+            T.succ_begin = shared_begin;
+            T.succ_end = shared_end;
             if (T.n_deps == 0) { if (T.flags & TF_HI) D.initial.push_back((int32_t)D.tasks.size()); else init_lo.push_back((int32_t)D.tasks.size()); }
             if (T.flags & TF_HI) D.seg_nhi[sg]++;
             D.tasks.push_back(T);

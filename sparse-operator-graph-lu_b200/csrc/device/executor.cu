@@ -521,10 +521,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
                     if (o != P.rank) { remote = true; continue; }
                     if (atomicSub(P.dep + nx, 1) == 1) {
+                        // the whole group (all row slices of the successor) becomes ready at once
+                        const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
                         __threadfence();
-                        const int pos = atomicAdd(P.tail[qq], 1);
-                        if (P.trace) P.trace[6 * (size_t)nx + 0] = gtime();
-                        ptx::st_release(P.ready[qq] + pos, nx);
+                        const int pos = atomicAdd(P.tail[qq], g);
+                        for (int k = 0; k < g; k++) {
+                            if (P.trace) P.trace[6 * (size_t)(nx + k) + 0] = gtime();
+                            ptx::st_release(P.ready[qq] + pos + k, nx + k);
+                        }
                     }
                 }
                 if (remote) {
@@ -534,9 +538,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                         const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
                         if (o == P.rank) continue;
                         if (atomicSub_system(P.deps[o] + nx, 1) == 1) {
+                            const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
                             __threadfence_system();
-                            const int pos = atomicAdd_system(P.tails[o][qq], 1);
-                            ptx::st_release_sys(P.readys[o][qq] + pos, nx);
+                            const int pos = atomicAdd_system(P.tails[o][qq], g);
+                            for (int k = 0; k < g; k++) ptx::st_release_sys(P.readys[o][qq] + pos + k, nx + k);
                         }
                     }
                 }

@@ -24,10 +24,15 @@ constexpr int REF_SHIFT = 29;
 constexpr int32_t REF_MASK = (1 << REF_SHIFT) - 1;
 constexpr int MAX_GPUS = 8;
 inline int32_t make_ref(int owner, int32_t local) { return (int32_t)(((uint32_t)owner << REF_SHIFT) | (uint32_t)local); }
-// task references in successor lists additionally carry the priority class of the successor
+// Task references in successor lists name a task GROUP (a task, or the 2 / 4 consecutive row slices of a
+// split GEMM task, which share the dependency counter of their first slice): owner | priority class of the
+// group | log2(group size) | local index of the first slice.
 constexpr int32_t TASK_HI_BIT = 1 << 28;
-constexpr int32_t TASK_LOCAL_MASK = TASK_HI_BIT - 1;
-inline int32_t make_task_ref(int owner, bool hi, int32_t local) { return make_ref(owner, local) | (hi ? TASK_HI_BIT : 0); }
+constexpr int TASK_SPLIT_SHIFT = 26;                       // 2 bits: log2(slices)
+constexpr int32_t TASK_LOCAL_MASK = (1 << TASK_SPLIT_SHIFT) - 1;
+inline int32_t make_task_ref(int owner, bool hi, int log2_slices, int32_t local) {
+    return make_ref(owner, local) | (hi ? TASK_HI_BIT : 0) | (log2_slices << TASK_SPLIT_SHIFT);
+}
 
 enum TaskType : int32_t {
     T_GEMM = 0,      // out = init +/- sum_p A_p * B_p   (mul / mulneg / mult chains, optional fused sub)
@@ -61,16 +66,24 @@ struct Task {          // 64 bytes = one 64-byte line: the scheduler needs ONE l
     int32_t out2;        // LU: slot of U
     int32_t init;        // GEMM + TF_INIT: slot of the initial value; LU + TF_LINV: slot of L^-1 (out3)
     int32_t succ_begin, succ_end;  // successor task ids (CSR)
-    int32_t n_deps;      // initial dependency counter
+    int32_t n_deps;      // initial dependency counter (of the group; only the leader's counter is used at run time)
     int32_t level;       // ASAP level (0 = ready at start)
     int32_t out4;        // LU + TF_UINV: slot of U^-1
     Pair first[2];       // copy of the first two operand pairs (saves a dependent fetch)
 };
 
+// row slices of one split GEMM task are consecutive; the first one (row0 == 0) leads the group
+inline int task_group_size(const Task& t) {
+    const int rows16 = (t.flags >> TF_NROWS_SHIFT) & 7;
+    return (t.type == T_GEMM && rows16 > 0) ? 4 / rows16 : 1;
+}
+inline bool task_is_leader(const Task& t) { return t.type != T_GEMM || ((t.flags >> TF_ROW0_SHIFT) & 3) == 0; }
+inline int task_log2_slices(const Task& t) { const int g = task_group_size(t); return g == 4 ? 2 : (g == 2 ? 1 : 0); }
+
 struct TaskGraph {
     std::vector<Task> tasks;
     std::vector<Pair> pairs;
-    std::vector<int32_t> succ;
+    std::vector<int32_t> succ;          // successor GROUP leaders (task indices); the slices of one task share their list
     std::vector<int32_t> initial;       // tasks with n_deps == 0, in task order
     std::vector<int32_t> slot_of;       // block id -> pool slot (0 = zero block / none)
     std::vector<int32_t> task_of;       // block id -> producing task (-1 = input / none)

@@ -128,7 +128,8 @@ int64_t soglu_problem_size(const soglu_problem* pp, const char* what) {
     return -1;
 }
 
-static void pack_ops(const std::vector<soglu::Op>& ops, int32_t* out) {
+static void pack_ops(const soglu::OpVec& ops, int32_t* out) {
+#pragma omp parallel for schedule(static)
     for (size_t k = 0; k < ops.size(); k++) {
         const soglu::Op& o = ops[k];
         int32_t* r = out + 8 * k;
@@ -168,7 +169,7 @@ int soglu_problem_get_f64(const soglu_problem* pp, const char* what, double* out
     auto cp = [&](const std::vector<double>& v) { std::memcpy(out, v.data(), v.size() * sizeof(double)); return (int)SOGLU_OK; };
     if (w == "b") return cp(p->b);
     if (w == "b_perm") return cp(p->b_perm);
-    if (w == "input_vals") return cp(p->plan.input_vals);
+    if (w == "input_vals") { std::memcpy(out, p->plan.input_vals.data(), p->plan.input_vals.size() * sizeof(double)); return SOGLU_OK; }
     if (w == "flops") { out[0] = p->flops; return SOGLU_OK; }
     if (w == "t_reorder") { out[0] = p->t_reorder; return SOGLU_OK; }
     if (w == "t_plan") { out[0] = p->t_plan; return SOGLU_OK; }

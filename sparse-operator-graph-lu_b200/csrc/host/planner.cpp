@@ -23,6 +23,9 @@
 #include <cstring>
 #include <memory>
 #include <sstream>
+#include <chrono>
+#include <cstdlib>
+#include <sys/mman.h>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -58,11 +61,49 @@ class NodePool {
     int64_t size() const { return count_; }
 };
 
+// Emission buffer: fixed-size chunks, so appending 10^8 ops never reallocates or copies.
+class OpStore {
+    static constexpr int SHIFT = 20;
+    static constexpr int64_t CHUNK = int64_t(1) << SHIFT;
+    std::vector<Op*> chunks_;
+    int64_t n_ = 0;
+  public:
+    OpStore() = default;
+    OpStore(const OpStore&) = delete;
+    OpStore& operator=(const OpStore&) = delete;
+    ~OpStore() { clear(); }
+    void clear() {
+        for (Op* c : chunks_) big_free(c, CHUNK * sizeof(Op));
+        chunks_.clear();
+        n_ = 0;
+    }
+    void push_back(const Op& o) {
+        if ((n_ >> SHIFT) >= (int64_t)chunks_.size()) chunks_.push_back(static_cast<Op*>(big_alloc(CHUNK * sizeof(Op))));
+        chunks_[n_ >> SHIFT][n_ & (CHUNK - 1)] = o;
+        n_++;
+    }
+    Op& operator[](int64_t i) { return chunks_[i >> SHIFT][i & (CHUNK - 1)]; }
+    const Op& operator[](int64_t i) const { return chunks_[i >> SHIFT][i & (CHUNK - 1)]; }
+    int64_t size() const { return n_; }
+};
+
+// SOGLU_TIMING=1 prints the planner's phase times to stderr (diagnostics only)
+struct PhaseTimer {
+    bool on = std::getenv("SOGLU_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[plan] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 inline int ilog2(int v) { return __builtin_popcount(v - 1); }  // v is a power of two
 
 struct Planner {
     NodePool T;
-    std::vector<Op> graph;
+    OpStore graph;        // ops in emission order
     int storage = 1;      // data::storageCount (id 0 = none)
     int seq = 0;          // operation::seq
     bool planL2 = false;
@@ -330,7 +371,8 @@ struct Planner {
         for (int q = 0; q < 4; q++) mark_outputs(T[a].sub[q], lastuse, marker);
     }
 
-    void block_plan(NodeId saved, NodeId savedu) {
+    void block_plan(NodeId saved, NodeId savedu, OpVec& sorted) {
+        PhaseTimer pt;
         const int64_t nops = (int64_t)graph.size();
         std::vector<int32_t> lastuse(storage, 0);
         stage.assign(storage, 0);
@@ -358,32 +400,28 @@ struct Planner {
                 }
             }
         }
-        // dead-op pruning (178-221)
+        pt.lap("liveness sweep");
+        // dead-op pruning (178-221): decided here, carried out by the stage scatter below
         int64_t waste = 0;
+#pragma omp parallel for schedule(static) reduction(+ : waste) if (nops > 200000)
         for (int64_t i = 0; i < nops; i++) {
             const Op& o = graph[i];
             if (lastuse[o.result] > 0) continue;
             if (o.result2 > 0 && lastuse[o.result2] > 0) continue;
             ++waste;
         }
-        if (planL2 || (uint64_t)waste > (uint64_t)nops / 25) {
-            int64_t w = 0;
-            for (int64_t i = 0; i < nops; i++) {
-                const Op& o = graph[i];
-                bool live = lastuse[o.result] > 0 || (o.result2 > 0 && lastuse[o.result2] > 0);
-                if (live) graph[w++] = o;   // sequence and group numbers are preserved
-            }
-            graph.resize(w);
-            graph.shrink_to_fit();
-            seq += 2 * (int)w;  // operation::sett (++seq) + memutil::newoperation (seq++) per kept op
-        }
-        log << "reduced ops to: " << graph.size() << "\n";
-        const int64_t n = (int64_t)graph.size();
+        const bool prune = planL2 || (uint64_t)waste > (uint64_t)nops / 25;
+        const int64_t n = prune ? nops - waste : nops;
+        if (prune) seq += 2 * (int)n;  // operation::sett (++seq) + memutil::newoperation (seq++) per kept op
+        log << "reduced ops to: " << n << "\n";
+        auto dead = [&](const Op& o) { return prune && !(lastuse[o.result] > 0 || (o.result2 > 0 && lastuse[o.result2] > 0)); };
+        pt.lap("prune decision");
 
-        // forward ASAP stage numbering (225-267)
+        // forward ASAP stage numbering over the kept ops (225-267); dead ops get stage -1
         int maxstg = 1;
-        for (int64_t i = 0; i < n; i++) {
+        for (int64_t i = 0; i < nops; i++) {
             Op& o = graph[i];
+            if (dead(o)) { o.stage = -1; continue; }
             int stg = 0;
             if (o.src > 0) {
                 stg = stage[o.src] + 1;
@@ -399,38 +437,68 @@ struct Planner {
             if (stg > maxstg) maxstg = stg;
         }
         // every single-result writer moves to its result's final stage (270-276)
-        for (int64_t i = n - 1; i >= 0; i--) {
+#pragma omp parallel for schedule(static) if (nops > 200000)
+        for (int64_t i = 0; i < nops; i++) {
             Op& o = graph[i];
-            if (o.result2 > 0) continue;
+            if (o.stage < 0 || o.result2 > 0) continue;
             if (o.result > 0 && stage[o.result] > o.stage) o.stage = stage[o.result];
         }
-        // total order (stage, group, result, src, seq) (operation.cpp:180-196)
+        pt.lap("stage numbering");
+        // total order (stage, group, result, src, seq) (operation.cpp:180-196): a parallel
+        // counting sort on the stage (which also drops the dead ops), then one sort per stage
         {
-            std::vector<int64_t> start(maxstg + 2, 0);
-            for (int64_t i = 0; i < n; i++) start[graph[i].stage + 1]++;
-            for (int s = 0; s <= maxstg; s++) start[s + 1] += start[s];
-            std::vector<Op> sorted(n);
-            {
-                std::vector<int64_t> pos(start.begin(), start.end() - 1);
-                for (int64_t i = 0; i < n; i++) sorted[pos[graph[i].stage]++] = graph[i];
+            int nth = 1;
+#ifdef _OPENMP
+            nth = omp_get_max_threads();
+#endif
+            if (nops < (1 << 16)) nth = 1;
+            const int64_t chunk = (nops + nth - 1) / nth;
+            const size_t S = (size_t)maxstg + 1;
+            std::vector<int64_t> cnt((size_t)nth * S, 0);   // [thread][stage]
+#pragma omp parallel for schedule(static, 1) num_threads(nth)
+            for (int t = 0; t < nth; t++) {
+                int64_t* c = cnt.data() + (size_t)t * S;
+                const int64_t lo = t * chunk, hi = std::min(nops, lo + chunk);
+                for (int64_t i = lo; i < hi; i++)
+                    if (graph[i].stage >= 0) c[graph[i].stage]++;
             }
-            graph.swap(sorted);
-            std::vector<Op>().swap(sorted);
+            std::vector<int64_t> start(S + 1, 0);
+            for (size_t st = 0; st < S; st++) {
+                int64_t run = start[st];
+                for (int t = 0; t < nth; t++) {
+                    int64_t c = cnt[(size_t)t * S + st];
+                    cnt[(size_t)t * S + st] = run;
+                    run += c;
+                }
+                start[st + 1] = run;
+            }
+            sorted.clear();
+            sorted.resize(n);
+#pragma omp parallel for schedule(static, 1) num_threads(nth)
+            for (int t = 0; t < nth; t++) {
+                int64_t* pos = cnt.data() + (size_t)t * S;
+                const int64_t lo = t * chunk, hi = std::min(nops, lo + chunk);
+                for (int64_t i = lo; i < hi; i++)
+                    if (graph[i].stage >= 0) sorted[pos[graph[i].stage]++] = graph[i];
+            }
+            graph.clear();
+            pt.lap("stage scatter");
             auto less = [](const Op& x, const Op& y) {
                 if (x.group != y.group) return x.group < y.group;
                 if (x.result != y.result) return x.result < y.result;
                 if (x.src != y.src) return x.src < y.src;
                 return x.seq < y.seq;
             };
-#pragma omp parallel for schedule(dynamic, 16)
-            for (int s = 0; s <= maxstg; s++)
-                if (start[s + 1] - start[s] > 1) std::sort(graph.begin() + start[s], graph.begin() + start[s + 1], less);
+#pragma omp parallel for schedule(dynamic, 16) if (nops > 200000)
+            for (int st = 0; st <= maxstg; st++)
+                if (start[st + 1] - start[st] > 1) std::sort(sorted.begin() + start[st], sorted.begin() + start[st + 1], less);
         }
+        pt.lap("sort");
         // split stages wider than 8000 ops (335-354)
         {
             int jump = 0, band = 0, stgc = 0;
             for (int64_t i = 0; i < n; i++) {
-                Op& o = graph[i];
+                Op& o = sorted[i];
                 if (o.stage > stgc) { stgc = o.stage; band = 0; }
                 if (band > 8000) { jump++; band = 0; }
                 o.stage += jump;
@@ -439,10 +507,11 @@ struct Planner {
         }
         // last reading stage per block (356-371)
         for (int64_t i = 0; i < n; i++) {
-            const Op& o = graph[i];
+            const Op& o = sorted[i];
             if (o.src > 0 && laststage[o.src] < o.stage) laststage[o.src] = o.stage;
             if (o.src2 > 0 && laststage[o.src2] < o.stage) laststage[o.src2] = o.stage;
         }
+        pt.lap("split + laststage");
     }
 
     void collect(NodeId m, int r0, int c0, int n, std::vector<BlockRef>& out) {
@@ -460,7 +529,36 @@ struct Cell { int row, col; double val; };
 
 }  // namespace
 
-double factor_flops(const std::vector<Op>& ops) {
+bool BlockValues::alloc_zero(size_t n_blocks) {
+    std::free(p_);
+    n_ = n_blocks * 4096;
+    p_ = n_ ? static_cast<double*>(std::malloc(n_ * sizeof(double))) : nullptr;
+    if (n_ && !p_) { n_ = 0; return false; }
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < (int64_t)n_blocks; b++) std::memset(p_ + (size_t)b * 4096, 0, 4096 * sizeof(double));
+    return true;
+}
+
+void* big_alloc(size_t bytes) {
+    if (bytes < (size_t(8) << 20)) {
+        void* p = std::malloc(bytes ? bytes : 1);
+        if (!p) throw std::bad_alloc();
+        return p;
+    }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) throw std::bad_alloc();
+#ifdef MADV_HUGEPAGE
+    madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+    return p;
+}
+void big_free(void* p, size_t bytes) {
+    if (!p) return;
+    if (bytes < (size_t(8) << 20)) std::free(p);
+    else munmap(p, bytes);
+}
+
+double factor_flops(const OpVec& ops) {
     double f = 0;
     for (const Op& o : ops) {
         switch (o.op) {
@@ -484,6 +582,7 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
         return 1;
     }
     Planner P;
+    PhaseTimer pt;
     const size_t nnz = idx_i.size();
     P.mSize = cfg.mSize;
     if (symmetric) P.log << "symmetric\n";
@@ -510,9 +609,9 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
     plan.coarse_emitted = (int)P.graph.size();
     P.log << "blocks: " << P.blockRows << " blockSize: " << P.blockSize << " inputSize: " << cfg.mSize
           << " extend: " << P.blockRows * P.blockSize << " op count: " << P.graph.size() << " storage: " << P.storage << "\n";
-    P.block_plan(bl, symmetric ? 0 : bu);
-    plan.coarse_ops = P.graph;
+    P.block_plan(bl, symmetric ? 0 : bu, plan.coarse_ops);
     plan.coarse_storage = P.storage;
+    pt.lap("coarse pass");
 
     // ===== expansion to 64-blocks (copyOperatorL2, 1332-1460) ==============================
     const NodeId coarse_blocks = P.blocks;
@@ -537,29 +636,45 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
             if ((x.row >> 6) == (y.row >> 6)) return (x.col >> 6) < (y.col >> 6);
             return (x.row >> 6) < (y.row >> 6);
         });
-        std::vector<double>& V = plan.input_vals;
+        pt.lap("  cell sort");
+        // pass 1 allocates ids in first-touch order, pass 2 fills the dense values once their
+        // number is known (one allocation, zeroed by all threads)
         auto block_of = [&](int bi, int bj) {
             int id = P.tree_get(P.blocks, bi, bj);
             if (id == 0) {
                 id = P.new_block();
                 P.tree_set(P.blocks, bi, bj, id);
                 in_alloc.push_back({id, bi, bj});
-                if (keep_values) V.resize(V.size() + 4096, 0.0);
             }
             return id;
         };
-        for (size_t k = 0; k < nnz; k++) {
-            int bi = cells[k].row >> 6, bj = cells[k].col >> 6;
-            int id = block_of(bi, bj);
-            if (keep_values) V[(size_t)(id - 1) * 4096 + (cells[k].row & 63) * 64 + (cells[k].col & 63)] = cells[k].val;
+        std::vector<int32_t> cell_block(keep_values ? nnz : 0);
+        {
+            int last_bi = -1, last_bj = -1, last_id = 0;
+            for (size_t k = 0; k < nnz; k++) {
+                int bi = cells[k].row >> 6, bj = cells[k].col >> 6;
+                if (bi != last_bi || bj != last_bj) { last_id = block_of(bi, bj); last_bi = bi; last_bj = bj; }
+                if (keep_values) cell_block[k] = last_id;
+            }
         }
-        for (int i = cfg.mSize; i < P.blockRows * 64; i++) {
-            int bi = i >> 6, ri = i & 63;
-            int id = block_of(bi, bi);
-            if (keep_values) V[(size_t)(id - 1) * 4096 + ri * 64 + ri] = 1.0;
+        for (int bi = cfg.mSize >> 6; bi < P.blockRows; bi++) block_of(bi, bi);   // identity padding
+        if (keep_values) {
+            BlockValues& V = plan.input_vals;
+            if (!V.alloc_zero((size_t)(P.storage - 1))) {
+                plan.log = P.log.str() + "planner: out of host memory for the input blocks\n";
+                return 3;
+            }
+            for (size_t k = 0; k < nnz; k++)
+                V[(size_t)(cell_block[k] - 1) * 4096 + (cells[k].row & 63) * 64 + (cells[k].col & 63)] = cells[k].val;
+            for (int i = cfg.mSize; i < P.blockRows * 64; i++) {
+                int bi = i >> 6, ri = i & 63;
+                int id = P.tree_get(P.blocks, bi, bi);
+                V[(size_t)(id - 1) * 4096 + ri * 64 + ri] = 1.0;
+            }
         }
         // input ids are 1..n_input in allocation order, so V is indexed by id-1
     }
+    pt.lap("fine input blocks");
     // bind coarse input ids to fine sub-quadtrees (matrixZoomSet, 1305-1315)
     {
         struct Fr { NodeId a, d; };
@@ -580,8 +695,7 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
                 }
         }
     }
-    std::vector<Op> graphL2;
-    graphL2.swap(P.graph);
+    const OpVec& graphL2 = plan.coarse_ops;
     P.seq += (int)graphL2.size();   // the reference re-allocates every coarse op (1359-1365)
     for (const Op& o : graphL2) {
         if (o.result > 0 && !L2[o.result]) L2[o.result] = P.T.make(levelL2);
@@ -640,12 +754,13 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
         if (!symmetric) stitch(bu, bu2);
         stitch(bl, bl2);
     }
+    pt.lap("fine emission");
     plan.fine_emitted = (int)P.graph.size();
     P.log << "blocks: " << P.blockRows << " blockSize: " << P.blockSize << " inputSize: " << cfg.mSize
           << " extend: " << P.blockRows * P.blockSize << " op count: " << P.graph.size() << " storage: " << P.storage << "\n";
-    P.block_plan(bl2, bu2);
+    P.block_plan(bl2, bu2, plan.ops);
+    pt.lap("fine block_plan");
 
-    plan.ops.swap(P.graph);
     plan.storage = P.storage;
     plan.stage.swap(P.stage);
     plan.laststage.swap(P.laststage);
@@ -671,6 +786,7 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
             }
         }
     }
+    pt.lap("collect + coordinates");
     plan.log = P.log.str();
     return 0;
 }

@@ -13,6 +13,9 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <cstdlib>
+#include <new>
+#include <utility>
 #include <vector>
 
 namespace soglu {
@@ -74,21 +77,57 @@ struct Op {                 // one DAG node; mirrors struct operation (operation
 };
 struct BlockRef { int32_t id, brow, bcol; };
 
+// Large host arrays (op lists of 10^8 entries): anonymous mappings advised to use 2 MiB pages, elements
+// default-initialised (no zero fill pass; fresh mappings are zero anyway).  Small sizes use malloc.
+void* big_alloc(size_t bytes);
+void big_free(void* p, size_t bytes);
+template <class T>
+struct BigAlloc {
+    using value_type = T;
+    BigAlloc() = default;
+    template <class U> BigAlloc(const BigAlloc<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(big_alloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t n) { big_free(p, n * sizeof(T)); }
+    template <class U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+    template <class U> bool operator==(const BigAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const BigAlloc<U>&) const { return false; }
+};
+using OpVec = std::vector<Op, BigAlloc<Op>>;
+
+// Dense values of the input blocks: one malloc, zeroed in parallel (first touch by all threads).
+class BlockValues {
+    double* p_ = nullptr;
+    size_t n_ = 0;
+  public:
+    BlockValues() = default;
+    BlockValues(const BlockValues&) = delete;
+    BlockValues& operator=(const BlockValues&) = delete;
+    BlockValues(BlockValues&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    BlockValues& operator=(BlockValues&& o) noexcept { if (this != &o) { std::free(p_); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; } return *this; }
+    ~BlockValues() { std::free(p_); }
+    bool alloc_zero(size_t n_blocks);   // false when out of memory
+    double* data() { return p_; }
+    const double* data() const { return p_; }
+    size_t size() const { return n_; }
+    double& operator[](size_t i) { return p_[i]; }
+};
+
 struct Plan {
     Config cfg;
     bool symmetric = false;
     // coarse (L2) pass, kept for the bit-exact checks
-    std::vector<Op> coarse_ops;
+    OpVec coarse_ops;
     int coarse_storage = 0;
     int coarse_emitted = 0;          // op count before pruning
     // fine pass
-    std::vector<Op> ops;             // sorted by (stage, group, result, src, seq)
+    OpVec ops;                       // sorted by (stage, group, result, src, seq)
     int fine_emitted = 0;
     int storage = 0;                 // data::storageCount: block ids are 1..storage-1, 0 = none
     std::vector<int32_t> stage;      // per block id (data::stage)
     std::vector<int32_t> laststage;  // per block id (data::laststage)
     std::vector<BlockRef> inputs;    // blocks filled by iniBlockStorage, quadtree (Z) order
-    std::vector<double> input_vals;  // dense 64x64 row-major per input block
+    BlockValues input_vals;          // dense 64x64 row-major per input block
     std::vector<BlockRef> L, U;      // factor leaves with block coordinates, quadtree order
     std::vector<int32_t> brow, bcol; // per block id: coordinates of the quadtree slot (or -1)
     std::string log;                 // the lines the reference prints while planning
@@ -100,6 +139,6 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
                const std::vector<double>& vals, Plan& plan, bool keep_values = true);
 
 // dense-block FLOP convention of SURVEY.md section 8(d)
-double factor_flops(const std::vector<Op>& ops);
+double factor_flops(const OpVec& ops);
 
 }  // namespace soglu

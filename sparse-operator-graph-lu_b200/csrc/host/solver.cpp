@@ -140,9 +140,10 @@ extern "C" int soglu_debug_compile_dist(const soglu_problem* pp, int64_t max_slo
     soglu::TaskGraph G;
     std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
     if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
-    int64_t deps = 0;
-    for (const soglu::Task& t : G.tasks) deps += t.n_deps;
-    int64_t v[16] = {(int64_t)G.tasks.size(), (int64_t)G.pairs.size(), (int64_t)G.succ.size(), (int64_t)G.initial.size(), G.n_slots, G.n_levels,
+    // deps = sum of the group counters (leaders); succ = decrements at run time (every slice walks its task's list)
+    int64_t deps = 0, releases = 0;
+    for (const soglu::Task& t : G.tasks) { if (soglu::task_is_leader(t)) deps += t.n_deps; releases += t.succ_end - t.succ_begin; }
+    int64_t v[16] = {(int64_t)G.tasks.size(), (int64_t)G.pairs.size(), releases, (int64_t)G.initial.size(), G.n_slots, G.n_levels,
                      G.fused_subs, G.fused_invs, G.aliased_invs, G.split_tasks, (int64_t)G.seg_begin.size() - 1, deps, 0, 0, 0, (int64_t)(G.flops * 1e-6)};
     for (int i = 0; i < 16; i++) out[i] = v[i];
     int64_t remote_edges = 0;
@@ -152,8 +153,9 @@ extern "C" int soglu_debug_compile_dist(const soglu_problem* pp, int64_t max_slo
         if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
         out[16 + 3 * r] = (int64_t)D.tasks.size(); out[17 + 3 * r] = G.slots_per_owner[r]; out[18 + 3 * r] = D.mirrored;
         remote_edges += D.remote_edges;
-        int64_t dd = 0; for (const soglu::Task& t : D.tasks) dd += t.n_deps;
-        out[12] += dd; out[13] += (int64_t)D.succ.size(); out[14] += D.remote_operands;
+        int64_t dd = 0, rr = 0;
+        for (const soglu::Task& t : D.tasks) { if (soglu::task_is_leader(t)) dd += t.n_deps; rr += t.succ_end - t.succ_begin; }
+        out[12] += dd; out[13] += rr; out[14] += D.remote_operands;
     }
     return SOGLU_OK;
 }
@@ -176,15 +178,145 @@ extern "C" int soglu_debug_compile(const soglu_problem* pp, int fuse_sub, int fu
     std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
     double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
-    int64_t deps = 0, maxdeps = 0, gemm = 0, lu = 0, subs = 0;
+    int64_t deps = 0, releases = 0, maxdeps = 0, gemm = 0, lu = 0, subs = 0;
     for (const soglu::Task& t : G.tasks) {
-        deps += t.n_deps; maxdeps = std::max<int64_t>(maxdeps, t.n_deps);
+        if (soglu::task_is_leader(t)) deps += t.n_deps;
+        releases += t.succ_end - t.succ_begin;
+        maxdeps = std::max<int64_t>(maxdeps, t.n_deps);
         gemm += t.type == soglu::T_GEMM; lu += t.type == soglu::T_LU; subs += t.type == soglu::T_SUB;
     }
-    int64_t v[16] = {(int64_t)G.tasks.size(), (int64_t)G.pairs.size(), (int64_t)G.succ.size(), (int64_t)G.initial.size(), G.n_slots, G.n_levels,
+    int64_t v[16] = {(int64_t)G.tasks.size(), (int64_t)G.pairs.size(), releases, (int64_t)G.initial.size(), G.n_slots, G.n_levels,
                      G.fused_subs, G.fused_invs, G.aliased_invs, G.split_tasks, (int64_t)G.seg_begin.size() - 1, deps, maxdeps, gemm, lu,
                      (int64_t)(dt * 1e6)};
     for (int i = 0; i < 16; i++) out[i] = v[i];
     (void)subs;
     return SOGLU_OK;
+}
+
+// Host simulation of the executor's release protocol on a compiled graph (one segment, optional process grid):
+// tasks are taken from the ready set in a seeded random order; a finishing task decrements the counter of every
+// successor GROUP LEADER once and the whole group becomes ready when it reaches zero -- exactly what the CUDA
+// executor does with its localized per-GPU arrays.  Checks that every task runs exactly once and that each operand
+// block is complete (all of its writers done) when a reader starts.  out[0] = tasks run, out[1] = violations.
+extern "C" int soglu_debug_simulate(const soglu_problem* pp, int split, int pr, int pc, int nb, uint64_t seed, int64_t* out) {
+    const Problem* p = reinterpret_cast<const Problem*>(pp);
+    const int world = pr * pc;
+    if (!p || !out || world < 1 || world > soglu::MAX_GPUS) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
+    const soglu::Plan& pl = p->plan;
+    const int64_t n = (int64_t)pl.ops.size();
+    std::vector<int32_t> src(n), src2(n), res(n), res2(n);
+    std::vector<uint8_t> op(n);
+    for (int64_t k = 0; k < n; k++) { const soglu::Op& o = pl.ops[k]; src[k] = o.src; src2[k] = o.src2; res[k] = o.result; res2[k] = o.result2; op[k] = o.op; }
+    std::vector<int32_t> in_ids(pl.inputs.size()), keep;
+    for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = (int32_t)(k + 1);
+    for (const auto& r : pl.L) keep.push_back(r.id);
+    for (const auto& r : pl.U) keep.push_back(r.id);
+    std::vector<int8_t> owners(pl.storage, 0);
+    if (world > 1)
+        for (int64_t id = 1; id < pl.storage; id++)
+            if (pl.brow[id] >= 0 && pl.bcol[id] >= 0) owners[id] = (int8_t)(((pl.brow[id] / nb) % pr) * pc + ((pl.bcol[id] / nb) % pc));
+    soglu::CompileOptions co;
+    co.split_narrow = split;
+    if (world > 1) { co.owner_of_id = owners.data(); co.n_owners = world; }
+    soglu::TaskGraph G;
+    std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
+    if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
+    // per-GPU arrays, as uploaded
+    std::vector<soglu::DistLayout> D(world);
+    for (int r = 0; r < world; r++) {
+        err = soglu::localize_tasks(G, r, D[r]);
+        if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
+    }
+    int64_t max_slots = 0;
+    for (int r = 0; r < world; r++) max_slots = std::max<int64_t>(max_slots, G.slots_per_owner[r]);
+    auto key = [&](int32_t ref) { return (int64_t)((uint32_t)ref >> soglu::REF_SHIFT) * max_slots + (ref & soglu::REF_MASK); };
+    std::vector<int32_t> writers((size_t)world * max_slots, 0);
+    auto for_outs = [&](const soglu::Task& T, auto&& fn) {
+        fn(T.out);
+        if (T.type == soglu::T_LU) { fn(T.out2); if (T.flags & soglu::TF_LINV) fn(T.init); if (T.flags & soglu::TF_UINV) fn(T.out4); }
+    };
+    for (int r = 0; r < world; r++)
+        for (const soglu::Task& T : D[r].tasks) for_outs(T, [&](int32_t ref) { writers[key(ref)]++; });
+    std::vector<std::vector<int32_t>> dep(world), runs(world);
+    std::vector<std::pair<int8_t, int32_t>> ready;
+    for (int r = 0; r < world; r++) {
+        dep[r].resize(D[r].tasks.size());
+        runs[r].assign(D[r].tasks.size(), 0);
+        for (size_t t = 0; t < D[r].tasks.size(); t++) dep[r][t] = D[r].tasks[t].n_deps;
+        for (int32_t t : D[r].initial) ready.push_back({(int8_t)r, t});
+    }
+    uint64_t rng = seed * 6364136223846793005ull + 1442695040888963407ull;
+    int64_t done = 0, bad = 0;
+    while (!ready.empty()) {
+        rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+        const size_t pick = (size_t)((rng >> 33) % ready.size());
+        const auto cur = ready[pick];
+        ready[pick] = ready.back();
+        ready.pop_back();
+        const int r = cur.first;
+        const soglu::Task& T = D[r].tasks[cur.second];
+        if (runs[r][cur.second]++) bad++;
+        for (int32_t k = 0; k < T.n_pairs; k++) {
+            const soglu::Pair& pq = D[r].pairs[T.pair_begin + k];
+            if (writers[key(pq.a)] != 0) bad++;
+            if ((T.type == soglu::T_GEMM || T.type == soglu::T_SUB) && writers[key(pq.b)] != 0) bad++;
+        }
+        if ((T.flags & soglu::TF_INIT) && writers[key(T.init)] != 0) bad++;
+        for_outs(T, [&](int32_t ref) { writers[key(ref)]--; });
+        done++;
+        for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+            const int32_t ref = D[r].succ[e];
+            const int o = (uint32_t)ref >> soglu::REF_SHIFT, nx = ref & soglu::TASK_LOCAL_MASK, g = 1 << ((ref >> soglu::TASK_SPLIT_SHIFT) & 3);
+            if (--dep[o][nx] == 0)
+                for (int q = 0; q < g; q++) ready.push_back({(int8_t)o, nx + q});
+        }
+    }
+    int64_t total = 0;
+    for (int r = 0; r < world; r++) {
+        total += (int64_t)D[r].tasks.size();
+        for (int32_t c : runs[r]) if (c != 1) bad++;
+    }
+    out[0] = done; out[1] = bad; out[2] = total;
+    return SOGLU_OK;
+}
+
+// FNV-1a over everything compile_tasks produces (regression guard for refactorings of the compiler: the task
+// order, operand order and slot assignment decide the rounding of the result, so they must not drift)
+extern "C" uint64_t soglu_debug_graph_hash(const soglu_problem* pp, int split, int64_t max_slots, int pr, int pc, int nb) {
+    const Problem* p = reinterpret_cast<const Problem*>(pp);
+    const int world = pr * pc;
+    if (!p || world < 1 || world > soglu::MAX_GPUS) return 0;
+    const soglu::Plan& pl = p->plan;
+    const int64_t n = (int64_t)pl.ops.size();
+    std::vector<int32_t> src(n), src2(n), res(n), res2(n);
+    std::vector<uint8_t> op(n);
+    for (int64_t k = 0; k < n; k++) { const soglu::Op& o = pl.ops[k]; src[k] = o.src; src2[k] = o.src2; res[k] = o.result; res2[k] = o.result2; op[k] = o.op; }
+    std::vector<int32_t> in_ids(pl.inputs.size()), keep;
+    for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = (int32_t)(k + 1);
+    for (const auto& r : pl.L) keep.push_back(r.id);
+    for (const auto& r : pl.U) keep.push_back(r.id);
+    std::vector<int8_t> owners(pl.storage, 0);
+    if (world > 1)
+        for (int64_t id = 1; id < pl.storage; id++)
+            if (pl.brow[id] >= 0 && pl.bcol[id] >= 0) owners[id] = (int8_t)(((pl.brow[id] / nb) % pr) * pc + ((pl.bcol[id] / nb) % pc));
+    soglu::CompileOptions co;
+    co.split_narrow = split; co.max_slots = max_slots;
+    if (world > 1) { co.owner_of_id = owners.data(); co.n_owners = world; }
+    soglu::TaskGraph G;
+    if (!soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G).empty()) return 0;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* d, size_t bytes) { const unsigned char* c = (const unsigned char*)d; for (size_t i = 0; i < bytes; i++) { h ^= c[i]; h *= 1099511628211ull; } };
+    mix(G.tasks.data(), G.tasks.size() * sizeof(soglu::Task));
+    mix(G.pairs.data(), G.pairs.size() * sizeof(soglu::Pair));
+    mix(G.succ.data(), G.succ.size() * 4);
+    mix(G.succ_enc.data(), G.succ_enc.size() * 4);
+    mix(G.initial.data(), G.initial.size() * 4);
+    mix(G.slot_of.data(), G.slot_of.size() * 4);
+    mix(G.task_of.data(), G.task_of.size() * 4);
+    mix(G.seg_begin.data(), G.seg_begin.size() * 4);
+    mix(G.seg_init.data(), G.seg_init.size() * 4);
+    mix(G.recycled.data(), G.recycled.size());
+    mix(G.owner_of.data(), G.owner_of.size());
+    mix(G.task_owner.data(), G.task_owner.size());
+    return h;
 }

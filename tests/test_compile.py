@@ -110,3 +110,17 @@ def test_multi_gpu_with_small_pools_uses_segments(sg, prob):
     assert e["segments"] > 1
     assert all(s <= cap for _, s, _ in e["per_rank"])
     assert sum(t for t, _, _ in e["per_rank"]) == e["tasks"]
+
+
+@pytest.mark.parametrize("split,pr,pc,nb,seed", [(0, 1, 1, 1, 1), (1, 1, 1, 1, 2), (1, 1, 1, 1, 3), (1, 2, 1, 2, 4), (1, 2, 2, 1, 5), (1, 4, 2, 4, 6)])
+def test_release_protocol_simulation(sg, prob, split, pr, pc, nb, seed):
+    """Host replay of the executor's dependency protocol on the per-GPU arrays it uploads, in a random
+    order: row slices of one task share their leader's counter and become ready together; every task
+    runs exactly once and never before all writers of its operands are done."""
+    L = sg.lib()
+    L.soglu_debug_simulate.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_uint64, ctypes.c_void_p]
+    out = (ctypes.c_int64 * 3)()
+    rc = L.soglu_debug_simulate(prob.h, split, pr, pc, nb, seed, out)
+    assert rc == 0, L.soglu_last_error().decode()
+    done, bad, total = list(out)
+    assert done == total and bad == 0
