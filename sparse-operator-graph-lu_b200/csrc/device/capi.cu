@@ -72,8 +72,8 @@ struct soglu_ctx {
     DevBuf in_dense;               // staging for dense input blocks until slots are known
     bool inputs_pending = false;
     int64_t n_ops = 0;
-    std::vector<int32_t> src, src2, result, result2;
-    std::vector<uint8_t> op;
+    BigVec<int32_t> src, src2, result, result2;   // released once the graph is compiled
+    BigVec<uint8_t> op;
     std::vector<int32_t> L_ids, L_brow, L_bcol, U_ids, U_brow, U_bcol;
     int32_t n_block_rows = 0;
     int symmetric = 0;
@@ -109,8 +109,8 @@ namespace {
 
 int fail(int code, const std::string& msg) { soglu::set_error(msg); return code; }
 
-template <typename T>
-int upload(DevBuf& b, const std::vector<T>& v, soglu_ctx* c) {
+template <typename T, typename A>
+int upload(DevBuf& b, const std::vector<T, A>& v, soglu_ctx* c) {
     CU(b.alloc(std::max<size_t>(v.size(), 1) * sizeof(T)));
     if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     c->h2d += (double)(v.size() * sizeof(T));
@@ -249,15 +249,15 @@ int finalize(soglu_ctx* c) {
         if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
     }
     // the op arrays are no longer needed on the host
-    std::vector<int32_t>().swap(c->src); std::vector<int32_t>().swap(c->src2);
-    std::vector<int32_t>().swap(c->result); std::vector<int32_t>().swap(c->result2);
-    std::vector<uint8_t>().swap(c->op);
+    BigVec<int32_t>().swap(c->src); BigVec<int32_t>().swap(c->src2);
+    BigVec<int32_t>().swap(c->result); BigVec<int32_t>().swap(c->result2);
+    BigVec<uint8_t>().swap(c->op);
 
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const std::vector<Task>& tasks_up = c->dist ? c->D.tasks : G.tasks;
-    const std::vector<Pair>& pairs_up = c->dist ? c->D.pairs : G.pairs;
-    const std::vector<int32_t>& succ_up = c->dist ? c->D.succ : G.succ_enc;
+    const BigVec<Task>& tasks_up = c->dist ? c->D.tasks : G.tasks;
+    const BigVec<Pair>& pairs_up = c->dist ? c->D.pairs : G.pairs;
+    const BigVec<int32_t>& succ_up = c->dist ? c->D.succ : G.succ_enc;
     const size_t pool_bytes = (size_t)G.slots_per_owner[c->dist ? c->rank : 0] * BLK_BYTES;
     const size_t aux = tasks_up.size() * (sizeof(Task) + 12) + pairs_up.size() * sizeof(Pair) + succ_up.size() * 4 + (256u << 20);
     if (pool_bytes + aux > free_b) {
@@ -523,9 +523,9 @@ int soglu_set_graph(soglu_ctx* c, int64_t n_ops, const int32_t* src, const int32
     if (!c || n_ops < 0 || (n_ops > 0 && (!src || !src2 || !op || !result || !result2))) return fail(SOGLU_ERR_ARG, "bad argument");
     if (c->compiled) return fail(SOGLU_ERR_ARG, "graph already compiled; create a new context for a new pattern");
     c->n_ops = n_ops;
-    c->src.assign(src, src + n_ops); c->src2.assign(src2, src2 + n_ops);
-    c->result.assign(result, result + n_ops); c->result2.assign(result2, result2 + n_ops);
-    c->op.assign(op, op + n_ops);
+    c->src.resize(n_ops); c->src2.resize(n_ops); c->result.resize(n_ops); c->result2.resize(n_ops); c->op.resize(n_ops);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_ops; i++) { c->src[i] = src[i]; c->src2[i] = src2[i]; c->result[i] = result[i]; c->result2[i] = result2[i]; c->op[i] = op[i]; }
     if (block_row && block_col) {
         if (!c->have_blocks) return fail(SOGLU_ERR_ARG, "soglu_set_blocks must precede soglu_set_graph when block coordinates are passed");
         c->brow.assign(block_row, block_row + c->n_ids);

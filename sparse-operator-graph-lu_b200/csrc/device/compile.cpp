@@ -18,6 +18,11 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <utility>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace soglu {
 namespace {
@@ -50,6 +55,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         t_last = t1;
     };
     if (n_ids < 1) return "n_block_ids must be >= 1";
+    if (n_ops > 0x7fffffff) return "too many operations";
     std::vector<IdInfo> info(n_ids);
     for (int64_t k = 0; k < n_input; k++) {
         int32_t id = input_ids[k];
@@ -59,57 +65,97 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     for (int32_t id : keep_ids)
         if (id > 0 && id < n_ids) info[id].keep = true;
 
+    // ---- validation + per-block writer / reader statistics --------------------------------------
+    // All passes over the op list run on every host thread; where the serial order matters (first writer
+    // of a block, first inverse of a factor, the lowest offending op) it is recovered with atomic minima.
     auto bad_id = [&](int32_t id) { return id < 0 || id >= n_ids; };
-    for (int64_t i = 0; i < n_ops; i++) {
-        uint8_t o = op[i];
-        if (!(o == OP_LU || o == OP_LOWERINV || o == OP_UPPERINV || o == OP_SUB || o == OP_MUL || o == OP_MULNEG || o == OP_LLT || o == OP_MULT)) {
-            snprintf(msg, sizeof msg, "op %lld: unsupported op code %d", (long long)i, (int)o);
-            return msg;
-        }
-        if (bad_id(src[i]) || bad_id(src2[i]) || bad_id(result[i]) || bad_id(result2[i]) || result[i] <= 0) {
-            snprintf(msg, sizeof msg, "op %lld: block id out of range", (long long)i);
-            return msg;
-        }
+    auto is_acc = [](uint8_t o) { return o == OP_MUL || o == OP_MULNEG || o == OP_MULT; };
+    auto op_error = [&](int64_t i) -> const char* {          // checks that need no other op
+        const uint8_t o = op[i];
+        if (!(o == OP_LU || o == OP_LOWERINV || o == OP_UPPERINV || o == OP_SUB || o == OP_MUL || o == OP_MULNEG || o == OP_LLT || o == OP_MULT))
+            return "unsupported op code";
+        if (bad_id(src[i]) || bad_id(src2[i]) || bad_id(result[i]) || bad_id(result2[i]) || result[i] <= 0) return "block id out of range";
         if (o == OP_LU && result2[i] <= 0) return "lu without second result";
-        if (src[i] == result[i] || src2[i] == result[i] || (result2[i] > 0 && (src[i] == result2[i] || result2[i] == result[i]))) {
-            snprintf(msg, sizeof msg, "op %lld reads its own result", (long long)i);
+        if (src[i] == result[i] || src2[i] == result[i] || (result2[i] > 0 && (src[i] == result2[i] || result2[i] == result[i])))
+            return "reads its own result";
+        if (info[result[i]].is_input || (o == OP_LU && info[result2[i]].is_input)) return "writes an input block";
+        return nullptr;
+    };
+    auto atomic_min = [](int64_t* p, int64_t v) {
+        int64_t cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+        while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    };
+    const int64_t NONE = INT64_MAX;
+#pragma omp parallel for schedule(static)
+    for (int64_t id = 0; id < n_ids; id++) info[id].first_writer = NONE;
+    {
+        int64_t first_bad = n_ops;
+#pragma omp parallel for schedule(static) reduction(min : first_bad)
+        for (int64_t i = 0; i < n_ops; i++) {
+            if (op_error(i)) { first_bad = std::min(first_bad, i); continue; }
+            const int32_t rs[2] = {result[i], op[i] == OP_LU ? result2[i] : 0};
+            for (int32_t r : rs) {
+                if (r <= 0) continue;
+                __atomic_fetch_add(&info[r].n_writers, 1, __ATOMIC_RELAXED);
+                atomic_min(&info[r].first_writer, i);
+            }
+            if (src[i] > 0) __atomic_fetch_add(&info[src[i]].n_readers, 1, __ATOMIC_RELAXED);
+            if (src2[i] > 0 && src2[i] != src[i]) __atomic_fetch_add(&info[src2[i]].n_readers, 1, __ATOMIC_RELAXED);
+        }
+        if (first_bad < n_ops) {
+            const char* what = op_error(first_bad);
+            if (std::string(what) == "unsupported op code") snprintf(msg, sizeof msg, "op %lld: unsupported op code %d", (long long)first_bad, (int)op[first_bad]);
+            else if (std::string(what) == "writes an input block")
+                snprintf(msg, sizeof msg, "op %lld writes input block %d", (long long)first_bad,
+                         info[result[first_bad]].is_input ? result[first_bad] : result2[first_bad]);
+            else if (std::string(what) == "lu without second result") snprintf(msg, sizeof msg, "lu without second result");
+            else if (std::string(what) == "reads its own result") snprintf(msg, sizeof msg, "op %lld reads its own result", (long long)first_bad);
+            else snprintf(msg, sizeof msg, "op %lld: %s", (long long)first_bad, what);
             return msg;
         }
-        int32_t rs[2] = {result[i], o == OP_LU ? result2[i] : 0};
-        for (int32_t r : rs) {
-            if (r <= 0) continue;
-            IdInfo& w = info[r];
-            if (w.is_input) { snprintf(msg, sizeof msg, "op %lld writes input block %d", (long long)i, r); return msg; }
-            if (w.n_writers == 0) { w.first_writer = i; w.kind = o; }
-            else {
-                bool acc = (o == OP_MUL || o == OP_MULNEG || o == OP_MULT);
-                if (w.kind != o || !acc) {
-                    snprintf(msg, sizeof msg, "block %d has writers of mixed or non-accumulating kinds", r);
-                    return msg;
-                }
-            }
-            w.n_writers++;
-        }
-        if (src[i] > 0) info[src[i]].n_readers++;
-        if (src2[i] > 0 && src2[i] != src[i]) info[src2[i]].n_readers++;
     }
-
+#pragma omp parallel for schedule(static)
+    for (int64_t id = 0; id < n_ids; id++) {
+        IdInfo& w = info[id];
+        if (w.first_writer == NONE) w.first_writer = -1;
+        else w.kind = op[w.first_writer];
+    }
+    {
+        // several writers of one block must all be accumulating ops of one kind
+        int64_t first_bad = n_ops;
+#pragma omp parallel for schedule(static) reduction(min : first_bad)
+        for (int64_t i = 0; i < n_ops; i++) {
+            const int32_t rs[2] = {result[i], op[i] == OP_LU ? result2[i] : 0};
+            for (int32_t r : rs)
+                if (r > 0 && info[r].n_writers > 1 && (info[r].kind != op[i] || !is_acc(op[i]))) first_bad = std::min(first_bad, i);
+        }
+        if (first_bad < n_ops) {
+            int32_t r = result[first_bad];
+            if (!(info[r].n_writers > 1 && (info[r].kind != op[first_bad] || !is_acc(op[first_bad])))) r = result2[first_bad];
+            snprintf(msg, sizeof msg, "block %d has writers of mixed or non-accumulating kinds", r);
+            return msg;
+        }
+    }
     lap("validate + id info");
+
     // ---- fusion decisions ------------------------------------------------------------
     std::vector<int64_t> fused_sub_of(opt.fuse_sub ? n_ids : 0, -1);  // product id -> index of the sub op
     if (opt.fuse_sub) {
+        int64_t nf = 0;
+#pragma omp parallel for schedule(static) reduction(+ : nf)
         for (int64_t i = 0; i < n_ops; i++) {
             if (op[i] != OP_SUB) continue;
             int32_t p = src[i];
             if (p <= 0) continue;
-            IdInfo& w = info[p];
+            IdInfo& w = info[p];     // read by this sub only (n_readers == 1): no other thread touches it
             if (w.is_input || w.keep || w.n_writers == 0 || w.n_readers != 1) continue;
             if (!(w.kind == OP_MUL || w.kind == OP_MULNEG || w.kind == OP_MULT)) continue;
             if (src2[i] == p) continue;
             w.fused_away = true;
             fused_sub_of[p] = i;
-            G.fused_subs++;
+            nf++;
         }
+        G.fused_subs = nf;
     }
 
     // Inverses: (a) every further lowerInv / upperInv of a block that already has one is the
@@ -118,124 +164,176 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     // 1035-1036, 1081-1082); (b) the first inverse of an lu factor is folded into the lu task.
     std::vector<char> op_fused(n_ops, 0);                 // 1 = folded into an lu task, 2 = alias
     std::vector<int32_t> alias_to(n_ids, 0);              // result id -> canonical result id
-    std::vector<int64_t> inv_of(n_ids, -1);               // source id -> first inverse op
-    for (int64_t i = 0; i < n_ops; i++) {
-        if (op[i] != OP_LOWERINV && op[i] != OP_UPPERINV) continue;
-        const int32_t f = src[i];
-        if (f <= 0) continue;
-        if (inv_of[f] >= 0) {
-            if (op[inv_of[f]] == op[i] && opt.fuse_inv && !info[result[i]].keep) {
-                alias_to[result[i]] = result[inv_of[f]];
-                op_fused[i] = 2;
-                G.aliased_invs++;
+    std::vector<int64_t> inv_of(n_ids, NONE);             // source id -> first inverse op
+    {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n_ops; i++)
+            if ((op[i] == OP_LOWERINV || op[i] == OP_UPPERINV) && src[i] > 0) atomic_min(&inv_of[src[i]], i);
+#pragma omp parallel for schedule(static)
+        for (int64_t id = 0; id < n_ids; id++)
+            if (inv_of[id] == NONE) inv_of[id] = -1;
+        int64_t n_alias = 0, n_fused = 0;
+#pragma omp parallel for schedule(static) reduction(+ : n_alias, n_fused)
+        for (int64_t i = 0; i < n_ops; i++) {
+            if (op[i] != OP_LOWERINV && op[i] != OP_UPPERINV) continue;
+            const int32_t f = src[i];
+            if (f <= 0) continue;
+            const int64_t first = inv_of[f];
+            if (first != i) {
+                if (op[first] == op[i] && opt.fuse_inv && !info[result[i]].keep) {
+                    alias_to[result[i]] = result[first];
+                    op_fused[i] = 2;
+                    n_alias++;
+                }
+                continue;
             }
-            continue;
+            if (!opt.fuse_inv) continue;
+            const IdInfo& w = info[f];
+            if (w.n_writers != 1 || w.kind != OP_LU) continue;
+            const int64_t lu_i = w.first_writer;
+            // lowerInv must read the L result, upperInv the U result of that lu
+            if (op[i] == OP_LOWERINV ? (result[lu_i] != f) : (result2[lu_i] != f)) continue;
+            op_fused[i] = 1;
+            n_fused++;
         }
-        inv_of[f] = i;
-        if (!opt.fuse_inv) continue;
-        const IdInfo& w = info[f];
-        if (w.n_writers != 1 || w.kind != OP_LU) continue;
-        const int64_t lu_i = w.first_writer;
-        // lowerInv must read the L result, upperInv the U result of that lu
-        if (op[i] == OP_LOWERINV ? (result[lu_i] != f) : (result2[lu_i] != f)) continue;
-        op_fused[i] = 1;
-        G.fused_invs++;
+        G.aliased_invs = n_alias;
+        G.fused_invs = n_fused;
     }
-
     lap("fusion decisions");
+
     // ---- one task per produced block (lu: one task, two blocks) -------------------------
     // task order = order of the first contributing op, i.e. the reference's stage order
     G.task_of.assign(n_ids, -1);
     G.slot_of.assign(n_ids, 0);
-    std::vector<int64_t> pair_count;  // per task
-    for (int64_t i = 0; i < n_ops; i++) {
-        int32_t r = result[i];
-        IdInfo& w = info[r];
-        if (w.first_writer != i) continue;     // only the first writer opens a task
-        if (w.fused_away) continue;            // opened by its sub instead
-        if (op_fused[i]) continue;             // inverse folded into its lu task
-        Task t = {};
-        t.out = r;                              // block ids for now; slots are patched below
-        t.n_pairs = 1;
-        switch (op[i]) {
-            case OP_LU:
-                t.type = T_LU;
-                t.out2 = result2[i];
-                if (inv_of[r] >= 0 && op_fused[inv_of[r]] == 1) { t.flags |= TF_LINV; t.init = result[inv_of[r]]; }
-                if (inv_of[result2[i]] >= 0 && op_fused[inv_of[result2[i]]] == 1) { t.flags |= TF_UINV; t.out4 = result[inv_of[result2[i]]]; }
-                break;
-            case OP_LLT: t.type = T_LLT; break;
-            case OP_LOWERINV: t.type = T_LOWERINV; break;
-            case OP_UPPERINV: t.type = T_UPPERINV; break;
-            case OP_MUL: t.type = T_GEMM; t.n_pairs = w.n_writers; break;
-            case OP_MULNEG: t.type = T_GEMM; t.flags = TF_NEGATE; t.n_pairs = w.n_writers; break;
-            case OP_MULT: t.type = T_GEMM; t.flags = TF_TRANSB; t.n_pairs = w.n_writers; break;
-            case OP_SUB: {
-                int32_t p = src[i];
-                if (p > 0 && info[p].fused_away && fused_sub_of[p] == i) {
-                    const IdInfo& pw = info[p];
-                    t.type = T_GEMM;
-                    t.n_pairs = pw.n_writers;
-                    t.flags = (pw.kind == OP_MULNEG ? 0 : TF_NEGATE) | (pw.kind == OP_MULT ? TF_TRANSB : 0);
-                    if (src2[i] > 0) { t.flags |= TF_INIT; t.init = src2[i]; }
-                } else {
-                    t.type = T_SUB;
+    auto opens_task = [&](int64_t i) {
+        const IdInfo& w = info[result[i]];
+        return w.first_writer == i && !w.fused_away && !op_fused[i];   // fused products are opened by their sub, folded inverses by their lu
+    };
+    {
+        int nth = 1;
+#ifdef _OPENMP
+        nth = omp_get_max_threads();
+#endif
+        const int64_t chunk = (n_ops + nth - 1) / nth;
+        std::vector<int64_t> first_task(nth + 1, 0);
+#pragma omp parallel for schedule(static, 1) num_threads(nth)
+        for (int c = 0; c < nth; c++) {
+            int64_t k = 0;
+            for (int64_t i = c * chunk, e = std::min(n_ops, i + chunk); i < e; i++) k += opens_task(i);
+            first_task[c + 1] = k;
+        }
+        for (int c = 0; c < nth; c++) first_task[c + 1] += first_task[c];
+        if (first_task[nth] > 0x7fffffff) return "too many tasks";
+        G.tasks.resize(first_task[nth]);
+#pragma omp parallel for schedule(static, 1) num_threads(nth)
+        for (int c = 0; c < nth; c++) {
+            int64_t tid = first_task[c];
+            for (int64_t i = c * chunk, e = std::min(n_ops, i + chunk); i < e; i++) {
+                if (!opens_task(i)) continue;
+                const int32_t r = result[i];
+                const IdInfo& w = info[r];
+                Task t = {};
+                t.out = r;                              // block ids for now; slots are patched below
+                t.n_pairs = 1;
+                switch (op[i]) {
+                    case OP_LU:
+                        t.type = T_LU;
+                        t.out2 = result2[i];
+                        if (inv_of[r] >= 0 && op_fused[inv_of[r]] == 1) { t.flags |= TF_LINV; t.init = result[inv_of[r]]; }
+                        if (inv_of[result2[i]] >= 0 && op_fused[inv_of[result2[i]]] == 1) { t.flags |= TF_UINV; t.out4 = result[inv_of[result2[i]]]; }
+                        break;
+                    case OP_LLT: t.type = T_LLT; break;
+                    case OP_LOWERINV: t.type = T_LOWERINV; break;
+                    case OP_UPPERINV: t.type = T_UPPERINV; break;
+                    case OP_MUL: t.type = T_GEMM; t.n_pairs = w.n_writers; break;
+                    case OP_MULNEG: t.type = T_GEMM; t.flags = TF_NEGATE; t.n_pairs = w.n_writers; break;
+                    case OP_MULT: t.type = T_GEMM; t.flags = TF_TRANSB; t.n_pairs = w.n_writers; break;
+                    case OP_SUB: {
+                        int32_t p = src[i];
+                        if (p > 0 && info[p].fused_away && fused_sub_of[p] == i) {
+                            const IdInfo& pw = info[p];
+                            t.type = T_GEMM;
+                            t.n_pairs = pw.n_writers;
+                            t.flags = (pw.kind == OP_MULNEG ? 0 : TF_NEGATE) | (pw.kind == OP_MULT ? TF_TRANSB : 0);
+                            if (src2[i] > 0) { t.flags |= TF_INIT; t.init = src2[i]; }
+                        } else {
+                            t.type = T_SUB;
+                        }
+                        break;
+                    }
                 }
-                break;
+                G.task_of[r] = (int32_t)tid;
+                if (t.type == T_LU) {
+                    G.task_of[t.out2] = (int32_t)tid;
+                    if (t.flags & TF_LINV) G.task_of[t.init] = (int32_t)tid;
+                    if (t.flags & TF_UINV) G.task_of[t.out4] = (int32_t)tid;
+                }
+                G.tasks[tid++] = t;
             }
         }
-        int32_t tid = (int32_t)G.tasks.size();
-        G.task_of[r] = tid;
-        if (t.type == T_LU) {
-            G.task_of[t.out2] = tid;
-            if (t.flags & TF_LINV) G.task_of[t.init] = tid;
-            if (t.flags & TF_UINV) G.task_of[t.out4] = tid;
-        }
-        G.tasks.push_back(t);
     }
     int64_t nt = (int64_t)G.tasks.size();
     // redirect fused products to the task of their sub's result
-    if (opt.fuse_sub)
+    if (opt.fuse_sub) {
+#pragma omp parallel for schedule(static)
         for (int64_t id = 1; id < n_ids; id++)
             if (info[id].fused_away) G.task_of[id] = G.task_of[result[fused_sub_of[id]]];
-
+    }
     // (pool slots are assigned after the pairs are known: recycling needs every block's last reader)
+#pragma omp parallel for schedule(static)
     for (int64_t id = 1; id < n_ids; id++)
         if (alias_to[id]) G.task_of[id] = G.task_of[alias_to[id]];
-
     lap("tasks");
+
     // ---- pairs ------------------------------------------------------------------------------
     {
         int64_t total = 0;
         for (Task& t : G.tasks) { t.pair_begin = (int32_t)total; total += t.n_pairs; }
         if (total > 0x7fffffff) return "too many operand pairs";
         G.pairs.assign(total, Pair{0, 0});
-        std::vector<int32_t> fill(nt, 0);
+        // the operands of an accumulation chain are summed in op-list order: threads claim positions atomically
+        // and every chain is then put back into op order
+        BigVec<int32_t> fill(nt, 0), pair_op(total);
+        double flops = 0;
+        int64_t gemm_pairs = 0;
+#pragma omp parallel for schedule(static) reduction(+ : flops, gemm_pairs)
         for (int64_t i = 0; i < n_ops; i++) {
-            int32_t r = result[i];
-            uint8_t o = op[i];
-            int32_t tid;
-            if (o == OP_MUL || o == OP_MULNEG || o == OP_MULT) {
-                tid = G.task_of[r];   // own task, or the fused sub's task
-                Task& t = G.tasks[tid];
-                G.pairs[t.pair_begin + fill[tid]++] = Pair{src[i], src2[i]};
-                G.flops += 524288.0;
-                G.n_gemm_pairs++;
+            const int32_t tid = G.task_of[result[i]];   // own task, or the task the op was folded into
+            const uint8_t o = op[i];
+            Task& t = G.tasks[tid];
+            if (is_acc(o)) {
+                const int32_t k = __atomic_fetch_add(&fill[tid], 1, __ATOMIC_RELAXED);
+                if (k < t.n_pairs) { G.pairs[t.pair_begin + k] = Pair{src[i], src2[i]}; pair_op[t.pair_begin + k] = (int32_t)i; }
+                flops += 524288.0;
+                gemm_pairs++;
             } else if (o == OP_SUB) {
-                tid = G.task_of[r];
-                Task& t = G.tasks[tid];
-                G.flops += 4096.0;
+                flops += 4096.0;
                 if (t.type == T_SUB) G.pairs[t.pair_begin] = Pair{src2[i], src[i]};   // a = S2, b = S1
             } else {
-                tid = G.task_of[r];
-                if (!op_fused[i]) G.pairs[G.tasks[tid].pair_begin] = Pair{src[i], 0};
-                G.flops += (o == OP_LU) ? 174763.0 : 87381.0;
+                if (!op_fused[i]) G.pairs[t.pair_begin] = Pair{src[i], 0};
+                flops += (o == OP_LU) ? 174763.0 : 87381.0;
             }
         }
-        for (int64_t t = 0; t < nt; t++)
-            if (G.tasks[t].type == T_GEMM && fill[t] != G.tasks[t].n_pairs) return "internal: pair count mismatch";
+        G.flops = flops;           // sums of integers below 2^53: exact in any order
+        G.n_gemm_pairs = gemm_pairs;
+        int mismatch = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(| : mismatch)
+        for (int64_t t = 0; t < nt; t++) {
+            const Task& T = G.tasks[t];
+            if (T.type != T_GEMM) continue;
+            if (fill[t] != T.n_pairs) { mismatch = 1; continue; }
+            const int32_t n = T.n_pairs, pb = T.pair_begin;
+            bool sorted = true;
+            for (int32_t k = 1; k < n; k++) sorted = sorted && pair_op[pb + k - 1] < pair_op[pb + k];
+            if (sorted) continue;
+            // small insertion sort by op index (chains are short: up to a few hundred operands)
+            std::vector<std::pair<int32_t, Pair>> tmp(n);
+            for (int32_t k = 0; k < n; k++) tmp[k] = {pair_op[pb + k], G.pairs[pb + k]};
+            std::sort(tmp.begin(), tmp.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            for (int32_t k = 0; k < n; k++) G.pairs[pb + k] = tmp[k].second;
+        }
+        if (mismatch) return "internal: pair count mismatch";
     }
-
     lap("pairs");
     // ---- multi-GPU: owners, mirrors of remote blocks and their fetch tasks ---------------------------
     // A task runs on the GPU that owns its result block.  A produced block that a GPU reads at least
@@ -307,7 +405,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                 });
             }
             // merged task order: every task followed by the fetch tasks of the blocks it completes
-            std::vector<Task> merged;
+            BigVec<Task> merged;
             merged.reserve(nt + (nid - n_ids));
             std::vector<int32_t> new_index(nt);
             std::vector<int8_t> town2;
@@ -441,7 +539,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     // predecessor lists in one flat array (capacity = operand count per task), sorted and made unique per task
     std::vector<int64_t> poff(nt + 1, 0);
     for (int64_t t = 0; t < nt; t++) poff[t + 1] = poff[t] + 2 * (int64_t)G.tasks[t].n_pairs + ((G.tasks[t].flags & TF_INIT) ? 1 : 0);
-    std::vector<int32_t> pflat(poff[nt]);
+    BigVec<int32_t> pflat(poff[nt]);
     std::vector<int32_t> pcnt(nt, 0);
     {
         int order_error = 0;
@@ -467,48 +565,47 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             }
             pcnt[t] = n;
         }
+        lap("  deps: pred lists");
         if (order_error) return "operation list is not in dependency order (a block is read before its producer's first op)";
         int64_t nsucc = 0;
         for (int64_t t = 0; t < nt; t++) { G.tasks[t].n_deps = pcnt[t]; nsucc += pcnt[t]; }
         if (nsucc > 0x7fffffff) return "too many dependency edges";
-        std::vector<int32_t> cnt(nt + 1, 0);
+        // transpose (predecessor lists -> successor lists): positions are claimed atomically, then every list is
+        // sorted, which restores the ascending task order a serial pass would give
+        BigVec<int32_t> cnt(nt + 1, 0);
+#pragma omp parallel for schedule(static)
         for (int64_t t = 0; t < nt; t++) {
             const int32_t* v = pflat.data() + poff[t];
-            for (int32_t k = 0; k < pcnt[t]; k++) cnt[v[k] + 1]++;
+            for (int32_t k = 0; k < pcnt[t]; k++) __atomic_fetch_add(&cnt[v[k] + 1], 1, __ATOMIC_RELAXED);
         }
         for (int64_t t = 0; t < nt; t++) cnt[t + 1] += cnt[t];
+        lap("  deps: count");
         G.succ.assign(nsucc, 0);
-        std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
-        for (int64_t t = 0; t < nt; t++) {
-            const int32_t* v = pflat.data() + poff[t];
-            for (int32_t k = 0; k < pcnt[t]; k++) G.succ[pos[v[k]]++] = (int32_t)t;
+        {
+            BigVec<int32_t> pos(cnt.begin(), cnt.end() - 1);
+#pragma omp parallel for schedule(static)
+            for (int64_t t = 0; t < nt; t++) {
+                const int32_t* v = pflat.data() + poff[t];
+                for (int32_t k = 0; k < pcnt[t]; k++) G.succ[__atomic_fetch_add(&pos[v[k]], 1, __ATOMIC_RELAXED)] = (int32_t)t;
+            }
         }
+        lap("  deps: fill");
+#pragma omp parallel for schedule(dynamic, 4096)
+        for (int64_t t = 0; t < nt; t++)
+            if (cnt[t + 1] - cnt[t] > 1) std::sort(G.succ.begin() + cnt[t], G.succ.begin() + cnt[t + 1]);
         for (int64_t t = 0; t < nt; t++) { G.tasks[t].succ_begin = cnt[t]; G.tasks[t].succ_end = cnt[t + 1]; }
     }
     lap("dependencies");
-    // ---- levels (Kahn) + cycle check -----------------------------------------------------------
+    // ---- levels: longest path from a source (every predecessor precedes its task, checked above) -----------
     {
-        std::vector<int32_t> deg(nt);
-        std::vector<int32_t> queue;
-        queue.reserve(nt);
-        for (int64_t t = 0; t < nt; t++) {
-            deg[t] = G.tasks[t].n_deps;
-            if (deg[t] == 0) { queue.push_back((int32_t)t); G.tasks[t].level = 0; }
-        }
-        G.initial = queue;
-        size_t head = 0;
         int32_t maxlev = 0;
-        while (head < queue.size()) {
-            int32_t t = queue[head++];
-            int32_t lv = G.tasks[t].level;
+        for (int64_t t = 0; t < nt; t++) {
+            const int32_t* v = pflat.data() + poff[t];
+            int32_t lv = 0;
+            for (int32_t k = 0; k < pcnt[t]; k++) lv = std::max(lv, G.tasks[v[k]].level + 1);
+            G.tasks[t].level = lv;
             maxlev = std::max(maxlev, lv);
-            for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
-                int32_t s = G.succ[e];
-                G.tasks[s].level = std::max(G.tasks[s].level, lv + 1);
-                if (--deg[s] == 0) queue.push_back(s);
-            }
         }
-        if ((int64_t)queue.size() != nt) return "operation list has a dependency cycle";
         // levels restart in every segment: make them globally increasing (segment order)
         const int nseg = (int)G.seg_begin.size() - 1;
         if (nseg > 1) {
@@ -548,7 +645,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             // decrements each successor group once, so a group waits for every slice of every predecessor, and the
             // slices share their task's successor list (no edge multiplication).
             const int64_t nt2 = base[nt];
-            std::vector<Task> tasks2(nt2);
+            BigVec<Task> tasks2(nt2);
 #pragma omp parallel for schedule(static)
             for (int64_t t = 0; t < nt; t++) {
                 const Task& T = G.tasks[t];
@@ -569,13 +666,15 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             for (int64_t e = 0; e < (int64_t)G.succ.size(); e++) G.succ[e] = base[G.succ[e]];
             {
                 std::vector<int8_t> own2(nt2);
+#pragma omp parallel for schedule(static)
                 for (int64_t t = 0; t < nt; t++)
                     for (int q = 0; q < split[t]; q++) own2[base[t] + q] = G.task_owner[t];
                 G.task_owner.swap(own2);
             }
             G.tasks.swap(tasks2);
-            for (int32_t& x : G.task_of)
-                if (x >= 0) x = base[x];
+#pragma omp parallel for schedule(static)
+            for (int64_t id = 0; id < (int64_t)G.task_of.size(); id++)
+                if (G.task_of[id] >= 0) G.task_of[id] = base[G.task_of[id]];
             for (int32_t& b : G.seg_begin) b = base[b];
         }
     }
@@ -677,25 +776,27 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             if (id <= 0 || G.slot_of[id] <= 0) return make_ref(reader, 0);     // the reader's own zero block
             return make_ref(G.owner_of[id], G.slot_of[id]);
         };
-        // pairs are shared by the row slices of one task: patch them once, per first slice
-        std::vector<char> pdone(G.pairs.size(), 0);
-        for (size_t t = 0; t < G.tasks.size(); t++) {
+        // pairs are shared by the row slices of one task: the leading slice patches them
+#pragma omp parallel for schedule(static)
+        for (int64_t t = 0; t < (int64_t)G.tasks.size(); t++) {
             Task& T = G.tasks[t];
             const int o = G.task_owner[t];
             T.out = ref(T.out, o);
             if (T.type == T_LU) T.out2 = ref(T.out2, o);
             if (T.flags & (TF_INIT | TF_LINV)) T.init = ref(T.init, o);
             if (T.flags & TF_UINV) T.out4 = ref(T.out4, o);
+            if (!task_is_leader(T)) continue;
             for (int32_t k = 0; k < T.n_pairs; k++) {
                 const size_t q = (size_t)T.pair_begin + k;
-                if (pdone[q]) continue;
-                pdone[q] = 1;
                 G.pairs[q].a = ref(G.pairs[q].a, o);
                 G.pairs[q].b = ref(G.pairs[q].b, o);
             }
         }
-        for (Task& T : G.tasks)
+#pragma omp parallel for schedule(static)
+        for (int64_t t = 0; t < (int64_t)G.tasks.size(); t++) {
+            Task& T = G.tasks[t];
             for (int k = 0; k < 2; k++) T.first[k] = (k < T.n_pairs) ? G.pairs[T.pair_begin + k] : Pair{0, 0};
+        }
     }
     lap("patch refs");
     return "";

@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include "../bigalloc.h"
+
 namespace soglu {
 
 // ---- block layout in HBM ---------------------------------------------------------------
@@ -81,9 +83,9 @@ inline bool task_is_leader(const Task& t) { return t.type != T_GEMM || ((t.flags
 inline int task_log2_slices(const Task& t) { const int g = task_group_size(t); return g == 4 ? 2 : (g == 2 ? 1 : 0); }
 
 struct TaskGraph {
-    std::vector<Task> tasks;
-    std::vector<Pair> pairs;
-    std::vector<int32_t> succ;          // successor GROUP leaders (task indices); the slices of one task share their list
+    BigVec<Task> tasks;
+    BigVec<Pair> pairs;
+    BigVec<int32_t> succ;          // successor GROUP leaders (task indices); the slices of one task share their list
     std::vector<int32_t> initial;       // tasks with n_deps == 0, in task order
     std::vector<int32_t> slot_of;       // block id -> pool slot (0 = zero block / none)
     std::vector<int32_t> task_of;       // block id -> producing task (-1 = input / none)
@@ -96,7 +98,7 @@ struct TaskGraph {
                                         // initially-ready tasks, then the others
     std::vector<int32_t> seg_nhi;       // per segment: number of high-priority tasks (length of its hi queue)
     std::vector<int32_t> seg_hi_ctas;   // per segment: CTAs (per GPU) dedicated to the hi queue
-    std::vector<int32_t> succ_enc;      // succ with the successor's priority bit (single-GPU upload)
+    BigVec<int32_t> succ_enc;           // succ with the successor's priority bit (single-GPU upload)
     int64_t n_hi = 0;                   // high-priority tasks
     double hi_threshold_us = 0, critical_path_us = 0;
     std::vector<uint8_t> recycled;      // block id -> its slot is reused later (contents do not survive)
@@ -141,9 +143,9 @@ struct DistLayout {     // one GPU's share of an owner-compiled TaskGraph
     std::vector<int8_t> task_owner;      // global task -> owner
     std::vector<int32_t> task_local;     // global task -> index in the owner's task array
     std::vector<int64_t> tasks_per_rank, slots_per_rank;
-    std::vector<Task> tasks;             // successor ids rewritten to make_ref(owner, local task)
-    std::vector<Pair> pairs;
-    std::vector<int32_t> succ;
+    BigVec<Task> tasks;                  // successor ids rewritten to make_ref(owner, local task)
+    BigVec<Pair> pairs;
+    BigVec<int32_t> succ;
     std::vector<int32_t> initial;        // local task ids, grouped by segment
     std::vector<int32_t> seg_begin, seg_init, seg_nhi;   // as in TaskGraph, for this GPU's tasks
     std::vector<std::vector<int32_t>> seg_begin_all;     // [owner][segment] first local task (peers' queue slices)

@@ -25,7 +25,6 @@
 #include <sstream>
 #include <chrono>
 #include <cstdlib>
-#include <sys/mman.h>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -537,25 +536,6 @@ bool BlockValues::alloc_zero(size_t n_blocks) {
 #pragma omp parallel for schedule(static)
     for (int64_t b = 0; b < (int64_t)n_blocks; b++) std::memset(p_ + (size_t)b * 4096, 0, 4096 * sizeof(double));
     return true;
-}
-
-void* big_alloc(size_t bytes) {
-    if (bytes < (size_t(8) << 20)) {
-        void* p = std::malloc(bytes ? bytes : 1);
-        if (!p) throw std::bad_alloc();
-        return p;
-    }
-    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-    if (p == MAP_FAILED) throw std::bad_alloc();
-#ifdef MADV_HUGEPAGE
-    madvise(p, bytes, MADV_HUGEPAGE);
-#endif
-    return p;
-}
-void big_free(void* p, size_t bytes) {
-    if (!p) return;
-    if (bytes < (size_t(8) << 20)) std::free(p);
-    else munmap(p, bytes);
 }
 
 double factor_flops(const OpVec& ops) {

@@ -14,9 +14,9 @@
 #include <cstdint>
 #include <string>
 #include <cstdlib>
-#include <new>
-#include <utility>
 #include <vector>
+
+#include "../bigalloc.h"
 
 namespace soglu {
 
@@ -77,23 +77,8 @@ struct Op {                 // one DAG node; mirrors struct operation (operation
 };
 struct BlockRef { int32_t id, brow, bcol; };
 
-// Large host arrays (op lists of 10^8 entries): anonymous mappings advised to use 2 MiB pages, elements
-// default-initialised (no zero fill pass; fresh mappings are zero anyway).  Small sizes use malloc.
-void* big_alloc(size_t bytes);
-void big_free(void* p, size_t bytes);
-template <class T>
-struct BigAlloc {
-    using value_type = T;
-    BigAlloc() = default;
-    template <class U> BigAlloc(const BigAlloc<U>&) {}
-    T* allocate(size_t n) { return static_cast<T*>(big_alloc(n * sizeof(T))); }
-    void deallocate(T* p, size_t n) { big_free(p, n * sizeof(T)); }
-    template <class U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
-    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
-    template <class U> bool operator==(const BigAlloc<U>&) const { return true; }
-    template <class U> bool operator!=(const BigAlloc<U>&) const { return false; }
-};
-using OpVec = std::vector<Op, BigAlloc<Op>>;
+// the op lists (10^8 entries at n = 10^6) live in huge-page backed vectors, see bigalloc.h
+using OpVec = BigVec<Op>;
 
 // Dense values of the input blocks: one malloc, zeroed in parallel (first touch by all threads).
 class BlockValues {

@@ -26,8 +26,9 @@ int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
     int rc = soglu_set_blocks(ctx, pl.storage, n_in, in_ids.data(), pl.input_vals.data());
     if (rc) return rc;
     const int64_t n = (int64_t)pl.ops.size();
-    std::vector<int32_t> src(n), src2(n), res(n), res2(n), stg(n);
-    std::vector<uint8_t> op(n);
+    soglu::BigVec<int32_t> src(n), src2(n), res(n), res2(n), stg(n);
+    soglu::BigVec<uint8_t> op(n);
+#pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < n; k++) {
         const soglu::Op& o = pl.ops[k];
         src[k] = o.src; src2[k] = o.src2; res[k] = o.result; res2[k] = o.result2; stg[k] = o.stage; op[k] = o.op;
