@@ -445,6 +445,7 @@ struct Planner {
         pt.lap("stage numbering");
         // total order (stage, group, result, src, seq) (operation.cpp:180-196): a parallel
         // counting sort on the stage (which also drops the dead ops), then one sort per stage
+        std::vector<int64_t> start((size_t)maxstg + 2, 0);   // first op of every stage in the sorted list
         {
             int nth = 1;
 #ifdef _OPENMP
@@ -461,7 +462,6 @@ struct Planner {
                 for (int64_t i = lo; i < hi; i++)
                     if (graph[i].stage >= 0) c[graph[i].stage]++;
             }
-            std::vector<int64_t> start(S + 1, 0);
             for (size_t st = 0; st < S; st++) {
                 int64_t run = start[st];
                 for (int t = 0; t < nth; t++) {
@@ -493,22 +493,30 @@ struct Planner {
                 if (start[st + 1] - start[st] > 1) std::sort(sorted.begin() + start[st], sorted.begin() + start[st + 1], less);
         }
         pt.lap("sort");
-        // split stages wider than 8000 ops (335-354)
+        // split stages wider than 8000 ops (335-354): the reference counts ops per stage in one serial scan and
+        // bumps the stage number after every 8001st op; with the stage boundaries known that is a prefix sum over
+        // the stages.  Then the last reading stage per block (356-371), a maximum.
         {
-            int jump = 0, band = 0, stgc = 0;
-            for (int64_t i = 0; i < n; i++) {
-                Op& o = sorted[i];
-                if (o.stage > stgc) { stgc = o.stage; band = 0; }
-                if (band > 8000) { jump++; band = 0; }
-                o.stage += jump;
-                band++;
+            std::vector<int32_t> jump((size_t)maxstg + 2, 0);
+            for (int st = 0; st <= maxstg; st++) {
+                const int64_t c = start[st + 1] - start[st];
+                jump[st + 1] = jump[st] + (c > 0 ? (int32_t)((c - 1) / 8001) : 0);
             }
-        }
-        // last reading stage per block (356-371)
-        for (int64_t i = 0; i < n; i++) {
-            const Op& o = sorted[i];
-            if (o.src > 0 && laststage[o.src] < o.stage) laststage[o.src] = o.stage;
-            if (o.src2 > 0 && laststage[o.src2] < o.stage) laststage[o.src2] = o.stage;
+            int32_t* last = laststage.data();
+            auto raise = [last](int32_t id, int32_t v) {
+                int32_t cur = __atomic_load_n(last + id, __ATOMIC_RELAXED);
+                while (cur < v && !__atomic_compare_exchange_n(last + id, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+            };
+#pragma omp parallel for schedule(dynamic, 64) if (n > 200000)
+            for (int st = 0; st <= maxstg; st++) {
+                const int64_t lo = start[st], hi = start[st + 1];
+                for (int64_t i = lo; i < hi; i++) {
+                    Op& o = sorted[i];
+                    o.stage += jump[st] + (int32_t)((i - lo) / 8001);
+                    if (o.src > 0) raise(o.src, o.stage);
+                    if (o.src2 > 0) raise(o.src2, o.stage);
+                }
+            }
         }
         pt.lap("split + laststage");
     }

@@ -115,3 +115,28 @@ def test_symmetric_and_disconnected_inputs_vs_live_reference(sg, oracle, tmp_pat
     oracle.free(h)
     xref = np.fromfile(out / "x.f64")
     assert np.linalg.norm(unpermute(p, x_ext) - xref) / np.linalg.norm(xref) <= 1e-12
+
+
+def test_wide_stage_split_vs_live_reference(sg, tmp_path):
+    """3D 48^3 is the smallest Laplacian whose widest dependency stage exceeds 8000 ops, so the reference's stage
+    split (BlockPlanner.cpp:335-354) and the multi-threaded stage sort are exercised: op list (incl. stage,
+    group and sequence numbers), per-block stages and factor structure bit-exact against a LIVE reference run."""
+    harness = ref_harness_path()
+    if harness is None:
+        pytest.skip("oracle/_ref not built (or host CPU lacks AVX-512)")
+    import gen_mtx
+    n, r, c, v = gen_mtx.generate("lap3d", 48)
+    path = str(tmp_path / "m.mtx")
+    gen_mtx.write_mtx(path, n, r, c, v)
+    out = tmp_path / "ref"
+    out.mkdir()
+    subprocess.run([harness, path, str(out)], check=True, capture_output=True, env=dict(os.environ, OMP_NUM_THREADS="8"))
+    p = sg.Problem.from_mtx(path)
+    rd = lambda f, dt: np.fromfile(out / f, dtype=dt)
+    ops = p.i32("ops")
+    assert np.bincount(ops[:, 5]).max() > 8000
+    np.testing.assert_array_equal(ops, rd("ops_fine.i32", np.int32).reshape(-1, 8))
+    np.testing.assert_array_equal(p.i32("stage"), rd("stage.i32", np.int32))
+    np.testing.assert_array_equal(p.i32("laststage"), rd("laststage.i32", np.int32))
+    np.testing.assert_array_equal(p.i32("L"), rd("L.i32", np.int32).reshape(-1, 3))
+    np.testing.assert_array_equal(p.i32("U"), rd("U.i32", np.int32).reshape(-1, 3))
