@@ -250,6 +250,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     import soglu_b200 as sg
+    sg.set_host_threads(max(1, (os.cpu_count() or 8) // max(1, world)))   # every rank plans the whole problem
 
     tmp = tempfile.mkdtemp(prefix="soglu_bench_r%d_" % rank)
     path = write_workload(sg, args.workload, tmp)
@@ -404,6 +405,7 @@ def main():
             xr, _ = ctx.solve(prob, refine=1)
             accuracy = {"residual_rel": resid(x), "residual_rel_after_1_refinement": resid(xr), "nan": int(np.isnan(x).sum()),
                         "note": "||Ax-b||/||b||, north-star gate 1e-12; refinement = FP64 residual + re-solve on the device"}
+        n_segments = max(1, ctx.segments())
         line = {
             "metric": "fp64_lu_factor_solve_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong" if use_dist else "weak", "vs_baseline": None,
@@ -411,7 +413,7 @@ def main():
             "config": {"workload": WORKLOADS[args.workload][2], "name": args.workload, "n": prob.size("dim"), "ops": prob.size("n_ops"),
                        "tasks": int(first["tasks"]), "pool_blocks": int(first["pool_blocks"]),
                        "parallelism": "1 GPU" if world == 1 else "one factorisation sharded over %d GPUs: 2D block-cyclic (%dx%d grid, 16x16-block squares), owner computes, NVLink peer pulls; solve on rank 0" % ((world,) + sg.default_grid(world)),
-                       "segments": int(first.get("segments", 1) if use_dist else first["kernel_launches"]),   # executor launches per factorisation (pool recycling)
+                       "segments": n_segments,   # executor launches per factorisation (pool recycling)
                        "l2": "inputs_exceed_l2 (block pool %.1f GB >> 126 MB L2)" % (first["pool_blocks"] * 34816 * 1e-9),
                        "factor_ms": t_factor * 1e3, "solve_ms": t_solve * 1e3, "factor_gflops": flops / t_factor * 1e-9,
                        "solve_gbs": sbytes / t_solve * 1e-9, "host_plan_s": t_plan, "first_call_s": t_first},
@@ -421,7 +423,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s", "frac": achieved / (peak * world),
                          "traffic": traffic if world == 1 else None,
                          "kernel": "executor_kernel (the whole factorisation DAG: %d persistent launch(es) per step per GPU; achieved = op-list FLOPs / "
-                                   "CUDA-event time of those launches, max over ranks)" % int(first.get("segments", 1) if use_dist else max(1, (launches // max(1, args.steps)) - 2)),
+                                   "CUDA-event time of those launches, max over ranks)" % n_segments,
                          "peak_source": peak_how + ("; x %d GPUs" % world if world > 1 else "")},
             "cpu_baseline": cpu,
             "accuracy": accuracy,

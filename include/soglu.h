@@ -169,6 +169,12 @@ double* soglu_solveLU(int dim, int valcount, int symmetric, const int* index_i, 
                       const double* vals, const double* b);
 void soglu_free(void* p);
 
+/* Host threads used by the front-end (ordering is serial; planner, task compiler and the array conversions
+ * are OpenMP loops, results independent of the count).  n <= 0 restores the OpenMP default.  The reference
+ * fixes its team at min(16, cores) (BlockPlanner.cpp:376-398); launchers such as torchrun export
+ * OMP_NUM_THREADS=1, which this call overrides.  Returns the thread count in effect. */
+int soglu_set_host_threads(int n);
+
 /* synthetic generators used by bench/tests; kind: "lap2d" "lap3d" "nine2d" */
 int soglu_write_stencil_mtx(const char* kind, int nx, int ny, int nz, int symmetric, const char* path);
 

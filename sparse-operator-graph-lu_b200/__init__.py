@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "soglu_problem_from_coo", "soglu_problem_free", "soglu_problem_size", "soglu_problem_get_i32", "soglu_problem_get_f64",
     "soglu_problem_log", "soglu_load_problem", "soglu_solve_problem", "soglu_solveLU", "soglu_free", "soglu_write_stencil_mtx",
     "soglu_create_dist", "soglu_dist_blob_bytes", "soglu_dist_export", "soglu_dist_import", "soglu_dist_reset", "soglu_dist_info",
-    "soglu_dist_segments", "soglu_dist_set_segment", "soglu_set_matrix", "soglu_solve_refined",
+    "soglu_dist_segments", "soglu_dist_set_segment", "soglu_set_matrix", "soglu_solve_refined", "soglu_set_host_threads",
 ]
 
 OP_NAMES = {1: "lu", 2: "lowerInv", 3: "upperInv", 4: "sub", 8: "mul", 9: "mulneg", 10: "llt", 11: "mult"}
@@ -88,6 +88,11 @@ def lib():
     L.soglu_dist_set_segment.argtypes = [vp, ctypes.c_int]
     _lib = L
     return L
+
+
+def set_host_threads(n=0):
+    """Threads of the host front-end (planner, task compiler); n <= 0 = all cores.  Overrides OMP_NUM_THREADS."""
+    return int(lib().soglu_set_host_threads(int(n)))
 
 
 def _check(rc):
@@ -238,6 +243,10 @@ class Context:
             ui, ur, uc = c(U[:, 0]), c(U[:, 1]), c(U[:, 2])
             _check(lib().soglu_set_factors(self.h, len(li), _ptr(li), _ptr(lr), _ptr(lc), len(ui), _ptr(ui), _ptr(ur), _ptr(uc),
                                            n_block_rows, int(symmetric)))
+
+    def segments(self):
+        """Executor launches per factorisation (more than one when pool slots are recycled); valid once compiled."""
+        return int(lib().soglu_dist_segments(self.h))
 
     def factor(self):
         st = Stats()

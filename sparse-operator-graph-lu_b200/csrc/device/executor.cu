@@ -2,22 +2,30 @@
 // stage loop of BlockPlanner::calculate, BlockPlanner.cpp:376-651) and the 64x64 FP64
 // block kernels it dispatches to (MatrixStdDouble.cpp, see per-function notes).
 //
-// One CTA per SM stays resident for the whole factorisation:
-//   warp 0      scheduler + TMA producer: claims the next slot of the global ready queue,
-//               waits until a finished predecessor publishes a task there, then streams the
-//               task's operand blocks into a 3-stage shared-memory ring with cp.async.bulk
-//               (34 816 B per block, mbarrier complete_tx).  It runs ahead of the math warps,
-//               so the loads of task N+1 overlap the MMAs and the write-back of task N.
+// One CTA per SM stays resident for a whole segment of the factorisation (one segment unless the block
+// pool is smaller than the number of blocks and slots are recycled between launches):
+//   warp 0      scheduler + TMA producer: claims the next slot of its ready queue (atomicAdd on the
+//               head), spins with ld.acquire until a finishing CTA publishes a task there, reads the
+//               64-byte task record and streams the operand blocks into a 3-stage shared-memory ring
+//               with cp.async.bulk (34 816 B per block, mbarrier complete_tx).  It runs ahead of the
+//               math warps, so the loads of task N+1 overlap the MMAs and the write-back of task N.
 //   warps 1..8  math: m8n8k4 FP64 tensor-core MMAs (DMMA) for the Schur updates
-//               C = init +/- sum_p A_p*B_p with the whole accumulation chain of one target
-//               block kept in registers and written once; shared-memory right-looking
-//               LU / Cholesky / triangular inverses / subtract for the other task types.
-//               After the write-back they decrement the dependency counters of the
-//               successor tasks and publish the ones that reach zero.
+//               C = init +/- sum_p A_p*B_p, the whole accumulation chain of one target block (or of
+//               a 16- / 32-row slice of it in narrow levels) kept in registers and written once;
+//               register-resident diagonal kernels for the rest: LU that also forms L^-1 and U^-1
+//               in the same sweep (lu3_reg), triangular inverses, Cholesky, subtract.
+//               After the write-back ALL math threads walk the task's successor list: one atomicSub
+//               on the successor group's dependency counter each; the thread that brings it to zero
+//               publishes the whole group (a task, or the 2 / 4 row slices of a split GEMM task,
+//               which share their leader's counter) at the tail of the ready queue.
+// Two queues exist (high priority / bulk, CTAs [0, n_hi_ctas) serve the first); the default is
+// n_hi_ctas = 0, one FIFO queue: the priority split measured slower (negative results).
 //
-// Memory-ordering protocol (gpu scope): writer CTA: st.global data -> bar.sync ->
-// __threadfence -> atomicSub(dep) [-> __threadfence -> atomicAdd(tail) -> st.release(ready)];
-// reader CTA: ld.acquire(ready) -> fence.proxy.async -> cp.async.bulk of the data.
+// Memory-ordering protocol: writer CTA: st.global data -> bar.sync -> __threadfence ->
+// atomicSub(dep) [-> __threadfence -> atomicAdd(tail) -> st.release(ready)]; reader CTA:
+// ld.acquire(ready) -> fence.proxy.async -> cp.async.bulk of the data.  Successors on the same GPU
+// use gpu scope; successors on a peer GPU (multi-GPU run: counters, queues and block pools of the
+// peers are mapped through CUDA IPC) use system-scope fences and atomics over NVLink.
 #include "executor.cuh"
 #include "ptx.cuh"
 

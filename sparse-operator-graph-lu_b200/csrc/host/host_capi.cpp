@@ -2,6 +2,9 @@
 // Mirrors the front half of SOGLU::solveLU (solver.cpp:121-163) and decompose_solveLU
 // up to the point where the reference calls BlockPlanner::calculate (solver.cpp:50-100).
 #include "problem.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include <chrono>
 #include <cstdio>
@@ -183,6 +186,16 @@ const char* soglu_problem_log(const soglu_problem* pp) {
 }
 
 void soglu_free(void* p) { std::free(p); }
+
+int soglu_set_host_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 // Synthetic stencil matrices: natural lexicographic numbering with x
 // fastest, rows emitted in order with ascending columns, %.17g, rhs 1 + 0.25*(i mod 7).

@@ -321,3 +321,18 @@ extern "C" uint64_t soglu_debug_graph_hash(const soglu_problem* pp, int split, i
     mix(G.task_owner.data(), G.task_owner.size());
     return h;
 }
+
+// compile a raw op list (the arrays of soglu_set_blocks / soglu_set_graph / soglu_set_factors) on the host only:
+// lets the CPU tests reach every validation error of the task compiler.  out = {tasks, pairs, slots, segments}.
+extern "C" int soglu_debug_compile_raw(int64_t n_ids, int64_t n_input, const int32_t* input_ids, int64_t n_ops, const int32_t* src,
+                                       const int32_t* src2, const uint8_t* op, const int32_t* result, const int32_t* result2,
+                                       int64_t n_keep, const int32_t* keep_ids, int64_t max_slots, int64_t* out) {
+    std::vector<int32_t> keep(keep_ids, keep_ids + (keep_ids ? n_keep : 0));
+    soglu::CompileOptions co;
+    co.max_slots = max_slots;
+    soglu::TaskGraph G;
+    std::string err = soglu::compile_tasks(n_ids, n_input, input_ids, n_ops, src, src2, op, result, result2, keep, co, G);
+    if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
+    if (out) { out[0] = (int64_t)G.tasks.size(); out[1] = (int64_t)G.pairs.size(); out[2] = G.n_slots; out[3] = (int64_t)G.seg_begin.size() - 1; }
+    return SOGLU_OK;
+}

@@ -124,3 +124,77 @@ def test_release_protocol_simulation(sg, prob, split, pr, pc, nb, seed):
     assert rc == 0, L.soglu_last_error().decode()
     done, bad, total = list(out)
     assert done == total and bad == 0
+
+
+# ---- raw op lists: every validation error of the task compiler (SURVEY.md Appendix E invariants) ----------
+LU, LINV, UINV, SUB, MUL, MULNEG, LLT, MULT = 1, 2, 3, 4, 8, 9, 10, 11
+
+
+def compile_raw(sg, n_ids, inputs, ops, keep=(), max_slots=0):
+    """ops: list of (op, src, src2, result, result2)."""
+    L = sg.lib()
+    L.soglu_debug_compile_raw.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 5 + \
+                                         [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    a = np.array(ops, dtype=np.int64).reshape(-1, 5)
+    col = lambda k, dt=np.int32: np.ascontiguousarray(a[:, k], dtype=dt)
+    op, src, src2, res, res2 = col(0, np.uint8), col(1), col(2), col(3), col(4)
+    ins = np.array(inputs, dtype=np.int32)
+    kp = np.array(keep, dtype=np.int32)
+    out = (ctypes.c_int64 * 4)()
+    ptr = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    rc = L.soglu_debug_compile_raw(n_ids, len(ins), ptr(ins), len(a), ptr(src), ptr(src2), ptr(op), ptr(res), ptr(res2), len(kp), ptr(kp), max_slots, out)
+    if rc:
+        raise sg.SogluError(L.soglu_last_error().decode())
+    return dict(zip(("tasks", "pairs", "slots", "segments"), out))
+
+
+GOOD = [(LU, 1, 0, 3, 4), (LINV, 3, 0, 5, 0), (UINV, 4, 0, 6, 0), (MUL, 5, 2, 7, 0), (MUL, 2, 6, 8, 0), (MUL, 8, 7, 9, 0),
+        (SUB, 9, 1, 10, 0), (LU, 10, 0, 11, 12)]     # inputs 1, 2; one 2x2 elimination step
+
+
+def test_raw_good_list_compiles(sg):
+    s = compile_raw(sg, 13, [1, 2], GOOD, keep=[3, 4, 7, 8, 11, 12])
+    # lu + both inverses fused into one task; the product 9 is folded into the sub: 2 lu + 3 GEMM tasks, and in
+    # these narrow levels every GEMM task is split into 4 row slices
+    assert s["tasks"] == 2 + 3 * 4 and s["pairs"] == 5 and s["segments"] == 1
+
+
+@pytest.mark.parametrize("ops,n_ids,msg", [
+    ([(7, 1, 0, 3, 0)], 13, "unsupported op code 7"),
+    ([(MUL, 1, 99, 3, 0)], 13, "block id out of range"),
+    ([(MUL, 1, 2, 0, 0)], 13, "block id out of range"),
+    ([(LU, 1, 0, 3, 0)], 13, "lu without second result"),
+    ([(MUL, 3, 2, 3, 0)], 13, "reads its own result"),
+    ([(LU, 1, 0, 3, 1)], 13, "reads its own result"),
+    ([(MUL, 1, 1, 2, 0)], 13, "writes input block 2"),
+    ([(LU, 1, 0, 3, 2)], 13, "writes input block 2"),
+    ([(MUL, 1, 2, 3, 0), (MULNEG, 1, 2, 3, 0)], 13, "block 3 has writers of mixed or non-accumulating kinds"),
+    ([(SUB, 1, 2, 3, 0), (SUB, 2, 1, 3, 0)], 13, "block 3 has writers of mixed or non-accumulating kinds"),
+    ([(LU, 1, 0, 3, 4), (LU, 2, 0, 5, 4)], 13, "block 4 has writers of mixed or non-accumulating kinds"),
+    ([(MUL, 3, 2, 4, 0), (MUL, 1, 2, 3, 0)], 13, "not in dependency order"),
+])
+def test_raw_validation_errors(sg, ops, n_ids, msg):
+    with pytest.raises(sg.SogluError) as e:
+        compile_raw(sg, n_ids, [1, 2], ops)
+    assert msg in str(e.value)
+
+
+def test_raw_error_reports_the_lowest_offending_op(sg):
+    ops = [(MUL, 1, 2, 3, 0)] * 5 + [(MUL, 4, 2, 4, 0)] + [(MUL, 1, 2, 3, 0)] * 50000 + [(MUL, 5, 2, 5, 0)]
+    with pytest.raises(sg.SogluError) as e:
+        compile_raw(sg, 13, [1, 2], ops)
+    assert "op 5 reads its own result" in str(e.value)
+
+
+def test_raw_accumulation_chain_keeps_op_order(sg):
+    # 3000 products into one block: the operand pairs of the chain must stay in op-list order (rounding), whatever
+    # thread claimed them
+    ops = [(MUL, 1, 2, 3, 0)] * 3000
+    s = compile_raw(sg, 4, [1, 2], ops, keep=[3])
+    assert s["tasks"] == 4 and s["pairs"] == 3000      # one chain, four row slices sharing the 3000 pairs
+
+
+def test_raw_pool_limits(sg):
+    with pytest.raises(sg.SogluError) as e:
+        compile_raw(sg, 13, [1, 2], GOOD, keep=[3, 4, 7, 8, 11, 12], max_slots=9)
+    assert "pool too small" in str(e.value)
