@@ -316,7 +316,11 @@ def main():
 
     # ---- end to end from host buffers (pinned), H2D + D2H inside the timed region ---------------
     n_in = prob.size("n_input")
-    vals_host = torch.from_numpy(prob.f64("input_vals")).pin_memory()
+    # the matrix goes up as the planner's duplicate-free entry list (block, position, value): pinned host buffers
+    ent_in = torch.from_numpy(prob.i32("entry_block") - 1).pin_memory()
+    ent_pos = torch.from_numpy(prob.i32("entry_pos")).pin_memory()
+    vals_host = torch.from_numpy(prob.f64("entry_val")).pin_memory()
+    ent_in_np, ent_pos_np = ent_in.numpy(), ent_pos.numpy()
     ids = np.arange(1, n_in + 1, dtype=np.int32)
     b_host = torch.from_numpy(prob.f64("b_perm")).pin_memory()
     x_host = torch.empty_like(b_host).pin_memory()
@@ -326,7 +330,7 @@ def main():
     st = sg.Stats()
 
     def e2e_step():
-        ctx.set_blocks(prob.size("storage"), ids, vals_np)                                 # H2D: dense input blocks (every rank: it keeps its share)
+        ctx.set_blocks_sparse(prob.size("storage"), ids, ent_in_np, ent_pos_np, vals_np)   # H2D: matrix entries (every rank: it keeps its share)
         factor()
         if rank == 0:
             rc = L.soglu_solve(ctx.h, b_np.ctypes.data_as(ctypes.c_void_p), x_np.ctypes.data_as(ctypes.c_void_p), ctypes.byref(st))  # H2D b, D2H x
@@ -343,7 +347,7 @@ def main():
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_s = reduce_max(e2e_s, "cuda" if use_dist else None)
-    h2d = float(vals_np.nbytes + b_np.nbytes)
+    h2d = float(vals_np.nbytes + ent_in_np.nbytes + ent_pos_np.nbytes + b_np.nbytes)
     d2h = float(x_np.nbytes)
     # the e2e result must be the same solution
     if rank == 0:

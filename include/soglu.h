@@ -75,6 +75,13 @@ void soglu_destroy(soglu_ctx* ctx);
  * n_block_ids = data::storageCount; the n_input blocks are the ones the planner filled. */
 int soglu_set_blocks(soglu_ctx* ctx, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids,
                      const double* input_dense_64x64_rowmajor);
+/* The same with the input blocks given as a duplicate-free entry list instead of dense arrays (the
+ * reference scatters the COO entries into its blocks one by one, BlockPlanner.cpp:1498-1519; a stencil
+ * block holds a few hundred non-zeros of 4096, so this cuts the host->device traffic ~30x): entry k sets
+ * element (entry_pos[k] / 64, entry_pos[k] % 64) of block input_ids[entry_input[k]] to vals[k]; every
+ * other element of an input block is zero.  The scatter runs on the device. */
+int soglu_set_blocks_sparse(soglu_ctx* ctx, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids,
+                            int64_t n_entries, const int32_t* entry_input, const int32_t* entry_pos, const double* vals);
 
 /* replaces data::graph (operation.h:37-52): parallel arrays, one entry per operation, in
  * the reference's scheduled order.  stage may be NULL (dependencies are derived from

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "soglu_problem_from_coo", "soglu_problem_free", "soglu_problem_size", "soglu_problem_get_i32", "soglu_problem_get_f64",
     "soglu_problem_log", "soglu_load_problem", "soglu_solve_problem", "soglu_solveLU", "soglu_free", "soglu_write_stencil_mtx",
     "soglu_create_dist", "soglu_dist_blob_bytes", "soglu_dist_export", "soglu_dist_import", "soglu_dist_reset", "soglu_dist_info",
-    "soglu_dist_segments", "soglu_dist_set_segment", "soglu_set_matrix", "soglu_solve_refined", "soglu_set_host_threads",
+    "soglu_dist_segments", "soglu_dist_set_segment", "soglu_set_matrix", "soglu_solve_refined", "soglu_set_host_threads", "soglu_set_blocks_sparse",
 ]
 
 OP_NAMES = {1: "lu", 2: "lowerInv", 3: "upperInv", 4: "sub", 8: "mul", 9: "mulneg", 10: "llt", 11: "mult"}
@@ -66,6 +66,7 @@ def lib():
     L.soglu_destroy.restype = None
     L.soglu_set_option.argtypes = [vp, cp, i64]
     L.soglu_set_blocks.argtypes = [vp, i64, i64, vp, vp]
+    L.soglu_set_blocks_sparse.argtypes = [vp, i64, i64, vp, i64, vp, vp, vp]
     L.soglu_set_graph.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.soglu_set_factors.argtypes = [vp, i64, vp, vp, vp, i64, vp, vp, vp, i32, ctypes.c_int]
     L.soglu_factor.argtypes = [vp, ctypes.POINTER(Stats)]
@@ -109,8 +110,9 @@ class Problem:
 
     _I32 = {"perm_new2old": ("dim", 1), "perm_old2new": ("dim", 1), "ops": ("n_ops", 8), "coarse_ops": ("coarse_ops", 8),
             "stage": ("storage", 1), "laststage": ("storage", 1), "block_row": ("storage", 1), "block_col": ("storage", 1),
-            "inputs": ("n_input", 3), "L": ("n_L", 3), "U": ("n_U", 3), "perm_i": ("nnz_expanded", 1), "perm_j": ("nnz_expanded", 1)}
-    _F64 = {"b": ("dim", 1), "b_perm": ("n_ext", 1), "input_vals": ("n_input", 4096), "flops": (None, 1),
+            "inputs": ("n_input", 3), "L": ("n_L", 3), "U": ("n_U", 3), "perm_i": ("nnz_expanded", 1), "perm_j": ("nnz_expanded", 1),
+            "entry_block": ("n_entries", 1), "entry_pos": ("n_entries", 1)}
+    _F64 = {"b": ("dim", 1), "b_perm": ("n_ext", 1), "input_vals": ("n_input", 4096), "entry_val": ("n_entries", 1), "flops": (None, 1),
             "t_reorder": (None, 1), "t_plan": (None, 1)}
 
     def __init__(self, handle):
@@ -224,6 +226,14 @@ class Context:
         input_ids = np.ascontiguousarray(input_ids, dtype=np.int32)
         assert dense.dtype == np.float64 and dense.flags["C_CONTIGUOUS"]
         _check(lib().soglu_set_blocks(self.h, int(n_ids), len(input_ids), _ptr(input_ids), _ptr(dense)))
+
+    def set_blocks_sparse(self, n_ids, input_ids, entry_input, entry_pos, vals):
+        """Input blocks as an entry list: vals[k] goes to element entry_pos[k] (row*64+col) of block
+        input_ids[entry_input[k]]; arrays must be contiguous int32 / float64 (pinned host memory is fine)."""
+        input_ids = np.ascontiguousarray(input_ids, dtype=np.int32)
+        for a, dt in ((entry_input, np.int32), (entry_pos, np.int32), (vals, np.float64)):
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"]
+        _check(lib().soglu_set_blocks_sparse(self.h, int(n_ids), len(input_ids), _ptr(input_ids), len(vals), _ptr(entry_input), _ptr(entry_pos), _ptr(vals)))
 
     def set_graph(self, ops, stage=None, brow=None, bcol=None):
         """ops: dict of int32 arrays src, src2, result, result2 and uint8 op."""

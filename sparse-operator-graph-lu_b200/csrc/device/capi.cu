@@ -70,6 +70,8 @@ struct soglu_ctx {
     int64_t n_ids = 0, n_input = 0;
     std::vector<int32_t> input_ids;
     DevBuf in_dense;               // staging for dense input blocks until slots are known
+    DevBuf in_entry_input, in_entry_pos, in_entry_val;   // staging for a sparse entry list (soglu_set_blocks_sparse)
+    int64_t n_entries = -1;        // >= 0: the pending inputs are an entry list
     bool inputs_pending = false;
     int64_t n_ops = 0;
     BigVec<int32_t> src, src2, result, result2;   // released once the graph is compiled
@@ -194,11 +196,19 @@ int pack_pending_inputs(soglu_ctx* c) {
     DevBuf dslots;
     int rc = upload(dslots, slots, c);
     if (rc) return rc;
-    CU(launch_pack_blocks(c->pool.as<double>(), c->in_dense.as<double>(), dslots.as<int32_t>(), c->n_input, c->stream));
-    c->launches++;
+    if (c->n_entries >= 0) {
+        CU(launch_scatter_entries(c->pool.as<double>(), dslots.as<int32_t>(), c->n_input, c->in_entry_input.as<int32_t>(), c->in_entry_pos.as<int32_t>(),
+                                  c->in_entry_val.as<double>(), c->n_entries, c->stream));
+        c->launches += c->n_entries > 0 ? 2 : 1;
+    } else {
+        CU(launch_pack_blocks(c->pool.as<double>(), c->in_dense.as<double>(), dslots.as<int32_t>(), c->n_input, c->stream));
+        c->launches++;
+    }
     CU(cudaStreamSynchronize(c->stream));
     dslots.release();
     c->in_dense.release();
+    c->in_entry_input.release(); c->in_entry_pos.release(); c->in_entry_val.release();
+    c->n_entries = -1;
     c->inputs_pending = false;
     return SOGLU_OK;
 }
@@ -468,7 +478,7 @@ void soglu_destroy(soglu_ctx* c) {
             for (void* p : {c->peer_pool[g], c->peer_dep[g], c->peer_ready[g], c->peer_counters[g]})
                 if (p) cudaIpcCloseMemHandle(p);
         }
-    for (DevBuf* b : {&c->in_dense, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
+    for (DevBuf* b : {&c->in_dense, &c->in_entry_input, &c->in_entry_pos, &c->in_entry_val, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
                       &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->d_y, &c->d_x, &c->trace, &c->m_rp, &c->m_ci, &c->m_v, &c->d_r, &c->d_xacc})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -494,9 +504,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     return SOGLU_OK;
 }
 
-int soglu_set_blocks(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, const double* dense) {
-    if (!c || n_block_ids < 1 || n_input < 0 || (n_input > 0 && (!input_ids || !dense))) return fail(SOGLU_ERR_ARG, "bad argument");
-    CU(cudaSetDevice(c->device));
+static int register_input_pattern(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids) {
     if (c->compiled) {
         // refactorisation with new values on the same pattern
         if (n_block_ids != c->n_ids || n_input != c->n_input || std::memcmp(input_ids, c->input_ids.data(), n_input * sizeof(int32_t)) != 0)
@@ -506,11 +514,50 @@ int soglu_set_blocks(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const i
         c->n_input = n_input;
         c->input_ids.assign(input_ids, input_ids + n_input);
     }
+    return SOGLU_OK;
+}
+
+int soglu_set_blocks(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, const double* dense) {
+    if (!c || n_block_ids < 1 || n_input < 0 || (n_input > 0 && (!input_ids || !dense))) return fail(SOGLU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    int rc = register_input_pattern(c, n_block_ids, n_input, input_ids);
+    if (rc) return rc;
     const size_t bytes = (size_t)n_input * BLK * BLK * sizeof(double);
     CU(c->in_dense.alloc(bytes));
     if (bytes) CU(cudaMemcpyAsync(c->in_dense.p, dense, bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->h2d += (double)bytes;
+    c->n_entries = -1;
+    c->inputs_pending = true;
+    c->have_blocks = true;
+    c->factored = false;
+    return SOGLU_OK;
+}
+
+int soglu_set_blocks_sparse(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, int64_t n_entries,
+                            const int32_t* entry_input, const int32_t* entry_pos, const double* vals) {
+    if (!c || n_block_ids < 1 || n_input < 0 || n_entries < 0 || (n_input > 0 && !input_ids) || (n_entries > 0 && (!entry_input || !entry_pos || !vals)))
+        return fail(SOGLU_ERR_ARG, "bad argument");
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t k = 0; k < n_entries; k++)
+        if (entry_input[k] < 0 || entry_input[k] >= n_input || entry_pos[k] < 0 || entry_pos[k] >= BLK * BLK) bad = 1;
+    if (bad) return fail(SOGLU_ERR_ARG, "soglu_set_blocks_sparse: entry outside its block or input list");
+    CU(cudaSetDevice(c->device));
+    int rc = register_input_pattern(c, n_block_ids, n_input, input_ids);
+    if (rc) return rc;
+    CU(c->in_entry_input.alloc(std::max<size_t>(n_entries, 1) * 4));
+    CU(c->in_entry_pos.alloc(std::max<size_t>(n_entries, 1) * 4));
+    CU(c->in_entry_val.alloc(std::max<size_t>(n_entries, 1) * 8));
+    if (n_entries) {
+        CU(cudaMemcpyAsync(c->in_entry_input.p, entry_input, (size_t)n_entries * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->in_entry_pos.p, entry_pos, (size_t)n_entries * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->in_entry_val.p, vals, (size_t)n_entries * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->h2d += (double)n_entries * 16.0;
+    c->in_dense.release();
+    c->n_entries = n_entries;
     c->inputs_pending = true;
     c->have_blocks = true;
     c->factored = false;

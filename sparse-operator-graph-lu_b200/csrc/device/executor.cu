@@ -632,6 +632,23 @@ __global__ void pack_blocks_kernel(double* __restrict__ pool, const double* __re
         }
     }
 }
+// sparse input upload: clear the input blocks this GPU owns, then scatter the entry list into them
+__global__ void zero_blocks_kernel(double* __restrict__ pool, const int32_t* __restrict__ slots, int64_t n) {
+    for (int64_t b = blockIdx.x; b < n; b += gridDim.x) {
+        if (slots[b] < 0) continue;
+        double2* dst = reinterpret_cast<double2*>(pool + (size_t)slots[b] * BLK_ELEMS);
+        for (int i = threadIdx.x; i < BLK_ELEMS / 2; i += blockDim.x) dst[i] = make_double2(0.0, 0.0);
+    }
+}
+__global__ void scatter_entries_kernel(double* __restrict__ pool, const int32_t* __restrict__ slots, const int32_t* __restrict__ entry_input,
+                                       const int32_t* __restrict__ entry_pos, const double* __restrict__ vals, int64_t n) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t sl = slots[entry_input[k]];
+        if (sl < 0) continue;         // block owned by another GPU
+        const int pos = entry_pos[k];
+        pool[(size_t)sl * BLK_ELEMS + (pos >> 6) * BLK_LD + (pos & 63)] = vals[k];
+    }
+}
 __global__ void unpack_block_kernel(const double* __restrict__ pool, int32_t slot, double* __restrict__ dense) {
     const double* src = pool + (size_t)slot * BLK_ELEMS;
     for (int i = threadIdx.x; i < BLK * BLK; i += blockDim.x) dense[i] = src[(i >> 6) * BLK_LD + (i & 63)];
@@ -670,6 +687,16 @@ cudaError_t launch_pack_blocks(double* pool, const double* dense, const int32_t*
     if (n <= 0) return cudaSuccess;
     int grid = (int)(n < 1184 ? n : 1184);
     pack_blocks_kernel<<<grid, 256, 0, stream>>>(pool, dense, slots, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter_entries(double* pool, const int32_t* slots, int64_t n_blocks, const int32_t* entry_input, const int32_t* entry_pos,
+                                   const double* vals, int64_t n_entries, cudaStream_t stream) {
+    if (n_blocks <= 0) return cudaSuccess;
+    zero_blocks_kernel<<<(int)(n_blocks < 1184 ? n_blocks : 1184), 256, 0, stream>>>(pool, slots, n_blocks);
+    if (n_entries > 0) {
+        const int64_t want = (n_entries + 255) / 256;
+        scatter_entries_kernel<<<(int)(want < 4736 ? want : 4736), 256, 0, stream>>>(pool, slots, entry_input, entry_pos, vals, n_entries);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_unpack_block(const double* pool, int32_t slot, double* dense, cudaStream_t stream) {

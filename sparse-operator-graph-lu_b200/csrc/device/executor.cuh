@@ -40,6 +40,8 @@ cudaError_t launch_diag_bench(double* pool, int iters, long long* cycles, cudaSt
 
 // scatter dense 64x64 blocks (row-major, ld 64) into pool slots (ld 68) and back
 cudaError_t launch_pack_blocks(double* pool, const double* dense, const int32_t* slots, int64_t n, cudaStream_t stream);
+cudaError_t launch_scatter_entries(double* pool, const int32_t* slots, int64_t n_blocks, const int32_t* entry_input, const int32_t* entry_pos,
+                                   const double* vals, int64_t n_entries, cudaStream_t stream);
 cudaError_t launch_unpack_block(const double* pool, int32_t slot, double* dense, cudaStream_t stream);
 
 // ---- block triangular solve -----------------------------------------------------------

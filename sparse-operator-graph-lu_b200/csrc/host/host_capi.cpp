@@ -117,6 +117,7 @@ int64_t soglu_problem_size(const soglu_problem* pp, const char* what) {
     if (w == "n_ops") return (int64_t)p->plan.ops.size();
     if (w == "fine_emitted") return p->plan.fine_emitted;
     if (w == "n_input") return (int64_t)p->plan.inputs.size();
+    if (w == "n_entries") return (int64_t)p->plan.entry_val.size();
     if (w == "n_L") return (int64_t)p->plan.L.size();
     if (w == "n_U") return (int64_t)p->plan.U.size();
     if (w == "coarse_ops") return (int64_t)p->plan.coarse_ops.size();
@@ -154,6 +155,8 @@ int soglu_problem_get_i32(const soglu_problem* pp, const char* what, int32_t* ou
     if (w == "laststage") return cp(p->plan.laststage);
     if (w == "block_row") return cp(p->plan.brow);
     if (w == "block_col") return cp(p->plan.bcol);
+    if (w == "entry_block") { std::memcpy(out, p->plan.entry_block.data(), p->plan.entry_block.size() * 4); return SOGLU_OK; }
+    if (w == "entry_pos") { std::memcpy(out, p->plan.entry_pos.data(), p->plan.entry_pos.size() * 4); return SOGLU_OK; }
     if (w == "perm_i") return cp(p->pi);
     if (w == "perm_j") return cp(p->pj);
     if (w == "ops") { pack_ops(p->plan.ops, out); return SOGLU_OK; }
@@ -172,7 +175,13 @@ int soglu_problem_get_f64(const soglu_problem* pp, const char* what, double* out
     auto cp = [&](const std::vector<double>& v) { std::memcpy(out, v.data(), v.size() * sizeof(double)); return (int)SOGLU_OK; };
     if (w == "b") return cp(p->b);
     if (w == "b_perm") return cp(p->b_perm);
-    if (w == "input_vals") { std::memcpy(out, p->plan.input_vals.data(), p->plan.input_vals.size() * sizeof(double)); return SOGLU_OK; }
+    if (w == "input_vals") {   // dense view of the entry list, built on demand
+        soglu::BlockValues V;
+        if (!p->plan.dense_inputs(V)) { soglu::set_error("out of host memory"); return SOGLU_ERR_OOM; }
+        std::memcpy(out, V.data(), V.size() * sizeof(double));
+        return SOGLU_OK;
+    }
+    if (w == "entry_val") { std::memcpy(out, p->plan.entry_val.data(), p->plan.entry_val.size() * sizeof(double)); return SOGLU_OK; }
     if (w == "flops") { out[0] = p->flops; return SOGLU_OK; }
     if (w == "t_reorder") { out[0] = p->t_reorder; return SOGLU_OK; }
     if (w == "t_plan") { out[0] = p->t_plan; return SOGLU_OK; }

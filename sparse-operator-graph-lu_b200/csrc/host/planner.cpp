@@ -546,6 +546,13 @@ bool BlockValues::alloc_zero(size_t n_blocks) {
     return true;
 }
 
+bool Plan::dense_inputs(BlockValues& V) const {
+    if (!V.alloc_zero(inputs.size())) return false;
+    const int64_t n = (int64_t)entry_val.size();
+    for (int64_t k = 0; k < n; k++) V[(size_t)(entry_block[k] - 1) * 4096 + entry_pos[k]] = entry_val[k];
+    return true;
+}
+
 double factor_flops(const OpVec& ops) {
     double f = 0;
     for (const Op& o : ops) {
@@ -625,8 +632,9 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
             return (x.row >> 6) < (y.row >> 6);
         });
         pt.lap("  cell sort");
-        // pass 1 allocates ids in first-touch order, pass 2 fills the dense values once their
-        // number is known (one allocation, zeroed by all threads)
+        // ids in first-touch order (BlockPlanner.cpp:1498-1519).  The values are kept as a duplicate-free entry
+        // list (input id, position in the 64x64 block, value): the cells of one block are contiguous after the
+        // sort, a repeated (row, col) keeps its last value exactly like the reference's scatter (1510).
         auto block_of = [&](int bi, int bj) {
             int id = P.tree_get(P.blocks, bi, bj);
             if (id == 0) {
@@ -636,31 +644,40 @@ int build_plan(const Config& cfg, bool symmetric, const std::vector<int>& idx_i,
             }
             return id;
         };
-        std::vector<int32_t> cell_block(keep_values ? nnz : 0);
+        if (keep_values) {
+            plan.entry_block.reserve(nnz + 64);
+            plan.entry_pos.reserve(nnz + 64);
+            plan.entry_val.reserve(nnz + 64);
+        }
         {
             int last_bi = -1, last_bj = -1, last_id = 0;
+            std::vector<int64_t> seen(4096, -1);      // position -> entry index, valid for entries >= block_first
+            int64_t block_first = 0;
             for (size_t k = 0; k < nnz; k++) {
                 int bi = cells[k].row >> 6, bj = cells[k].col >> 6;
-                if (bi != last_bi || bj != last_bj) { last_id = block_of(bi, bj); last_bi = bi; last_bj = bj; }
-                if (keep_values) cell_block[k] = last_id;
+                if (bi != last_bi || bj != last_bj) {
+                    last_id = block_of(bi, bj);
+                    last_bi = bi; last_bj = bj;
+                    block_first = (int64_t)plan.entry_val.size();
+                }
+                if (!keep_values) continue;
+                const int pos = (cells[k].row & 63) * 64 + (cells[k].col & 63);
+                if (seen[pos] >= block_first) { plan.entry_val[seen[pos]] = cells[k].val; continue; }
+                seen[pos] = (int64_t)plan.entry_val.size();
+                plan.entry_block.push_back(last_id);
+                plan.entry_pos.push_back(pos);
+                plan.entry_val.push_back(cells[k].val);
             }
         }
-        for (int bi = cfg.mSize >> 6; bi < P.blockRows; bi++) block_of(bi, bi);   // identity padding
-        if (keep_values) {
-            BlockValues& V = plan.input_vals;
-            if (!V.alloc_zero((size_t)(P.storage - 1))) {
-                plan.log = P.log.str() + "planner: out of host memory for the input blocks\n";
-                return 3;
-            }
-            for (size_t k = 0; k < nnz; k++)
-                V[(size_t)(cell_block[k] - 1) * 4096 + (cells[k].row & 63) * 64 + (cells[k].col & 63)] = cells[k].val;
+        for (int bi = cfg.mSize >> 6; bi < P.blockRows; bi++) block_of(bi, bi);   // identity padding (1520-1528)
+        if (keep_values)
             for (int i = cfg.mSize; i < P.blockRows * 64; i++) {
-                int bi = i >> 6, ri = i & 63;
-                int id = P.tree_get(P.blocks, bi, bi);
-                V[(size_t)(id - 1) * 4096 + ri * 64 + ri] = 1.0;
+                const int bi = i >> 6, ri = i & 63;
+                plan.entry_block.push_back(P.tree_get(P.blocks, bi, bi));
+                plan.entry_pos.push_back(ri * 64 + ri);
+                plan.entry_val.push_back(1.0);
             }
-        }
-        // input ids are 1..n_input in allocation order, so V is indexed by id-1
+        // input ids are 1..n_input in allocation order
     }
     pt.lap("fine input blocks");
     // bind coarse input ids to fine sub-quadtrees (matrixZoomSet, 1305-1315)

@@ -112,7 +112,11 @@ struct Plan {
     std::vector<int32_t> stage;      // per block id (data::stage)
     std::vector<int32_t> laststage;  // per block id (data::laststage)
     std::vector<BlockRef> inputs;    // blocks filled by iniBlockStorage, quadtree (Z) order
-    BlockValues input_vals;          // dense 64x64 row-major per input block
+    // values of the input blocks, duplicate-free: input block id (1..n_input, ids are handed out in allocation
+    // order), position row*64+col inside the block, value; the identity padding is included
+    BigVec<int32_t> entry_block, entry_pos;
+    BigVec<double> entry_val;
+    bool dense_inputs(BlockValues& out) const;   // dense 64x64 row-major per input block (index id-1), on demand
     std::vector<BlockRef> L, U;      // factor leaves with block coordinates, quadtree order
     std::vector<int32_t> brow, bcol; // per block id: coordinates of the quadtree slot (or -1)
     std::string log;                 // the lines the reference prints while planning

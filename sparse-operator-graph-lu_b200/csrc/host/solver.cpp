@@ -19,11 +19,15 @@ int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
     const Problem* p = reinterpret_cast<const Problem*>(pp);
     if (!ctx || !p) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
     const soglu::Plan& pl = p->plan;
-    // input blocks: ids are 1..n_input in allocation order and input_vals is indexed by id-1
+    // input blocks: ids are 1..n_input in allocation order; their values go up as the sparse entry list
     const int64_t n_in = (int64_t)pl.inputs.size();
     std::vector<int32_t> in_ids(n_in);
     for (int64_t k = 0; k < n_in; k++) in_ids[k] = (int32_t)(k + 1);
-    int rc = soglu_set_blocks(ctx, pl.storage, n_in, in_ids.data(), pl.input_vals.data());
+    const int64_t n_ent = (int64_t)pl.entry_val.size();
+    soglu::BigVec<int32_t> ent_in(n_ent);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_ent; k++) ent_in[k] = pl.entry_block[k] - 1;
+    int rc = soglu_set_blocks_sparse(ctx, pl.storage, n_in, in_ids.data(), n_ent, ent_in.data(), pl.entry_pos.data(), pl.entry_val.data());
     if (rc) return rc;
     const int64_t n = (int64_t)pl.ops.size();
     soglu::BigVec<int32_t> src(n), src2(n), res(n), res2(n), stg(n);

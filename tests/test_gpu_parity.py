@@ -340,3 +340,52 @@ def test_symmetric_disconnected_matrix(sg, oracle):
     b = gen_mtx.rhs(n)
     assert np.linalg.norm(ax - b) / np.linalg.norm(b) <= 1e-12
     ctx.close()
+
+
+def test_sparse_input_upload_equals_dense_upload(sg, tmp_path):
+    """soglu_set_blocks_sparse (entry list scattered on the device) must leave exactly the blocks that
+    soglu_set_blocks (dense 64x64 arrays) leaves: same factors bit for bit, also when the values change on
+    the same pattern (refactorisation) and when the entries arrive in another order."""
+    p = sg.Problem.from_mtx(write_case_mtx("lap3d_13x11x9", tmp_path))
+    ops = p.i32("ops")
+    n_in = p.size("n_input")
+    ids = np.arange(1, n_in + 1, dtype=np.int32)
+    graph = {"op": ops[:, 0], "src": ops[:, 1], "src2": ops[:, 2], "result": ops[:, 3], "result2": ops[:, 4]}
+    ent_in, ent_pos, ent_val = p.i32("entry_block") - 1, p.i32("entry_pos"), p.f64("entry_val")
+
+    def run(upload):
+        ctx = sg.Context(0)
+        upload(ctx, 1.0)
+        ctx.set_graph(graph)
+        ctx.set_factors(p.i32("L"), p.i32("U"), p.size("block_rows"))
+        ctx.factor()
+        first = [ctx.get_block(int(i)) for i in p.i32("U")[:40, 0]]
+        upload(ctx, 3.0)                       # new values, same pattern
+        ctx.factor()
+        second = [ctx.get_block(int(i)) for i in p.i32("U")[:40, 0]]
+        x_ext, _ = ctx.solve_ext(p.f64("b_perm"))
+        ctx.close()
+        return first, second, x_ext
+
+    dense = p.f64("input_vals")
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(ent_val))
+    d1, d2, xd = run(lambda ctx, f: ctx.set_blocks(p.size("storage"), ids, np.ascontiguousarray(dense * f)))
+    s1, s2, xs = run(lambda ctx, f: ctx.set_blocks_sparse(p.size("storage"), ids, np.ascontiguousarray(ent_in[perm]), np.ascontiguousarray(ent_pos[perm]),
+                                                          np.ascontiguousarray(ent_val[perm] * f)))
+    for a, b in zip(d1 + d2, s1 + s2):
+        assert np.array_equal(a, b)
+    assert np.array_equal(xd, xs)
+    assert not np.array_equal(d1[0], d2[0])    # the second factorisation really saw the new values
+
+
+def test_sparse_input_upload_rejects_bad_entries(sg):
+    ctx = sg.Context(0)
+    ids = np.array([1], dtype=np.int32)
+    ok = (np.array([0], dtype=np.int32), np.array([65], dtype=np.int32), np.array([2.0]))
+    ctx.set_blocks_sparse(4, ids, *ok)
+    for bad_in, bad_pos in ((1, 0), (-1, 0), (0, 4096), (0, -1)):
+        with pytest.raises(sg.SogluError) as e:
+            ctx.set_blocks_sparse(4, ids, np.array([bad_in], dtype=np.int32), np.array([bad_pos], dtype=np.int32), np.array([1.0]))
+        assert "entry outside" in str(e.value)
+    ctx.close()

@@ -140,3 +140,36 @@ def test_wide_stage_split_vs_live_reference(sg, tmp_path):
     np.testing.assert_array_equal(p.i32("laststage"), rd("laststage.i32", np.int32))
     np.testing.assert_array_equal(p.i32("L"), rd("L.i32", np.int32).reshape(-1, 3))
     np.testing.assert_array_equal(p.i32("U"), rd("U.i32", np.int32).reshape(-1, 3))
+
+
+def test_duplicate_entries_keep_the_reference_value(sg, tmp_path):
+    """A .mtx that lists some (row, col) twice: the reference scatters the sorted cells one by one, so the later
+    cell wins (BlockPlanner.cpp:1498-1519).  Our duplicate-free entry list (what goes to the GPU) and its dense
+    view must hold the same values as the blocks of a LIVE reference run."""
+    harness = ref_harness_path()
+    if harness is None:
+        pytest.skip("oracle/_ref not built (or host CPU lacks AVX-512)")
+    import gen_mtx
+    n, r, c, v = gen_mtx.banded(300, 40, 6, seed=11)
+    rng = np.random.default_rng(3)
+    pick = rng.choice(len(v), 60, replace=False)
+    r2, c2, v2 = np.concatenate([r, r[pick]]), np.concatenate([c, c[pick]]), np.concatenate([v, v[pick] * 1.5 + 0.25])
+    order = rng.permutation(len(v2))
+    path = str(tmp_path / "dup.mtx")
+    gen_mtx.write_mtx(path, n, r2[order], c2[order], v2[order])
+    out = tmp_path / "ref"
+    out.mkdir()
+    subprocess.run([harness, path, str(out), "--blocks"], check=True, capture_output=True, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    p = sg.Problem.from_mtx(path)
+    leaves = np.fromfile(out / "inputs.i32", dtype=np.int32).reshape(-1, 3)
+    ref_dense = np.fromfile(out / "inputs.f64").reshape(len(leaves), 4096)
+    mine = p.f64("input_vals")
+    np.testing.assert_array_equal(p.i32("inputs"), leaves)
+    np.testing.assert_array_equal(mine[leaves[:, 0] - 1], ref_dense)
+    # the entry list is duplicate-free and reproduces the dense view
+    eb, ep, ev = p.i32("entry_block"), p.i32("entry_pos"), p.f64("entry_val")
+    keys = eb.astype(np.int64) * 4096 + ep
+    assert len(np.unique(keys)) == len(keys) and len(keys) < len(v2) + (p.size("n_ext") - n) + 1
+    dense = np.zeros_like(mine)
+    dense[eb - 1, ep] = ev
+    np.testing.assert_array_equal(dense, mine)
