@@ -390,6 +390,7 @@ int64_t soglu_dist_blob_bytes(void) { return (int64_t)sizeof(DistBlob); }
 
 // compile + allocate this GPU's share, then write the IPC handles of its pool / counters / queue
 int soglu_dist_export(soglu_ctx* c, void* blob) {
+    try {
     if (!c || !blob) return fail(SOGLU_ERR_ARG, "bad argument");
     CU(cudaSetDevice(c->device));
     int rc = finalize(c);
@@ -405,10 +406,16 @@ int soglu_dist_export(soglu_ctx* c, void* blob) {
     }
     std::memcpy(blob, &b, sizeof b);
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 // all_blobs: world blobs in rank order (gathered by the caller, e.g. torch.distributed.all_gather)
 int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
+    try {
     if (!c || !all_blobs) return fail(SOGLU_ERR_ARG, "bad argument");
     if (!c->compiled) return fail(SOGLU_ERR_ARG, "soglu_dist_export must precede soglu_dist_import");
     CU(cudaSetDevice(c->device));
@@ -426,6 +433,11 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
     }
     c->peers_ready = true;
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 // reset this GPU's dependency counters and ready queue; the caller must put a barrier across all
@@ -518,6 +530,7 @@ static int register_input_pattern(soglu_ctx* c, int64_t n_block_ids, int64_t n_i
 }
 
 int soglu_set_blocks(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, const double* dense) {
+    try {
     if (!c || n_block_ids < 1 || n_input < 0 || (n_input > 0 && (!input_ids || !dense))) return fail(SOGLU_ERR_ARG, "bad argument");
     CU(cudaSetDevice(c->device));
     int rc = register_input_pattern(c, n_block_ids, n_input, input_ids);
@@ -532,10 +545,16 @@ int soglu_set_blocks(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const i
     c->have_blocks = true;
     c->factored = false;
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 int soglu_set_blocks_sparse(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, int64_t n_entries,
                             const int32_t* entry_input, const int32_t* entry_pos, const double* vals) {
+    try {
     if (!c || n_block_ids < 1 || n_input < 0 || n_entries < 0 || (n_input > 0 && !input_ids) || (n_entries > 0 && (!entry_input || !entry_pos || !vals)))
         return fail(SOGLU_ERR_ARG, "bad argument");
     int bad = 0;
@@ -562,10 +581,16 @@ int soglu_set_blocks_sparse(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, 
     c->have_blocks = true;
     c->factored = false;
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 int soglu_set_graph(soglu_ctx* c, int64_t n_ops, const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,
                     const int32_t* result2, const int32_t* stage, const int32_t* block_row, const int32_t* block_col) {
+    try {
     (void)stage;
     if (!c || n_ops < 0 || (n_ops > 0 && (!src || !src2 || !op || !result || !result2))) return fail(SOGLU_ERR_ARG, "bad argument");
     if (c->compiled) return fail(SOGLU_ERR_ARG, "graph already compiled; create a new context for a new pattern");
@@ -580,10 +605,16 @@ int soglu_set_graph(soglu_ctx* c, int64_t n_ops, const int32_t* src, const int32
     }
     c->have_graph = true;
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 int soglu_set_factors(soglu_ctx* c, int64_t nL, const int32_t* L_ids, const int32_t* L_brow, const int32_t* L_bcol, int64_t nU,
                       const int32_t* U_ids, const int32_t* U_brow, const int32_t* U_bcol, int32_t n_block_rows, int symmetric) {
+    try {
     if (!c || nL <= 0 || !L_ids || !L_brow || !L_bcol || n_block_rows <= 0) return fail(SOGLU_ERR_ARG, "bad argument");
     if (!symmetric && (nU <= 0 || !U_ids || !U_brow || !U_bcol)) return fail(SOGLU_ERR_ARG, "U factor missing");
     if (c->compiled) return fail(SOGLU_ERR_ARG, "graph already compiled; create a new context for a new pattern");
@@ -593,9 +624,15 @@ int soglu_set_factors(soglu_ctx* c, int64_t nL, const int32_t* L_ids, const int3
     c->symmetric = symmetric ? 1 : 0;
     c->have_factors = true;
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 int soglu_factor(soglu_ctx* c, soglu_stats* out) {
+    try {
     if (!c) return fail(SOGLU_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     const int64_t launches0 = c->launches;
@@ -707,6 +744,11 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
         out->d2h_bytes = c->d2h;
     }
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 // one forward/back substitution on device buffers: rhs (n_ext) -> sol (n_ext)
@@ -778,11 +820,24 @@ int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* o
 
 // solve + `steps` rounds of iterative refinement on the device (needs soglu_set_matrix)
 int soglu_solve_refined(soglu_ctx* c, const double* b_ext, double* x_ext, int steps, soglu_stats* out) {
+    try {
+    try {
     return solve_impl(c, b_ext, x_ext, steps < 0 ? 0 : steps, out);
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 // CSR of the permuted system padded with the identity to n_block_rows*64 rows (what the factors factorise)
 int soglu_set_matrix(soglu_ctx* c, int64_t n_ext, int64_t nnz, const int64_t* row_ptr, const int32_t* col, const double* val) {
+    try {
     if (!c || n_ext <= 0 || nnz < 0 || !row_ptr || (nnz > 0 && (!col || !val))) return fail(SOGLU_ERR_ARG, "bad argument");
     CU(cudaSetDevice(c->device));
     CU(c->m_rp.alloc((size_t)(n_ext + 1) * 8)); CU(c->m_ci.alloc(std::max<size_t>(nnz, 1) * 4)); CU(c->m_v.alloc(std::max<size_t>(nnz, 1) * 8));
@@ -795,6 +850,11 @@ int soglu_set_matrix(soglu_ctx* c, int64_t n_ext, int64_t nnz, const int64_t* ro
     c->m_n = n_ext; c->m_nnz = nnz;
     c->h2d += (double)((n_ext + 1) * 8 + nnz * 12);
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 // debug: cycles of lu / write-out / inverses / total for one diagonal block (slot 1 = first input)
@@ -842,6 +902,7 @@ int64_t soglu_debug_trace(soglu_ctx* c, unsigned long long* trace_out, int32_t* 
 }
 
 int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {
+    try {
     if (!c || !out_64x64) return fail(SOGLU_ERR_ARG, "bad argument");
     if (!c->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled yet");
     if (id <= 0 || id >= c->n_ids) return fail(SOGLU_ERR_ARG, "block id out of range");
@@ -859,6 +920,11 @@ int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {
     CU(cudaStreamSynchronize(c->stream));
     tmp.release();
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
 }
 
 }  // extern "C"

@@ -7,6 +7,8 @@
 #endif
 
 #include <chrono>
+#include <new>
+#include <stdexcept>
 #include <cstdio>
 #include <cstring>
 #include <sstream>
@@ -81,9 +83,20 @@ int soglu_abi_version(void) { return SOGLU_ABI_VERSION; }
 int soglu_problem_from_coo(int32_t dim, int64_t nnz, int symmetric, const int32_t* index_i, const int32_t* index_j,
                            const double* vals, const double* b, soglu_problem** out) {
     if (!out || dim <= 0 || nnz < 0 || !index_i || !index_j || !vals) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
-    Problem* P = new Problem();
-    int rc = soglu::prepare_problem(*P, dim, nnz, symmetric != 0, index_i, index_j, vals, b);
-    if (rc) { delete P; return rc; }
+    Problem* P = nullptr;
+    try {
+        P = new Problem();
+        int rc = soglu::prepare_problem(*P, dim, nnz, symmetric != 0, index_i, index_j, vals, b);
+        if (rc) { delete P; return rc; }
+    } catch (const std::bad_alloc&) {     // no exception may cross the C ABI
+        delete P;
+        soglu::set_error("out of host memory while planning");
+        return SOGLU_ERR_OOM;
+    } catch (const std::exception& e) {
+        delete P;
+        soglu::set_error(std::string("internal error: ") + e.what());
+        return SOGLU_ERR_PLAN;
+    }
     *out = reinterpret_cast<soglu_problem*>(P);
     return SOGLU_OK;
 }
@@ -94,9 +107,14 @@ int soglu_problem_from_mtx(const char* path, soglu_problem** out) {
     size_t pos = fname.find(".mtx");
     if (pos == std::string::npos) { soglu::set_error("usage: ./solve filename.mtx"); return SOGLU_ERR_ARG; }
     soglu::Coo a;
-    if (soglu::read_mtx(fname, a) == 0) { soglu::set_error("Can not open file"); return SOGLU_ERR_IO; }
     std::vector<double> b;
-    soglu::read_array(fname.substr(0, pos) + "_b.mtx", a.n, b);
+    try {
+        if (soglu::read_mtx(fname, a) == 0) { soglu::set_error("Can not open file"); return SOGLU_ERR_IO; }
+        soglu::read_array(fname.substr(0, pos) + "_b.mtx", a.n, b);
+    } catch (const std::exception& e) {
+        soglu::set_error(std::string("reading the matrix failed: ") + e.what());
+        return SOGLU_ERR_IO;
+    }
     return soglu_problem_from_coo(a.n, (int64_t)a.v.size(), a.symmetric, a.i.data(), a.j.data(), a.v.data(), b.data(), out);
 }
 

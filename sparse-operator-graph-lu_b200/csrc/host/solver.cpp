@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <new>
+#include <stdexcept>
 #include <vector>
 
 #include "problem.h"
@@ -16,6 +18,7 @@ using soglu::Problem;
 extern "C" {
 
 int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
+    try {
     const Problem* p = reinterpret_cast<const Problem*>(pp);
     if (!ctx || !p) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
     const soglu::Plan& pl = p->plan;
@@ -48,9 +51,17 @@ int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
     split(pl.U, ui, ur, uc);
     return soglu_set_factors(ctx, (int64_t)li.size(), li.data(), lr.data(), lc.data(), (int64_t)ui.size(), ui.data(), ur.data(), uc.data(),
                              p->cfg.blockRows, p->symmetric ? 1 : 0);
+    } catch (const std::bad_alloc&) {
+        soglu::set_error("out of host memory");
+        return SOGLU_ERR_OOM;
+    } catch (const std::exception& e) {
+        soglu::set_error(std::string("internal error: ") + e.what());
+        return SOGLU_ERR_ARG;
+    }
 }
 
 int soglu_solve_problem(soglu_ctx* ctx, const soglu_problem* pp, const double* b, double* x, int refine, soglu_stats* out) {
+    try {
     const Problem* p = reinterpret_cast<const Problem*>(pp);
     if (!ctx || !p || !x) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
     if (refine > 0) {
@@ -82,6 +93,13 @@ int soglu_solve_problem(soglu_ctx* ctx, const soglu_problem* pp, const double* b
     // un-permute (GOrder::reOrderResult, GPSOrder.cpp:41-53)
     for (int i = 0; i < p->dim; i++) x[i] = xext[p->ord.reverseOrder[i]];
     return SOGLU_OK;
+    } catch (const std::bad_alloc&) {
+        soglu::set_error("out of host memory");
+        return SOGLU_ERR_OOM;
+    } catch (const std::exception& e) {
+        soglu::set_error(std::string("internal error: ") + e.what());
+        return SOGLU_ERR_ARG;
+    }
 }
 
 double* soglu_solveLU(int dim, int valcount, int symmetric, const int* index_i, const int* index_j, const double* vals, const double* b) {
