@@ -173,7 +173,7 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
     // explicit inverses of the diagonal blocks, where the factorisation produced them (fused lu tasks)
     std::unordered_map<int32_t, int32_t> inv_of_ref;   // reference of a diagonal factor block -> reference of its inverse
     for (const Task& T : c->G.tasks)
-        if (T.type == T_LU) {
+        if (T.type == T_LU || T.type == T_LLT) {      // llt: L^-1 also serves the transposed sweep, (L^T)^-1 = (L^-1)^T
             if (T.flags & TF_LINV) inv_of_ref[T.out] = T.init;
             if (T.flags & TF_UINV) inv_of_ref[T.out2] = T.out4;
         }

@@ -189,10 +189,10 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             }
             if (!opt.fuse_inv) continue;
             const IdInfo& w = info[f];
-            if (w.n_writers != 1 || w.kind != OP_LU) continue;
+            if (w.n_writers != 1 || (w.kind != OP_LU && w.kind != OP_LLT)) continue;
             const int64_t lu_i = w.first_writer;
-            // lowerInv must read the L result, upperInv the U result of that lu
-            if (op[i] == OP_LOWERINV ? (result[lu_i] != f) : (result2[lu_i] != f)) continue;
+            // lowerInv must read the L result, upperInv the U result of that lu; an llt only has L
+            if (w.kind == OP_LLT ? (op[i] != OP_LOWERINV) : (op[i] == OP_LOWERINV ? (result[lu_i] != f) : (result2[lu_i] != f))) continue;
             op_fused[i] = 1;
             n_fused++;
         }
@@ -242,7 +242,10 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                         if (inv_of[r] >= 0 && op_fused[inv_of[r]] == 1) { t.flags |= TF_LINV; t.init = result[inv_of[r]]; }
                         if (inv_of[result2[i]] >= 0 && op_fused[inv_of[result2[i]]] == 1) { t.flags |= TF_UINV; t.out4 = result[inv_of[result2[i]]]; }
                         break;
-                    case OP_LLT: t.type = T_LLT; break;
+                    case OP_LLT:
+                        t.type = T_LLT;
+                        if (inv_of[r] >= 0 && op_fused[inv_of[r]] == 1) { t.flags |= TF_LINV; t.init = result[inv_of[r]]; }
+                        break;
                     case OP_LOWERINV: t.type = T_LOWERINV; break;
                     case OP_UPPERINV: t.type = T_UPPERINV; break;
                     case OP_MUL: t.type = T_GEMM; t.n_pairs = w.n_writers; break;
@@ -263,8 +266,8 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                     }
                 }
                 G.task_of[r] = (int32_t)tid;
-                if (t.type == T_LU) {
-                    G.task_of[t.out2] = (int32_t)tid;
+                if (t.type == T_LU) G.task_of[t.out2] = (int32_t)tid;
+                if (t.type == T_LU || t.type == T_LLT) {
                     if (t.flags & TF_LINV) G.task_of[t.init] = (int32_t)tid;
                     if (t.flags & TF_UINV) G.task_of[t.out4] = (int32_t)tid;
                 }
@@ -359,8 +362,9 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         for (int64_t t = 0; t < nt; t++) town[t] = G.owner_of[cn(G.tasks[t].out)];
         for (int64_t t = 0; t < nt; t++) {
             const Task& T = G.tasks[t];
-            if (T.type == T_LU && (G.owner_of[T.out2] != town[t] || ((T.flags & TF_LINV) && G.owner_of[cn(T.init)] != town[t]) ||
-                                   ((T.flags & TF_UINV) && G.owner_of[cn(T.out4)] != town[t])))
+            if ((T.type == T_LU && G.owner_of[T.out2] != town[t]) ||
+                ((T.type == T_LU || T.type == T_LLT) && (((T.flags & TF_LINV) && G.owner_of[cn(T.init)] != town[t]) ||
+                                                         ((T.flags & TF_UINV) && G.owner_of[cn(T.out4)] != town[t]))))
                 return "lu outputs with different owners";
         }
         auto for_src = [&](Task& T, auto&& fn) {
@@ -473,8 +477,8 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                 const Task& T = G.tasks[t];
                 auto touch = [&](int32_t id) { if (id > 0) { id = canon(id); if (last_touch[id] < t) last_touch[id] = (int32_t)t; } };
                 touch(T.out);
-                if (T.type == T_LU) {
-                    touch(T.out2);
+                if (T.type == T_LU) touch(T.out2);
+                if (T.type == T_LU || T.type == T_LLT) {
                     if (T.flags & TF_LINV) { touch(T.init); pinned[canon(T.init)] = 1; }
                     if (T.flags & TF_UINV) { touch(T.out4); pinned[canon(T.out4)] = 1; }
                 }
@@ -500,8 +504,8 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                 const Task& T = G.tasks[t];
                 int32_t outs[4] = {T.out, 0, 0, 0};
                 int no = 1;
-                if (T.type == T_LU) {
-                    outs[no++] = T.out2;
+                if (T.type == T_LU) outs[no++] = T.out2;
+                if (T.type == T_LU || T.type == T_LLT) {
                     if (T.flags & TF_LINV) outs[no++] = T.init;
                     if (T.flags & TF_UINV) outs[no++] = T.out4;
                 }
@@ -693,7 +697,7 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             switch (T.type) {
                 case T_GEMM: c = 2.1f * T.n_pairs * (((T.flags >> TF_NROWS_SHIFT) & 7) / 4.f); break;
                 case T_LU: c = (T.flags & (TF_LINV | TF_UINV)) ? 20.f : 12.f; break;
-                case T_LLT: c = 15.f; break;
+                case T_LLT: c = (T.flags & TF_LINV) ? 18.f : 12.f; break;
                 case T_LOWERINV: case T_UPPERINV: c = 7.f; break;
                 default: c = 1.f; break;
             }

@@ -72,13 +72,6 @@ constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
 // ---- small block kernels on a block resident in shared memory (256 math threads) -------
 __device__ __forceinline__ void math_sync() { ptx::named_bar_sync(BAR_MATH, N_MATH); }
 
-__device__ __forceinline__ void store_block(double* __restrict__ g, const double* __restrict__ s, int ct) {
-    // 4352 doubles = 2176 double2, coalesced 16-byte stores
-    const double2* s2 = reinterpret_cast<const double2*>(s);
-    double2* g2 = reinterpret_cast<double2*>(g);
-#pragma unroll 3
-    for (int i = ct; i < BLK_ELEMS / 2; i += N_MATH) g2[i] = s2[i];
-}
 
 // ---- diagonal-block kernels, register resident ---------------------------------------------
 // Thread (ty, tx) of the 16x16 grid of math threads owns the 16 elements (ty+16r, tx+16c) of
@@ -96,7 +89,14 @@ __device__ __forceinline__ void store_block(double* __restrict__ g, const double
 //   U^-1:  (U^T)^-1 by the same forward elimination with multipliers u_ki / u_kk taken from
 //          the pivot row, scaled by 1/u_ii at the end and written back transposed.
 // So the fused lu + lowerInv + upperInv task costs one elimination sweep instead of three.
-template <bool WITH_INV, int DBG = 0>
+// WU = false skips W_U (Cholesky only needs L^-1); LLT selects lltdcmpSimple's pivot clamp (p < 1e-20 -> 1e-20,
+// MatrixStdDouble.cpp:2640) instead of ludcmpSimple's (|p| < 1e-9 -> +-1e-9, 2745).
+template <bool LLT>
+__device__ __forceinline__ double clamp_pivot(double p) {
+    if (LLT) return (p < 1e-20) ? 1e-20 : p;
+    return (p < 1e-9 && p > -1e-9) ? ((p < 0) ? -1e-9 : 1e-9) : p;
+}
+template <bool WITH_INV, int DBG = 0, bool WU = true, bool LLT = false>
 __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* __restrict__ xbuf, double (&a)[4][4], double (&wl)[4][4],
                                         double (&wu)[4][4], int ct) {
     const int ty = ct >> 4, tx = ct & 15;
@@ -111,14 +111,13 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             a[r][c] = As[(ty + 16 * r) * BLK_LD + tx + 16 * c];
-            if (WITH_INV) wl[r][c] = wu[r][c] = (r == c && ty == tx) ? 1.0 : 0.0;
+            if (WITH_INV) { wl[r][c] = (r == c && ty == tx) ? 1.0 : 0.0; if (WU) wu[r][c] = wl[r][c]; }
         }
     // The reciprocal of pivot k+1 is formed by the warp that owns element (k+1,k+1) as soon as
     // pivot k has updated it, and published with the pivot row: the other warps' updates of
     // pivot k overlap that division instead of every thread waiting for 1/p after the barrier.
     if (ct == 0) {
-        double p = a[0][0];
-        if (p < 1e-9 && p > -1e-9) p = (p < 0) ? -1e-9 : 1e-9;
+        const double p = clamp_pivot<LLT>(a[0][0]);
         a[0][0] = p;
         const double ip0 = ptx::fast_rcp(p);
         ipnext[0] = ip0;
@@ -135,7 +134,7 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
                 for (int c = kr; c < 4; c++) rowbuf[pb + tx + 16 * c] = a[kr][c];
                 if (WITH_INV) {
 #pragma unroll
-                    for (int c = 0; c <= kr; c++) { wlbuf[pb + tx + 16 * c] = wl[kr][c]; wubuf[pb + tx + 16 * c] = wu[kr][c]; }
+                    for (int c = 0; c <= kr; c++) { wlbuf[pb + tx + 16 * c] = wl[kr][c]; if (WU) wubuf[pb + tx + 16 * c] = wu[kr][c]; }
                 }
             }
             if (tx == ko) {
@@ -154,8 +153,7 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
                 if (!(DBG & 2) && k1 < BLK && (ty >> 1) == (ko1 >> 1)) {
                     own_next = (ty == ko1) && (tx == ko1);
                     const double a_sel = (ko != 15) ? a[kr][kr] : a[kr < 3 ? kr + 1 : 3][kr < 3 ? kr + 1 : 3];
-                    double p = fma(-(colbuf[pb + k1] * ip), rowbuf[pb + k1], a_sel);
-                    if (p < 1e-9 && p > -1e-9) p = (p < 0) ? -1e-9 : 1e-9;
+                    const double p = clamp_pivot<LLT>(fma(-(colbuf[pb + k1] * ip), rowbuf[pb + k1], a_sel));
                     const double ipn = ptx::fast_rcp(p);
                     p_next = p;
                     if (own_next) {
@@ -166,18 +164,18 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
             }
             double cbv[4], rbv[4], rbi[4], wlv[4], wuv[4];
 #pragma unroll
-            for (int r = kr; r < 4; r++) { cbv[r] = colbuf[pb + ty + 16 * r]; if (WITH_INV) rbi[r] = rowbuf[pb + ty + 16 * r]; }
+            for (int r = kr; r < 4; r++) { cbv[r] = colbuf[pb + ty + 16 * r]; if (WITH_INV && WU) rbi[r] = rowbuf[pb + ty + 16 * r]; }
 #pragma unroll
             for (int c = kr; c < 4; c++) rbv[c] = rowbuf[pb + tx + 16 * c];
             if (WITH_INV) {
 #pragma unroll
-                for (int c = 0; c <= kr; c++) { wlv[c] = wlbuf[pb + tx + 16 * c]; wuv[c] = wubuf[pb + tx + 16 * c]; }
+                for (int c = 0; c <= kr; c++) { wlv[c] = wlbuf[pb + tx + 16 * c]; if (WU) wuv[c] = wubuf[pb + tx + 16 * c]; }
             }
             // Finished rows / columns are switched off by zeroing their multiplier / pivot-row
             // entry (a few selects per pivot) instead of predicating every update.
             const bool cedge = tx > ko, wedge = tx <= ko;
             rbv[kr] = cedge ? rbv[kr] : 0.0;
-            if (WITH_INV) { wlv[kr] = wedge ? wlv[kr] : 0.0; wuv[kr] = wedge ? wuv[kr] : 0.0; }
+            if (WITH_INV) { wlv[kr] = wedge ? wlv[kr] : 0.0; if (WU) wuv[kr] = wedge ? wuv[kr] : 0.0; }
 #pragma unroll
             for (int r = kr; r < 4; r++) {
                 const bool ract = (r > kr) || (ty > ko);
@@ -188,11 +186,11 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
                 }
                 if (ract && tx == ko) a[r][kr] = l;
                 if (WITH_INV) {
-                    const double m = ract ? rbi[r] * ip : 0.0;
+                    const double m = (WU && ract) ? rbi[r] * ip : 0.0;
 #pragma unroll
                     for (int c = 0; c <= kr; c++) {
                         wl[r][c] = fma(-l, wlv[c], wl[r][c]);
-                        wu[r][c] = fma(-m, wuv[c], wu[r][c]);
+                        if (WU) wu[r][c] = fma(-m, wuv[c], wu[r][c]);
                     }
                 }
             }
@@ -301,31 +299,43 @@ __device__ __forceinline__ void tri_inv_task(const double* __restrict__ Tm, doub
     }
 }
 
-// L = chol(A) reading the lower triangle, pivot < 1e-20 clamped (lltdcmpSimple,
-// MatrixStdDouble.cpp:2629-2668).  A is used as workspace, L goes to Lb.
-__device__ void llt_block(double* __restrict__ A, double* __restrict__ Lb, int ct) {
+// L = chol(A), pivot < 1e-20 clamped (lltdcmpSimple, MatrixStdDouble.cpp:2629-2668), optionally with the fused
+// lowerInv of that L (inv_lower uses the stored diagonal, 2787-2802).  Same register-resident sweep as the LU task:
+// A = L1 * U with unit L1 and u_kk = d_k, so chol(A) = L1 * diag(sqrt(d)) and chol(A)^-1 = diag(1/sqrt(d)) * L1^-1.
+// Only the symmetric (LL^T) path of the planner emits this task (BlockPlanner.cpp:941-989).
+__device__ __forceinline__ void llt_task(const double* __restrict__ As, double* __restrict__ xbuf, const ExecParams& P, const StageDesc& d, int ct) {
     const int ty = ct >> 4, tx = ct & 15;
-    for (int i = ct; i < BLK_ELEMS; i += N_MATH) Lb[i] = 0.0;
+    double a[4][4], wl[4][4], wu[4][4];
+    const bool inv = d.flags & TF_LINV;
+    if (inv) lu3_reg<true, 0, false, true>(As, xbuf, a, wl, wu, ct);
+    else lu3_reg<false, 0, false, true>(As, xbuf, a, wl, wu, ct);
+    double* sq = xbuf;          // [64] sqrt(d_k)       (the sweep's exchange buffers are free again)
+    double* isq = xbuf + 64;    // [64] 1 / sqrt(d_k)
     math_sync();
-    for (int k = 0; k < BLK; k++) {
-        double p = A[k * BLK_LD + k];
-        if (p < 1e-20) p = 1e-20;
-        const double lkk = sqrt(p);
-        const double il = 1.0 / lkk;
+    if (ty == tx) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const int i = ty + 16 * r;
-            if (i <= k) continue;
-            const double lik = A[i * BLK_LD + k] * il;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int j = tx + 16 * c;
-                if (j > k && j <= i) A[i * BLK_LD + j] -= lik * (A[j * BLK_LD + k] * il);
-            }
-            if (tx == (k & 15)) Lb[i * BLK_LD + k] = lik;
+            const double s = sqrt(a[r][r]);
+            sq[ty + 16 * r] = s;
+            isq[ty + 16 * r] = 1.0 / s;
         }
-        if (ct == 0) Lb[k * BLK_LD + k] = lkk;
-        math_sync();
+    }
+    math_sync();
+    double* gL = blk_ptr(P, d.out);
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int i = ty + 16 * r, j = tx + 16 * c;
+            gL[i * BLK_LD + j] = (j < i) ? a[r][c] * sq[j] : (j == i ? sq[i] : 0.0);
+        }
+    if (!inv) return;
+    double* g = blk_ptr(P, d.init);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const double di = isq[ty + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 4; c++) g[(ty + 16 * r) * BLK_LD + tx + 16 * c] = wl[r][c] * di;
     }
 }
 
@@ -497,8 +507,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     lu_task(As, ctl->scratch, P, d, ct);
                     break;
                 case T_LLT:
-                    llt_block(As, Bs, ct);
-                    store_block(out, Bs, ct);
+                    llt_task(As, ctl->scratch, P, d, ct);
                     break;
                 case T_LOWERINV:
                     tri_inv_task<false>(As, ctl->scratch, out, ct);

@@ -256,7 +256,8 @@ extern "C" int soglu_debug_simulate(const soglu_problem* pp, int split, int pr, 
     std::vector<int32_t> writers((size_t)world * max_slots, 0);
     auto for_outs = [&](const soglu::Task& T, auto&& fn) {
         fn(T.out);
-        if (T.type == soglu::T_LU) { fn(T.out2); if (T.flags & soglu::TF_LINV) fn(T.init); if (T.flags & soglu::TF_UINV) fn(T.out4); }
+        if (T.type == soglu::T_LU) fn(T.out2);
+        if (T.type == soglu::T_LU || T.type == soglu::T_LLT) { if (T.flags & soglu::TF_LINV) fn(T.init); if (T.flags & soglu::TF_UINV) fn(T.out4); }
     };
     for (int r = 0; r < world; r++)
         for (const soglu::Task& T : D[r].tasks) for_outs(T, [&](int32_t ref) { writers[key(ref)]++; });

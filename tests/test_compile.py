@@ -198,3 +198,22 @@ def test_raw_pool_limits(sg):
     with pytest.raises(sg.SogluError) as e:
         compile_raw(sg, 13, [1, 2], GOOD, keep=[3, 4, 7, 8, 11, 12], max_slots=9)
     assert "pool too small" in str(e.value)
+
+
+def test_symmetric_path_fuses_cholesky_and_inverse(sg, tmp_path_factory):
+    """LL^T path (BlockPlanner.cpp:941-989): the lowerInv of an llt result is folded into the llt task and
+    repeated inverses alias it, as on the LU path; the release protocol still runs every task once."""
+    p = sg.Problem.from_mtx(write_case_mtx("lap2d_64_sym", tmp_path_factory.mktemp("s")))
+    ops = p.i32("ops")
+    n_llt, n_inv = int((ops[:, 0] == 10).sum()), int((ops[:, 0] == 2).sum())
+    plain = compile_stats(sg, p, 1, 0, 0)
+    fused = compile_stats(sg, p, 1, 1, 0)
+    assert n_llt > 0 and (ops[:, 0] == 1).sum() == 0
+    assert fused["fused_invs"] + fused["aliased_invs"] == n_inv and fused["fused_invs"] <= n_llt
+    assert fused["tasks"] == plain["tasks"] - n_inv and fused["levels"] < plain["levels"]
+    L = sg.lib()
+    L.soglu_debug_simulate.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_uint64, ctypes.c_void_p]
+    for cfg in ((1, 1, 1, 1), (1, 2, 2, 1)):
+        out = (ctypes.c_int64 * 3)()
+        assert L.soglu_debug_simulate(p.h, *cfg, 7, out) == 0
+        assert out[0] == out[2] and out[1] == 0

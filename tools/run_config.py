@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Factor + solve one BASELINE.json config on the GPU from an in-memory COO matrix and report timings,
 residuals (raw and after one refinement step) and, optionally, the difference to the unmodified reference.
-usage: run_config.py <kind> <dims...> [--ref] [key=value executor options]
+usage: run_config.py <kind> <dims...> [--ref] [--sym] [key=value executor options]
   kinds: lap2d NX [NY] | lap3d NX [NY NZ] | nine2d NX [NY] | banded N [W] [K]"""
 import os, subprocess, sys, tempfile, time
 import numpy as np
@@ -13,9 +13,16 @@ import soglu_b200 as sg
 args = [a for a in sys.argv[1:] if "=" not in a and not a.startswith("--")]
 opts = [a for a in sys.argv[1:] if "=" in a]
 want_ref = "--ref" in sys.argv
+want_sym = "--sym" in sys.argv          # symmetric storage (lower triangle) -> the planner's LL^T path
 kind, dims = args[0], [int(a) for a in args[1:]]
 t = time.time(); n, r, c, v = gen_mtx.generate(kind, *dims); b = gen_mtx.rhs(n); print("generate %.1f s  n=%d nnz=%d" % (time.time() - t, n, len(v)), flush=True)
-t = time.time(); p = sg.Problem.from_coo(n, r, c, v, b); print("reorder+plan %.1f s" % (time.time() - t), flush=True)
+t = time.time()
+if want_sym:
+    low = r >= c
+    p = sg.Problem.from_coo(n, r[low], c[low], v[low], b, symmetric=True)
+else:
+    p = sg.Problem.from_coo(n, r, c, v, b)
+print("reorder+plan %.1f s%s" % (time.time() - t, "  (symmetric storage, LL^T path)" if want_sym else ""), flush=True)
 print(p.log.strip().splitlines()[0])
 print("ops %d storage %d L %d U %d stages %d flops %.4e" % (p.size("n_ops"), p.size("storage"), p.size("n_L"), p.size("n_U"), p.size("max_stage"), p.f64("flops")[0]), flush=True)
 ctx = sg.Context(0)
