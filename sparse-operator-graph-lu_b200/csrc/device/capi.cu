@@ -53,7 +53,6 @@ struct soglu_ctx {
     int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
     int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;
-    int64_t opt_diag_mode = 1;     // diagonal-block kernels: 1 = two pivots per barrier, 0 = one (cross-check)
     int64_t opt_grid = 0;          // override CTA count (0 = all resident)
     int64_t opt_trace = 0;         // record per-task timestamps (debug; adds overhead)
     DevBuf trace;
@@ -506,7 +505,6 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     if (k == "exec_mode") c->opt_exec_mode = value;
     else if (k == "fuse_sub") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_sub must be set before the first factor"); c->opt_fuse_sub = value; }
     else if (k == "fuse_inv") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_inv must be set before the first factor"); c->opt_fuse_inv = value; }
-    else if (k == "diag_mode") c->opt_diag_mode = value ? 1 : 0;
     else if (k == "split") { if (c->compiled) return fail(SOGLU_ERR_ARG, "split must be set before the first factor"); c->opt_split = value; }
     else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
     else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
@@ -656,7 +654,6 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     P.tasks = c->tasks.as<Task>();
     P.pairs = c->pairs.as<Pair>();
     P.succ = c->succ.as<int32_t>();
-    P.diag_mode = (int32_t)c->opt_diag_mode;
     P.dep = c->dep.as<int32_t>();
     P.trace = nullptr;
     if (c->opt_trace && nt > 0) {
@@ -866,7 +863,7 @@ int soglu_debug_diag_bench(soglu_ctx* c, int iters, long long* cycles4) {
     DevBuf d;
     CU(d.alloc(128));
     CU(launch_diag_bench(c->pool.as<double>(), iters, d.as<long long>(), c->stream));
-    CU(cudaMemcpyAsync(cycles4, d.p, 128, cudaMemcpyDeviceToHost, c->stream));   // 16 counters
+    CU(cudaMemcpyAsync(cycles4, d.p, 80, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     d.release();
     return SOGLU_OK;

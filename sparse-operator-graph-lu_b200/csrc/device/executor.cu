@@ -28,7 +28,6 @@
 // peers are mapped through CUDA IPC) use system-scope fences and atomics over NVLink.
 #include "executor.cuh"
 #include "ptx.cuh"
-#include "diag2.cuh"
 
 namespace soglu {
 
@@ -65,7 +64,7 @@ struct __align__(16) SmemCtl {
     uint64_t full[N_STAGES];
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
-    double scratch[1096];  // pivot row/column exchange buffers of the register-resident diag kernels (diag2::SCRATCH_DOUBLES)
+    double scratch[584];   // pivot row/column exchange buffers of the register-resident diag kernels
 };
 
 constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
@@ -202,34 +201,12 @@ __device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* _
     }
 }
 
-// two pivots per barrier (diag2.cuh): 32 intervals of publish -> barrier -> eliminate
-static_assert(diag2::SCRATCH_DOUBLES <= 1096 && diag2::LD == BLK_LD, "diag2 buffers");
-template <bool WITH_INV, bool WU, bool LLT>
-__device__ __forceinline__ void diag2_sweep(const double* __restrict__ As, double* __restrict__ xbuf, double (&a)[4][4], double (&wl)[4][4],
-                                            double (&wu)[4][4], int ct) {
-    const int ty = ct >> 4, tx = ct & 15;
-    diag2::init<WITH_INV, WU, LLT>(As, xbuf, a, wl, wu, ty, tx);
-#pragma unroll
-    for (int kr = 0; kr < 4; kr++) {
-#pragma unroll 1
-        for (int ko = 0; ko < 16; ko += 2) {
-            math_sync();
-            diag2::eliminate2<WITH_INV, WU, LLT>(kr, ko, (ko >> 1) & 1, xbuf, a, wl, wu, ty, tx);
-        }
-    }
-}
-
 __device__ __forceinline__ void lu_task(const double* __restrict__ As, double* __restrict__ xbuf, const ExecParams& P, const StageDesc& d, int ct) {
     const int ty = ct >> 4, tx = ct & 15;
     double a[4][4], wl[4][4], wu[4][4];
     const bool inv = d.flags & (TF_LINV | TF_UINV);
-    if (P.diag_mode == 0) {       // one pivot per barrier (kept for cross-checks)
-        if (inv) lu3_reg<true>(As, xbuf, a, wl, wu, ct);
-        else lu3_reg<false>(As, xbuf, a, wl, wu, ct);
-    } else {
-        if (inv) diag2_sweep<true, true, false>(As, xbuf, a, wl, wu, ct);
-        else diag2_sweep<false, false, false>(As, xbuf, a, wl, wu, ct);
-    }
+    if (inv) lu3_reg<true>(As, xbuf, a, wl, wu, ct);
+    else lu3_reg<false>(As, xbuf, a, wl, wu, ct);
     double* gL = blk_ptr(P, d.out);
     double* gU = blk_ptr(P, d.out2);
 #pragma unroll
@@ -252,7 +229,7 @@ __device__ __forceinline__ void lu_task(const double* __restrict__ As, double* _
     }
     if (d.flags & TF_UINV) {
         double* g = blk_ptr(P, d.out4);
-        const double* ipbuf = xbuf + (P.diag_mode == 0 ? 512 : diag2::IPBUF);
+        const double* ipbuf = xbuf + 512;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const double di = ipbuf[ty + 16 * r];
@@ -330,13 +307,8 @@ __device__ __forceinline__ void llt_task(const double* __restrict__ As, double* 
     const int ty = ct >> 4, tx = ct & 15;
     double a[4][4], wl[4][4], wu[4][4];
     const bool inv = d.flags & TF_LINV;
-    if (P.diag_mode == 0) {
-        if (inv) lu3_reg<true, 0, false, true>(As, xbuf, a, wl, wu, ct);
-        else lu3_reg<false, 0, false, true>(As, xbuf, a, wl, wu, ct);
-    } else {
-        if (inv) diag2_sweep<true, false, true>(As, xbuf, a, wl, wu, ct);
-        else diag2_sweep<false, false, true>(As, xbuf, a, wl, wu, ct);
-    }
+    if (inv) lu3_reg<true, 0, false, true>(As, xbuf, a, wl, wu, ct);
+    else lu3_reg<false, 0, false, true>(As, xbuf, a, wl, wu, ct);
     double* sq = xbuf;          // [64] sqrt(d_k)       (the sweep's exchange buffers are free again)
     double* isq = xbuf + 64;    // [64] 1 / sqrt(d_k)
     math_sync();
@@ -545,12 +517,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     break;
                 default: break;
             }
-            // The accumulators carry nothing across a non-GEMM task (a chain's first stage clears them): say so, or
-            // the compiler keeps 16 registers alive through the diagonal kernels, which need all 168.
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
         }
         // ---- task complete: make the result visible, then release the successors ---------
         math_sync();
@@ -573,12 +539,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     if (o != P.rank) { remote = true; continue; }
                     if (atomicSub(P.dep + nx, 1) == 1) {
                         // the whole group (all row slices of the successor) becomes ready at once
+                        // (the fence below + the strong relaxed stores form the release; the consumers ld.acquire)
                         const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
                         __threadfence();
                         const int pos = atomicAdd(P.tail[qq], g);
                         for (int k = 0; k < g; k++) {
                             if (P.trace) P.trace[6 * (size_t)(nx + k) + 0] = gtime();
-                            ptx::st_release(P.ready[qq] + pos + k, nx + k);
+                            ptx::st_relaxed(P.ready[qq] + pos + k, nx + k);
                         }
                     }
                 }
@@ -592,7 +559,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                             const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
                             __threadfence_system();
                             const int pos = atomicAdd_system(P.tails[o][qq], g);
-                            for (int k = 0; k < g; k++) ptx::st_release_sys(P.readys[o][qq] + pos + k, nx + k);
+                            for (int k = 0; k < g; k++) ptx::st_relaxed_sys(P.readys[o][qq] + pos + k, nx + k);
                         }
                     }
                 }
@@ -660,25 +627,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
         math_sync();
         long long c6 = clock64();
         t_lu3 += c1 - c0; t_lu += c2 - c1; t_invl += c4 - c3; t_invu += c6 - c5;
-        // two pivots per barrier: fused lu, plain lu, fused llt
-        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
-        math_sync();
-        BP.diag_mode = 1;
-        d.flags = TF_LINV | TF_UINV;
-        long long g0 = clock64();
-        lu_task(As, ctl->scratch, BP, d, ct);
-        math_sync();
-        long long g1 = clock64();
-        d.flags = 0;
-        lu_task(As, ctl->scratch, BP, d, ct);
-        math_sync();
-        long long g2 = clock64();
-        d.flags = TF_LINV;
-        llt_task(As, ctl->scratch, BP, d, ct);
-        math_sync();
-        long long g3 = clock64();
-        BP.diag_mode = 0;
-        if (ct == 0 && it == iters - 1) { cycles[10] = g1 - g0; cycles[11] = g2 - g1; cycles[12] = g3 - g2; }
     }
     if (ct == 0) { cycles[0] = t_lu3 / iters; cycles[1] = t_lu / iters; cycles[2] = t_invl / iters; cycles[3] = t_invu / iters; }
 }

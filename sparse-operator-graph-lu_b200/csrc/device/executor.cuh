@@ -28,7 +28,6 @@ struct ExecParams {
     int32_t n_tasks[2];    // queue lengths for this launch
     int32_t n_hi_ctas;     // CTAs dedicated to queue 0
     int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
-    int32_t diag_mode;     // diagonal-block kernels: 1 = two pivots per barrier (diag2.cuh), 0 = one pivot per barrier
     unsigned long long* trace;   // optional: 6 x u64 per task (published, claimed, loaded, computed, signalled, smid)
 };
 

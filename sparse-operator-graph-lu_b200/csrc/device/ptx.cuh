@@ -60,6 +60,14 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// strong relaxed stores: after ONE fence of the matching scope they complete a release pattern (fence + strong
+// write), so a thread that publishes several queue entries pays for one fence instead of one per st.release
+__device__ __forceinline__ void st_relaxed(int* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(int* p, int v) {
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

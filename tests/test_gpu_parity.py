@@ -389,23 +389,3 @@ def test_sparse_input_upload_rejects_bad_entries(sg):
             ctx.set_blocks_sparse(4, ids, np.array([bad_in], dtype=np.int32), np.array([bad_pos], dtype=np.int32), np.array([1.0]))
         assert "entry outside" in str(e.value)
     ctx.close()
-
-
-@pytest.mark.parametrize("case", ["lap3d_13x11x9", "lap2d_64_sym", "banded_3000"])
-def test_diag_kernel_variants_agree(sg, tmp_path, case):
-    """The diagonal-block tasks (lu / llt with fused inverses) exist as a one-pivot-per-barrier sweep and as the
-    default two-pivots-per-barrier sweep (csrc/device/diag2.cuh, emulated on the host by tests/emu): same
-    factorisation up to the order of two subtractions, both within the parity gate of the golden reference x."""
-    g = load_golden(case)
-    p = sg.Problem.from_mtx(write_case_mtx(case, tmp_path))
-    xs = []
-    for mode in (0, 1):
-        ctx = sg.Context(0)
-        ctx.set_option("diag_mode", mode)
-        ctx.load(p)
-        ctx.factor()
-        x, _ = ctx.solve(p)
-        xs.append(x)
-        assert _rel(x, g["x"]) <= TOL_X
-        ctx.close()
-    assert _rel(xs[0], xs[1]) <= 1e-12
