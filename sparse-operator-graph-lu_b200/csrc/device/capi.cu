@@ -48,6 +48,7 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
+    int64_t opt_hi_shared = 0;     // > 0: tasks with less estimated slack than this (us) go to a high-priority queue every CTA serves first
     int64_t opt_hi_ctas = 0;       // CTAs dedicated to a high-priority queue of small-slack tasks; 0 (default) = one FIFO
                                    // queue: measured SLOWER with 16 (100^3: 2.58 -> 2.73 s on 1 GPU, 1.64 -> 1.91 s on 4)
     int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
@@ -227,6 +228,7 @@ int finalize(soglu_ctx* c) {
     co.split_narrow = (int)c->opt_split;
     co.n_sms = c->sms;
     co.hi_ctas = (int)std::max<int64_t>(0, std::min<int64_t>(c->opt_hi_ctas, c->exec_grid / 2));
+    if (c->opt_hi_shared > 0) { co.hi_ctas = 0; co.hi_slack_us = (double)c->opt_hi_shared; }
     {
         // pool capacity: what is free now minus the graph arrays (estimated from the op count) and a margin
         size_t free_b = 0, total_b = 0;
@@ -509,6 +511,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
     else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
     else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
+    else if (k == "hi_shared") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_shared must be set before the first factor"); c->opt_hi_shared = value; }
     else if (k == "hi_ctas") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_ctas must be set before the first factor"); c->opt_hi_ctas = value; }
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
@@ -674,6 +677,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
         const int32_t want = (sg < (int)G.seg_hi_ctas.size()) ? G.seg_hi_ctas[sg] : (int32_t)c->opt_hi_ctas;
         P.n_hi_ctas = (P.n_tasks[0] > 0 && P.n_tasks[1] > 0) ? (int32_t)std::min<int64_t>(want, grid / 2) : (P.n_tasks[0] > 0 ? grid : 0);
         if (c->opt_hi_ctas <= 0) P.n_hi_ctas = 0;
+        if (c->opt_hi_shared > 0) P.n_hi_ctas = -1;     // shared high-priority queue (executor.cu)
         if (c->dist)
             for (int g = 0; g < c->world; g++) {
                 int32_t* rb = (int32_t*)c->peer_ready[g] + c->D.seg_begin_all[g][sg];

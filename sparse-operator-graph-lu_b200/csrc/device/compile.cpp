@@ -12,6 +12,7 @@
 //     that chain: R = S2 -/+ sum A*B   (removes one level of the critical path
 //     lu -> inv -> mul -> mul -> sub -> lu and one block write + two block reads).
 #include "tasks.h"
+#include "model.h"
 
 #include <algorithm>
 #include <cmath>
@@ -688,20 +689,21 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     // FIFO queue a released critical-chain task waits behind every bulk update published before it (247 us
     // on average at 100^3), which stretches the chain; the small-slack tasks get their own queue.
     G.seg_nhi.assign(G.seg_begin.size() - 1, 0);
-    if (opt.hi_ctas > 0 && !G.tasks.empty()) {
+    if ((opt.hi_ctas > 0 || opt.hi_slack_us > 0) && !G.tasks.empty()) {
         const int64_t n2 = (int64_t)G.tasks.size();
         std::vector<float> dur(n2), tl(n2, 0.f), bl(n2, 0.f);
+        const ModelParams M;     // one dependent hop through a task under the measured cost model (model.h)
         for (int64_t t = 0; t < n2; t++) {
             const Task& T = G.tasks[t];
-            float c = 1.f;
+            double c = 1.0;
             switch (T.type) {
-                case T_GEMM: c = 2.1f * T.n_pairs * (((T.flags >> TF_NROWS_SHIFT) & 7) / 4.f); break;
-                case T_LU: c = (T.flags & (TF_LINV | TF_UINV)) ? 20.f : 12.f; break;
-                case T_LLT: c = (T.flags & TF_LINV) ? 18.f : 12.f; break;
-                case T_LOWERINV: case T_UPPERINV: c = 7.f; break;
-                default: c = 1.f; break;
+                case T_GEMM: { const int r16 = (T.flags >> TF_NROWS_SHIFT) & 7; c = T.n_pairs * (r16 == 4 ? M.t_pair : (r16 == 2 ? M.t_pair_half : M.t_pair_quarter)); break; }
+                case T_LU: c = (T.flags & (TF_LINV | TF_UINV)) ? M.t_lu_fused : M.t_lu; break;
+                case T_LLT: c = (T.flags & TF_LINV) ? M.t_llt_fused : M.t_lu; break;
+                case T_LOWERINV: case T_UPPERINV: c = M.t_inv; break;
+                default: c = M.t_sub; break;
             }
-            dur[t] = 6.f + c;
+            dur[t] = (float)(M.t_desc + M.t_load + c + M.t_epilogue + M.t_release + M.t_poll);
         }
         for (int64_t t = 0; t < n2; t++)     // tasks are in topological order; successors are group leaders
             for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
@@ -717,8 +719,10 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         std::vector<float> cp(nseg, 0.f);
         for (int sg = 0; sg < nseg; sg++)
             for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) cp[sg] = std::max(cp[sg], tl[t] + bl[t]);
-        float theta = 400.f;
-        for (int round = 0; round < 10; round++) {
+        // dedicated CTAs (hi_ctas): the threshold shrinks until those CTAs are at most half busy; shared queue
+        // (hi_slack_us): every CTA serves the high-priority queue first, the threshold is fixed
+        float theta = opt.hi_slack_us > 0 ? (float)opt.hi_slack_us : 400.f;
+        for (int round = 0; round < 10 && opt.hi_slack_us <= 0; round++) {
             bool ok = true;
             for (int sg = 0; sg < nseg && ok; sg++) {
                 double busy = 0;
@@ -774,6 +778,101 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         }
     }
     lap("priority + initial");
+    // ---- chain analysis (diagnostics + input of a second compile, CompileOptions::analyze_chains) --------------
+    // Under the cost model of model.h: fin[t] = earliest time a successor of t can start, as compiled (a task starts
+    // when ALL operands are ready), and fin_e[t] = the same if every accumulation chain may be cut once into an
+    // early part (the pairs that are ready first, plus the initial value) and a late part that starts from it.
+    // A cut is proposed when it moves the task's own finish by cut_min_gain_us and the task has little slack.
+    if (opt.analyze_chains && !G.tasks.empty()) {
+        const ModelParams M;
+        const int64_t n2 = (int64_t)G.tasks.size();
+        const float o_in = (float)(M.t_desc + M.t_load), o_out = (float)(M.t_epilogue + M.t_release + M.t_poll);
+        auto stage_us = [&](const Task& T) -> float {
+            switch (T.type) {
+                case T_GEMM: { const int r16 = (T.flags >> TF_NROWS_SHIFT) & 7; return (float)(r16 == 4 ? M.t_pair : (r16 == 2 ? M.t_pair_half : M.t_pair_quarter)); }
+                case T_SUB: return (float)M.t_sub;
+                case T_LU: return (float)((T.flags & (TF_LINV | TF_UINV)) ? M.t_lu_fused : M.t_lu);
+                case T_LLT: return (float)((T.flags & TF_LINV) ? M.t_llt_fused : M.t_lu);
+                default: return (float)M.t_inv;
+            }
+        };
+        std::vector<float> fin(n2, 0.f), fin_e(n2, 0.f);
+        std::vector<int32_t> best_k(n2, 0);
+        std::vector<std::pair<float, int32_t>> rs;   // (ready time, position) of the pairs of one chain
+        for (int64_t t = 0; t < n2; t++) {
+            const Task& T = G.tasks[t];
+            if (!task_is_leader(T)) {
+                const int64_t lead = t - ((T.flags >> TF_ROW0_SHIFT) & 3) / std::max(1, (T.flags >> TF_NROWS_SHIFT) & 7);
+                fin[t] = fin[lead]; fin_e[t] = fin_e[lead];
+                continue;
+            }
+            const float ts = stage_us(T);
+            const int n = (T.type == T_GEMM) ? T.n_pairs : 1;
+            auto ready = [&](int32_t id, const std::vector<float>& f) -> float {
+                if (id <= 0) return 0.f;
+                const int32_t p = G.task_of[id];
+                return (p >= 0 && p != t) ? f[p] : 0.f;
+            };
+            float r_all = 0.f, ri = 0.f, ri_e = 0.f;
+            if (T.flags & TF_INIT) { ri = ready(T.init, fin); ri_e = ready(T.init, fin_e); }
+            rs.clear();
+            for (int k = 0; k < T.n_pairs; k++) {
+                const Pair& pr = G.pairs[T.pair_begin + k];
+                r_all = std::max(r_all, std::max(ready(pr.a, fin), ready(pr.b, fin)));
+                if (T.type == T_GEMM) rs.push_back({std::max(ready(pr.a, fin_e), ready(pr.b, fin_e)), k});
+            }
+            fin[t] = std::max(r_all, ri) + o_in + n * ts + o_out;
+            if (T.type != T_GEMM) {
+                float r = 0.f;
+                for (int k = 0; k < T.n_pairs; k++) r = std::max(r, std::max(ready(G.pairs[T.pair_begin + k].a, fin_e), ready(G.pairs[T.pair_begin + k].b, fin_e)));
+                fin_e[t] = r + o_in + n * ts + o_out;
+                continue;
+            }
+            std::stable_sort(rs.begin(), rs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            const float r_last = rs.back().first;
+            float best = std::max(r_last, ri_e) + o_in + n * ts + o_out;
+            int bk = 0;
+            for (int k = 1; k < n; k++) {
+                const float fe = std::max(rs[k - 1].first, ri_e) + o_in + k * ts + o_out;
+                const float f = std::max(fe, r_last) + o_in + (n - k) * ts + o_out;
+                if (f < best - (float)opt.cut_min_gain_us) { best = f; bk = k; }
+            }
+            fin_e[t] = best;
+            best_k[t] = bk;
+        }
+        for (int64_t t = 0; t < n2; t++) { G.cp_us = std::max(G.cp_us, (double)fin[t]); G.cp_early_us = std::max(G.cp_early_us, (double)fin_e[t]); }
+        // slack under the early-start times: a cut only matters on (near-)critical tasks
+        std::vector<float> bot(n2, 0.f);     // longest path from the END of the task to the end of the factorisation
+        for (int64_t t = n2 - 1; t >= 0; t--) {
+            const Task& T = G.tasks[t];
+            float m = 0.f;
+            for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+                const Task& S = G.tasks[G.succ[e]];
+                m = std::max(m, bot[G.succ[e]] + o_in + ((S.type == T_GEMM) ? S.n_pairs : 1) * stage_us(S) + o_out);
+            }
+            bot[t] = m;
+        }
+        for (int64_t t = 0; t < n2; t++) {
+            const Task& T = G.tasks[t];
+            if (T.type != T_GEMM || !task_is_leader(T) || best_k[t] == 0) continue;
+            if (G.cp_early_us - (fin_e[t] + bot[t]) > opt.cut_max_slack_us) continue;
+            // recompute the order of the chain (cheap: only the chosen tasks)
+            rs.clear();
+            for (int k = 0; k < T.n_pairs; k++) {
+                const Pair& pr = G.pairs[T.pair_begin + k];
+                auto rd = [&](int32_t id) { if (id <= 0) return 0.f; const int32_t p = G.task_of[id]; return (p >= 0 && p != t) ? fin_e[p] : 0.f; };
+                rs.push_back({std::max(rd(pr.a), rd(pr.b)), k});
+            }
+            std::stable_sort(rs.begin(), rs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            ChainCut c;
+            c.out_id = T.out;
+            c.n_early = best_k[t];
+            for (int k = 0; k < best_k[t]; k++) c.early_pos.push_back(rs[k].second);
+            std::sort(c.early_pos.begin(), c.early_pos.end());
+            G.cuts.push_back(std::move(c));
+        }
+        lap("chain analysis");
+    }
     // ---- patch block ids -> block references (owner in the top bits; plain slots on one GPU) --------
     {
         auto ref = [&](int32_t id, int reader) -> int32_t {

@@ -18,8 +18,10 @@
 //               on the successor group's dependency counter each; the thread that brings it to zero
 //               publishes the whole group (a task, or the 2 / 4 row slices of a split GEMM task,
 //               which share their leader's counter) at the tail of the ready queue.
-// Two queues exist (high priority / bulk, CTAs [0, n_hi_ctas) serve the first); the default is
-// n_hi_ctas = 0, one FIFO queue: the priority split measured slower (negative results).
+// Two queues exist (high priority / bulk); the default is one FIFO queue.  Option hi_ctas dedicates CTAs
+// [0, n_hi_ctas) to the first (measured slower, DESIGN.md negative results); option hi_shared lets EVERY CTA
+// take published high-priority tasks before its next bulk slot (the host model predicts -5.5 % at 100^3;
+// not yet measured on the GPU, off by default).
 //
 // Memory-ordering protocol: writer CTA: st.global data -> bar.sync -> __threadfence ->
 // atomicSub(dep) [-> __threadfence -> atomicAdd(tail) -> st.release(ready)]; reader CTA:
@@ -424,23 +426,54 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     if (two) ptx::bulk_g2s(As + BLK_ELEMS, blk_ptr(P, pr.b), BLK_BYTES, &ctl->full[s]);
                 }
             };
-            // CTAs 0..n_hi_ctas-1 serve the high-priority queue, the others the bulk queue; each claims the next
-            // slot of its queue and waits until a finishing CTA publishes a task there
-            const int q = (blockIdx.x < (unsigned)P.n_hi_ctas) ? 0 : 1;
-            while (true) {
-                const int slot = atomicAdd(P.head[q], 1);
-                if (slot >= P.n_tasks[q]) {
-                    const int s = it % N_STAGES;
-                    ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);
-                    ctl->desc[s].type = T_EXIT;
-                    ptx::mbar_arrive(&ctl->full[s]);
-                    break;
+            // tell the math warps to leave once every queue this CTA serves is exhausted
+            auto quit = [&]() {
+                const int s = it % N_STAGES;
+                ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);
+                ctl->desc[s].type = T_EXIT;
+                ptx::mbar_arrive(&ctl->full[s]);
+            };
+            if (P.n_hi_ctas >= 0) {
+                // CTAs 0..n_hi_ctas-1 serve the high-priority queue, the others the bulk queue; each claims the next
+                // slot of its queue and waits until a finishing CTA publishes a task there
+                const int q = (blockIdx.x < (unsigned)P.n_hi_ctas) ? 0 : 1;
+                while (true) {
+                    const int slot = atomicAdd(P.head[q], 1);
+                    if (slot >= P.n_tasks[q]) break;
+                    int t;
+                    if (P.world > 1) { while ((t = ptx::ld_acquire_sys(P.ready[q] + slot)) < 0) {} }
+                    else { while ((t = ptx::ld_acquire(P.ready[q] + slot)) < 0) {} }
+                    issue(t);
                 }
-                int t;
-                if (P.world > 1) { while ((t = ptx::ld_acquire_sys(P.ready[q] + slot)) < 0) {} }
-                else { while ((t = ptx::ld_acquire(P.ready[q] + slot)) < 0) {} }
-                issue(t);
+            } else {
+                // Shared high-priority queue (option hi_shared): EVERY CTA takes the entry at the head of queue 0 if
+                // it is already published (compare-and-swap on the head, never waits there) before it looks at its
+                // pre-claimed slot of the bulk queue; while that slot is still empty it keeps serving queue 0.
+                const int n_hi = P.n_tasks[0], n_lo = P.n_tasks[1];
+                int mine = -1;            // pre-claimed bulk slot
+                bool lo_left = n_lo > 0;
+                while (true) {
+                    const int h = *(volatile int*)P.head[0];
+                    if (h < n_hi) {
+                        const int t = (P.world > 1) ? ptx::ld_acquire_sys(P.ready[0] + h) : ptx::ld_acquire(P.ready[0] + h);
+                        if (t >= 0) {
+                            if (atomicCAS(P.head[0], h, h + 1) == h) issue(t);
+                            continue;
+                        }
+                    }
+                    if (mine < 0 && lo_left) {
+                        mine = atomicAdd(P.head[1], 1);
+                        if (mine >= n_lo) { mine = -1; lo_left = false; }
+                    }
+                    if (mine >= 0) {
+                        const int t = (P.world > 1) ? ptx::ld_acquire_sys(P.ready[1] + mine) : ptx::ld_acquire(P.ready[1] + mine);
+                        if (t >= 0) { mine = -1; issue(t); }
+                    } else if (h >= n_hi) {
+                        break;            // both queues exhausted (the head only grows)
+                    }
+                }
             }
+            quit();
         }
         return;
     }

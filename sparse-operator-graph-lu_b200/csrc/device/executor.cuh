@@ -26,7 +26,7 @@ struct ExecParams {
     int32_t* head[2];      // next queue slot to claim
     int32_t* tail[2];      // next queue slot to publish
     int32_t n_tasks[2];    // queue lengths for this launch
-    int32_t n_hi_ctas;     // CTAs dedicated to queue 0
+    int32_t n_hi_ctas;     // CTAs dedicated to queue 0; -1 = shared: every CTA serves queue 0 first (option hi_shared)
     int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
     unsigned long long* trace;   // optional: 6 x u64 per task (published, claimed, loaded, computed, signalled, smid)
 };

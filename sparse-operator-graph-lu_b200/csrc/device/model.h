@@ -1,0 +1,39 @@
+// Timed host model of the persistent executor: see model.cpp.  Diagnostics only.
+#pragma once
+#include "tasks.h"
+
+namespace soglu {
+
+struct ModelParams {        // microseconds, measured with the executor's trace option on a B200
+    int n_ctas = 148;
+    double t_pair = 2.38;          // one 64x64x64 product, whole block, 8 math warps of one SM
+    double t_pair_half = 1.25;     // 32-row slice
+    double t_pair_quarter = 0.72;  // 16-row slice
+    double t_lu_fused = 18.8;      // lu + both inverses in one sweep (37 k cycles) + write-back
+    double t_lu = 12.0;
+    double t_llt_fused = 17.0;
+    double t_inv = 7.0;
+    double t_sub = 0.6;
+    double t_epilogue = 0.4;       // result write-back + barrier
+    double t_release = 1.5;        // store visibility + dependency atomics + publication
+    double t_poll = 1.5;           // a spinning scheduler sees the published task
+    double t_poll_hit = 0.8;       // the task was already there when the slot was claimed
+    double t_desc = 0.6;           // task record fetch
+    double t_load = 1.3;           // bulk copy of one operand pair into shared memory
+    double t_launch = 30.0;        // per segment (cooperative launch + drain)
+    double t_cas = 0.5;            // policy 2: extra compare-and-swap to take a high-priority task
+    double hi_slack_us = 100.0;    // policy 2: tasks with less slack than this are high priority
+    int policy = 0;                // 0 = the executor's FIFO ready queue; 1 = ideal list scheduling by longest remaining path (what-if)
+};
+
+struct ModelResult {
+    double makespan_us = 0;        // sum over segments
+    double critical_path_us = 0;   // longest dependent chain under the same durations (infinite SMs)
+    double busy_us = 0;            // sum of math time over all CTAs
+    int64_t n_tasks = 0;
+    int64_t n_hi = 0;              // policy 2: tasks in the high-priority class
+};
+
+ModelResult model_executor(const TaskGraph& G, const ModelParams& M);
+
+}  // namespace soglu
