@@ -48,6 +48,7 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
+    int64_t opt_chain_cuts = 0;    // > 0: cut accumulation chains of tasks within this slack (us) of the critical path (two-pass compile)
     int64_t opt_hi_shared = 0;     // > 0: tasks with less estimated slack than this (us) go to a high-priority queue every CTA serves first
     int64_t opt_hi_ctas = 0;       // CTAs dedicated to a high-priority queue of small-slack tasks; 0 (default) = one FIFO
                                    // queue: measured SLOWER with 16 (100^3: 2.58 -> 2.73 s on 1 GPU, 1.64 -> 1.91 s on 4)
@@ -252,10 +253,20 @@ int finalize(soglu_ctx* c) {
         co.n_owners = c->world;
         co.mirror_min = (int)std::max<int64_t>(1, c->opt_mirror_min);
     }
+    if (c->opt_chain_cuts > 0) { co.analyze_chains = true; co.cut_max_slack_us = (double)c->opt_chain_cuts; }
     std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
                                     c->result.data(), c->result2.data(), keep, co, c->G);
     if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
     TaskGraph& G = c->G;
+    if (c->opt_chain_cuts > 0 && !G.cuts.empty()) {
+        // second pass: the early pairs of every proposed chain become their own task (compile.cpp, chain analysis)
+        const std::vector<ChainCut> cuts = std::move(G.cuts);
+        co.analyze_chains = false;
+        co.chain_cuts = &cuts;
+        err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
+                            c->result.data(), c->result2.data(), keep, co, c->G);
+        if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
+    }
     if (c->dist) {
         err = localize_tasks(G, c->rank, c->D);
         if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
@@ -511,6 +522,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
     else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
     else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
+    else if (k == "chain_cuts") { if (c->compiled) return fail(SOGLU_ERR_ARG, "chain_cuts must be set before the first factor"); c->opt_chain_cuts = value; }
     else if (k == "hi_shared") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_shared must be set before the first factor"); c->opt_hi_shared = value; }
     else if (k == "hi_ctas") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_ctas must be set before the first factor"); c->opt_hi_ctas = value; }
     else if (k == "grid") c->opt_grid = value;

@@ -40,7 +40,7 @@ struct IdInfo {
 };
 }  // namespace
 
-std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_ids, int64_t n_ops,
+std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* input_ids, int64_t n_ops,
                           const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,
                           const int32_t* result2, const std::vector<int32_t>& keep_ids, const CompileOptions& opt,
                           TaskGraph& G) {
@@ -55,21 +55,26 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         std::fprintf(stderr, "[compile] %-25s %8.3f s\n", what, std::chrono::duration<double>(t1 - t_last).count());
         t_last = t1;
     };
-    if (n_ids < 1) return "n_block_ids must be >= 1";
+    if (n_ids_caller < 1) return "n_block_ids must be >= 1";
+    // Chain cuts (CompileOptions::chain_cuts): the early part of a cut accumulation chain writes a temporary block;
+    // the temporaries get the ids n_ids_caller .. n_ids-1 and are ordinary blocks for everything below.
+    const int64_t n_cuts = opt.chain_cuts ? (int64_t)opt.chain_cuts->size() : 0;
+    const int64_t n_ids = n_ids_caller + n_cuts;
+    if (n_ids > 0x7fffffff) return "too many block ids";
     if (n_ops > 0x7fffffff) return "too many operations";
     std::vector<IdInfo> info(n_ids);
     for (int64_t k = 0; k < n_input; k++) {
         int32_t id = input_ids[k];
-        if (id <= 0 || id >= n_ids) return "input block id out of range";
+        if (id <= 0 || id >= n_ids_caller) return "input block id out of range";
         info[id].is_input = true;
     }
     for (int32_t id : keep_ids)
-        if (id > 0 && id < n_ids) info[id].keep = true;
+        if (id > 0 && id < n_ids_caller) info[id].keep = true;
 
     // ---- validation + per-block writer / reader statistics --------------------------------------
     // All passes over the op list run on every host thread; where the serial order matters (first writer
     // of a block, first inverse of a factor, the lowest offending op) it is recovered with atomic minima.
-    auto bad_id = [&](int32_t id) { return id < 0 || id >= n_ids; };
+    auto bad_id = [&](int32_t id) { return id < 0 || id >= n_ids_caller; };
     auto is_acc = [](uint8_t o) { return o == OP_MUL || o == OP_MULNEG || o == OP_MULT; };
     auto op_error = [&](int64_t i) -> const char* {          // checks that need no other op
         const uint8_t o = op[i];
@@ -210,6 +215,29 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         const IdInfo& w = info[result[i]];
         return w.first_writer == i && !w.fused_away && !op_fused[i];   // fused products are opened by their sub, folded inverses by their lu
     };
+    // chain cuts by the block id the (uncut) task produces; a cut is applied if it still fits the chain
+    std::vector<int32_t> cut_of(n_cuts ? n_ids : 0, -1);
+    for (int64_t c = 0; c < n_cuts; c++) {
+        const ChainCut& cc = (*opt.chain_cuts)[c];
+        if (cc.out_id > 0 && cc.out_id < n_ids_caller && cut_of[cc.out_id] < 0) cut_of[cc.out_id] = (int32_t)c;
+    }
+    // number of operand pairs of the task op i opens, if it is a GEMM task (0 otherwise)
+    auto chain_len = [&](int64_t i) -> int32_t {
+        const uint8_t o = op[i];
+        if (is_acc(o)) return info[result[i]].n_writers;
+        if (o == OP_SUB && src[i] > 0 && info[src[i]].fused_away && fused_sub_of[src[i]] == i) return info[src[i]].n_writers;
+        return 0;
+    };
+    auto cut_for = [&](int64_t i) -> int32_t {       // index of the applicable cut of the task op i opens, or -1
+        if (!n_cuts) return -1;
+        const int32_t c = cut_of[result[i]];
+        if (c < 0) return -1;
+        const ChainCut& cc = (*opt.chain_cuts)[c];
+        const int32_t n = chain_len(i);
+        if (cc.n_early <= 0 || cc.n_early >= n || (int32_t)cc.early_pos.size() != cc.n_early || cc.early_pos.back() >= n) return -1;
+        return c;
+    };
+    std::vector<int32_t> cut_of_task;                // final task of a cut chain -> cut index (its early task precedes it)
     {
         int nth = 1;
 #ifdef _OPENMP
@@ -220,12 +248,14 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
 #pragma omp parallel for schedule(static, 1) num_threads(nth)
         for (int c = 0; c < nth; c++) {
             int64_t k = 0;
-            for (int64_t i = c * chunk, e = std::min(n_ops, i + chunk); i < e; i++) k += opens_task(i);
+            for (int64_t i = c * chunk, e = std::min(n_ops, i + chunk); i < e; i++)
+                if (opens_task(i)) k += (cut_for(i) >= 0) ? 2 : 1;
             first_task[c + 1] = k;
         }
         for (int c = 0; c < nth; c++) first_task[c + 1] += first_task[c];
         if (first_task[nth] > 0x7fffffff) return "too many tasks";
         G.tasks.resize(first_task[nth]);
+        if (n_cuts) cut_of_task.assign(first_task[nth], -1);
 #pragma omp parallel for schedule(static, 1) num_threads(nth)
         for (int c = 0; c < nth; c++) {
             int64_t tid = first_task[c];
@@ -265,6 +295,23 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
                         }
                         break;
                     }
+                }
+                const int32_t cut = (t.type == T_GEMM) ? cut_for(i) : -1;
+                if (cut >= 0) {
+                    // early part: tmp = init -/+ sum over the early pairs; the final task starts from tmp
+                    const ChainCut& cc = (*opt.chain_cuts)[cut];
+                    const int32_t tmp = (int32_t)(n_ids_caller + cut);
+                    Task e1 = t;
+                    e1.out = tmp;
+                    e1.n_pairs = cc.n_early;
+                    IdInfo& tw = info[tmp];
+                    tw.n_writers = 1; tw.n_readers = 1; tw.kind = OP_MUL; tw.first_writer = i;
+                    G.task_of[tmp] = (int32_t)tid;
+                    G.tasks[tid++] = e1;
+                    t.n_pairs -= cc.n_early;
+                    t.flags = (t.flags & (TF_NEGATE | TF_TRANSB)) | TF_INIT;
+                    t.init = tmp;
+                    cut_of_task[tid] = cut;
                 }
                 G.task_of[r] = (int32_t)tid;
                 if (t.type == T_LU) G.task_of[t.out2] = (int32_t)tid;
@@ -307,7 +354,9 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
             Task& t = G.tasks[tid];
             if (is_acc(o)) {
                 const int32_t k = __atomic_fetch_add(&fill[tid], 1, __ATOMIC_RELAXED);
-                if (k < t.n_pairs) { G.pairs[t.pair_begin + k] = Pair{src[i], src2[i]}; pair_op[t.pair_begin + k] = (int32_t)i; }
+                int32_t pb = t.pair_begin, np = t.n_pairs;
+                if (n_cuts && cut_of_task[tid] >= 0) { pb = G.tasks[tid - 1].pair_begin; np += G.tasks[tid - 1].n_pairs; }
+                if (k < np) { G.pairs[pb + k] = Pair{src[i], src2[i]}; pair_op[pb + k] = (int32_t)i; }
                 flops += 524288.0;
                 gemm_pairs++;
             } else if (o == OP_SUB) {
@@ -325,18 +374,32 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
         for (int64_t t = 0; t < nt; t++) {
             const Task& T = G.tasks[t];
             if (T.type != T_GEMM) continue;
-            if (fill[t] != T.n_pairs) { mismatch = 1; continue; }
-            const int32_t n = T.n_pairs, pb = T.pair_begin;
+            const int32_t cut = n_cuts ? cut_of_task[t] : -1;
+            if (n_cuts && cut < 0 && t + 1 < nt && cut_of_task[t + 1] >= 0) continue;   // early part: filled through its final task
+            int32_t n = T.n_pairs, pb = T.pair_begin;
+            if (cut >= 0) { pb = G.tasks[t - 1].pair_begin; n += G.tasks[t - 1].n_pairs; }
+            if (fill[t] != n) { mismatch = 1; continue; }
             bool sorted = true;
             for (int32_t k = 1; k < n; k++) sorted = sorted && pair_op[pb + k - 1] < pair_op[pb + k];
-            if (sorted) continue;
-            // small insertion sort by op index (chains are short: up to a few hundred operands)
+            if (sorted && cut < 0) continue;
+            // sort by op index (chains are short: up to a few hundred operands)
             std::vector<std::pair<int32_t, Pair>> tmp(n);
             for (int32_t k = 0; k < n; k++) tmp[k] = {pair_op[pb + k], G.pairs[pb + k]};
-            std::sort(tmp.begin(), tmp.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-            for (int32_t k = 0; k < n; k++) G.pairs[pb + k] = tmp[k].second;
+            if (!sorted) std::sort(tmp.begin(), tmp.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            if (cut < 0) {
+                for (int32_t k = 0; k < n; k++) G.pairs[pb + k] = tmp[k].second;
+            } else {
+                // the early positions (in op order) first, then the rest (in op order)
+                const ChainCut& cc = (*opt.chain_cuts)[cut];
+                std::vector<char> early(n, 0);
+                for (int32_t q : cc.early_pos) early[q] = 1;
+                int32_t w = pb;
+                for (int32_t k = 0; k < n; k++) if (early[k]) G.pairs[w++] = tmp[k].second;
+                for (int32_t k = 0; k < n; k++) if (!early[k]) G.pairs[w++] = tmp[k].second;
+            }
         }
         if (mismatch) return "internal: pair count mismatch";
+        if (n_cuts) for (int64_t t = 0; t < nt; t++) G.chain_splits += cut_of_task[t] >= 0;
     }
     lap("pairs");
     // ---- multi-GPU: owners, mirrors of remote blocks and their fetch tasks ---------------------------
@@ -352,10 +415,14 @@ std::string compile_tasks(int64_t n_ids, int64_t n_input, const int32_t* input_i
     if (nown > 1) {
         if (nown > MAX_GPUS) return "too many GPUs";
         if (opt.owner_of_id)
-            for (int64_t id = 1; id < n_ids; id++) {
+            for (int64_t id = 1; id < n_ids_caller; id++) {
                 if (opt.owner_of_id[id] < 0 || opt.owner_of_id[id] >= nown) return "block owner out of range";
                 G.owner_of[id] = opt.owner_of_id[id];
             }
+        for (int64_t c = 0; c < n_cuts; c++) {       // a temporary lives where the block it becomes lives
+            const int32_t o = (*opt.chain_cuts)[c].out_id;
+            if (o > 0 && o < n_ids_caller) G.owner_of[n_ids_caller + c] = G.owner_of[o];
+        }
         for (int64_t id = 1; id < n_ids; id++)
             if (alias_to[id]) G.owner_of[id] = G.owner_of[alias_to[id]];
         auto cn = [&](int32_t id) { return alias_to[id] ? alias_to[id] : id; };

@@ -69,19 +69,41 @@ ModelResult model_executor(const TaskGraph& G, const ModelParams& M) {
     for (int64_t t = 0; t < nt; t++) dep[t] = G.tasks[t].n_deps;
 
     // longest paths under the model's durations (successor lists name group leaders; slices are alike)
-    std::vector<float> top(nt, 0.f), bot(nt, 0.f);
+    const int NG = std::max(1, G.n_owners);
+    auto owner_of_task = [&](int32_t t) { return NG > 1 ? (int)G.task_owner[t] : 0; };
+    std::vector<float> top(nt, 0.f), bot(nt, 0.f), hop(nt);
+    for (int64_t t = 0; t < nt; t++) {
+        const Task& T = G.tasks[t];
+        double h = hop_time(T, M);
+        if (NG > 1) {      // an operand in a peer's HBM
+            const uint32_t me = (uint32_t)owner_of_task((int32_t)t);
+            const bool two = (T.type == T_GEMM || T.type == T_SUB);
+            bool remote = false;
+            for (int p = 0, n = n_stages(T); p < n && !remote; p++) {
+                const Pair& pr = G.pairs[T.pair_begin + p];
+                remote = ((uint32_t)pr.a >> REF_SHIFT) != me || (two && ((uint32_t)pr.b >> REF_SHIFT) != me);
+            }
+            if (remote) h += M.t_load_remote - M.t_load;
+        }
+        hop[t] = (float)h;
+    }
+    const float d_remote = (float)(M.t_release_remote - M.t_release);
     for (int64_t t = 0; t < nt; t++) {
         const Task& T = G.tasks[t];
         const int32_t lead = leader_of(G, (int32_t)t);
         if (lead != t) top[t] = top[lead];
-        const float d = (float)hop_time(T, M);
-        for (int32_t s = T.succ_begin; s < T.succ_end; s++) top[G.succ[s]] = std::max(top[G.succ[s]], top[t] + d);
+        const int me = owner_of_task((int32_t)t);
+        for (int32_t s = T.succ_begin; s < T.succ_end; s++) {
+            const int32_t nx = G.succ[s];
+            top[nx] = std::max(top[nx], top[t] + hop[t] + (owner_of_task(nx) != me ? d_remote : 0.f));
+        }
     }
     for (int64_t t = nt - 1; t >= 0; t--) {
         const Task& T = G.tasks[t];
+        const int me = owner_of_task((int32_t)t);
         float m = 0.f;
-        for (int32_t s = T.succ_begin; s < T.succ_end; s++) m = std::max(m, bot[G.succ[s]]);
-        bot[t] = m + (float)hop_time(T, M);
+        for (int32_t s = T.succ_begin; s < T.succ_end; s++) m = std::max(m, bot[G.succ[s]] + (owner_of_task(G.succ[s]) != me ? d_remote : 0.f));
+        bot[t] = m + hop[t];
     }
     std::vector<char> hi(nt, 0);
     for (int sg = 0; sg < nseg; sg++) {
@@ -96,41 +118,54 @@ ModelResult model_executor(const TaskGraph& G, const ModelParams& M) {
             }
     }
 
+    // Several GPUs (owner-compiled graph): every GPU has its own CTAs and ready queues; releasing a successor on a peer
+    // and loading an operand block from a peer (fetch tasks, unmirrored operands) cost NVLink round trips.
+    struct Gpu {
+        std::vector<int32_t> queue, waiting;
+        std::vector<double> pub;
+        int32_t head = 0, tail = 0, n_bulk = 0;
+        std::deque<int32_t> hiq;
+        std::priority_queue<std::pair<float, int32_t>> ready_pq;
+        std::vector<int32_t> idle;
+    };
     for (int sg = 0; sg < nseg; sg++) {
         const int32_t t0 = G.seg_begin[sg], t1 = G.seg_begin[sg + 1];
-        int32_t n_bulk = 0;
-        for (int32_t t = t0; t < t1; t++) n_bulk += !hi[t];
-        std::vector<int32_t> queue(n_bulk, -1);          // the (bulk) FIFO ready queue
-        std::vector<double> pub(n_bulk, 1e300);          // when the entry becomes visible
-        std::vector<int32_t> waiting(n_bulk, -1);        // CTA that pre-claimed the slot
-        int32_t head = 0, tail = 0;
-        std::deque<int32_t> hiq;                                         // policy 2
-        std::priority_queue<std::pair<float, int32_t>> ready_pq;         // policy 1: (remaining path, task)
-        std::vector<int32_t> idle;                                       // policies 1, 2: spinning CTAs (lazy deletion)
-        std::vector<char> spinning(W, 0);
-        std::vector<int32_t> own(W, -1);                                 // pre-claimed bulk slot
+        std::vector<Gpu> gpu(NG);
+        for (int32_t t = t0; t < t1; t++) gpu[owner_of_task(t)].n_bulk += !hi[t];
+        for (Gpu& g : gpu) { g.queue.assign(g.n_bulk, -1); g.pub.assign(g.n_bulk, 1e300); g.waiting.assign(g.n_bulk, -1); }
+        const int WT = W * NG;
+        std::vector<char> spinning(WT, 0);
+        std::vector<int32_t> own(WT, -1);                                // pre-claimed bulk slot
         for (int32_t k = G.seg_init[2 * sg]; k < G.seg_init[2 * sg + 2]; k++) {
             const int32_t t = G.initial[k];
-            if (M.policy == 1) ready_pq.push({bot[t], t});
-            else if (hi[t]) hiq.push_back(t);
-            else { queue[tail] = t; pub[tail] = 0.0; tail++; }
+            Gpu& g = gpu[owner_of_task(t)];
+            if (M.policy == 1) g.ready_pq.push({bot[t], t});
+            else if (hi[t]) g.hiq.push_back(t);
+            else { g.queue[g.tail] = t; g.pub[g.tail] = 0.0; g.tail++; }
         }
-        std::vector<double> math_free(W, 0.0);
-        std::vector<double> rel(W * 3, 0.0);       // when ring stage (it % 3) of a CTA is free again
-        std::vector<uint32_t> it(W, 0);
+        std::vector<double> math_free(WT, 0.0);
+        std::vector<double> rel(WT * 3, 0.0);      // when ring stage (it % 3) of a CTA is free again
+        std::vector<uint32_t> it(WT, 0);
         std::priority_queue<Ev> pq;
-        for (int c = 0; c < W; c++) pq.push({0.0, EV_CLAIM, c, -1});
+        for (int c = 0; c < WT; c++) pq.push({0.0, EV_CLAIM, c, -1});
         double seg_end = 0.0;
         // begin(): the producer of `cta` knows at time tb which task it got
         auto begin = [&](int cta, int32_t task, double tb) {
             const Task& T = G.tasks[task];
             const int nst = n_stages(T);
             const double ts = stage_time(T, M);
+            const uint32_t me = (uint32_t)(cta / W);
             double issue = tb + M.t_desc, m = math_free[cta];
             for (int p = 0; p < nst; p++, it[cta]++) {
                 double& r = rel[cta * 3 + it[cta] % 3];
                 issue = std::max(issue, r);
-                m = std::max(m, issue + M.t_load) + ts;
+                double tl_ = M.t_load;
+                if (NG > 1) {
+                    const Pair& pr = G.pairs[T.pair_begin + p];
+                    const bool two = (T.type == T_GEMM || T.type == T_SUB);
+                    if (((uint32_t)pr.a >> REF_SHIFT) != me || (two && ((uint32_t)pr.b >> REF_SHIFT) != me)) { tl_ = M.t_load_remote; R.remote_loads++; }
+                }
+                m = std::max(m, issue + tl_) + ts;
                 r = m;                              // the stage is free again once the math warps consumed it
             }
             m += M.t_epilogue;
@@ -139,10 +174,10 @@ ModelResult model_executor(const TaskGraph& G, const ModelParams& M) {
             pq.push({m, EV_FINISH, cta, task});
             pq.push({issue + 0.05, EV_CLAIM, cta, -1});    // the producer claims again right after its last issue
         };
-        auto pop_idle = [&]() -> int {
-            while (!idle.empty()) {
-                const int c = idle.back();
-                idle.pop_back();
+        auto pop_idle = [&](Gpu& g) -> int {
+            while (!g.idle.empty()) {
+                const int c = g.idle.back();
+                g.idle.pop_back();
                 if (spinning[c]) { spinning[c] = 0; return c; }
             }
             return -1;
@@ -153,63 +188,69 @@ ModelResult model_executor(const TaskGraph& G, const ModelParams& M) {
             switch (e.kind) {
                 case EV_CLAIM: {
                     const int c = e.cta;
+                    Gpu& g = gpu[c / W];
                     if (M.policy == 1) {
-                        if (!ready_pq.empty()) { const int32_t t = ready_pq.top().second; ready_pq.pop(); begin(c, t, e.t + M.t_poll_hit); }
-                        else { spinning[c] = 1; idle.push_back(c); }
+                        if (!g.ready_pq.empty()) { const int32_t t = g.ready_pq.top().second; g.ready_pq.pop(); begin(c, t, e.t + M.t_poll_hit); }
+                        else { spinning[c] = 1; g.idle.push_back(c); }
                         break;
                     }
-                    if (M.policy == 2 && !hiq.empty()) {
-                        const int32_t t = hiq.front();
-                        hiq.pop_front();
+                    if (M.policy == 2 && !g.hiq.empty()) {
+                        const int32_t t = g.hiq.front();
+                        g.hiq.pop_front();
                         begin(c, t, e.t + M.t_poll_hit + M.t_cas);
                         break;
                     }
                     if (own[c] < 0) {
-                        if (head >= n_bulk) {       // no bulk work left: policy 0 exits, policy 2 keeps serving the hi queue
-                            if (M.policy == 2) { spinning[c] = 1; idle.push_back(c); }
+                        if (g.head >= g.n_bulk) {   // no bulk work left: policy 0 exits, policy 2 keeps serving the hi queue
+                            if (M.policy == 2) { spinning[c] = 1; g.idle.push_back(c); }
                             break;
                         }
-                        own[c] = head++;
-                        waiting[own[c]] = c;
+                        own[c] = g.head++;
+                        g.waiting[own[c]] = c;
                     }
-                    if (pub[own[c]] <= e.t) { const int32_t slot = own[c]; own[c] = -1; begin(c, queue[slot], e.t + M.t_poll_hit); }
-                    else { spinning[c] = 1; if (M.policy == 2) idle.push_back(c); }
+                    if (g.pub[own[c]] <= e.t) { const int32_t slot = own[c]; own[c] = -1; begin(c, g.queue[slot], e.t + M.t_poll_hit); }
+                    else { spinning[c] = 1; if (M.policy == 2) g.idle.push_back(c); }
                     break;
                 }
                 case EV_PUBLISH: {
+                    Gpu& g = gpu[owner_of_task(e.task)];
                     if (M.policy == 1) {
-                        const int c = pop_idle();
+                        const int c = pop_idle(g);
                         if (c >= 0) begin(c, e.task, e.t + M.t_poll);
-                        else ready_pq.push({bot[e.task], e.task});
+                        else g.ready_pq.push({bot[e.task], e.task});
                     } else if (hi[e.task]) {
-                        const int c = pop_idle();   // keeps its pre-claimed bulk slot for afterwards
+                        const int c = pop_idle(g);  // keeps its pre-claimed bulk slot for afterwards
                         if (c >= 0) begin(c, e.task, e.t + M.t_poll + M.t_cas);
-                        else hiq.push_back(e.task);
+                        else g.hiq.push_back(e.task);
                     } else {
                         const int32_t slot = e.cta;
-                        pub[slot] = e.t;
-                        const int c = waiting[slot];
-                        if (c >= 0 && spinning[c] && own[c] == slot) { spinning[c] = 0; own[c] = -1; begin(c, queue[slot], e.t + M.t_poll); }
+                        g.pub[slot] = e.t;
+                        const int c = g.waiting[slot];
+                        if (c >= 0 && spinning[c] && own[c] == slot) { spinning[c] = 0; own[c] = -1; begin(c, g.queue[slot], e.t + M.t_poll); }
                     }
                     break;
                 }
                 case EV_FINISH: {
                     seg_end = std::max(seg_end, e.t);
                     const Task& T = G.tasks[e.task];
+                    const int me = e.cta / W;
                     for (int32_t s = T.succ_begin; s < T.succ_end; s++) {
                         const int32_t nx = G.succ[s];
                         if (--dep[nx] != 0) continue;
-                        for (int q = 0, g = task_group_size(G.tasks[nx]); q < g; q++) {
+                        const int o = owner_of_task(nx);
+                        Gpu& g = gpu[o];
+                        if (o != me) R.remote_releases++;
+                        for (int q = 0, gs = task_group_size(G.tasks[nx]); q < gs; q++) {
                             int32_t slot = -1;
-                            if (M.policy != 1 && !hi[nx + q]) { slot = tail++; queue[slot] = nx + q; }   // atomicAdd(tail) at release time
-                            pq.push({e.t + M.t_release, EV_PUBLISH, slot, nx + q});
+                            if (M.policy != 1 && !hi[nx + q]) { slot = g.tail++; g.queue[slot] = nx + q; }   // atomicAdd(tail) at release time
+                            pq.push({e.t + (o == me ? M.t_release : M.t_release_remote), EV_PUBLISH, slot, nx + q});
                         }
                     }
                     break;
                 }
             }
         }
-        R.makespan_us += seg_end + M.t_launch;
+        R.makespan_us += seg_end + (NG > 1 ? M.t_launch_dist : M.t_launch);
     }
     return R;
 }

@@ -21,6 +21,9 @@ struct ModelParams {        // microseconds, measured with the executor's trace 
     double t_desc = 0.6;           // task record fetch
     double t_load = 1.3;           // bulk copy of one operand pair into shared memory
     double t_launch = 30.0;        // per segment (cooperative launch + drain)
+    double t_release_remote = 5.5; // successor on a peer GPU: system-scope fence + two NVLink atomics + remote store
+    double t_load_remote = 4.0;    // operand pair with a block in a peer's HBM (fetch tasks, unmirrored operands)
+    double t_launch_dist = 300.0;  // per segment with a host barrier across ranks
     double t_cas = 0.5;            // policy 2: extra compare-and-swap to take a high-priority task
     double hi_slack_us = 100.0;    // policy 2: tasks with less slack than this are high priority
     int policy = 0;                // 0 = the executor's FIFO ready queue; 1 = ideal list scheduling by longest remaining path (what-if)
@@ -31,6 +34,7 @@ struct ModelResult {
     double critical_path_us = 0;   // longest dependent chain under the same durations (infinite SMs)
     double busy_us = 0;            // sum of math time over all CTAs
     int64_t n_tasks = 0;
+    int64_t remote_loads = 0, remote_releases = 0;
     int64_t n_hi = 0;              // policy 2: tasks in the high-priority class
 };
 

@@ -363,7 +363,7 @@ extern "C" int soglu_debug_compile_raw(int64_t n_ids, int64_t n_input, const int
 // Timed model of the executor on the compiled graph of a problem (device/model.cpp; diagnostics, host only).
 // opts[8] = {split_narrow, max_slots, pr, pc, nb, chains, policy, hi_slack_us for the compiler}; params: n_params doubles overriding ModelParams in
 // declaration order (NaN = keep the default); out[12] = {makespan_us, critical_path_us, busy_us, tasks, segments, pairs, hi tasks, cp_us, cp_early_us, proposed cuts,
-// cp_us after the cuts, cuts applied}.
+// cp_us after the cuts, cuts applied, operand pairs loaded from a peer, successor groups released on a peer}.
 #include "../device/model.h"
 #include <cmath>
 extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, const double* params, int n_params, double* out) {
@@ -381,6 +381,15 @@ extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, c
     for (const auto& r : pl.U) keep.push_back(r.id);
     soglu::CompileOptions co;
     co.split_narrow = (int)opts[0]; co.max_slots = opts[1];
+    const int pr = (int)std::max<int64_t>(1, opts[2]), pc = (int)std::max<int64_t>(1, opts[3]), nb = (int)std::max<int64_t>(1, opts[4]), world = pr * pc;
+    if (world > soglu::MAX_GPUS) { soglu::set_error("bad process grid"); return SOGLU_ERR_ARG; }
+    std::vector<int8_t> owners;
+    if (world > 1) {     // 2D block-cyclic ownership of nb x nb squares, as soglu_create_dist
+        owners.assign(pl.storage, 0);
+        for (int64_t id = 1; id < pl.storage; id++)
+            if (pl.brow[id] >= 0 && pl.bcol[id] >= 0) owners[id] = (int8_t)(((pl.brow[id] / nb) % pr) * pc + ((pl.bcol[id] / nb) % pc));
+        co.owner_of_id = owners.data(); co.n_owners = world;
+    }
     const int chains = (int)opts[5];   // 0 = off, 1 = analyse only, 2 = analyse + recompile with the proposed cuts
     co.analyze_chains = chains > 0;
     const int policy = (int)opts[6];
@@ -400,7 +409,7 @@ extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, c
     soglu::ModelParams M;
     M.policy = policy;
     double* field[] = {nullptr, &M.t_pair, &M.t_pair_half, &M.t_pair_quarter, &M.t_lu_fused, &M.t_lu, &M.t_llt_fused, &M.t_inv, &M.t_sub,
-                       &M.t_epilogue, &M.t_release, &M.t_poll, &M.t_poll_hit, &M.t_desc, &M.t_load, &M.t_launch, &M.t_cas, &M.hi_slack_us};
+                       &M.t_epilogue, &M.t_release, &M.t_poll, &M.t_poll_hit, &M.t_desc, &M.t_load, &M.t_launch, &M.t_cas, &M.hi_slack_us, &M.t_release_remote, &M.t_load_remote, &M.t_launch_dist};
     for (int k = 0; k < n_params && k < (int)(sizeof field / sizeof field[0]); k++) {
         if (!params || std::isnan(params[k])) continue;
         if (k == 0) M.n_ctas = (int)params[0]; else *field[k] = params[k];
@@ -408,6 +417,7 @@ extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, c
     const soglu::ModelResult R = soglu::model_executor(G, M);
     out[0] = R.makespan_us; out[1] = R.critical_path_us; out[2] = R.busy_us; out[3] = (double)G.tasks.size();
     out[4] = (double)G.seg_begin.size() - 1; out[5] = (double)G.pairs.size(); out[6] = (double)R.n_hi;
+    out[12] = (double)R.remote_loads; out[13] = (double)R.remote_releases;
     return SOGLU_OK;
 }
 

@@ -1,0 +1,116 @@
+"""The compiled task graph, executed on the host (tests/emu/emu_tasks.cpp, test infrastructure), must reproduce the
+factors the reference's operation list defines -- checked against the oracle, no GPU.  Covers what the task compiler
+does to the list: fused sub / inverse tasks, aliased inverses, row slices, slot recycling, and the chain cuts of
+option chain_cuts (early part of an accumulation chain as its own task)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, write_case_mtx
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def emu(sg, tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libemu_tasks.so")
+    pkg = os.path.join(ROOT, "sparse-operator-graph-lu_b200")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-shared", "-o", out, os.path.join(ROOT, "tests", "emu", "emu_tasks.cpp"),
+                    "-L" + pkg, "-lsoglu_b200", "-Wl,-rpath," + pkg], check=True)
+    L = ctypes.CDLL(out)
+    vp, i64 = ctypes.c_void_p, ctypes.c_int64
+    L.emu_run.argtypes = [i64, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, ctypes.c_int, ctypes.c_double, i64, ctypes.c_int, ctypes.c_uint64, vp, vp, ctypes.c_char_p, ctypes.c_int]
+    return L
+
+
+def run_emu(emu, p, mode=0, slack=1e9, max_slots=0, split=1, seed=12345):
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ops = p.i32("ops")
+    cols = [np.ascontiguousarray(ops[:, k]) for k in range(5)]
+    opc = np.ascontiguousarray(ops[:, 0].astype(np.uint8))
+    n_in = p.size("n_input")
+    ids = np.arange(1, n_in + 1, dtype=np.int32)
+    vals = p.f64("input_vals")
+    keep = np.ascontiguousarray(np.concatenate([p.i32("L")[:, 0], p.i32("U")[:, 0]]).astype(np.int32))
+    out = np.zeros((len(keep), 64, 64))
+    stats = np.zeros(5, dtype=np.int64)
+    err = ctypes.create_string_buffer(256)
+    rc = emu.emu_run(p.size("storage"), n_in, ptr(ids), ptr(vals), len(ops), ptr(cols[1]), ptr(cols[2]), ptr(opc), ptr(cols[3]), ptr(cols[4]),
+                     len(keep), ptr(keep), mode, slack, max_slots, split, seed, ptr(out), ptr(stats), err, 256)
+    assert rc == 0, err.value.decode()
+    return keep, out, dict(zip("tasks segments slots cuts split_tasks".split(), stats.tolist()))
+
+
+def check_against_oracle(oracle, p, keep, blocks):
+    x_ref, h = oracle.run(p)
+    num = den = 0.0
+    for k, bid in enumerate(keep):
+        ref = oracle.block(h, bid)
+        num += float(np.sum((blocks[k] - ref) ** 2))
+        den += float(np.sum(ref ** 2))
+    oracle.free(h)
+    assert np.sqrt(num / den) <= TOL
+    # and the solution from the emulated factors (block substitution by the oracle)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    h2 = oracle.L.oracle_create(p.size("storage"))
+    oracle.L.oracle_set_inputs(h2, len(keep), ptr(keep), ptr(np.ascontiguousarray(blocks)))
+    Lf, Uf = np.ascontiguousarray(p.i32("L")), np.ascontiguousarray(p.i32("U"))
+    b = p.f64("b_perm")
+    x = np.zeros_like(b)
+    rc = oracle.L.oracle_solve(h2, len(Lf), ptr(Lf), len(Uf), ptr(Uf) if len(Uf) else None, p.size("block_rows"), p.size("symmetric"), ptr(b), ptr(x))
+    oracle.free(h2)
+    assert rc == 0
+    assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) <= TOL
+
+
+CASES = ["lap2d_64", "lap2d_64_sym", "nine2d_40", "lap3d_13x11x9", "lap3d_24", "lap3d_16_sym", "banded_3000"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_compiled_graph_reproduces_the_factors(sg, emu, oracle, tmp_path, name):
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    keep, blocks, st = run_emu(emu, p)
+    assert st["cuts"] == 0 and st["segments"] == 1
+    check_against_oracle(oracle, p, keep, blocks)
+
+
+@pytest.mark.parametrize("name,max_slots", [("lap3d_24", 5200), ("lap2d_64", 800)])
+def test_slot_recycling_keeps_the_factors(sg, emu, oracle, tmp_path, name, max_slots):
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    keep, blocks, st = run_emu(emu, p, max_slots=max_slots)
+    assert st["segments"] > 1 and st["slots"] <= max_slots
+    check_against_oracle(oracle, p, keep, blocks)
+
+
+@pytest.mark.parametrize("name,slack,split", [("lap3d_24", 1e9, 1), ("lap3d_24", 50.0, 1), ("lap3d_24", 1e9, 0), ("nine2d_40", 1e9, 1),
+                                              ("lap3d_16_sym", 1e9, 1), ("banded_3000", 1e9, 1), ("lap2d_64", 1e9, 1)])
+def test_chain_cuts_keep_the_factors(sg, emu, oracle, tmp_path, name, slack, split):
+    """Option chain_cuts: tasks near the critical path start their accumulation chain before the last operands exist;
+    the early pairs become a task of their own that writes a temporary block.  Same factors within the tolerance."""
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    _, _, st0 = run_emu(emu, p, split=split)
+    keep, blocks, st = run_emu(emu, p, mode=1, slack=slack, split=split)
+    if name in ("lap3d_24", "banded_3000"):
+        assert st["cuts"] > 0
+    assert st["tasks"] >= st0["tasks"] + st["cuts"]          # one more task per cut (more with row slices)
+    check_against_oracle(oracle, p, keep, blocks)
+
+
+def test_execution_order_does_not_matter(sg, emu, tmp_path):
+    """Task order and two random dependency-driven orders give bitwise the same factors (each task's arithmetic is fixed)."""
+    p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
+    for mode in (0, 1):
+        _, b0, _ = run_emu(emu, p, mode=mode, seed=0)
+        for seed in (1, 2):
+            _, b, _ = run_emu(emu, p, mode=mode, seed=seed)
+            np.testing.assert_array_equal(b, b0)
+
+
+def test_chain_cuts_with_recycling(sg, emu, oracle, tmp_path):
+    p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
+    keep, blocks, st = run_emu(emu, p, mode=1, slack=1e9, max_slots=6000)
+    assert st["cuts"] > 0 and st["segments"] > 1
+    check_against_oracle(oracle, p, keep, blocks)

@@ -415,3 +415,27 @@ def test_shared_priority_queue(sg, tmp_path, name, slack):
         np.testing.assert_array_equal(x, x0)
     ctx.close()
     ref.close()
+
+
+@experimental
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name,slack", [("lap3d_24", 10 ** 9), ("lap3d_24", 50), ("banded_3000", 10 ** 9), ("lap3d_16_sym", 10 ** 9)])
+def test_chain_cuts(sg, tmp_path, name, slack):
+    """Option chain_cuts: near-critical accumulation chains are cut into an early task (writes a temporary block) and a
+    late task that starts from it.  Same solution within the parity tolerance (the summation order changes)."""
+    g = load_golden(name)
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    ref = sg.Context(0)
+    ref.load(p)
+    f0 = ref.factor()
+    x0, _ = ref.solve(p)
+    ctx = sg.Context(0)
+    ctx.set_option("chain_cuts", slack)
+    ctx.load(p)
+    fs = ctx.factor()
+    assert fs["tasks"] > f0["tasks"]
+    x, _ = ctx.solve(p)
+    assert _rel(x, x0) <= 1e-12
+    assert _rel(x, g["x"]) <= TOL_X
+    ctx.close()
+    ref.close()
