@@ -48,6 +48,7 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
+    int64_t opt_lu_mode = 0;       // 1: blocked diagonal-block kernel (lu_blocked.cuh)
     int64_t opt_chain_cuts = 0;    // > 0: cut accumulation chains of tasks within this slack (us) of the critical path (two-pass compile)
     int64_t opt_hi_shared = 0;     // > 0: tasks with less estimated slack than this (us) go to a high-priority queue every CTA serves first
     int64_t opt_hi_ctas = 0;       // CTAs dedicated to a high-priority queue of small-slack tasks; 0 (default) = one FIFO
@@ -525,6 +526,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "chain_cuts") { if (c->compiled) return fail(SOGLU_ERR_ARG, "chain_cuts must be set before the first factor"); c->opt_chain_cuts = value; }
     else if (k == "hi_shared") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_shared must be set before the first factor"); c->opt_hi_shared = value; }
     else if (k == "hi_ctas") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_ctas must be set before the first factor"); c->opt_hi_ctas = value; }
+    else if (k == "lu_mode") c->opt_lu_mode = value;
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
@@ -671,6 +673,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     P.succ = c->succ.as<int32_t>();
     P.dep = c->dep.as<int32_t>();
     P.trace = nullptr;
+    P.lu_mode = (int32_t)c->opt_lu_mode;
     if (c->opt_trace && nt > 0) {
         if (!c->trace.p) CU(c->trace.alloc((size_t)nt * 6 * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->trace.p, 0, (size_t)nt * 6 * sizeof(unsigned long long), c->stream));
@@ -875,11 +878,12 @@ int soglu_set_matrix(soglu_ctx* c, int64_t n_ext, int64_t nnz, const int64_t* ro
 
 // debug: cycles of lu / write-out / inverses / total for one diagonal block (slot 1 = first input)
 int soglu_debug_diag_bench(soglu_ctx* c, int iters, long long* cycles4) {
-    if (!c || !c->compiled || c->G.n_slots < 8) return fail(SOGLU_ERR_ARG, "need a compiled problem");
+    if (!c || !c->compiled || c->G.n_slots < 12) return fail(SOGLU_ERR_ARG, "need a compiled problem");
     DevBuf d;
     CU(d.alloc(128));
+    CU(cudaMemsetAsync(d.p, 0, 128, c->stream));
     CU(launch_diag_bench(c->pool.as<double>(), iters, d.as<long long>(), c->stream));
-    CU(cudaMemcpyAsync(cycles4, d.p, 80, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(cycles4, d.p, 96, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     d.release();
     return SOGLU_OK;

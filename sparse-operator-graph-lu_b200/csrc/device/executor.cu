@@ -30,6 +30,7 @@
 // peers are mapped through CUDA IPC) use system-scope fences and atomics over NVLink.
 #include "executor.cuh"
 #include "ptx.cuh"
+#include "lu_blocked.cuh"
 
 namespace soglu {
 
@@ -66,7 +67,7 @@ struct __align__(16) SmemCtl {
     uint64_t full[N_STAGES];
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
-    double scratch[584];   // pivot row/column exchange buffers of the register-resident diag kernels
+    double scratch[lub::SCRATCH_DOUBLES > 584 ? lub::SCRATCH_DOUBLES : 584];   // exchange buffers of the diag kernels (lu3_reg: 584, lu_blocked: 1394)
 };
 
 constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
@@ -241,6 +242,29 @@ __device__ __forceinline__ void lu_task(const double* __restrict__ As, double* _
     }
 }
 
+// The same task with the blocked kernel (lu_blocked.cuh, option lu_mode = 1): factorisation in place in the stage's A
+// half, packed inverses in its (unused) B half, then the four result blocks are written out row by row.
+// A real function call (not inlined): its registers are allocated apart from the executor loop, which sits at the
+// 168-register limit of a 288-thread CTA; everything is passed by value so that ExecParams stays in the constant bank.
+__device__ __noinline__ void lu_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gU, double* gLi, double* gUi, int ct) {
+    const bool inv = gLi != nullptr || gUi != nullptr;
+    if (inv) lub::lu_blocked<true, false>(As, Ws, scr, ct);
+    else lub::lu_blocked<false, false>(As, nullptr, scr, ct);
+    for (int e = ct; e < BLK * BLK; e += N_MATH) {
+        const int i = e >> 6, j = e & 63, o = i * BLK_LD + j;
+        const double v = As[o];
+        gL[o] = (j < i) ? v : (j == i ? 1.0 : 0.0);
+        gU[o] = (j >= i) ? v : 0.0;
+        if (inv) {
+            const double w = Ws[o];
+            if (gLi) gLi[o] = (j < i) ? w : (j == i ? 1.0 : 0.0);
+            if (gUi) gUi[o] = (j >= i) ? w : 0.0;
+        }
+    }
+    // the stage was written through the generic proxy; the next bulk copy into it comes through the async proxy
+    ptx::fence_proxy_async();
+}
+
 // Y = T^-1 for a triangular block T in shared memory, general diagonal (standalone lowerInv /
 // upperInv tasks).  Forward elimination on W = unscaled rows of the inverse; TRANS inverts an
 // upper-triangular T through its transpose (multipliers read from row k, result written back
@@ -383,6 +407,10 @@ __device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const do
         }
 }
 
+// LU_MODE selects the diagonal-block kernel at compile time: the blocked one is a real function call, and a call in the
+// task loop changes the register allocation of the whole kernel (spills at the 168-register limit), so the default
+// instantiation must not contain it.
+template <int LU_MODE>
 __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
@@ -537,7 +565,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     break;
                 }
                 case T_LU:
-                    lu_task(As, ctl->scratch, P, d, ct);
+                    if (LU_MODE == 1) {
+                        lu_task_blocked(As, Bs, ctl->scratch, out, blk_ptr(P, d.out2), (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr,
+                                        (d.flags & TF_UINV) ? blk_ptr(P, d.out4) : nullptr, ct);
+                        // no accumulation chain spans another task: tell the compiler the accumulators are dead across the call
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                    }
+                    else lu_task(As, ctl->scratch, P, d, ct);
                     break;
                 case T_LLT:
                     llt_task(As, ctl->scratch, P, d, ct);
@@ -647,6 +684,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
             if (ct == 0 && it == iters - 1) { cycles[4] = e1 - e0; cycles[5] = e2 - e1; cycles[6] = e3 - e2; cycles[7] = e4 - e3; cycles[8] = e5 - e4; cycles[9] = e6 - e5; }
             if (a[0][0] == 1.2345e-300) pool[0] = a[1][1] + a[2][2] + a[3][3];
         }
+        {
+            // blocked kernel: fused (slots 8..11 receive L, U, L^-1, U^-1) and factors only
+            double* Ws = As + BLK_ELEMS;
+            d.out = 8; d.out2 = 9; d.init = 10; d.out4 = 11;
+            d.flags = TF_LINV | TF_UINV;
+            for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
+            math_sync();
+            long long b0 = clock64();
+            lu_task_blocked(As, Ws, ctl->scratch, pool + 8 * (size_t)BLK_ELEMS, pool + 9 * (size_t)BLK_ELEMS, pool + 10 * (size_t)BLK_ELEMS, pool + 11 * (size_t)BLK_ELEMS, ct);
+            math_sync();
+            long long b1 = clock64();
+            for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
+            math_sync();
+            d.flags = 0;
+            long long b2 = clock64();
+            lu_task_blocked(As, Ws, ctl->scratch, pool + 8 * (size_t)BLK_ELEMS, pool + 9 * (size_t)BLK_ELEMS, nullptr, nullptr, ct);
+            math_sync();
+            long long b3 = clock64();
+            if (ct == 0 && it == iters - 1) { cycles[10] = b1 - b0; cycles[11] = b3 - b2; }
+            d.out = 2; d.out2 = 3; d.init = 4; d.out4 = 5;
+        }
         for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[2 * BLK_ELEMS + i];
         math_sync();
         long long c3 = clock64();
@@ -702,21 +760,22 @@ __global__ void unpack_block_kernel(const double* __restrict__ pool, int32_t slo
 size_t executor_smem_bytes() { return SMEM_BYTES; }
 
 int executor_max_grid(int device) {
-    cudaFuncSetAttribute(executor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(executor_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, executor_kernel, N_THREADS, SMEM_BYTES) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, executor_kernel<0>, N_THREADS, SMEM_BYTES) != cudaSuccess) return 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
 
 cudaError_t launch_executor(const ExecParams& p, int grid, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(executor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    const void* kernel = (p.lu_mode == 1) ? (const void*)executor_kernel<1> : (const void*)executor_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
     ExecParams pp = p;
     void* args[] = {&pp};
     // cooperative launch: the runtime guarantees that all CTAs are co-resident, which the
     // claim-then-wait ready queue relies on
-    return cudaLaunchCooperativeKernel((const void*)executor_kernel, dim3(grid), dim3(N_THREADS), args, SMEM_BYTES, stream);
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(N_THREADS), args, SMEM_BYTES, stream);
 }
 
 cudaError_t launch_diag_bench(double* pool, int iters, long long* cycles, cudaStream_t stream) {

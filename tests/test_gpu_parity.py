@@ -439,3 +439,30 @@ def test_chain_cuts(sg, tmp_path, name, slack):
     assert _rel(x, g["x"]) <= TOL_X
     ctx.close()
     ref.close()
+
+
+@experimental
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name", ["lap2d_64", "lap3d_24", "nine2d_40", "banded_3000", "lap3d_13x11x9"])
+def test_blocked_diagonal_kernel(sg, oracle, tmp_path, name):
+    """Option lu_mode=1: 16-column panels on the FP64 tensor cores instead of one pivot per barrier (lu_blocked.cuh,
+    emulated on the host by tests/test_lub_emulation.py).  Same factors within the parity tolerance."""
+    g = load_golden(name)
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    ctx = sg.Context(0)
+    ctx.set_option("lu_mode", 1)
+    ctx.load(p)
+    ctx.factor()
+    x, _ = ctx.solve(p)
+    assert _rel(x, g["x"]) <= TOL_X
+    x_ext, h = oracle.run(p)
+    worst = 0.0
+    for bid in list(p.i32("L")[:40, 0]) + list(p.i32("U")[:40, 0]):
+        ref = oracle.block(h, bid)
+        worst = max(worst, float(np.abs(ctx.get_block(bid) - ref).max() / max(1.0, np.abs(ref).max())))
+    oracle.free(h)
+    assert worst <= 1e-10
+    ctx.factor()                                  # twice: the stage buffers are reused as work space
+    x2, _ = ctx.solve(p)
+    np.testing.assert_array_equal(x2, x)
+    ctx.close()
