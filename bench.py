@@ -233,6 +233,8 @@ def main():
     ap.add_argument("--workload", default="lap3d_100", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", default="lap3d_64", choices=sorted(WORKLOADS), help="workload the CPU reference is timed on (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="executor option passed to soglu_set_option before the first factorisation (hi_shared, chain_cuts, lu_mode, ...); recorded in config.options")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
@@ -269,6 +271,9 @@ def main():
             torch.cuda.synchronize(dev)
 
     ctx = sg.Context(dev, rank, world)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     t0 = time.perf_counter()
     ctx.load(prob)
     if use_dist:
@@ -420,7 +425,8 @@ def main():
                        "segments": n_segments,   # executor launches per factorisation (pool recycling)
                        "l2": "inputs_exceed_l2 (block pool %.1f GB >> 126 MB L2)" % (first["pool_blocks"] * 34816 * 1e-9),
                        "factor_ms": t_factor * 1e3, "solve_ms": t_solve * 1e3, "factor_gflops": flops / t_factor * 1e-9,
-                       "solve_gbs": sbytes / t_solve * 1e-9, "host_plan_s": t_plan, "first_call_s": t_first},
+                       "solve_gbs": sbytes / t_solve * 1e-9, "host_plan_s": t_plan, "first_call_s": t_first,
+                       "options": dict(kv.split("=") for kv in args.opt)},
             "e2e": {"value": aggregate_gflops(flops + sflops, e2e_s, 1 if use_dist else world), "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),

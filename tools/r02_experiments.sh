@@ -1,0 +1,27 @@
+#!/bin/bash
+# First GPU call of round 2: validates and measures the options that were written without a GPU in round 1
+# (hi_shared, chain_cuts, lu_mode=1).  Every step runs under its own timeout so that a hang in an unmeasured
+# path cannot take the box down.  usage (from the repo root):
+#   gpurun --timeout 1500 -- 'bash tools/r02_experiments.sh > gpurun_out/r02_experiments.log 2>&1'
+set -u
+mkdir -p gpurun_out
+run() { echo; echo "=== $*"; timeout "${T:-300}" "$@"; echo "--- exit $?"; }
+
+python -c "import __graft_entry__ as g; g.build()"
+# 1. correctness of the new paths (opt-in tests)
+T=600 SOGLU_EXPERIMENTAL=1 run python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "shared_priority or chain_cuts or blocked_diagonal"
+# 2. the diagonal-block kernels in isolation (cycles)
+T=120 run python tools/diag_bench.py
+# 3. latency-bound configs, one option at a time
+for cfg in "lap3d 64" "nine2d 1024" "banded 200000"; do
+  T=300 run python tools/run_config.py $cfg
+  T=300 run python tools/run_config.py $cfg lu_mode=1
+  T=300 run python tools/run_config.py $cfg chain_cuts=200
+  T=300 run python tools/run_config.py $cfg hi_shared=1000
+  T=300 run python tools/run_config.py $cfg lu_mode=1 chain_cuts=200
+done
+# 4. the headline (100^3, throughput-bound): shared high-priority queue, thresholds around the model's optimum
+for s in 300 1000 3000; do
+  T=420 run python bench.py --steps 2 --warmup 3 --no-cpu-baseline --opt hi_shared=$s
+done
+T=420 run python bench.py --steps 2 --warmup 3 --no-cpu-baseline --opt hi_shared=1000 --opt lu_mode=1
