@@ -48,6 +48,7 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
+    int64_t opt_split_slack = 0;   // > 0: GEMM tasks within this slack (us) of the longest chain are row-split in wide levels too
     int64_t opt_lu_mode = 0;       // 1: blocked diagonal-block kernel (lu_blocked.cuh)
     int64_t opt_chain_cuts = 0;    // > 0: cut accumulation chains of tasks within this slack (us) of the critical path (two-pass compile)
     int64_t opt_hi_shared = 0;     // > 0: tasks with less estimated slack than this (us) go to a high-priority queue every CTA serves first
@@ -229,6 +230,7 @@ int finalize(soglu_ctx* c) {
     co.fuse_inv = c->opt_fuse_inv != 0;
     co.split_narrow = (int)c->opt_split;
     co.n_sms = c->sms;
+    co.split_slack_us = (double)std::max<int64_t>(0, c->opt_split_slack);
     co.hi_ctas = (int)std::max<int64_t>(0, std::min<int64_t>(c->opt_hi_ctas, c->exec_grid / 2));
     if (c->opt_hi_shared > 0) { co.hi_ctas = 0; co.hi_slack_us = (double)c->opt_hi_shared; }
     {
@@ -523,6 +525,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
     else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
     else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
+    else if (k == "split_slack") { if (c->compiled) return fail(SOGLU_ERR_ARG, "split_slack must be set before the first factor"); c->opt_split_slack = value; }
     else if (k == "chain_cuts") { if (c->compiled) return fail(SOGLU_ERR_ARG, "chain_cuts must be set before the first factor"); c->opt_chain_cuts = value; }
     else if (k == "hi_shared") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_shared must be set before the first factor"); c->opt_hi_shared = value; }
     else if (k == "hi_ctas") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_ctas must be set before the first factor"); c->opt_hi_ctas = value; }

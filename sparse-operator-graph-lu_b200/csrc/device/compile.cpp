@@ -709,6 +709,38 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
                 if (4 * w <= opt.n_sms) split[t] = 4;
                 else if (2 * w <= opt.n_sms) split[t] = 2;
             }
+        }
+        if (opt.split_slack_us > 0) {
+            // A task on (or near) the longest dependent chain delays everything behind it even when its level is wide:
+            // split those too.  Slack = longest chain - longest chain through the task, under the cost model of
+            // model.h with the width-based slices chosen above.
+            const ModelParams M;
+            std::vector<float> dur(nt), tl(nt, 0.f), bl(nt, 0.f);
+            for (int64_t t = 0; t < nt; t++) {
+                const Task& T = G.tasks[t];
+                double c;
+                switch (T.type) {
+                    case T_GEMM: c = T.n_pairs * (split[t] == 1 ? M.t_pair : (split[t] == 2 ? M.t_pair_half : M.t_pair_quarter)); break;
+                    case T_LU: c = (T.flags & (TF_LINV | TF_UINV)) ? M.t_lu_fused : M.t_lu; break;
+                    case T_LLT: c = (T.flags & TF_LINV) ? M.t_llt_fused : M.t_lu; break;
+                    case T_LOWERINV: case T_UPPERINV: c = M.t_inv; break;
+                    default: c = M.t_sub; break;
+                }
+                dur[t] = (float)(M.t_desc + M.t_load + c + M.t_epilogue + M.t_release + M.t_poll);
+            }
+            for (int64_t t = 0; t < nt; t++)
+                for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) tl[G.succ[e]] = std::max(tl[G.succ[e]], tl[t] + dur[t]);
+            float cp = 0.f;
+            for (int64_t t = nt - 1; t >= 0; t--) {
+                float m = 0.f;
+                for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) m = std::max(m, bl[G.succ[e]]);
+                bl[t] = dur[t] + m;
+                cp = std::max(cp, tl[t] + bl[t]);
+            }
+            for (int64_t t = 0; t < nt; t++)
+                if (G.tasks[t].type == T_GEMM && split[t] < 4 && cp - (tl[t] + bl[t]) < (float)opt.split_slack_us) split[t] = 4;
+        }
+        for (int64_t t = 0; t < nt; t++) {
             base[t + 1] = base[t] + split[t];
             if (split[t] > 1) G.split_tasks++;
         }

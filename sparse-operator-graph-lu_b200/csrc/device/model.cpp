@@ -105,6 +105,31 @@ ModelResult model_executor(const TaskGraph& G, const ModelParams& M) {
         for (int32_t s = T.succ_begin; s < T.succ_end; s++) m = std::max(m, bot[G.succ[s]] + (owner_of_task(G.succ[s]) != me ? d_remote : 0.f));
         bot[t] = m + hop[t];
     }
+    // composition of the longest chain (first segment's start to the last task): walk it from its head
+    if (nt > 0) {
+        int64_t cur = 0;
+        for (int64_t t = 0; t < nt; t++)
+            if (top[t] == 0.f && bot[t] > bot[cur]) cur = t;
+        while (true) {
+            const Task& T = G.tasks[cur];
+            const int kind = (T.type == T_GEMM) ? (((T.flags >> TF_NROWS_SHIFT) & 7) == 4 ? 0 : (((T.flags >> TF_NROWS_SHIFT) & 7) == 2 ? 1 : 2))
+                                                : ((T.type == T_LU || T.type == T_LLT) ? 3 : (T.type == T_SUB ? 4 : 5));
+            R.chain_tasks[kind]++;
+            R.chain_math_us[kind] += n_stages(T) * stage_time(T, M);
+            R.chain_overhead_us += hop[cur] - n_stages(T) * stage_time(T, M);
+            if (T.type == T_GEMM) R.chain_pairs[kind] += T.n_pairs;
+            int64_t nx = -1;
+            const int me = owner_of_task((int32_t)cur);
+            float best = -1.f;
+            for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+                const float v = bot[G.succ[e]] + (owner_of_task(G.succ[e]) != me ? d_remote : 0.f);
+                if (v > best) { best = v; nx = G.succ[e]; }
+            }
+            if (nx < 0) break;
+            if (owner_of_task((int32_t)nx) != me) { R.chain_overhead_us += d_remote; R.chain_remote_hops++; }
+            cur = nx;
+        }
+    }
     std::vector<char> hi(nt, 0);
     for (int sg = 0; sg < nseg; sg++) {
         float cp = 0.f;

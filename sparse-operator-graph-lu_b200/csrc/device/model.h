@@ -35,6 +35,9 @@ struct ModelResult {
     double busy_us = 0;            // sum of math time over all CTAs
     int64_t n_tasks = 0;
     int64_t remote_loads = 0, remote_releases = 0;
+    // the longest dependent chain by task kind: 0 GEMM whole block, 1 half, 2 quarter, 3 lu / llt, 4 sub / copy, 5 inverse
+    int64_t chain_tasks[6] = {0, 0, 0, 0, 0, 0}, chain_pairs[6] = {0, 0, 0, 0, 0, 0}, chain_remote_hops = 0;
+    double chain_math_us[6] = {0, 0, 0, 0, 0, 0}, chain_overhead_us = 0;
     int64_t n_hi = 0;              // policy 2: tasks in the high-priority class
 };
 

@@ -361,9 +361,10 @@ extern "C" int soglu_debug_compile_raw(int64_t n_ids, int64_t n_input, const int
 }
 
 // Timed model of the executor on the compiled graph of a problem (device/model.cpp; diagnostics, host only).
-// opts[8] = {split_narrow, max_slots, pr, pc, nb, chains, policy, hi_slack_us for the compiler}; params: n_params doubles overriding ModelParams in
+// opts[9] = {split_narrow, max_slots, pr, pc, nb, chains, policy, hi_slack_us for the compiler, split_slack_us}; params: n_params doubles overriding ModelParams in
 // declaration order (NaN = keep the default); out[12] = {makespan_us, critical_path_us, busy_us, tasks, segments, pairs, hi tasks, cp_us, cp_early_us, proposed cuts,
-// cp_us after the cuts, cuts applied, operand pairs loaded from a peer, successor groups released on a peer}.
+// cp_us after the cuts, cuts applied, operand pairs loaded from a peer, successor groups released on a peer,
+// longest chain: tasks[6], math us[6], pairs[6] by kind (GEMM whole / half / quarter, lu, sub, inverse), overhead us, remote hops}.
 #include "../device/model.h"
 #include <cmath>
 extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, const double* params, int n_params, double* out) {
@@ -394,6 +395,7 @@ extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, c
     co.analyze_chains = chains > 0;
     const int policy = (int)opts[6];
     co.hi_slack_us = (double)opts[7];   // > 0: the compiler classifies (as the executor option hi_shared does)
+    co.split_slack_us = (double)opts[8];
     soglu::TaskGraph G;
     std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
     if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
@@ -418,6 +420,8 @@ extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, c
     out[0] = R.makespan_us; out[1] = R.critical_path_us; out[2] = R.busy_us; out[3] = (double)G.tasks.size();
     out[4] = (double)G.seg_begin.size() - 1; out[5] = (double)G.pairs.size(); out[6] = (double)R.n_hi;
     out[12] = (double)R.remote_loads; out[13] = (double)R.remote_releases;
+    for (int k = 0; k < 6; k++) { out[14 + k] = (double)R.chain_tasks[k]; out[20 + k] = R.chain_math_us[k]; out[26 + k] = (double)R.chain_pairs[k]; }
+    out[32] = R.chain_overhead_us; out[33] = (double)R.chain_remote_hops;
     return SOGLU_OK;
 }
 

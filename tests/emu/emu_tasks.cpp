@@ -72,6 +72,7 @@ void inv_upper(const double* u, double* y) {     // U Y = I
 }
 }  // namespace
 
+// split: bit 0 = row slices in narrow levels, bit 1 = also near-critical tasks (split_slack), bit 2 = 8 SMs.
 // mode: 0 = default compile, 1 = analyse chains + recompile with the proposed cuts.  max_slots > 0 forces slot
 // recycling.  keep_out: n_keep dense 64x64 blocks.  stats = {tasks, segments, slots, chain cuts applied, row-split tasks}.
 extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids, const double* input_dense, int64_t n_ops, const int32_t* src,
@@ -81,7 +82,9 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
     std::vector<int32_t> keep(keep_ids, keep_ids + n_keep);
     CompileOptions co;
     co.max_slots = max_slots;
-    co.split_narrow = split;
+    co.split_narrow = split & 1;
+    if (split & 2) co.split_slack_us = 100.0;     // also split near-critical GEMM tasks of wide levels
+    if (split & 4) co.n_sms = 8;                  // pretend the GPU is small: the small test cases get wide levels too
     TaskGraph G;
     auto fail = [&](const std::string& e) { std::snprintf(err_out, err_len, "%s", e.c_str()); return 1; };
     if (mode == 1) { co.analyze_chains = true; co.cut_max_slack_us = cut_max_slack_us; }

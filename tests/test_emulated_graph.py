@@ -99,6 +99,18 @@ def test_chain_cuts_keep_the_factors(sg, emu, oracle, tmp_path, name, slack, spl
     check_against_oracle(oracle, p, keep, blocks)
 
 
+@pytest.mark.parametrize("name", ["lap3d_24", "banded_3000"])
+def test_slack_based_row_split_is_bitwise_neutral(sg, emu, oracle, tmp_path, name):
+    """Option split_slack: near-critical GEMM tasks are cut into row slices in wide levels too.  A slice computes its rows
+    exactly as the whole task would, so the factors do not change by a bit."""
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    keep, b0, st0 = run_emu(emu, p, split=5)      # 8 SMs: most levels of the small case count as wide
+    _, b1, st1 = run_emu(emu, p, split=7)
+    assert st1["tasks"] > st0["tasks"] and st1["split_tasks"] > st0["split_tasks"]
+    np.testing.assert_array_equal(b1, b0)
+    check_against_oracle(oracle, p, keep, b1)
+
+
 def test_execution_order_does_not_matter(sg, emu, tmp_path):
     """Task order and two random dependency-driven orders give bitwise the same factors (each task's arithmetic is fixed)."""
     p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))

@@ -466,3 +466,24 @@ def test_blocked_diagonal_kernel(sg, oracle, tmp_path, name):
     x2, _ = ctx.solve(p)
     np.testing.assert_array_equal(x2, x)
     ctx.close()
+
+
+@experimental
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name", ["lap3d_24", "banded_3000"])
+def test_slack_split(sg, tmp_path, name):
+    """Option split_slack: row slices for near-critical GEMM tasks in wide levels; bitwise the same solution."""
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    ref = sg.Context(0)
+    ref.load(p)
+    f0 = ref.factor()
+    x0, _ = ref.solve(p)
+    ctx = sg.Context(0)
+    ctx.set_option("split_slack", 100)
+    ctx.load(p)
+    fs = ctx.factor()
+    assert fs["tasks"] > f0["tasks"]
+    x, _ = ctx.solve(p)
+    np.testing.assert_array_equal(x, x0)
+    ctx.close()
+    ref.close()

@@ -15,20 +15,22 @@ PARAMS = ["n_ctas", "t_pair", "t_pair_half", "t_pair_quarter", "t_lu_fused", "t_
           "t_release", "t_poll", "t_poll_hit", "t_desc", "t_load", "t_launch", "t_cas", "hi_slack_us", "t_release_remote", "t_load_remote", "t_launch_dist"]
 
 
-def model(p, split=1, max_slots=0, chains=0, policy=0, compile_hi_slack=0, grid=(1, 1, 16), **kw):
+def model(p, split=1, max_slots=0, chains=0, policy=0, compile_hi_slack=0, grid=(1, 1, 16), split_slack=0, **kw):
     L = sg.lib()
     L.soglu_debug_model.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
-    opts = np.array([split, max_slots, grid[0], grid[1], grid[2], chains, policy, compile_hi_slack], dtype=np.int64)
+    opts = np.array([split, max_slots, grid[0], grid[1], grid[2], chains, policy, compile_hi_slack, split_slack], dtype=np.int64)
     par = np.full(len(PARAMS), np.nan)
     for k, v in kw.items():
         par[PARAMS.index(k)] = v
-    out = np.zeros(14)
+    out = np.zeros(34)
     rc = L.soglu_debug_model(p.h, opts.ctypes.data, par.ctypes.data, len(par), out.ctypes.data)
     if rc:
         raise RuntimeError(L.soglu_last_error().decode())
     return dict(makespan_ms=out[0] * 1e-3, critical_ms=out[1] * 1e-3, busy_ms_per_cta=out[2] * 1e-3 / (kw.get("n_ctas", 148) * grid[0] * grid[1]),
                 tasks=int(out[3]), segments=int(out[4]), pairs=int(out[5]), hi=int(out[6]),
-                cp_ms=out[7] * 1e-3, cp_early_ms=out[8] * 1e-3, cuts=int(out[9]), cp_cut_ms=out[10] * 1e-3, cuts_applied=int(out[11]), remote_loads=int(out[12]), remote_releases=int(out[13]))
+                cp_ms=out[7] * 1e-3, cp_early_ms=out[8] * 1e-3, cuts=int(out[9]), cp_cut_ms=out[10] * 1e-3, cuts_applied=int(out[11]), remote_loads=int(out[12]), remote_releases=int(out[13]),
+                chain=dict(kinds="gemm64 gemm32 gemm16 lu sub inv".split(), tasks=out[14:20].astype(int).tolist(), math_ms=(out[20:26] * 1e-3).round(1).tolist(),
+                           pairs=out[26:32].astype(int).tolist(), overhead_ms=round(out[32] * 1e-3, 1), remote_hops=int(out[33])))
 
 
 def problem(kind, dims):
@@ -40,7 +42,7 @@ if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if "=" not in a]
     kv = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
     p = problem(args[0], [int(a) for a in args[1:]])
-    split = int(kv.pop("split", 1)); ms = int(kv.pop("max_slots", 0)); ch = int(kv.pop("chains", 0)); pol = int(kv.pop("policy", 0)); chs = int(kv.pop("compile_hi_slack", 0)); grid = tuple(int(x) for x in kv.pop("grid", "1x1x16").split("x"))
+    split = int(kv.pop("split", 1)); ms = int(kv.pop("max_slots", 0)); ch = int(kv.pop("chains", 0)); pol = int(kv.pop("policy", 0)); chs = int(kv.pop("compile_hi_slack", 0)); grid = tuple(int(x) for x in kv.pop("grid", "1x1x16").split("x")); ssl = int(kv.pop("split_slack", 0))
     t = time.time()
-    r = model(p, split, ms, ch, pol, chs, grid, **{k: float(v) for k, v in kv.items()})
+    r = model(p, split, ms, ch, pol, chs, grid, ssl, **{k: float(v) for k, v in kv.items()})
     print(r, "(%.1f s)" % (time.time() - t))
