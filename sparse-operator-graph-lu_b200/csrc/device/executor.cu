@@ -31,6 +31,7 @@
 #include "executor.cuh"
 #include "ptx.cuh"
 #include "lu_blocked.cuh"
+#include "ready_queue.cuh"
 
 namespace soglu {
 
@@ -474,32 +475,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     issue(t);
                 }
             } else {
-                // Shared high-priority queue (option hi_shared): EVERY CTA takes the entry at the head of queue 0 if
-                // it is already published (compare-and-swap on the head, never waits there) before it looks at its
-                // pre-claimed slot of the bulk queue; while that slot is still empty it keeps serving queue 0.
-                const int n_hi = P.n_tasks[0], n_lo = P.n_tasks[1];
-                int mine = -1;            // pre-claimed bulk slot
-                bool lo_left = n_lo > 0;
-                while (true) {
-                    const int h = *(volatile int*)P.head[0];
-                    if (h < n_hi) {
-                        const int t = (P.world > 1) ? ptx::ld_acquire_sys(P.ready[0] + h) : ptx::ld_acquire(P.ready[0] + h);
-                        if (t >= 0) {
-                            if (atomicCAS(P.head[0], h, h + 1) == h) issue(t);
-                            continue;
-                        }
-                    }
-                    if (mine < 0 && lo_left) {
-                        mine = atomicAdd(P.head[1], 1);
-                        if (mine >= n_lo) { mine = -1; lo_left = false; }
-                    }
-                    if (mine >= 0) {
-                        const int t = (P.world > 1) ? ptx::ld_acquire_sys(P.ready[1] + mine) : ptx::ld_acquire(P.ready[1] + mine);
-                        if (t >= 0) { mine = -1; issue(t); }
-                    } else if (h >= n_hi) {
-                        break;            // both queues exhausted (the head only grows)
-                    }
-                }
+                // Shared high-priority queue (option hi_shared): every CTA takes published entries of queue 0 before it
+                // looks at its pre-claimed slot of the bulk queue (ready_queue.cuh; the same loop runs on the host in
+                // tests/emu/emu_queue.cpp)
+                struct DevQueues {
+                    const ExecParams& P;
+                    __device__ __forceinline__ int head_hi() { return *(volatile int*)P.head[0]; }
+                    __device__ __forceinline__ int ready_hi(int s) { return (P.world > 1) ? ptx::ld_acquire_sys(P.ready[0] + s) : ptx::ld_acquire(P.ready[0] + s); }
+                    __device__ __forceinline__ bool cas_head_hi(int h) { return atomicCAS(P.head[0], h, h + 1) == h; }
+                    __device__ __forceinline__ int claim_lo() { return atomicAdd(P.head[1], 1); }
+                    __device__ __forceinline__ int ready_lo(int s) { return (P.world > 1) ? ptx::ld_acquire_sys(P.ready[1] + s) : ptx::ld_acquire(P.ready[1] + s); }
+                } dq{P};
+                serve_shared_queues(dq, P.n_tasks[0], P.n_tasks[1], issue);
             }
             quit();
         }
