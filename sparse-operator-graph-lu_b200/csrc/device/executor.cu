@@ -68,10 +68,12 @@ struct __align__(16) SmemCtl {
     uint64_t full[N_STAGES];
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
-    double scratch[lub::SCRATCH_DOUBLES > 584 ? lub::SCRATCH_DOUBLES : 584];   // exchange buffers of the diag kernels (lu3_reg: 584, lu_blocked: 1394)
+    double scratch[584];   // pivot row/column exchange buffers of the register-resident diag kernels
 };
 
 constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
+// the blocked diagonal kernel (LU_MODE 1) keeps its own scratch behind SmemCtl, so the default launch is unchanged
+constexpr size_t SMEM_BYTES_LUB = SMEM_BYTES + (size_t)lub::SCRATCH_DOUBLES * sizeof(double);
 
 // ---- small block kernels on a block resident in shared memory (256 math threads) -------
 __device__ __forceinline__ void math_sync() { ptx::named_bar_sync(BAR_MATH, N_MATH); }
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 }
                 case T_LU:
                     if (LU_MODE == 1) {
-                        lu_task_blocked(As, Bs, ctl->scratch, out, blk_ptr(P, d.out2), (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr,
+                        lu_task_blocked(As, Bs, reinterpret_cast<double*>(ctl + 1), out, blk_ptr(P, d.out2), (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr,
                                         (d.flags & TF_UINV) ? blk_ptr(P, d.out4) : nullptr, ct);
                         // no accumulation chain spans another task: tell the compiler the accumulators are dead across the call
 #pragma unroll
@@ -679,14 +681,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
             for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
             math_sync();
             long long b0 = clock64();
-            lu_task_blocked(As, Ws, ctl->scratch, pool + 8 * (size_t)BLK_ELEMS, pool + 9 * (size_t)BLK_ELEMS, pool + 10 * (size_t)BLK_ELEMS, pool + 11 * (size_t)BLK_ELEMS, ct);
+            lu_task_blocked(As, Ws, reinterpret_cast<double*>(ctl + 1), pool + 8 * (size_t)BLK_ELEMS, pool + 9 * (size_t)BLK_ELEMS, pool + 10 * (size_t)BLK_ELEMS, pool + 11 * (size_t)BLK_ELEMS, ct);
             math_sync();
             long long b1 = clock64();
             for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
             math_sync();
             d.flags = 0;
             long long b2 = clock64();
-            lu_task_blocked(As, Ws, ctl->scratch, pool + 8 * (size_t)BLK_ELEMS, pool + 9 * (size_t)BLK_ELEMS, nullptr, nullptr, ct);
+            lu_task_blocked(As, Ws, reinterpret_cast<double*>(ctl + 1), pool + 8 * (size_t)BLK_ELEMS, pool + 9 * (size_t)BLK_ELEMS, nullptr, nullptr, ct);
             math_sync();
             long long b3 = clock64();
             if (ct == 0 && it == iters - 1) { cycles[10] = b1 - b0; cycles[11] = b3 - b2; }
@@ -756,19 +758,20 @@ int executor_max_grid(int device) {
 
 cudaError_t launch_executor(const ExecParams& p, int grid, cudaStream_t stream) {
     const void* kernel = (p.lu_mode == 1) ? (const void*)executor_kernel<1> : (const void*)executor_kernel<0>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    const size_t smem = (p.lu_mode == 1) ? SMEM_BYTES_LUB : SMEM_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     ExecParams pp = p;
     void* args[] = {&pp};
     // cooperative launch: the runtime guarantees that all CTAs are co-resident, which the
     // claim-then-wait ready queue relies on
-    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(N_THREADS), args, SMEM_BYTES, stream);
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(N_THREADS), args, smem, stream);
 }
 
 cudaError_t launch_diag_bench(double* pool, int iters, long long* cycles, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(diag_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(diag_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_LUB);
     if (e != cudaSuccess) return e;
-    diag_bench_kernel<<<1, N_THREADS, SMEM_BYTES, stream>>>(pool, iters, cycles);
+    diag_bench_kernel<<<1, N_THREADS, SMEM_BYTES_LUB, stream>>>(pool, iters, cycles);
     return cudaGetLastError();
 }
 
