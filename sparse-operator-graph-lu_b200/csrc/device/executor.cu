@@ -268,6 +268,26 @@ __device__ __noinline__ void lu_task_blocked(double* As, double* Ws, double* scr
     ptx::fence_proxy_async();
 }
 
+// Cholesky through the blocked kernel (lltdcmpSimple + inv_lower, MatrixStdDouble.cpp:2629-2668, 2787-2802): the sweep
+// gives A = L1 D L1^T with unit L1, so chol(A) = L1 sqrt(D) and chol(A)^-1 = D^-1/2 L1^-1, as in llt_task.
+__device__ __noinline__ void llt_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gLi, int ct) {
+    if (gLi) lub::lu_blocked<true, true, false>(As, Ws, scr, ct);
+    else lub::lu_blocked<false, true, false>(As, nullptr, scr, ct);
+    double* sq = scr;           // [64] sqrt(d_k), [64] 1 / sqrt(d_k)   (the kernel's scratch is free again)
+    if (ct < 64) {
+        const double s = sqrt(As[ct * BLK_LD + ct]);
+        sq[ct] = s;
+        sq[64 + ct] = 1.0 / s;
+    }
+    math_sync();
+    for (int e = ct; e < BLK * BLK; e += N_MATH) {
+        const int i = e >> 6, j = e & 63, o = i * BLK_LD + j;
+        gL[o] = (j < i) ? As[o] * sq[j] : (j == i ? sq[i] : 0.0);
+        if (gLi) gLi[o] = ((j < i) ? Ws[o] : (j == i ? 1.0 : 0.0)) * sq[64 + i];
+    }
+    ptx::fence_proxy_async();
+}
+
 // Y = T^-1 for a triangular block T in shared memory, general diagonal (standalone lowerInv /
 // upperInv tasks).  Forward elimination on W = unscaled rows of the inverse; TRANS inverts an
 // upper-triangular T through its transpose (multipliers read from row k, result written back
@@ -566,7 +586,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     else lu_task(As, ctl->scratch, P, d, ct);
                     break;
                 case T_LLT:
-                    llt_task(As, ctl->scratch, P, d, ct);
+                    if (LU_MODE == 1) {
+                        llt_task_blocked(As, Bs, reinterpret_cast<double*>(ctl + 1), out, (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr, ct);
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                    } else {
+                        llt_task(As, ctl->scratch, P, d, ct);
+                    }
                     break;
                 case T_LOWERINV:
                     tri_inv_task<false>(As, ctl->scratch, out, ct);

@@ -185,7 +185,7 @@ LUB_FN void col_strip(double* X, const double* udi, int lane) {
     for (int ni = 0; ni < 2; ni++) { X[g * LD + 8 * ni + 2 * t] = c[ni][0]; X[g * LD + 8 * ni + 2 * t + 1] = c[ni][1]; }
 }
 
-template <bool WITH_INV>
+template <bool WITH_INV, bool WU>
 LUB_FN void panel_strips(double* S, double* W, const double* ldi, const double* udi, int kb, int warp, int lane) {
     const int d0 = 16 * kb;
     // items 0..5: row strips (S to the right of the diagonal block, then W_L to its left), 6..11: column strips
@@ -198,11 +198,11 @@ LUB_FN void panel_strips(double* S, double* W, const double* ldi, const double* 
         } else if (item < 12) {
             const int q = item - 6, n_s = 2 * (3 - kb);
             if (q < n_s) col_strip(S + (d0 + 16 + 8 * q) * LD + d0, udi, lane);
-            else if (WITH_INV) col_strip(W + (8 * (q - n_s)) * LD + d0, udi, lane);
+            else if (WITH_INV && WU) col_strip(W + (8 * (q - n_s)) * LD + d0, udi, lane);
         } else if (WITH_INV) {
             for (int e = lane; e < 256; e += 32) {
                 const int i = e >> 4, j = e & 15;
-                W[(d0 + i) * LD + d0 + j] = (j < i) ? ldi[i * DLD + j] : udi[i * DLD + j];
+                W[(d0 + i) * LD + d0 + j] = (j < i) ? ldi[i * DLD + j] : (WU ? udi[i * DLD + j] : 0.0);
             }
         }
     }
@@ -238,7 +238,9 @@ LUB_FN void trailing_tile(double* S, double* W, const double* ldi, const double*
 
 // ---- the task: S (64x64, ld 68) holds A on entry and packed L\U on exit; W (64x64, ld 68) receives the packed
 // inverses (WITH_INV); scr = SCRATCH_DOUBLES doubles; ct = 0..255.  Ends with a barrier: S and W are complete.
-template <bool WITH_INV, bool LLT>
+// LLT selects lltdcmpSimple's pivot clamp (the Cholesky factor is L * sqrt(diag U), formed by the caller);
+// WU = false skips U^-1 (the symmetric path only needs L^-1).
+template <bool WITH_INV, bool LLT, bool WU = true>
 LUB_FN void lu_blocked(double* S, double* W, double* scr, int ct) {
     const int warp = ct >> 5, lane = ct & 31;
     if (WITH_INV) {
@@ -249,11 +251,11 @@ LUB_FN void lu_blocked(double* S, double* W, double* scr, int ct) {
     for (int kb = 0; kb < 4; kb++) {
         const double* ldi = scr + (kb & 1) * SCR_BUF + SCR_LDI;
         const double* udi = scr + (kb & 1) * SCR_BUF + SCR_UDI;
-        panel_strips<WITH_INV>(S, W, ldi, udi, kb, warp, lane);
+        panel_strips<WITH_INV, WU>(S, W, ldi, udi, kb, warp, lane);
         hw::sync_math();
         if (kb == 3) break;
         const int R = 2 * (3 - kb), Q = 2 * (kb + 1);
-        const int total = R * R + (WITH_INV ? 2 * R * Q : 0);
+        const int total = R * R + (WITH_INV ? (WU ? 2 : 1) * R * Q : 0);      // the W_U tiles come last
         if (warp == 0) {
             // the next diagonal block first, then its factorisation while the other warps finish the update
             trailing_tile(S, W, ldi, udi, kb, 0, lane);

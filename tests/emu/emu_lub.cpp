@@ -59,6 +59,18 @@ static void run(const std::vector<double>& A, std::vector<double>& S, std::vecto
     for (auto& t : th) t.join();
 }
 
+// Cholesky variant: the sweep with lltdcmpSimple's clamp, no U^-1
+static void run_llt(const std::vector<double>& A, std::vector<double>& S, std::vector<double>& W) {
+    S.assign(64 * LD, 0.0);
+    W.assign(64 * LD, 7.7e300);
+    std::vector<double> scr(SCRATCH_DOUBLES, 3.3e300);
+    for (int i = 0; i < 64; i++) for (int j = 0; j < 64; j++) S[i * LD + j] = A[i * 64 + j];
+    std::vector<std::thread> th;
+    for (int ct = 0; ct < 256; ct++)
+        th.emplace_back([&, ct]() { tl_ct = ct; lu_blocked<true, true, false>(S.data(), W.data(), scr.data(), ct); });
+    for (auto& t : th) t.join();
+}
+
 static double clampLU(double p) { return (p < 1e-9 && p > -1e-9) ? ((p < 0) ? -1e-9 : 1e-9) : p; }
 static void ref_lu(std::vector<double> a, std::vector<double>& out) {
     for (int k = 0; k < 64; k++) {
@@ -134,8 +146,27 @@ int main() {
         run<false>(A, S2, W2);
         for (int i = 0; i < 64; i++) for (int j = 0; j < 64; j++) worst_noinv = std::fmax(worst_noinv, std::fabs(S2[i * LD + j] - S[i * LD + j]));
     }
+    // symmetric positive definite block: chol = L1 sqrt(D), chol^-1 = D^-1/2 L1^-1 as llt_task_blocked writes them
+    double worst_chol = 0, worst_cinv = 0;
+    for (int trial = 0; trial < 2; trial++) {
+        std::vector<double> A(4096), Sm(4096), S, W;
+        for (auto& v : A) v = rnd();
+        for (int i = 0; i < 64; i++) for (int j = 0; j < 64; j++) { double s = 0; for (int k = 0; k < 64; k++) s += A[i * 64 + k] * A[j * 64 + k]; Sm[i * 64 + j] = s / 64 + (i == j); }
+        run_llt(Sm, S, W);
+        std::vector<double> C(4096, 0), Ci(4096, 0);
+        for (int i = 0; i < 64; i++) for (int j = 0; j <= i; j++) {
+            C[i * 64 + j] = (j < i ? S[i * LD + j] : 1.0) * std::sqrt(S[j * LD + j]);
+            Ci[i * 64 + j] = (j < i ? W[i * LD + j] : 1.0) / std::sqrt(S[i * LD + i]);
+        }
+        for (int i = 0; i < 64; i++) for (int j = i + 1; j < 64; j++) if (W[i * LD + j] != 0.0) worst_cinv = 1.0;   // no U^-1 was asked for
+        double r = 0;
+        for (int i = 0; i < 64; i++) for (int j = 0; j < 64; j++) { double s = 0; for (int k = 0; k < 64; k++) s += C[i * 64 + k] * C[j * 64 + k]; r = std::fmax(r, std::fabs(s - Sm[i * 64 + j])); }
+        worst_chol = std::fmax(worst_chol, r);
+        worst_cinv = std::fmax(worst_cinv, maxabs_prod_minus_eye(Ci, C));
+    }
+    std::printf("chol %.3e  chol_inv %.3e\n", worst_chol, worst_cinv);
     std::printf("lu_vs_ref %.3e  clamped %.3e  Linv %.3e  Uinv %.3e  noinv_diff %.3e\n", worst_lu, worst_clamped, worst_li, worst_ui, worst_noinv);
-    const bool ok = worst_lu < 1e-13 && worst_clamped < 1e-7 && worst_li < 1e-13 && worst_ui < 1e-13 && worst_noinv == 0.0;
+    const bool ok = worst_lu < 1e-13 && worst_clamped < 1e-7 && worst_li < 1e-13 && worst_ui < 1e-13 && worst_noinv == 0.0 && worst_chol < 1e-13 && worst_cinv < 1e-13;
     std::printf(ok ? "OK\n" : "FAIL\n");
     return ok ? 0 : 1;
 }
