@@ -27,6 +27,7 @@
 
 #if defined(SOGLU_LUB_HOST)
 #define LUB_FN static inline
+#define LUB_NOINLINE static
 namespace soglu {
 namespace lub {
 namespace hw {   // provided by the host harness
@@ -41,6 +42,7 @@ double rcp(double x);
 #else
 #include "ptx.cuh"
 #define LUB_FN __device__ __forceinline__
+#define LUB_NOINLINE __device__ __noinline__     // one copy of the unrolled 16-pivot sweep per variant (20 KB of code each)
 namespace soglu {
 namespace lub {
 namespace hw {
@@ -69,6 +71,8 @@ constexpr int SCR_IP = SCR_ROWU + 32;        // [16] 1 / u_kk
 constexpr int SCR_IPK = SCR_IP + 16;         // [2]  1 / u_kk of the pivot in use
 constexpr int SCRATCH_DOUBLES = SCR_IPK + 2; // 1394
 
+struct alignas(16) D2 { double x, y; };     // 16-byte shared-memory accesses (every offset below is even)
+
 template <bool LLT>
 LUB_FN double clamp_pivot(double p) {
     if (LLT) return (p < 1e-20) ? 1e-20 : p;
@@ -81,7 +85,7 @@ LUB_FN double clamp_pivot(double p) {
 // and m'_r = d_kr / d_kk times row k of W_U from W_U (the transposed elimination that inverts U, as in lu3_reg).
 // Results: D overwritten with packed L\U, ldi = L_D^-1 (full 16x16, unit diagonal), udi = U_D^-1 (full 16x16).
 template <bool LLT>
-LUB_FN void diag16(double* D, double* ldi, double* udi, double* scr, int lane) {
+LUB_NOINLINE void diag16(double* D, double* ldi, double* udi, double* scr, int lane) {
     const int r = lane >> 1, h = lane & 1;
     double* rowA = scr + SCR_ROWA;
     double* rowL = scr + SCR_ROWL;
@@ -106,13 +110,22 @@ LUB_FN void diag16(double* D, double* ldi, double* udi, double* scr, int lane) {
         const int hk = k >> 3, jk = k & 7, pb = (k & 1) * 16;
         if (r == k) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) { rowA[pb + 8 * h + j] = a[j]; rowL[pb + 8 * h + j] = wl[j]; rowU[pb + 8 * h + j] = wu[j]; }
+            for (int j = 0; j < 8; j += 2) {
+                *reinterpret_cast<D2*>(rowA + pb + 8 * h + j) = D2{a[j], a[j + 1]};
+                *reinterpret_cast<D2*>(rowL + pb + 8 * h + j) = D2{wl[j], wl[j + 1]};
+                *reinterpret_cast<D2*>(rowU + pb + 8 * h + j) = D2{wu[j], wu[j + 1]};
+            }
         }
         hw::sync_warp();     // row k and 1 / d_kk are visible; the buffers of pivot k - 1 may be overwritten at k + 1
         const double ip = ipk[k & 1];
         double ra[8], rl[8], ru[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { ra[j] = rowA[pb + 8 * h + j]; rl[j] = rowL[pb + 8 * h + j]; ru[j] = rowU[pb + 8 * h + j]; }
+        for (int j = 0; j < 8; j += 2) {
+            const D2 va = *reinterpret_cast<const D2*>(rowA + pb + 8 * h + j);
+            const D2 vl = *reinterpret_cast<const D2*>(rowL + pb + 8 * h + j);
+            const D2 vu = *reinterpret_cast<const D2*>(rowU + pb + 8 * h + j);
+            ra[j] = va.x; ra[j + 1] = va.y; rl[j] = vl.x; rl[j + 1] = vl.y; ru[j] = vu.x; ru[j + 1] = vu.y;
+        }
         const double mc = a[jk] * ip;                             // d_rk / d_kk, meaningful in the half that holds column k
         double m = hw::shfl(mc, (lane & ~1) | hk);
         const bool act = r > k;
