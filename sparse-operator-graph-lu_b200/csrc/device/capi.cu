@@ -49,6 +49,7 @@ struct soglu_ctx {
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
     int64_t opt_split_slack = 0;   // > 0: GEMM tasks within this slack (us) of the longest chain are row-split in wide levels too
+    int64_t opt_prefetch = 0;      // executor prefetch bits (executor.cuh)
     int64_t opt_lu_mode = 0;       // 1: blocked diagonal-block kernel (lu_blocked.cuh)
     int64_t opt_chain_cuts = 0;    // > 0: cut accumulation chains of tasks within this slack (us) of the critical path (two-pass compile)
     int64_t opt_hi_shared = 0;     // > 0: tasks with less estimated slack than this (us) go to a high-priority queue every CTA serves first
@@ -530,6 +531,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "hi_shared") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_shared must be set before the first factor"); c->opt_hi_shared = value; }
     else if (k == "hi_ctas") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_ctas must be set before the first factor"); c->opt_hi_ctas = value; }
     else if (k == "lu_mode") c->opt_lu_mode = value;
+    else if (k == "prefetch") c->opt_prefetch = value;
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
@@ -677,6 +679,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     P.dep = c->dep.as<int32_t>();
     P.trace = nullptr;
     P.lu_mode = (int32_t)c->opt_lu_mode;
+    P.prefetch = (int32_t)c->opt_prefetch;
     if (c->opt_trace && nt > 0) {
         if (!c->trace.p) CU(c->trace.alloc((size_t)nt * 6 * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->trace.p, 0, (size_t)nt * 6 * sizeof(unsigned long long), c->stream));

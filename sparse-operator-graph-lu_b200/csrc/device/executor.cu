@@ -460,14 +460,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 ptx::fence_proxy_async();
                 const int nst = (T.type == T_GEMM) ? T.n_pairs : 1;
                 const bool two = (T.type == T_GEMM || T.type == T_SUB);
+                // option prefetch bit 0: the operand pair of stage p + 1 is fetched before the wait for stage p's buffer,
+                // so its latency (the pair list of a long chain lives in HBM) overlaps the wait instead of following it
+                const bool ahead = P.prefetch & 1;
+                Pair nxt = T.first[0];
                 for (int p = 0; p < nst; p++, it++) {
                     const int s = it % N_STAGES;
+                    Pair pa = nxt;
+                    if (ahead && p + 1 < nst) nxt = (p == 0) ? T.first[1] : P.pairs[T.pair_begin + p + 1];
                     ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);
                     StageDesc d;
                     d.type = T.type; d.flags = T.flags; d.task = t; d.out = T.out; d.out2 = T.out2; d.init = T.init; d.out4 = T.out4;
                     d.first_last = (p == 0 ? 1 : 0) | (p == nst - 1 ? 2 : 0);
                     ctl->desc[s] = d;
-                    const Pair pr = (p == 0) ? T.first[0] : ((p == 1) ? T.first[1] : P.pairs[T.pair_begin + p]);
+                    const Pair pr = ahead ? pa : ((p == 0) ? T.first[0] : ((p == 1) ? T.first[1] : P.pairs[T.pair_begin + p]));
                     double* As = stage_base + (size_t)s * (STAGE_BYTES / 8);
                     // GEMM row slice: only rows [16*row0, 16*(row0+nrows)) of A are needed (same place in smem)
                     const int a_off = (T.type == T_GEMM) ? ((T.flags >> TF_ROW0_SHIFT) & 3) * 16 * BLK_LD : 0;
@@ -624,6 +630,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     const int32_t ref = P.succ[e];
                     const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
                     if (o != P.rank) { remote = true; continue; }
+                    // option prefetch bit 1: pull the successor's task record (HBM: the table does not fit L2) towards L2
+                    // while the counter is being decremented, for the scheduler that will read it after the pick-up
+                    if (P.prefetch & 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.tasks + nx));
                     if (atomicSub(P.dep + nx, 1) == 1) {
                         // the whole group (all row slices of the successor) becomes ready at once
                         // (the fence below + the strong relaxed stores form the release; the consumers ld.acquire)

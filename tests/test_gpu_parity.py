@@ -487,3 +487,24 @@ def test_slack_split(sg, tmp_path, name):
     np.testing.assert_array_equal(x, x0)
     ctx.close()
     ref.close()
+
+
+@experimental
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("bits", [1, 2, 3])
+def test_prefetch_options(sg, tmp_path, bits):
+    """Option prefetch: operand-pair lookahead in the scheduler lane / task-record prefetch by the releasing threads.
+    Read-only prefetches: bitwise the same solution."""
+    p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
+    ref = sg.Context(0)
+    ref.load(p)
+    ref.factor()
+    x0, _ = ref.solve(p)
+    ctx = sg.Context(0)
+    ctx.set_option("prefetch", bits)
+    ctx.load(p)
+    ctx.factor()
+    x, _ = ctx.solve(p)
+    np.testing.assert_array_equal(x, x0)
+    ctx.close()
+    ref.close()

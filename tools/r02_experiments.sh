@@ -9,7 +9,7 @@ run() { echo; echo "=== $*"; timeout "${T:-300}" "$@"; echo "--- exit $?"; }
 
 python -c "import __graft_entry__ as g; g.build()"
 # 1. correctness of the new paths (opt-in tests)
-T=600 SOGLU_EXPERIMENTAL=1 run python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "shared_priority or chain_cuts or blocked_diagonal or slack_split"
+T=600 SOGLU_EXPERIMENTAL=1 run python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "shared_priority or chain_cuts or blocked_diagonal or slack_split or prefetch"
 # 2. the diagonal-block kernels in isolation (cycles)
 T=120 run python tools/diag_bench.py
 # 3. latency-bound configs, one option at a time
@@ -19,6 +19,8 @@ for cfg in "lap3d 64" "nine2d 1024" "banded 200000"; do
   T=300 run python tools/run_config.py $cfg chain_cuts=200
   T=300 run python tools/run_config.py $cfg hi_shared=1000
   T=300 run python tools/run_config.py $cfg split_slack=100
+  T=300 run python tools/run_config.py $cfg prefetch=1
+  T=300 run python tools/run_config.py $cfg prefetch=3
   T=300 run python tools/run_config.py $cfg lu_mode=1 chain_cuts=200 split_slack=100
 done
 # 4. the headline (100^3, throughput-bound): shared high-priority queue, thresholds around the model's optimum
