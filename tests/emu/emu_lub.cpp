@@ -18,11 +18,18 @@ namespace {
 pthread_barrier_t g_cta, g_warp[8];
 double g_xa[8][32], g_xb[8][32];
 thread_local int tl_ct = 0;
+thread_local unsigned long long tl_rng = 88172645463325252ull;
+// random yields shake the interleaving of the 256 host threads, so that an access that is only safe because of
+// lock-step execution (a missing barrier in the device code) shows up as a wrong result here
+inline void jitter() {
+    tl_rng ^= tl_rng << 13; tl_rng ^= tl_rng >> 7; tl_rng ^= tl_rng << 17;
+    if ((tl_rng & 15) == 0) std::this_thread::yield();
+}
 }  // namespace
 
 namespace soglu { namespace lub { namespace hw {
-void sync_warp() { pthread_barrier_wait(&g_warp[tl_ct >> 5]); }
-void sync_math() { pthread_barrier_wait(&g_cta); }
+void sync_warp() { jitter(); pthread_barrier_wait(&g_warp[tl_ct >> 5]); jitter(); }
+void sync_math() { jitter(); pthread_barrier_wait(&g_cta); jitter(); }
 double shfl(double v, int src) {
     const int w = tl_ct >> 5, l = tl_ct & 31;
     g_xa[w][l] = v;
@@ -55,7 +62,7 @@ static void run(const std::vector<double>& A, std::vector<double>& S, std::vecto
     for (int i = 0; i < 64; i++) for (int j = 0; j < 64; j++) S[i * LD + j] = A[i * 64 + j];
     std::vector<std::thread> th;
     for (int ct = 0; ct < 256; ct++)
-        th.emplace_back([&, ct]() { tl_ct = ct; lu_blocked<WITH_INV, false>(S.data(), WITH_INV ? W.data() : nullptr, scr.data(), ct); });
+        th.emplace_back([&, ct]() { tl_ct = ct; tl_rng += 977u * ct; lu_blocked<WITH_INV, false>(S.data(), WITH_INV ? W.data() : nullptr, scr.data(), ct); });
     for (auto& t : th) t.join();
 }
 
