@@ -716,18 +716,7 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
             // model.h with the width-based slices chosen above.
             const ModelParams M;
             std::vector<float> dur(nt), tl(nt, 0.f), bl(nt, 0.f);
-            for (int64_t t = 0; t < nt; t++) {
-                const Task& T = G.tasks[t];
-                double c;
-                switch (T.type) {
-                    case T_GEMM: c = T.n_pairs * (split[t] == 1 ? M.t_pair : (split[t] == 2 ? M.t_pair_half : M.t_pair_quarter)); break;
-                    case T_LU: c = (T.flags & (TF_LINV | TF_UINV)) ? M.t_lu_fused : M.t_lu; break;
-                    case T_LLT: c = (T.flags & TF_LINV) ? M.t_llt_fused : M.t_lu; break;
-                    case T_LOWERINV: case T_UPPERINV: c = M.t_inv; break;
-                    default: c = M.t_sub; break;
-                }
-                dur[t] = (float)(M.t_desc + M.t_load + c + M.t_epilogue + M.t_release + M.t_poll);
-            }
+            for (int64_t t = 0; t < nt; t++) dur[t] = (float)model_hop_us(G.tasks[t], M, 4 / split[t]);
             for (int64_t t = 0; t < nt; t++)
                 for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) tl[G.succ[e]] = std::max(tl[G.succ[e]], tl[t] + dur[t]);
             float cp = 0.f;
@@ -792,18 +781,7 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         const int64_t n2 = (int64_t)G.tasks.size();
         std::vector<float> dur(n2), tl(n2, 0.f), bl(n2, 0.f);
         const ModelParams M;     // one dependent hop through a task under the measured cost model (model.h)
-        for (int64_t t = 0; t < n2; t++) {
-            const Task& T = G.tasks[t];
-            double c = 1.0;
-            switch (T.type) {
-                case T_GEMM: { const int r16 = (T.flags >> TF_NROWS_SHIFT) & 7; c = T.n_pairs * (r16 == 4 ? M.t_pair : (r16 == 2 ? M.t_pair_half : M.t_pair_quarter)); break; }
-                case T_LU: c = (T.flags & (TF_LINV | TF_UINV)) ? M.t_lu_fused : M.t_lu; break;
-                case T_LLT: c = (T.flags & TF_LINV) ? M.t_llt_fused : M.t_lu; break;
-                case T_LOWERINV: case T_UPPERINV: c = M.t_inv; break;
-                default: c = M.t_sub; break;
-            }
-            dur[t] = (float)(M.t_desc + M.t_load + c + M.t_epilogue + M.t_release + M.t_poll);
-        }
+        for (int64_t t = 0; t < n2; t++) dur[t] = (float)model_hop_us(G.tasks[t], M);
         for (int64_t t = 0; t < n2; t++)     // tasks are in topological order; successors are group leaders
             for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
                 const int32_t s2 = G.succ[e];
@@ -885,16 +863,8 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
     if (opt.analyze_chains && !G.tasks.empty()) {
         const ModelParams M;
         const int64_t n2 = (int64_t)G.tasks.size();
-        const float o_in = (float)(M.t_desc + M.t_load), o_out = (float)(M.t_epilogue + M.t_release + M.t_poll);
-        auto stage_us = [&](const Task& T) -> float {
-            switch (T.type) {
-                case T_GEMM: { const int r16 = (T.flags >> TF_NROWS_SHIFT) & 7; return (float)(r16 == 4 ? M.t_pair : (r16 == 2 ? M.t_pair_half : M.t_pair_quarter)); }
-                case T_SUB: return (float)M.t_sub;
-                case T_LU: return (float)((T.flags & (TF_LINV | TF_UINV)) ? M.t_lu_fused : M.t_lu);
-                case T_LLT: return (float)((T.flags & TF_LINV) ? M.t_llt_fused : M.t_lu);
-                default: return (float)M.t_inv;
-            }
-        };
+        const float o_in = (float)model_in_us(M), o_out = (float)model_out_us(M);
+        auto stage_us = [&](const Task& T) -> float { return (float)model_stage_us(T, M); };
         std::vector<float> fin(n2, 0.f), fin_e(n2, 0.f);
         std::vector<int32_t> best_k(n2, 0);
         std::vector<std::pair<float, int32_t>> rs;   // (ready time, position) of the pairs of one chain

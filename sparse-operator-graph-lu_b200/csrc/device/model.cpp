@@ -33,24 +33,9 @@ struct Ev {
     bool operator<(const Ev& o) const { return t > o.t; }   // min-heap
 };
 
-inline double stage_time(const Task& T, const ModelParams& M) {
-    switch (T.type) {
-        case T_GEMM: {
-            const int r16 = (T.flags >> TF_NROWS_SHIFT) & 7;
-            return r16 == 4 ? M.t_pair : (r16 == 2 ? M.t_pair_half : M.t_pair_quarter);
-        }
-        case T_SUB: return M.t_sub;
-        case T_LU: return (T.flags & (TF_LINV | TF_UINV)) ? M.t_lu_fused : M.t_lu;
-        case T_LLT: return (T.flags & TF_LINV) ? M.t_llt_fused : M.t_lu;
-        case T_LOWERINV: case T_UPPERINV: return M.t_inv;
-        default: return 1.0;
-    }
-}
-inline int n_stages(const Task& T) { return T.type == T_GEMM ? T.n_pairs : 1; }
-// one dependent hop through the task: fetch, first operands, math, write-back, release, pick-up by the successor
-inline double hop_time(const Task& T, const ModelParams& M) {
-    return M.t_desc + M.t_load + n_stages(T) * stage_time(T, M) + M.t_epilogue + M.t_release + M.t_poll;
-}
+inline double stage_time(const Task& T, const ModelParams& M) { return model_stage_us(T, M); }
+inline int n_stages(const Task& T) { return model_stages(T); }
+inline double hop_time(const Task& T, const ModelParams& M) { return model_hop_us(T, M); }
 inline int32_t leader_of(const TaskGraph& G, int32_t t) {
     const Task& T = G.tasks[t];
     if (T.type != T_GEMM) return t;

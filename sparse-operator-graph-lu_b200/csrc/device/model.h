@@ -29,6 +29,29 @@ struct ModelParams {        // microseconds, measured with the executor's trace 
     int policy = 0;                // 0 = the executor's FIFO ready queue; 1 = ideal list scheduling by longest remaining path (what-if)
 };
 
+// ---- the cost model, shared by the executor model and by the task compiler's slack / chain estimates ---------------
+// time of ONE operand stage of a task; rows16 overrides the slice height of a GEMM task (4 = whole block, 2, 1)
+inline double model_stage_us(const Task& T, const ModelParams& M, int rows16 = -1) {
+    switch (T.type) {
+        case T_GEMM: {
+            const int r16 = rows16 > 0 ? rows16 : (T.flags >> TF_NROWS_SHIFT) & 7;
+            return r16 == 4 ? M.t_pair : (r16 == 2 ? M.t_pair_half : M.t_pair_quarter);
+        }
+        case T_SUB: return M.t_sub;
+        case T_LU: return (T.flags & (TF_LINV | TF_UINV)) ? M.t_lu_fused : M.t_lu;
+        case T_LLT: return (T.flags & TF_LINV) ? M.t_llt_fused : M.t_lu;
+        case T_LOWERINV: case T_UPPERINV: return M.t_inv;
+        default: return 1.0;
+    }
+}
+inline int model_stages(const Task& T) { return T.type == T_GEMM ? T.n_pairs : 1; }
+inline double model_in_us(const ModelParams& M) { return M.t_desc + M.t_load; }                    // pick-up to first math
+inline double model_out_us(const ModelParams& M) { return M.t_epilogue + M.t_release + M.t_poll; }  // last math to the successor's pick-up
+// one dependent hop through the task: fetch, first operands, math, write-back, release, pick-up by the successor
+inline double model_hop_us(const Task& T, const ModelParams& M, int rows16 = -1) {
+    return model_in_us(M) + model_stages(T) * model_stage_us(T, M, rows16) + model_out_us(M);
+}
+
 struct ModelResult {
     double makespan_us = 0;        // sum over segments
     double critical_path_us = 0;   // longest dependent chain under the same durations (infinite SMs)
