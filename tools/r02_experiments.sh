@@ -10,6 +10,9 @@ run() { echo; echo "=== $*"; timeout "${T:-300}" "$@"; echo "--- exit $?"; }
 python -c "import __graft_entry__ as g; g.build()"
 # 1. correctness of the new paths (opt-in tests)
 T=600 SOGLU_EXPERIMENTAL=1 run python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "shared_priority or chain_cuts or blocked_diagonal or slack_split or prefetch"
+# 2a. can the L2 -> SM path deliver the operands of the DMMA loop at its peak rate?
+/usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o gpurun_out/operand_bw tools/operand_bw.cu
+T=120 run gpurun_out/operand_bw
 # 2. the diagonal-block kernels in isolation (cycles)
 T=120 run python tools/diag_bench.py
 # 3. latency-bound configs, one option at a time
