@@ -63,6 +63,9 @@ def main():
     print("critical chain: %d tasks, spans %.3f ms of %.3f ms" % (len(chain), (sig[chain[-1]] - clm[chain[0]]) * 1e-3, total * 1e-3))
     print("  by phase (ms):", {k: round(v * 1e-3, 3) for k, v in cat.items()})
     print("  by type: ", {k: (v[0], "%.2f us/task total" % (v[1] / v[0]), "%.2f us compute" % (v[2] / v[0])) for k, v in bytype.items()})
+    n = max(1, len(chain))
+    print("  for tools/model.py (means along the chain): t_release=%.2f t_poll=%.2f t_desc+t_load=%.2f  (signal phase %.2f us is part of t_release when it precedes the publication)"
+          % (cat["publish-gap"] / n, cat["q-wait"] / n, cat["load"] / n, cat["signal"] / n))
     # SM utilisation: busy = sum over tasks of (sig - lod) / (n_sm * total)
     busy = (sig - lod).sum()
     print("math-warp busy fraction: %.3f (148 SMs)" % (busy / (148 * total)))
