@@ -75,10 +75,12 @@ void inv_upper(const double* u, double* y) {     // U Y = I
 // split: bit 0 = row slices in narrow levels, bit 1 = also near-critical tasks (split_slack), bit 2 = 8 SMs.
 // mode: 0 = default compile, 1 = analyse chains + recompile with the proposed cuts.  max_slots > 0 forces slot
 // recycling.  keep_out: n_keep dense 64x64 blocks.  stats = {tasks, segments, slots, chain cuts applied, row-split tasks}.
+// grid = {pr, pc, nb} with brow / bcol per block id: the graph is compiled for pr*pc owners (2D block-cyclic squares of
+// nb blocks, mirrors of remote blocks filled by fetch tasks) and every owner gets its own pool here.
 extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids, const double* input_dense, int64_t n_ops, const int32_t* src,
                        const int32_t* src2, const uint8_t* op, const int32_t* result, const int32_t* result2, int64_t n_keep,
                        const int32_t* keep_ids, int mode, double cut_max_slack_us, int64_t max_slots, int split, uint64_t order_seed, double* keep_out, int64_t* stats,
-                       char* err_out, int err_len) {
+                       char* err_out, int err_len, const int32_t* grid, const int32_t* brow, const int32_t* bcol) {
     std::vector<int32_t> keep(keep_ids, keep_ids + n_keep);
     CompileOptions co;
     co.max_slots = max_slots;
@@ -87,6 +89,15 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
     if (split & 4) co.n_sms = 8;                  // pretend the GPU is small: the small test cases get wide levels too
     TaskGraph G;
     auto fail = [&](const std::string& e) { std::snprintf(err_out, err_len, "%s", e.c_str()); return 1; };
+    std::vector<int8_t> owners;
+    const int world = grid ? grid[0] * grid[1] : 1;
+    if (world > 1) {
+        owners.assign(n_ids, 0);
+        for (int64_t id = 1; id < n_ids; id++)
+            if (brow[id] >= 0 && bcol[id] >= 0) owners[id] = (int8_t)(((brow[id] / grid[2]) % grid[0]) * grid[1] + ((bcol[id] / grid[2]) % grid[1]));
+        co.owner_of_id = owners.data();
+        co.n_owners = world;
+    }
     if (mode == 1) { co.analyze_chains = true; co.cut_max_slack_us = cut_max_slack_us; }
     std::string err = compile_tasks(n_ids, n_input, input_ids, n_ops, src, src2, op, result, result2, keep, co, G);
     if (!err.empty()) return fail(err);
@@ -97,9 +108,13 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
         err = compile_tasks(n_ids, n_input, input_ids, n_ops, src, src2, op, result, result2, keep, co, G);
         if (!err.empty()) return fail(err);
     }
-    std::vector<double> pool((size_t)G.n_slots * NN, 0.0);     // slot 0 stays the zero block
-    auto blk = [&](int32_t ref) { return pool.data() + (size_t)(ref & REF_MASK) * NN; };
-    for (int64_t k = 0; k < n_input; k++) std::memcpy(blk(G.slot_of[input_ids[k]]), input_dense + k * NN, NN * sizeof(double));
+    // one pool per owner; slot 0 of each stays its zero block
+    int64_t stride = 0;
+    for (int64_t sl : G.slots_per_owner) stride = std::max(stride, sl);
+    std::vector<double> pool((size_t)stride * world * NN, 0.0);
+    auto blk = [&](int32_t ref) { return pool.data() + ((size_t)((uint32_t)ref >> REF_SHIFT) * stride + (size_t)(ref & REF_MASK)) * NN; };
+    auto ref_of = [&](int32_t id) { return make_ref(G.owner_of[id], G.slot_of[id]); };
+    for (int64_t k = 0; k < n_input; k++) std::memcpy(blk(ref_of(input_ids[k])), input_dense + k * NN, NN * sizeof(double));
     std::vector<double> acc(NN);
     // Execution order: the task order (seed 0), or -- like the executor -- whatever the dependency counters allow:
     // per segment, a seeded random pick from the ready set; a finishing task decrements every successor group once and
@@ -188,8 +203,10 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
     }
     for (int64_t k = 0; k < n_keep; k++) {
         if (G.recycled[keep_ids[k]]) return fail("a kept block was recycled");
-        std::memcpy(keep_out + k * NN, blk(G.slot_of[keep_ids[k]]), NN * sizeof(double));
+        std::memcpy(keep_out + k * NN, blk(ref_of(keep_ids[k])), NN * sizeof(double));
     }
-    stats[0] = (int64_t)G.tasks.size(); stats[1] = (int64_t)G.seg_begin.size() - 1; stats[2] = G.n_slots; stats[3] = G.chain_splits; stats[4] = G.split_tasks;
+    stats[0] = (int64_t)G.tasks.size(); stats[1] = (int64_t)G.seg_begin.size() - 1; stats[2] = stride; stats[3] = G.chain_splits; stats[4] = G.split_tasks;
+    stats[5] = 0;
+    for (int64_t m : G.mirrors_per_owner) stats[5] += m;
     return 0;
 }

@@ -22,11 +22,11 @@ def emu(sg, tmp_path_factory):
                     "-L" + pkg, "-lsoglu_b200", "-Wl,-rpath," + pkg], check=True)
     L = ctypes.CDLL(out)
     vp, i64 = ctypes.c_void_p, ctypes.c_int64
-    L.emu_run.argtypes = [i64, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, ctypes.c_int, ctypes.c_double, i64, ctypes.c_int, ctypes.c_uint64, vp, vp, ctypes.c_char_p, ctypes.c_int]
+    L.emu_run.argtypes = [i64, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, ctypes.c_int, ctypes.c_double, i64, ctypes.c_int, ctypes.c_uint64, vp, vp, ctypes.c_char_p, ctypes.c_int, vp, vp, vp]
     return L
 
 
-def run_emu(emu, p, mode=0, slack=1e9, max_slots=0, split=1, seed=12345):
+def run_emu(emu, p, mode=0, slack=1e9, max_slots=0, split=1, seed=12345, grid=None):
     ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     ops = p.i32("ops")
     cols = [np.ascontiguousarray(ops[:, k]) for k in range(5)]
@@ -36,12 +36,15 @@ def run_emu(emu, p, mode=0, slack=1e9, max_slots=0, split=1, seed=12345):
     vals = p.f64("input_vals")
     keep = np.ascontiguousarray(np.concatenate([p.i32("L")[:, 0], p.i32("U")[:, 0]]).astype(np.int32))
     out = np.zeros((len(keep), 64, 64))
-    stats = np.zeros(5, dtype=np.int64)
+    stats = np.zeros(6, dtype=np.int64)
+    g = np.array(grid if grid else (1, 1, 1), dtype=np.int32)
+    brow, bcol = np.ascontiguousarray(p.i32("block_row")), np.ascontiguousarray(p.i32("block_col"))
     err = ctypes.create_string_buffer(256)
     rc = emu.emu_run(p.size("storage"), n_in, ptr(ids), ptr(vals), len(ops), ptr(cols[1]), ptr(cols[2]), ptr(opc), ptr(cols[3]), ptr(cols[4]),
-                     len(keep), ptr(keep), mode, slack, max_slots, split, seed, ptr(out), ptr(stats), err, 256)
+                     len(keep), ptr(keep), mode, slack, max_slots, split, seed, ptr(out), ptr(stats), err, 256,
+                     ptr(g) if grid else None, ptr(brow), ptr(bcol))
     assert rc == 0, err.value.decode()
-    return keep, out, dict(zip("tasks segments slots cuts split_tasks".split(), stats.tolist()))
+    return keep, out, dict(zip("tasks segments slots cuts split_tasks mirrors".split(), stats.tolist()))
 
 
 def check_against_oracle(oracle, p, keep, blocks):
@@ -119,6 +122,21 @@ def test_execution_order_does_not_matter(sg, emu, tmp_path):
         for seed in (1, 2):
             _, b, _ = run_emu(emu, p, mode=mode, seed=seed)
             np.testing.assert_array_equal(b, b0)
+
+
+@pytest.mark.parametrize("grid,mode,max_slots", [((2, 1, 2), 0, 0), ((2, 2, 1), 0, 0), ((4, 2, 4), 0, 0), ((2, 2, 2), 1, 0), ((2, 1, 4), 0, 4000), ((2, 2, 2), 1, 2500)])
+def test_sharded_graph_reproduces_the_factors(sg, emu, oracle, tmp_path, grid, mode, max_slots):
+    """The graph compiled for several GPUs (owner-computes, remote blocks mirrored by fetch tasks, per-owner pools), with
+    and without chain cuts and pool recycling, run in a dependency-driven random order: same factors as the oracle."""
+    p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
+    _, _, st0 = run_emu(emu, p)
+    keep, blocks, st = run_emu(emu, p, mode=mode, max_slots=max_slots, grid=grid)
+    assert st["mirrors"] > 0 and st["tasks"] > st0["tasks"]
+    if max_slots:
+        assert st["segments"] > 1
+    if mode:
+        assert st["cuts"] > 0
+    check_against_oracle(oracle, p, keep, blocks)
 
 
 def test_chain_cuts_with_recycling(sg, emu, oracle, tmp_path):
