@@ -144,3 +144,96 @@ def test_chain_cuts_with_recycling(sg, emu, oracle, tmp_path):
     keep, blocks, st = run_emu(emu, p, mode=1, slack=1e9, max_slots=6000)
     assert st["cuts"] > 0 and st["segments"] > 1
     check_against_oracle(oracle, p, keep, blocks)
+
+
+# ---- random operation lists (not from the planner): the compiled graph must still mean what the list says ------------------
+LU, LINV, UINV, SUB, MUL, MULNEG, LLT, MULT = 1, 2, 3, 4, 8, 9, 10, 11
+
+
+def random_op_list(seed, n_steps=60):
+    """A random valid list in the sense of SURVEY.md App. E: topological, one kind of writers per block, chains complete
+    before they are read.  Blocks are kept small in norm (products of [-1,1]/64 entries) and lu / llt only see diagonally
+    dominant / SPD blocks, so the comparison is not dominated by conditioning."""
+    rng = np.random.default_rng(seed)
+    blocks, kinds = [None], ["none"]                 # id 0 = none
+    def new_input(kind):
+        a = rng.uniform(-1, 1, (64, 64)) / 64
+        if kind == "dom":
+            a += np.eye(64) * rng.uniform(1.5, 3.0)
+        if kind == "spd":
+            a = a @ a.T + np.eye(64) * rng.uniform(1.0, 2.0)
+        blocks.append(a); kinds.append(kind)
+        return len(blocks) - 1
+    inputs = [new_input(k) for k in ["dom", "dom", "gen", "gen", "gen", "spd", "gen", "dom"]]
+    n_input = len(inputs)
+    ops = []
+    def new_id(kind):
+        blocks.append(None); kinds.append(kind)
+        return len(blocks) - 1
+    def pick(*ks):
+        c = [i for i in range(1, len(kinds)) if kinds[i] in ks]
+        return int(rng.choice(c)) if c else 0
+    for _ in range(n_steps):
+        what = rng.choice(["chain", "chain", "chain", "sub", "sub", "lu", "inv", "llt", "negcopy"])
+        if what == "chain":
+            code = int(rng.choice([MUL, MUL, MULNEG, MULT]))
+            pairs = [(pick("gen", "prod", "sub", "linv", "uinv", "L", "U"), pick("gen", "prod", "sub", "L", "U", "linv")) for _k in range(int(rng.integers(1, 6)))]
+            r = new_id("prod")
+            for a_, b_ in pairs:
+                ops.append((code, a_, b_, r, 0))
+        elif what == "sub":
+            s1 = pick("prod", "gen")
+            s2 = pick("dom", "gen", "sub", "domsub")
+            if s1 == s2:
+                continue
+            r = new_id("domsub" if kinds[s2] in ("dom", "domsub") else "sub")
+            ops.append((SUB, s1, s2, r, 0))
+        elif what == "negcopy":
+            s = pick("prod", "gen", "sub")
+            r = new_id("sub")
+            ops.append((SUB, s, 0, r, 0) if rng.random() < 0.5 else (SUB, 0, s, r, 0))
+        elif what == "lu":
+            s = pick("dom", "domsub")
+            l, u = new_id("L"), new_id("U")
+            ops.append((LU, s, 0, l, u))
+        elif what == "llt":
+            s = pick("spd")
+            ops.append((LLT, s, 0, new_id("L"), 0))
+        elif what == "inv":
+            s = pick("L", "U")
+            if s:
+                ops.append((LINV if kinds[s] == "L" else UINV, s, 0, new_id("linv" if kinds[s] == "L" else "uinv"), 0))
+    produced = sorted({o[3] for o in ops} | {o[4] for o in ops if o[4] > 0})
+    keep = [i for i in produced if kinds[i] in ("L", "U") or rng.random() < 0.3]
+    dense = np.ascontiguousarray(np.stack([blocks[i] for i in inputs]))
+    return len(blocks), np.array(inputs, dtype=np.int32), dense, np.array(ops, dtype=np.int64), np.array(keep, dtype=np.int32), n_input
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("variant", ["default", "cuts", "small_pool"])
+def test_random_operation_lists(emu, oracle, seed, variant):
+    n_ids, inputs, dense, ops, keep, n_input = random_op_list(seed)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    col = lambda k, dt=np.int32: np.ascontiguousarray(ops[:, k], dtype=dt)
+    opc, src, src2, res, res2 = col(0, np.uint8), col(1), col(2), col(3), col(4)
+    # the list as written (oracle: one op after the other)
+    h = oracle.L.oracle_create(n_ids)
+    oracle.L.oracle_set_inputs(h, len(inputs), ptr(inputs), ptr(dense))
+    rc = oracle.L.oracle_factor(h, len(ops), ptr(src), ptr(src2), ptr(opc), ptr(res), ptr(res2))
+    assert rc == 0
+    ref = np.stack([oracle.block(h, int(i)) for i in keep])
+    oracle.free(h)
+    # the compiled graph
+    out = np.zeros((len(keep), 64, 64))
+    stats = np.zeros(6, dtype=np.int64)
+    err = ctypes.create_string_buffer(256)
+    mode, slack, max_slots = (1, 1e9, 0) if variant == "cuts" else (0, 0.0, 0)
+    if variant == "small_pool":
+        max_slots = n_input + len(keep) + 14
+    rc = emu.emu_run(n_ids, len(inputs), ptr(inputs), ptr(dense), len(ops), ptr(src), ptr(src2), ptr(opc), ptr(res), ptr(res2), len(keep), ptr(keep),
+                     mode, slack, max_slots, 1, 1000 + seed, ptr(out), ptr(stats), err, 256, None, None, None)
+    if rc != 0 and variant == "small_pool" and b"pool too small" in err.value:
+        pytest.skip("live set larger than the tiny pool")
+    assert rc == 0, err.value.decode()
+    assert np.isfinite(ref).all() and np.isfinite(out).all()
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) <= TOL
