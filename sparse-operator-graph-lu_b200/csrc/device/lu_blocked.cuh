@@ -140,11 +140,14 @@ LUB_NOINLINE void diag16(double* D, double* ldi, double* udi, double* scr, int l
         }
         if (act && h == hk) a[jk] = m;                            // the multiplier is the entry of L
         if (k < 15) {
+            // next pivot: clamp + reciprocal.  Every lane runs the arithmetic on its own element (straight-line code: the
+            // reciprocal's latency overlaps the updates above instead of a one-lane divergent branch); only the lane that
+            // owns d(k+1, k+1) keeps and publishes the result (visible after the next sync).
             const int k1 = k + 1, hk1 = k1 >> 3, jk1 = k1 & 7;
-            if (r == k1 && h == hk1) {                            // next pivot: clamp, reciprocal (visible after the next sync)
-                const double p = clamp_pivot<LLT>(a[jk1]);
+            const double p = clamp_pivot<LLT>(a[jk1]);
+            const double ipn = hw::rcp(p);
+            if (r == k1 && h == hk1) {
                 a[jk1] = p;
-                const double ipn = hw::rcp(p);
                 ipk[k1 & 1] = ipn;
                 ip16[k1] = ipn;
             }
