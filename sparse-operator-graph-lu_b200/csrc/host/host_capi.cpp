@@ -285,3 +285,12 @@ int soglu_write_stencil_mtx(const char* kind, int nx, int ny, int nz, int symmet
 }
 
 }  // extern "C"
+
+// the raw MatrixMarket reader (tests): entries in file order, meta = {dimension, symmetric}; returns the entry count
+extern "C" int64_t soglu_debug_read_mtx(const char* path, int64_t cap, int32_t* i, int32_t* j, double* v, int64_t* meta) {
+    soglu::Coo c;
+    const long n = soglu::read_mtx(path ? path : "", c);
+    if (meta) { meta[0] = c.n; meta[1] = c.symmetric ? 1 : 0; }
+    for (long k = 0; k < n && k < cap; k++) { i[k] = c.i[k]; j[k] = c.j[k]; v[k] = c.v[k]; }
+    return n;
+}
