@@ -361,7 +361,7 @@ extern "C" int soglu_debug_compile_raw(int64_t n_ids, int64_t n_input, const int
 }
 
 // Timed model of the executor on the compiled graph of a problem (device/model.cpp; diagnostics, host only).
-// opts[9] = {split_narrow, max_slots, pr, pc, nb, chains, policy, hi_slack_us for the compiler, split_slack_us}; params: n_params doubles overriding ModelParams in
+// opts[10] = {split_narrow, max_slots, pr, pc, nb, chains, policy, hi_slack_us for the compiler, split_slack_us, n_sms for the split rule}; params: n_params doubles overriding ModelParams in
 // declaration order (NaN = keep the default); out[12] = {makespan_us, critical_path_us, busy_us, tasks, segments, pairs, hi tasks, cp_us, cp_early_us, proposed cuts,
 // cp_us after the cuts, cuts applied, operand pairs loaded from a peer, successor groups released on a peer,
 // longest chain: tasks[6], math us[6], pairs[6] by kind (GEMM whole / half / quarter, lu, sub, inverse), overhead us, remote hops}.
@@ -396,6 +396,7 @@ extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, c
     const int policy = (int)opts[6];
     co.hi_slack_us = (double)opts[7];   // > 0: the compiler classifies (as the executor option hi_shared does)
     co.split_slack_us = (double)opts[8];
+    if (opts[9] > 0) co.n_sms = (int)opts[9];     // width against which a level counts as narrow (what-if; the model keeps 148 CTAs)
     soglu::TaskGraph G;
     std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
     if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }

@@ -15,10 +15,10 @@ PARAMS = ["n_ctas", "t_pair", "t_pair_half", "t_pair_quarter", "t_lu_fused", "t_
           "t_release", "t_poll", "t_poll_hit", "t_desc", "t_load", "t_launch", "t_cas", "hi_slack_us", "t_release_remote", "t_load_remote", "t_launch_dist"]
 
 
-def model(p, split=1, max_slots=0, chains=0, policy=0, compile_hi_slack=0, grid=(1, 1, 16), split_slack=0, **kw):
+def model(p, split=1, max_slots=0, chains=0, policy=0, compile_hi_slack=0, grid=(1, 1, 16), split_slack=0, split_width=0, **kw):
     L = sg.lib()
     L.soglu_debug_model.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
-    opts = np.array([split, max_slots, grid[0], grid[1], grid[2], chains, policy, compile_hi_slack, split_slack], dtype=np.int64)
+    opts = np.array([split, max_slots, grid[0], grid[1], grid[2], chains, policy, compile_hi_slack, split_slack, split_width], dtype=np.int64)
     par = np.full(len(PARAMS), np.nan)
     for k, v in kw.items():
         par[PARAMS.index(k)] = v
@@ -42,7 +42,7 @@ if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if "=" not in a]
     kv = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
     p = problem(args[0], [int(a) for a in args[1:]])
-    split = int(kv.pop("split", 1)); ms = int(kv.pop("max_slots", 0)); ch = int(kv.pop("chains", 0)); pol = int(kv.pop("policy", 0)); chs = int(kv.pop("compile_hi_slack", 0)); grid = tuple(int(x) for x in kv.pop("grid", "1x1x16").split("x")); ssl = int(kv.pop("split_slack", 0))
+    split = int(kv.pop("split", 1)); ms = int(kv.pop("max_slots", 0)); ch = int(kv.pop("chains", 0)); pol = int(kv.pop("policy", 0)); chs = int(kv.pop("compile_hi_slack", 0)); grid = tuple(int(x) for x in kv.pop("grid", "1x1x16").split("x")); ssl = int(kv.pop("split_slack", 0)); sw = int(kv.pop("split_width", 0))
     t = time.time()
-    r = model(p, split, ms, ch, pol, chs, grid, ssl, **{k: float(v) for k, v in kv.items()})
+    r = model(p, split, ms, ch, pol, chs, grid, ssl, sw, **{k: float(v) for k, v in kv.items()})
     print(r, "(%.1f s)" % (time.time() - t))
