@@ -15,17 +15,10 @@ T=600 SOGLU_EXPERIMENTAL=1 run python -m pytest tests/test_gpu_parity.py -q -x -
 T=120 run gpurun_out/operand_bw
 # 2. the diagonal-block kernels in isolation (cycles)
 T=120 run python tools/diag_bench.py
-# 3. latency-bound configs, one option at a time
-for cfg in "lap3d 64" "nine2d 1024" "banded 200000"; do
-  T=300 run python tools/run_config.py $cfg
-  T=300 run python tools/run_config.py $cfg lu_mode=1
-  T=300 run python tools/run_config.py $cfg chain_cuts=200
-  T=300 run python tools/run_config.py $cfg hi_shared=1000
-  T=300 run python tools/run_config.py $cfg split_slack=100
-  T=300 run python tools/run_config.py $cfg prefetch=1
-  T=300 run python tools/run_config.py $cfg prefetch=3
-  T=300 run python tools/run_config.py $cfg lu_mode=1 chain_cuts=200 split_slack=100
-done
+# 3. latency-bound configs: planned once, every option in a fresh context (risky variants last)
+T=420 run python tools/r02_sweep.py lap3d 64
+T=600 run python tools/r02_sweep.py nine2d 1024
+T=420 run python tools/r02_sweep.py banded 200000
 # 4. the headline (100^3, throughput-bound): shared high-priority queue, thresholds around the model's optimum
 for s in 300 1000 3000; do
   T=420 run python bench.py --steps 2 --warmup 3 --no-cpu-baseline --opt hi_shared=$s
