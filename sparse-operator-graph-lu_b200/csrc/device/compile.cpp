@@ -940,6 +940,37 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
             std::sort(c.early_pos.begin(), c.early_pos.end());
             G.cuts.push_back(std::move(c));
         }
+        // Shared-operand pairs (diagnostics): two bulk GEMM tasks with the same left-operand sequence could
+        // run as ONE task that loads every A block once (3 instead of 4 block loads per two products).  Candidates:
+        // whole-block tasks with plenty of slack, the same flags and chain, ready at about the same time, and no
+        // successor of the first in between (the pair would sit at the second task's place in the order).
+        {
+            struct Cand { uint64_t key; int32_t task; };
+            std::vector<Cand> cand;
+            for (int64_t t = 0; t < n2; t++) {
+                const Task& T = G.tasks[t];
+                if (T.type != T_GEMM || T.n_pairs < 2 || ((T.flags >> TF_NROWS_SHIFT) & 7) != 4) continue;
+                if (G.cp_early_us - (fin_e[t] + bot[t]) < opt.dual_min_slack_us) continue;
+                uint64_t h = 1469598103934665603ull ^ (uint64_t)(T.flags & (TF_NEGATE | TF_TRANSB | TF_INIT)) ^ ((uint64_t)T.n_pairs << 8) ^ ((uint64_t)G.task_owner[t] << 40);
+                for (int k = 0; k < T.n_pairs; k++) { h ^= (uint64_t)(uint32_t)G.pairs[T.pair_begin + k].a; h *= 1099511628211ull; }
+                cand.push_back({h, (int32_t)t});
+            }
+            std::sort(cand.begin(), cand.end(), [](const Cand& x, const Cand& y) { return x.key != y.key ? x.key < y.key : x.task < y.task; });
+            int64_t pairs_formed = 0, covered = 0;
+            for (size_t q = 0; q + 1 < cand.size();) {
+                const int32_t t1 = cand[q].task, t2 = cand[q + 1].task;
+                bool ok = cand[q].key == cand[q + 1].key && std::fabs(fin_e[t1] - fin_e[t2]) < 50.f;
+                if (ok) {
+                    const Task &A = G.tasks[t1], &B = G.tasks[t2];
+                    for (int k = 0; k < A.n_pairs && ok; k++) ok = G.pairs[A.pair_begin + k].a == G.pairs[B.pair_begin + k].a;
+                    for (int32_t e = A.succ_begin; e < A.succ_end && ok; e++) ok = G.succ[e] > t2;
+                }
+                if (ok) { pairs_formed++; covered += 2 * (int64_t)G.tasks[t1].n_pairs; q += 2; }
+                else q++;
+            }
+            G.dual_pairs = pairs_formed;
+            G.dual_covered_pairs = covered;
+        }
         lap("chain analysis");
     }
     // ---- patch block ids -> block references (owner in the top bits; plain slots on one GPU) --------

@@ -127,6 +127,7 @@ struct TaskGraph {
     double cp_us = 0, cp_early_us = 0;
     std::vector<ChainCut> cuts;
     int64_t chain_splits = 0;  // cuts applied (CompileOptions::chain_cuts)
+    int64_t dual_pairs = 0, dual_covered_pairs = 0;   // chain analysis: task pairs that could share their left operands, operand pairs in them
 };
 
 struct CompileOptions {
@@ -155,6 +156,7 @@ struct CompileOptions {
     // them: the early pairs become their own task writing a temporary block that the late part starts from.
     bool analyze_chains = false;
     double cut_min_gain_us = 1.5;     // propose a cut only if the estimated finish of the task moves by at least this
+    double dual_min_slack_us = 300.0; // shared-operand pairs are only looked for among tasks with at least this slack
     double cut_max_slack_us = 200.0;  // ... and the task lies within this slack of the critical path
     const std::vector<ChainCut>* chain_cuts = nullptr;
 };

@@ -364,7 +364,8 @@ extern "C" int soglu_debug_compile_raw(int64_t n_ids, int64_t n_input, const int
 // opts[10] = {split_narrow, max_slots, pr, pc, nb, chains, policy, hi_slack_us for the compiler, split_slack_us, n_sms for the split rule}; params: n_params doubles overriding ModelParams in
 // declaration order (NaN = keep the default); out[12] = {makespan_us, critical_path_us, busy_us, tasks, segments, pairs, hi tasks, cp_us, cp_early_us, proposed cuts,
 // cp_us after the cuts, cuts applied, operand pairs loaded from a peer, successor groups released on a peer,
-// longest chain: tasks[6], math us[6], pairs[6] by kind (GEMM whole / half / quarter, lu, sub, inverse), overhead us, remote hops}.
+// longest chain: tasks[6], math us[6], pairs[6] by kind (GEMM whole / half / quarter, lu, sub, inverse), overhead us, remote hops,
+// shared-operand task pairs, operand pairs in them}.
 #include "../device/model.h"
 #include <cmath>
 extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, const double* params, int n_params, double* out) {
@@ -401,6 +402,7 @@ extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, c
     std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
     if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
     out[7] = G.cp_us; out[8] = G.cp_early_us; out[9] = (double)G.cuts.size();
+    out[34] = (double)G.dual_pairs; out[35] = (double)G.dual_covered_pairs;
     if (chains > 1 && !G.cuts.empty()) {
         const std::vector<soglu::ChainCut> cuts = std::move(G.cuts);
         co.analyze_chains = true;

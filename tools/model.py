@@ -22,13 +22,13 @@ def model(p, split=1, max_slots=0, chains=0, policy=0, compile_hi_slack=0, grid=
     par = np.full(len(PARAMS), np.nan)
     for k, v in kw.items():
         par[PARAMS.index(k)] = v
-    out = np.zeros(34)
+    out = np.zeros(36)
     rc = L.soglu_debug_model(p.h, opts.ctypes.data, par.ctypes.data, len(par), out.ctypes.data)
     if rc:
         raise RuntimeError(L.soglu_last_error().decode())
     return dict(makespan_ms=out[0] * 1e-3, critical_ms=out[1] * 1e-3, busy_ms_per_cta=out[2] * 1e-3 / (kw.get("n_ctas", 148) * grid[0] * grid[1]),
                 tasks=int(out[3]), segments=int(out[4]), pairs=int(out[5]), hi=int(out[6]),
-                cp_ms=out[7] * 1e-3, cp_early_ms=out[8] * 1e-3, cuts=int(out[9]), cp_cut_ms=out[10] * 1e-3, cuts_applied=int(out[11]), remote_loads=int(out[12]), remote_releases=int(out[13]),
+                cp_ms=out[7] * 1e-3, cp_early_ms=out[8] * 1e-3, cuts=int(out[9]), cp_cut_ms=out[10] * 1e-3, cuts_applied=int(out[11]), remote_loads=int(out[12]), remote_releases=int(out[13]), dual_tasks=int(out[34]), dual_covered_pairs=int(out[35]),
                 chain=dict(kinds="gemm64 gemm32 gemm16 lu sub inv".split(), tasks=out[14:20].astype(int).tolist(), math_ms=(out[20:26] * 1e-3).round(1).tolist(),
                            pairs=out[26:32].astype(int).tolist(), overhead_ms=round(out[32] * 1e-3, 1), remote_hops=int(out[33])))
 
