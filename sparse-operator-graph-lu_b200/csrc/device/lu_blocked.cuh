@@ -21,7 +21,9 @@
 // W_L / W_U are the forward eliminations of the identity: [S | I] row operations give L^-1, [S ; I] column operations
 // give U^-1 (blockwise the same recurrences as inv_lower / inv_upper).  L^-1 has a unit diagonal, so both inverses
 // share one 64x64 array: strictly lower part = L^-1, upper part with diagonal = U^-1.  Two CTA barriers per panel
-// (8 in total) instead of 64.  Estimated 9-11 k cycles; tests/emu/emu_lub.cpp runs THIS code on the host with
+// (8 in total) instead of 64.  Estimated 10-15 k cycles (the one-warp 16x16 sweep dominates: ~110 SASS instructions per
+// pivot; its structural zeros -- W_L / W_U columns beyond the pivot, finished columns of D -- are not skipped yet);
+// tests/emu/emu_lub.cpp runs THIS code on the host with
 // one thread per CUDA thread (pthread barriers, emulated DMMA fragments and shuffles) against a plain LU.
 #pragma once
 
