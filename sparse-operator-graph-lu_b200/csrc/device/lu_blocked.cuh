@@ -21,8 +21,8 @@
 // W_L / W_U are the forward eliminations of the identity: [S | I] row operations give L^-1, [S ; I] column operations
 // give U^-1 (blockwise the same recurrences as inv_lower / inv_upper).  L^-1 has a unit diagonal, so both inverses
 // share one 64x64 array: strictly lower part = L^-1, upper part with diagonal = U^-1.  Two CTA barriers per panel
-// (8 in total) instead of 64.  Estimated 10-15 k cycles (the one-warp 16x16 sweep dominates: ~110 SASS instructions per
-// pivot; its structural zeros -- W_L / W_U columns beyond the pivot, finished columns of D -- are not skipped yet);
+// (8 in total) instead of 64.  Estimated 10-15 k cycles (the one-warp 16x16 sweep dominates: ~100 SASS instructions per
+// pivot, structural zeros of W_L / W_U and the finished columns of D skipped per unrolled pivot);
 // tests/emu/emu_lub.cpp runs THIS code on the host with
 // one thread per CUDA thread (pthread barriers, emulated DMMA fragments and shuffles) against a plain LU.
 #pragma once
@@ -120,13 +120,22 @@ LUB_NOINLINE void diag16(double* D, double* ldi, double* udi, double* scr, int l
         }
         hw::sync_warp();     // row k and 1 / d_kk are visible; the buffers of pivot k - 1 may be overwritten at k + 1
         const double ip = ipk[k & 1];
+        // Structural zeros, known per unrolled pivot: row k of W_L / W_U is zero beyond column k, so for k < 8 only the
+        // columns j <= k can change (in either half); and for k >= 8 the columns j <= k - 8 of D are finished in both halves.
+        const int jw = (k < 8) ? k + 1 : 8;        // W_L / W_U columns j < jw are updated
+        const int ja = (k >= 8) ? k - 7 : 0;       // D columns j >= ja are updated
         double ra[8], rl[8], ru[8];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-            const D2 va = *reinterpret_cast<const D2*>(rowA + pb + 8 * h + j);
-            const D2 vl = *reinterpret_cast<const D2*>(rowL + pb + 8 * h + j);
-            const D2 vu = *reinterpret_cast<const D2*>(rowU + pb + 8 * h + j);
-            ra[j] = va.x; ra[j + 1] = va.y; rl[j] = vl.x; rl[j + 1] = vl.y; ru[j] = vu.x; ru[j + 1] = vu.y;
+            if (j + 1 >= ja) {
+                const D2 va = *reinterpret_cast<const D2*>(rowA + pb + 8 * h + j);
+                ra[j] = va.x; ra[j + 1] = va.y;
+            }
+            if (j < jw) {
+                const D2 vl = *reinterpret_cast<const D2*>(rowL + pb + 8 * h + j);
+                const D2 vu = *reinterpret_cast<const D2*>(rowU + pb + 8 * h + j);
+                rl[j] = vl.x; rl[j + 1] = vl.y; ru[j] = vu.x; ru[j + 1] = vu.y;
+            }
         }
         const double mc = a[jk] * ip;                             // d_rk / d_kk, meaningful in the half that holds column k
         double m = hw::shfl(mc, (lane & ~1) | hk);
@@ -135,10 +144,14 @@ LUB_NOINLINE void diag16(double* D, double* ldi, double* udi, double* scr, int l
         const double m2 = act ? rowA[pb + r] * ip : 0.0;          // d_kr / d_kk
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const double rv = (8 * h + j > k) ? ra[j] : 0.0;      // columns <= k of D are finished
-            a[j] = fma(-m, rv, a[j]);
-            wl[j] = fma(-m, rl[j], wl[j]);
-            wu[j] = fma(-m2, ru[j], wu[j]);
+            if (j >= ja) {
+                const double rv = (8 * h + j > k) ? ra[j] : 0.0;  // columns <= k of D are finished
+                a[j] = fma(-m, rv, a[j]);
+            }
+            if (j < jw) {
+                wl[j] = fma(-m, rl[j], wl[j]);
+                wu[j] = fma(-m2, ru[j], wu[j]);
+            }
         }
         if (act && h == hk) a[jk] = m;                            // the multiplier is the entry of L
         if (k < 15) {
