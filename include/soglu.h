@@ -113,8 +113,11 @@ int soglu_solve_refined(soglu_ctx* ctx, const double* b_ext, double* x_ext, int 
 /* parity helpers: read back one block (dense 64x64) after soglu_factor; error if the block
  * was recycled (only inputs of later ops, L and U are guaranteed to survive). */
 int soglu_get_block(soglu_ctx* ctx, int32_t id, double* out_64x64);
-/* run the op list one reference stage at a time with plain per-stage launches instead of
- * the persistent executor (debug / cross-check path; same kernels' math). */
+/* Tuning / debug knobs, to be set before the first soglu_factor (INTEGRATION.md lists them all).  None changes what is
+ * computed.  "exec_mode" = 1 runs the op list one dependency level at a time with plain per-level launches instead of
+ * the persistent executor (cross-check path; same kernels' math); "max_slots" caps the block pool; "split", "fuse_sub",
+ * "fuse_inv" switch compiler transformations; "hi_shared", "split_slack", "chain_cuts", "lu_mode", "prefetch" select
+ * scheduling / kernel variants that are off by default; "trace" records per-task timestamps. */
 int soglu_set_option(soglu_ctx* ctx, const char* key, int64_t value);
 
 /* ---------------- A2. multi-GPU: one process per GPU, 2D block-cyclic block ownership -------
