@@ -15,8 +15,10 @@
 // and afterwards x (returned by solveLU, NOT the _x.mtx file -- main.cpp:61 writes
 // data::b) and the permutation (GOrder::newOrder / reverseOrder, GPSOrder.cpp:448).
 //
-// usage: ref_harness <file.mtx> <outdir> [--blocks] [--nofactors]
+// usage: ref_harness <file.mtx> <outdir> [--blocks] [--lean]
 //   --blocks     also dump dense values of every input block and every L/U block
+//   --lean       timing + x only: skip the op-list / stage / factor-coordinate dumps (4.7 GB of op records
+//                at 100^3); what bench.py uses for the CPU baseline on the full-size configs
 // All dumps are raw little-endian arrays; meta.txt lists the counts.
 #include <cstdio>
 #include <cstdlib>
@@ -42,7 +44,7 @@
 using namespace SOGLU;
 
 static std::string g_out;
-static bool g_blocks = false;
+static bool g_blocks = false, g_lean = false;
 static FILE* g_meta = nullptr;
 static double g_t_factor = 0, g_t_solve = 0;
 
@@ -104,7 +106,7 @@ extern "C" {
 // ---- hook 1: coarse plan is complete when copyOperatorL2 is entered (solver.cpp:90-92)
 void __real__ZN5SOGLU12BlockPlanner14copyOperatorL2EPNS_6matrixES2_S2_S2_S2_i(matrix*, matrix*, matrix*, matrix*, matrix*, int);
 void __wrap__ZN5SOGLU12BlockPlanner14copyOperatorL2EPNS_6matrixES2_S2_S2_S2_i(matrix* a, matrix* l, matrix* u, matrix* l2, matrix* u2, int n) {
-    dump_graph("ops_coarse.i32");
+    if (!g_lean) dump_graph("ops_coarse.i32");
     fprintf(g_meta, "coarse_ops %zu\ncoarse_storage %d\ncoarse_block_rows %d\ncoarse_block_size %d\n",
             data::graph.size(), data::storageCount, data::blockRows, data::blockSize);
     __real__ZN5SOGLU12BlockPlanner14copyOperatorL2EPNS_6matrixES2_S2_S2_S2_i(a, l, u, l2, u2, n);
@@ -113,12 +115,14 @@ void __wrap__ZN5SOGLU12BlockPlanner14copyOperatorL2EPNS_6matrixES2_S2_S2_S2_i(ma
 // ---- hook 2: fine plan is complete when calculate is entered (solver.cpp:106)
 void __real__ZN5SOGLU12BlockPlanner9calculateEv();
 void __wrap__ZN5SOGLU12BlockPlanner9calculateEv() {
-    dump_graph("ops_fine.i32");
-    write_raw("stage.i32", data::stage.get(), sizeof(int) * data::storageCount);
-    write_raw("laststage.i32", data::laststage.get(), sizeof(int) * data::storageCount);
     std::vector<Leaf> in;
     walk(data::blocks, 0, 0, data::blockRows, in);
-    write_raw("inputs.i32", in.data(), in.size() * sizeof(Leaf));
+    if (!g_lean) {
+        dump_graph("ops_fine.i32");
+        write_raw("stage.i32", data::stage.get(), sizeof(int) * data::storageCount);
+        write_raw("laststage.i32", data::laststage.get(), sizeof(int) * data::storageCount);
+        write_raw("inputs.i32", in.data(), in.size() * sizeof(Leaf));
+    }
     if (g_blocks) dump_leaf_blocks("inputs.f64", in);
     fprintf(g_meta, "fine_ops %zu\nstorage %d\nblock_rows %d\nn_input %zu\nmsize %d\nsymmetric %d\n",
             data::graph.size(), data::storageCount, data::blockRows, in.size(), data::mSize, (int)data::symmetric);
@@ -133,15 +137,17 @@ void __wrap__ZN5SOGLU12BlockPlanner5solveEPNS_6matrixES2_Pdi(matrix* bl, matrix*
     std::vector<Leaf> L, U;
     walk(bl, 0, 0, data::blockRows, L);
     walk(bu, 0, 0, data::blockRows, U);
-    write_raw("L.i32", L.data(), L.size() * sizeof(Leaf));
-    write_raw("U.i32", U.data(), U.size() * sizeof(Leaf));
-    write_raw("b_perm.f64", b, sizeof(double) * n);
+    if (!g_lean) {
+        write_raw("L.i32", L.data(), L.size() * sizeof(Leaf));
+        write_raw("U.i32", U.data(), U.size() * sizeof(Leaf));
+        write_raw("b_perm.f64", b, sizeof(double) * n);
+    }
     if (g_blocks) { dump_leaf_blocks("L.f64", L); dump_leaf_blocks("U.f64", U); }
     fprintf(g_meta, "n_L %zu\nn_U %zu\nn_ext %d\n", L.size(), U.size(), n);
     auto t0 = std::chrono::steady_clock::now();
     __real__ZN5SOGLU12BlockPlanner5solveEPNS_6matrixES2_Pdi(bl, bu, b, n);
     g_t_solve = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    write_raw("x_perm.f64", data::x, sizeof(double) * data::mSize);
+    if (!g_lean) write_raw("x_perm.f64", data::x, sizeof(double) * data::mSize);
 }
 }
 
@@ -149,7 +155,10 @@ int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: ref_harness file.mtx outdir [--blocks]\n"); return 1; }
     std::string fname = argv[1];
     g_out = argv[2];
-    for (int i = 3; i < argc; i++) if (!strcmp(argv[i], "--blocks")) g_blocks = true;
+    for (int i = 3; i < argc; i++) {
+        if (!strcmp(argv[i], "--blocks")) g_blocks = true;
+        if (!strcmp(argv[i], "--lean")) g_lean = true;
+    }
     g_meta = fopen((g_out + "/meta.txt").c_str(), "w");
     if (!g_meta) { perror("meta.txt"); return 2; }
 
@@ -157,10 +166,12 @@ int main(int argc, char** argv) {
     std::string base = fname.substr(0, fname.find(".mtx"));
     if (mtx::readMTX(fname) == 0) return 3;
     mtx::readArray(base + "_b.mtx", mtx::mSize);
-    write_raw("coo_i.i32", mtx::indexi, sizeof(int) * mtx::valcount);
-    write_raw("coo_j.i32", mtx::indexj, sizeof(int) * mtx::valcount);
-    write_raw("coo_v.f64", mtx::vals, sizeof(double) * mtx::valcount);
-    write_raw("b.f64", mtx::b, sizeof(double) * mtx::mSize);
+    if (!g_lean) {
+        write_raw("coo_i.i32", mtx::indexi, sizeof(int) * mtx::valcount);
+        write_raw("coo_j.i32", mtx::indexj, sizeof(int) * mtx::valcount);
+        write_raw("coo_v.f64", mtx::vals, sizeof(double) * mtx::valcount);
+        write_raw("b.f64", mtx::b, sizeof(double) * mtx::mSize);
+    }
 
     auto t0 = std::chrono::steady_clock::now();
     double* x = solveLU(mtx::mSize, mtx::valcount, mtx::symmetric, mtx::indexi, mtx::indexj, mtx::vals, mtx::b);
@@ -168,8 +179,10 @@ int main(int argc, char** argv) {
     double err = mtx::checkResult(x);
 
     write_raw("x.f64", x, sizeof(double) * mtx::mSize);
-    write_raw("perm_new2old.i32", GOrder::newOrder, sizeof(int) * mtx::mSize);
-    write_raw("perm_old2new.i32", GOrder::reverseOrder, sizeof(int) * mtx::mSize);
+    if (!g_lean) {
+        write_raw("perm_new2old.i32", GOrder::newOrder, sizeof(int) * mtx::mSize);
+        write_raw("perm_old2new.i32", GOrder::reverseOrder, sizeof(int) * mtx::mSize);
+    }
     fprintf(g_meta, "dim %d\nnnz %d\nfile_symmetric %d\nmax_rhs_error %.17g\nt_factor %.6f\nt_solve %.6f\nt_total %.6f\n",
             mtx::mSize, mtx::valcount, (int)mtx::symmetric, err, g_t_factor, g_t_solve, t_total);
     fclose(g_meta);
