@@ -48,9 +48,9 @@ struct soglu_ctx {
     int64_t opt_exec_mode = 0;     // 0 persistent DAG executor, 1 one launch per level (debug)
     int64_t opt_fuse_sub = 1;
     int64_t opt_fuse_inv = 1;
-    int64_t opt_split_slack = 0;   // > 0: GEMM tasks within this slack (us) of the longest chain are row-split in wide levels too
+    int64_t opt_split_slack = 100; // GEMM tasks within this slack (us) of the longest chain are row-split in wide levels too (measured -5..6 % on the
+                                   // latency-bound configs, profiles/r02_call1_options.md); 0 = narrow levels only
     int64_t opt_prefetch = 0;      // executor prefetch bits (executor.cuh)
-    int64_t opt_lu_mode = 0;       // 1: blocked diagonal-block kernel (lu_blocked.cuh)
     int64_t opt_chain_cuts = 0;    // > 0: cut accumulation chains of tasks within this slack (us) of the critical path (two-pass compile)
     int64_t opt_hi_shared = 0;     // > 0: tasks with less estimated slack than this (us) go to a high-priority queue every CTA serves first
     int64_t opt_hi_ctas = 0;       // CTAs dedicated to a high-priority queue of small-slack tasks; 0 (default) = one FIFO
@@ -530,7 +530,6 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "chain_cuts") { if (c->compiled) return fail(SOGLU_ERR_ARG, "chain_cuts must be set before the first factor"); c->opt_chain_cuts = value; }
     else if (k == "hi_shared") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_shared must be set before the first factor"); c->opt_hi_shared = value; }
     else if (k == "hi_ctas") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_ctas must be set before the first factor"); c->opt_hi_ctas = value; }
-    else if (k == "lu_mode") c->opt_lu_mode = value;
     else if (k == "prefetch") c->opt_prefetch = value;
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
@@ -678,7 +677,6 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     P.succ = c->succ.as<int32_t>();
     P.dep = c->dep.as<int32_t>();
     P.trace = nullptr;
-    P.lu_mode = (int32_t)c->opt_lu_mode;
     P.prefetch = (int32_t)c->opt_prefetch;
     if (c->opt_trace && nt > 0) {
         if (!c->trace.p) CU(c->trace.alloc((size_t)nt * 6 * sizeof(unsigned long long)));

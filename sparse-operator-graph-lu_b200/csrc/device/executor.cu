@@ -12,16 +12,13 @@
 //   warps 1..8  math: m8n8k4 FP64 tensor-core MMAs (DMMA) for the Schur updates
 //               C = init +/- sum_p A_p*B_p, the whole accumulation chain of one target block (or of
 //               a 16- / 32-row slice of it in narrow levels) kept in registers and written once;
-//               register-resident diagonal kernels for the rest: LU that also forms L^-1 and U^-1
-//               in the same sweep (lu3_reg), triangular inverses, Cholesky, subtract.
+//               the blocked diagonal-block kernel for the rest (lu_blocked.cuh: LU / Cholesky that also form
+//               L^-1 and U^-1, one warp on the pivot chain, four streaming behind it, DMMA trailing updates),
+//               standalone triangular inverses, subtract.
 //               After the write-back ALL math threads walk the task's successor list: one atomicSub
 //               on the successor group's dependency counter each; the thread that brings it to zero
 //               publishes the whole group (a task, or the 2 / 4 row slices of a split GEMM task,
 //               which share their leader's counter) at the tail of the ready queue.
-// Two queues exist (high priority / bulk); the default is one FIFO queue.  Option hi_ctas dedicates CTAs
-// [0, n_hi_ctas) to the first (measured slower, DESIGN.md negative results); option hi_shared lets EVERY CTA
-// take published high-priority tasks before its next bulk slot (the host model predicts -5.5 % at 100^3;
-// not yet measured on the GPU, off by default).
 //
 // Memory-ordering protocol: writer CTA: st.global data -> bar.sync -> __threadfence ->
 // atomicSub(dep) [-> __threadfence -> atomicAdd(tail) -> st.release(ready)]; reader CTA:
@@ -68,212 +65,49 @@ struct __align__(16) SmemCtl {
     uint64_t full[N_STAGES];
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
-    double scratch[584];   // pivot row/column exchange buffers of the register-resident diag kernels
+    double scratch[192];   // row exchange buffer + reciprocals of the standalone triangular inverses
 };
 
-constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl);
-// the blocked diagonal kernel (LU_MODE 1) keeps its own scratch behind SmemCtl, so the default launch is unchanged
-constexpr size_t SMEM_BYTES_LUB = SMEM_BYTES + (size_t)lub::SCRATCH_DOUBLES * sizeof(double);
+// the blocked diagonal kernel keeps its scratch (pivot barriers, panel inverses) behind SmemCtl
+constexpr size_t SMEM_BYTES = (size_t)N_STAGES * STAGE_BYTES + sizeof(SmemCtl) + (size_t)lub::SCRATCH_DOUBLES * sizeof(double);
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 
 // ---- small block kernels on a block resident in shared memory (256 math threads) -------
 __device__ __forceinline__ void math_sync() { ptx::named_bar_sync(BAR_MATH, N_MATH); }
 
 
-// ---- diagonal-block kernels, register resident ---------------------------------------------
-// Thread (ty, tx) of the 16x16 grid of math threads owns the 16 elements (ty+16r, tx+16c) of
-// every 64x64 matrix involved.  Per pivot only the pivot row / column travel through shared
-// memory (double-buffered, ONE barrier per pivot); the loop over 16-pivot groups is unrolled
-// so finished row / column groups drop out statically, and the body is branch-free so that
-// all shared-memory loads of a pivot are in flight together.
-//
-// lu3_reg: (L, U) = LU(A) without pivoting, unit-diagonal L, |u_kk| < 1e-9 clamped
-// sign-preserving (ludcmpSimple, MatrixStdDouble.cpp:2711-2784; plain FP64 instead of x87 long
-// double) and, in the SAME 64-pivot loop, both triangular inverses (inv_lower / inv_upper,
-// MatrixStdDouble.cpp:2787-2802, 2829-2866):
-//   L^-1:  forward elimination W_i -= l_ik * W_k  -- column k of L is exactly the multiplier
-//          column the LU step has just formed;
-//   U^-1:  (U^T)^-1 by the same forward elimination with multipliers u_ki / u_kk taken from
-//          the pivot row, scaled by 1/u_ii at the end and written back transposed.
-// So the fused lu + lowerInv + upperInv task costs one elimination sweep instead of three.
-// WU = false skips W_U (Cholesky only needs L^-1); LLT selects lltdcmpSimple's pivot clamp (p < 1e-20 -> 1e-20,
-// MatrixStdDouble.cpp:2640) instead of ludcmpSimple's (|p| < 1e-9 -> +-1e-9, 2745).
-template <bool LLT>
-__device__ __forceinline__ double clamp_pivot(double p) {
-    if (LLT) return (p < 1e-20) ? 1e-20 : p;
-    return (p < 1e-9 && p > -1e-9) ? ((p < 0) ? -1e-9 : 1e-9) : p;
-}
-template <bool WITH_INV, int DBG = 0, bool WU = true, bool LLT = false>
-__device__ __forceinline__ void lu3_reg(const double* __restrict__ As, double* __restrict__ xbuf, double (&a)[4][4], double (&wl)[4][4],
-                                        double (&wu)[4][4], int ct) {
-    const int ty = ct >> 4, tx = ct & 15;
-    double* rowbuf = xbuf;         // [2][64] pivot row of A
-    double* colbuf = xbuf + 128;   // [2][64] pivot column of A
-    double* wlbuf = xbuf + 256;    // [2][64] row k of W_L
-    double* wubuf = xbuf + 384;    // [2][64] row k of W_U
-    double* ipbuf = xbuf + 512;    // [64]    1 / u_kk
-    double* ipnext = xbuf + 576;   // [2]     1 / u_kk of the pivot about to be used (double-buffered)
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            a[r][c] = As[(ty + 16 * r) * BLK_LD + tx + 16 * c];
-            if (WITH_INV) { wl[r][c] = (r == c && ty == tx) ? 1.0 : 0.0; if (WU) wu[r][c] = wl[r][c]; }
-        }
-    // The reciprocal of pivot k+1 is formed by the warp that owns element (k+1,k+1) as soon as
-    // pivot k has updated it, and published with the pivot row: the other warps' updates of
-    // pivot k overlap that division instead of every thread waiting for 1/p after the barrier.
-    if (ct == 0) {
-        const double p = clamp_pivot<LLT>(a[0][0]);
-        a[0][0] = p;
-        const double ip0 = ptx::fast_rcp(p);
-        ipnext[0] = ip0;
-        if (WITH_INV) ipbuf[0] = ip0;
-    }
-#pragma unroll
-    for (int kr = 0; kr < 4; kr++) {
-#pragma unroll 1
-        for (int ko = 0; ko < 16; ko++) {
-            const int k = 16 * kr + ko;
-            const int pb = (k & 1) * 64;
-            if (ty == ko) {
-#pragma unroll
-                for (int c = kr; c < 4; c++) rowbuf[pb + tx + 16 * c] = a[kr][c];
-                if (WITH_INV) {
-#pragma unroll
-                    for (int c = 0; c <= kr; c++) { wlbuf[pb + tx + 16 * c] = wl[kr][c]; if (WU) wubuf[pb + tx + 16 * c] = wu[kr][c]; }
-                }
-            }
-            if (tx == ko) {
-#pragma unroll
-                for (int r = kr; r < 4; r++) colbuf[pb + ty + 16 * r] = a[r][kr];
-            }
-            if (!(DBG & 1)) math_sync();
-            const double ip = (DBG & 2) ? 1.0 : ipnext[k & 1];
-            // Next pivot first: the warp owning element (k+1,k+1) applies pivot k to that one element,
-            // clamps it and forms its reciprocal BEFORE its share of the trailing update, so the
-            // division overlaps the other warps' updates (warp-uniform branch, no divergence).
-            bool own_next = false;
-            double p_next = 0.0;
-            {
-                const int k1 = k + 1, ko1 = k1 & 15;
-                if (!(DBG & 2) && k1 < BLK && (ty >> 1) == (ko1 >> 1)) {
-                    own_next = (ty == ko1) && (tx == ko1);
-                    const double a_sel = (ko != 15) ? a[kr][kr] : a[kr < 3 ? kr + 1 : 3][kr < 3 ? kr + 1 : 3];
-                    const double p = clamp_pivot<LLT>(fma(-(colbuf[pb + k1] * ip), rowbuf[pb + k1], a_sel));
-                    const double ipn = ptx::fast_rcp(p);
-                    p_next = p;
-                    if (own_next) {
-                        ipnext[k1 & 1] = ipn;
-                        if (WITH_INV) ipbuf[k1] = ipn;
-                    }
-                }
-            }
-            double cbv[4], rbv[4], rbi[4], wlv[4], wuv[4];
-#pragma unroll
-            for (int r = kr; r < 4; r++) { cbv[r] = colbuf[pb + ty + 16 * r]; if (WITH_INV && WU) rbi[r] = rowbuf[pb + ty + 16 * r]; }
-#pragma unroll
-            for (int c = kr; c < 4; c++) rbv[c] = rowbuf[pb + tx + 16 * c];
-            if (WITH_INV) {
-#pragma unroll
-                for (int c = 0; c <= kr; c++) { wlv[c] = wlbuf[pb + tx + 16 * c]; if (WU) wuv[c] = wubuf[pb + tx + 16 * c]; }
-            }
-            // Finished rows / columns are switched off by zeroing their multiplier / pivot-row
-            // entry (a few selects per pivot) instead of predicating every update.
-            const bool cedge = tx > ko, wedge = tx <= ko;
-            rbv[kr] = cedge ? rbv[kr] : 0.0;
-            if (WITH_INV) { wlv[kr] = wedge ? wlv[kr] : 0.0; if (WU) wuv[kr] = wedge ? wuv[kr] : 0.0; }
-#pragma unroll
-            for (int r = kr; r < 4; r++) {
-                const bool ract = (r > kr) || (ty > ko);
-                const double l = ract ? cbv[r] * ip : 0.0;
-                if (!(DBG & 4)) {
-#pragma unroll
-                    for (int c = kr; c < 4; c++) a[r][c] = fma(-l, rbv[c], a[r][c]);
-                }
-                if (ract && tx == ko) a[r][kr] = l;
-                if (WITH_INV) {
-                    const double m = (WU && ract) ? rbi[r] * ip : 0.0;
-#pragma unroll
-                    for (int c = 0; c <= kr; c++) {
-                        wl[r][c] = fma(-l, wlv[c], wl[r][c]);
-                        if (WU) wu[r][c] = fma(-m, wuv[c], wu[r][c]);
-                    }
-                }
-            }
-            if (own_next) {   // the loops above produced the unclamped value; keep the clamped pivot
-                if (ko != 15) a[kr][kr] = p_next; else a[kr < 3 ? kr + 1 : 3][kr < 3 ? kr + 1 : 3] = p_next;
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void lu_task(const double* __restrict__ As, double* __restrict__ xbuf, const ExecParams& P, const StageDesc& d, int ct) {
-    const int ty = ct >> 4, tx = ct & 15;
-    double a[4][4], wl[4][4], wu[4][4];
-    const bool inv = d.flags & (TF_LINV | TF_UINV);
-    if (inv) lu3_reg<true>(As, xbuf, a, wl, wu, ct);
-    else lu3_reg<false>(As, xbuf, a, wl, wu, ct);
-    double* gL = blk_ptr(P, d.out);
-    double* gU = blk_ptr(P, d.out2);
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int i = ty + 16 * r, j = tx + 16 * c, o = i * BLK_LD + j;
-            const double v = a[r][c];
-            gL[o] = (j < i) ? v : (j == i ? 1.0 : 0.0);
-            gU[o] = (j >= i) ? v : 0.0;
-        }
-    if (!inv) return;
-    math_sync();   // ipbuf complete
-    if (d.flags & TF_LINV) {
-        double* g = blk_ptr(P, d.init);
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) g[(ty + 16 * r) * BLK_LD + tx + 16 * c] = wl[r][c];
-    }
-    if (d.flags & TF_UINV) {
-        double* g = blk_ptr(P, d.out4);
-        const double* ipbuf = xbuf + 512;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const double di = ipbuf[ty + 16 * r];
-#pragma unroll
-            for (int c = 0; c < 4; c++) g[(tx + 16 * c) * BLK_LD + ty + 16 * r] = wu[r][c] * di;   // transposed
-        }
-    }
-}
-
-// The same task with the blocked kernel (lu_blocked.cuh, option lu_mode = 1): factorisation in place in the stage's A
-// half, packed inverses in its (unused) B half, then the four result blocks are written out row by row.
-// A real function call (not inlined): its registers are allocated apart from the executor loop, which sits at the
-// 168-register limit of a 288-thread CTA; everything is passed by value so that ExecParams stays in the constant bank.
-__device__ __noinline__ void lu_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gU, double* gLi, double* gUi, int ct) {
+// ---- diagonal-block tasks: lu_blocked.cuh factors the block in place in the stage's A half and leaves the packed
+// inverses in its (unused) B half; the result blocks are then written out with 16-byte stores.
+// (L, U) = LU(A) without pivoting, unit-diagonal L, |u_kk| < 1e-9 clamped sign-preserving (ludcmpSimple,
+// MatrixStdDouble.cpp:2711-2784; plain FP64 instead of x87 long double) and, fused, both triangular inverses
+// (inv_lower / inv_upper, MatrixStdDouble.cpp:2787-2802, 2829-2866).
+__device__ __forceinline__ void lu_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gU, double* gLi, double* gUi, int ct) {
     const bool inv = gLi != nullptr || gUi != nullptr;
     if (inv) lub::lu_blocked<true, false>(As, Ws, scr, ct);
     else lub::lu_blocked<false, false>(As, nullptr, scr, ct);
-    for (int e = ct; e < BLK * BLK; e += N_MATH) {
-        const int i = e >> 6, j = e & 63, o = i * BLK_LD + j;
-        const double v = As[o];
-        gL[o] = (j < i) ? v : (j == i ? 1.0 : 0.0);
-        gU[o] = (j >= i) ? v : 0.0;
+    for (int e = ct; e < BLK * BLK / 2; e += N_MATH) {
+        const int i = e >> 5, j = (e & 31) * 2, o = i * BLK_LD + j;
+        const double2 v = *reinterpret_cast<const double2*>(As + o);
+        *reinterpret_cast<double2*>(gL + o) = make_double2(j < i ? v.x : (j == i ? 1.0 : 0.0), j + 1 < i ? v.y : (j + 1 == i ? 1.0 : 0.0));
+        *reinterpret_cast<double2*>(gU + o) = make_double2(j >= i ? v.x : 0.0, j + 1 >= i ? v.y : 0.0);
         if (inv) {
-            const double w = Ws[o];
-            if (gLi) gLi[o] = (j < i) ? w : (j == i ? 1.0 : 0.0);
-            if (gUi) gUi[o] = (j >= i) ? w : 0.0;
+            const double2 w = *reinterpret_cast<const double2*>(Ws + o);
+            if (gLi) *reinterpret_cast<double2*>(gLi + o) = make_double2(j < i ? w.x : (j == i ? 1.0 : 0.0), j + 1 < i ? w.y : (j + 1 == i ? 1.0 : 0.0));
+            if (gUi) *reinterpret_cast<double2*>(gUi + o) = make_double2(j >= i ? w.x : 0.0, j + 1 >= i ? w.y : 0.0);
         }
     }
     // the stage was written through the generic proxy; the next bulk copy into it comes through the async proxy
     ptx::fence_proxy_async();
 }
 
-// Cholesky through the blocked kernel (lltdcmpSimple + inv_lower, MatrixStdDouble.cpp:2629-2668, 2787-2802): the sweep
-// gives A = L1 D L1^T with unit L1, so chol(A) = L1 sqrt(D) and chol(A)^-1 = D^-1/2 L1^-1, as in llt_task.
-__device__ __noinline__ void llt_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gLi, int ct) {
+// L = chol(A), pivot < 1e-20 clamped (lltdcmpSimple, MatrixStdDouble.cpp:2629-2668), optionally with the fused lowerInv of
+// that L (inv_lower uses the stored diagonal, 2787-2802).  The blocked sweep gives A = L1 D L1^T with unit L1, so
+// chol(A) = L1 sqrt(D) and chol(A)^-1 = D^-1/2 L1^-1.  Only the symmetric (LL^T) path of the planner emits this task
+// (BlockPlanner.cpp:941-989).
+__device__ __forceinline__ void llt_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gLi, int ct) {
     if (gLi) lub::lu_blocked<true, true, false>(As, Ws, scr, ct);
     else lub::lu_blocked<false, true, false>(As, nullptr, scr, ct);
-    double* sq = scr;           // [64] sqrt(d_k), [64] 1 / sqrt(d_k)   (the kernel's scratch is free again)
+    double* sq = scr + lub::SCR_LDI;   // [64] sqrt(d_k), [64] 1 / sqrt(d_k)   (the panel-inverse scratch is free again)
     if (ct < 64) {
         const double s = sqrt(As[ct * BLK_LD + ct]);
         sq[ct] = s;
@@ -285,6 +119,7 @@ __device__ __noinline__ void llt_task_blocked(double* As, double* Ws, double* sc
         gL[o] = (j < i) ? As[o] * sq[j] : (j == i ? sq[i] : 0.0);
         if (gLi) gLi[o] = ((j < i) ? Ws[o] : (j == i ? 1.0 : 0.0)) * sq[64 + i];
     }
+    math_sync();                       // sq is read by everyone before the next task's kernel reuses the scratch
     ptx::fence_proxy_async();
 }
 
@@ -348,46 +183,6 @@ __device__ __forceinline__ void tri_inv_task(const double* __restrict__ Tm, doub
     }
 }
 
-// L = chol(A), pivot < 1e-20 clamped (lltdcmpSimple, MatrixStdDouble.cpp:2629-2668), optionally with the fused
-// lowerInv of that L (inv_lower uses the stored diagonal, 2787-2802).  Same register-resident sweep as the LU task:
-// A = L1 * U with unit L1 and u_kk = d_k, so chol(A) = L1 * diag(sqrt(d)) and chol(A)^-1 = diag(1/sqrt(d)) * L1^-1.
-// Only the symmetric (LL^T) path of the planner emits this task (BlockPlanner.cpp:941-989).
-__device__ __forceinline__ void llt_task(const double* __restrict__ As, double* __restrict__ xbuf, const ExecParams& P, const StageDesc& d, int ct) {
-    const int ty = ct >> 4, tx = ct & 15;
-    double a[4][4], wl[4][4], wu[4][4];
-    const bool inv = d.flags & TF_LINV;
-    if (inv) lu3_reg<true, 0, false, true>(As, xbuf, a, wl, wu, ct);
-    else lu3_reg<false, 0, false, true>(As, xbuf, a, wl, wu, ct);
-    double* sq = xbuf;          // [64] sqrt(d_k)       (the sweep's exchange buffers are free again)
-    double* isq = xbuf + 64;    // [64] 1 / sqrt(d_k)
-    math_sync();
-    if (ty == tx) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const double s = sqrt(a[r][r]);
-            sq[ty + 16 * r] = s;
-            isq[ty + 16 * r] = 1.0 / s;
-        }
-    }
-    math_sync();
-    double* gL = blk_ptr(P, d.out);
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int i = ty + 16 * r, j = tx + 16 * c;
-            gL[i * BLK_LD + j] = (j < i) ? a[r][c] * sq[j] : (j == i ? sq[i] : 0.0);
-        }
-    if (!inv) return;
-    double* g = blk_ptr(P, d.init);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const double di = isq[ty + 16 * r];
-#pragma unroll
-        for (int c = 0; c < 4; c++) g[(ty + 16 * r) * BLK_LD + tx + 16 * c] = wl[r][c] * di;
-    }
-}
-
 // ---- Schur update: acc += A(rows) * B(64x64) from shared memory, FP64 tensor cores ------------
 // A warp owns MT x NT DMMA tiles (8x8 each) starting at (row_base, col_base); 16 k-steps of 4.
 // Whole block (64 rows): 8 warps x (4 x 2 tiles); half (32 rows): 8 x (2 x 2); quarter: 8 x (2 x 1).
@@ -430,10 +225,6 @@ __device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const do
         }
 }
 
-// LU_MODE selects the diagonal-block kernel at compile time: the blocked one is a real function call, and a call in the
-// task loop changes the register allocation of the whole kernel (spills at the 168-register limit), so the default
-// instantiation must not contain it.
-template <int LU_MODE>
 __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
@@ -524,6 +315,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
     // ======================= math warps ====================================================
     const int mw = warp - 1;                 // 0..7
     const int ct = threadIdx.x - 32;         // 0..255
+    double* lub_scr = reinterpret_cast<double*>(ctl + 1);
+    lub::lu_setup(lub_scr, ct);              // pivot barriers of the diagonal-block kernel, once per launch
     double acc[4][2][2];
     for (uint32_t it = 0;; it++) {
         const int s = it % N_STAGES;
@@ -580,27 +373,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                     break;
                 }
                 case T_LU:
-                    if (LU_MODE == 1) {
-                        lu_task_blocked(As, Bs, reinterpret_cast<double*>(ctl + 1), out, blk_ptr(P, d.out2), (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr,
-                                        (d.flags & TF_UINV) ? blk_ptr(P, d.out4) : nullptr, ct);
-                        // no accumulation chain spans another task: tell the compiler the accumulators are dead across the call
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                            for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-                    }
-                    else lu_task(As, ctl->scratch, P, d, ct);
+                    lu_task_blocked(As, Bs, lub_scr, out, blk_ptr(P, d.out2), (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr,
+                                    (d.flags & TF_UINV) ? blk_ptr(P, d.out4) : nullptr, ct);
                     break;
                 case T_LLT:
-                    if (LU_MODE == 1) {
-                        llt_task_blocked(As, Bs, reinterpret_cast<double*>(ctl + 1), out, (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr, ct);
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                            for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-                    } else {
-                        llt_task(As, ctl->scratch, P, d, ct);
-                    }
+                    llt_task_blocked(As, Bs, lub_scr, out, (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr, ct);
                     break;
                 case T_LOWERINV:
                     tri_inv_task<false>(As, ctl->scratch, out, ct);
@@ -668,82 +445,45 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
     }
 }
 
-// debug micro-benchmark: cycle counts of the diagonal-block kernels in isolation (1 CTA)
+// debug micro-benchmark: cycle counts of the diagonal-block kernels in isolation (1 CTA); pool slot 1 = the block,
+// slots 2..5 receive L, U, L^-1, U^-1, slots 6 / 7 the standalone inverses of L and U
 __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, int iters, long long* cycles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
+    double* Ws = As + BLK_ELEMS;
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (size_t)N_STAGES * STAGE_BYTES);
+    double* scr = reinterpret_cast<double*>(ctl + 1);
     if (threadIdx.x < 32) return;
     const int ct = threadIdx.x - 32;
-    ExecParams BP = {};
-    BP.pools[0] = pool; BP.pool = pool; BP.world = 1;
+    lub::lu_setup(scr, ct);
+    auto slot = [&](int sl) { return pool + (size_t)sl * BLK_ELEMS; };
     long long t_lu3 = 0, t_lu = 0, t_invl = 0, t_invu = 0;
     for (int it = 0; it < iters; it++) {
-        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
+        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = slot(1)[i];
         math_sync();
-        StageDesc d = {};
-        d.out = 2; d.out2 = 3; d.init = 4; d.out4 = 5;
-        d.flags = TF_LINV | TF_UINV;
         long long c0 = clock64();
-        lu_task(As, ctl->scratch, BP, d, ct);
+        lu_task_blocked(As, Ws, scr, slot(2), slot(3), slot(4), slot(5), ct);
         math_sync();
         long long c1 = clock64();
-        d.flags = 0;
-        lu_task(As, ctl->scratch, BP, d, ct);
+        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = slot(1)[i];
         math_sync();
         long long c2 = clock64();
-        {
-            double a[4][4], wl[4][4], wu[4][4];
-            long long e0 = clock64();
-            lu3_reg<false, 1>(As, ctl->scratch, a, wl, wu, ct); math_sync();
-            long long e1 = clock64();
-            lu3_reg<false, 2>(As, ctl->scratch, a, wl, wu, ct); math_sync();
-            long long e2 = clock64();
-            lu3_reg<false, 4>(As, ctl->scratch, a, wl, wu, ct); math_sync();
-            long long e3 = clock64();
-            lu3_reg<false, 6>(As, ctl->scratch, a, wl, wu, ct); math_sync();
-            long long e4 = clock64();
-            lu3_reg<false, 7>(As, ctl->scratch, a, wl, wu, ct); math_sync();
-            long long e5 = clock64();
-            lu3_reg<false, 0>(As, ctl->scratch, a, wl, wu, ct); math_sync();
-            long long e6 = clock64();
-            if (ct == 0 && it == iters - 1) { cycles[4] = e1 - e0; cycles[5] = e2 - e1; cycles[6] = e3 - e2; cycles[7] = e4 - e3; cycles[8] = e5 - e4; cycles[9] = e6 - e5; }
-            if (a[0][0] == 1.2345e-300) pool[0] = a[1][1] + a[2][2] + a[3][3];
-        }
-        {
-            // blocked kernel: fused (slots 8..11 receive L, U, L^-1, U^-1) and factors only
-            double* Ws = As + BLK_ELEMS;
-            d.out = 8; d.out2 = 9; d.init = 10; d.out4 = 11;
-            d.flags = TF_LINV | TF_UINV;
-            for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
-            math_sync();
-            long long b0 = clock64();
-            lu_task_blocked(As, Ws, reinterpret_cast<double*>(ctl + 1), pool + 8 * (size_t)BLK_ELEMS, pool + 9 * (size_t)BLK_ELEMS, pool + 10 * (size_t)BLK_ELEMS, pool + 11 * (size_t)BLK_ELEMS, ct);
-            math_sync();
-            long long b1 = clock64();
-            for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[BLK_ELEMS + i];
-            math_sync();
-            d.flags = 0;
-            long long b2 = clock64();
-            lu_task_blocked(As, Ws, reinterpret_cast<double*>(ctl + 1), pool + 8 * (size_t)BLK_ELEMS, pool + 9 * (size_t)BLK_ELEMS, nullptr, nullptr, ct);
-            math_sync();
-            long long b3 = clock64();
-            if (ct == 0 && it == iters - 1) { cycles[10] = b1 - b0; cycles[11] = b3 - b2; }
-            d.out = 2; d.out2 = 3; d.init = 4; d.out4 = 5;
-        }
-        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[2 * BLK_ELEMS + i];
+        lu_task_blocked(As, Ws, scr, slot(2), slot(3), nullptr, nullptr, ct);
         math_sync();
         long long c3 = clock64();
-        tri_inv_task<false>(As, ctl->scratch, pool + 6 * (size_t)BLK_ELEMS, ct);
+        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = slot(2)[i];
         math_sync();
         long long c4 = clock64();
-        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = pool[3 * BLK_ELEMS + i];
+        tri_inv_task<false>(As, ctl->scratch, slot(6), ct);
         math_sync();
         long long c5 = clock64();
-        tri_inv_task<true>(As, ctl->scratch, pool + 7 * (size_t)BLK_ELEMS, ct);
+        for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = slot(3)[i];
         math_sync();
         long long c6 = clock64();
-        t_lu3 += c1 - c0; t_lu += c2 - c1; t_invl += c4 - c3; t_invu += c6 - c5;
+        tri_inv_task<true>(As, ctl->scratch, slot(7), ct);
+        math_sync();
+        long long c7 = clock64();
+        t_lu3 += c1 - c0; t_lu += c3 - c2; t_invl += c5 - c4; t_invu += c7 - c6;
     }
     if (ct == 0) { cycles[0] = t_lu3 / iters; cycles[1] = t_lu / iters; cycles[2] = t_invl / iters; cycles[3] = t_invu / iters; }
 }
@@ -786,16 +526,16 @@ __global__ void unpack_block_kernel(const double* __restrict__ pool, int32_t slo
 size_t executor_smem_bytes() { return SMEM_BYTES; }
 
 int executor_max_grid(int device) {
-    cudaFuncSetAttribute(executor_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(executor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, executor_kernel<0>, N_THREADS, SMEM_BYTES) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, executor_kernel, N_THREADS, SMEM_BYTES) != cudaSuccess) return 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
 
 cudaError_t launch_executor(const ExecParams& p, int grid, cudaStream_t stream) {
-    const void* kernel = (p.lu_mode == 1) ? (const void*)executor_kernel<1> : (const void*)executor_kernel<0>;
-    const size_t smem = (p.lu_mode == 1) ? SMEM_BYTES_LUB : SMEM_BYTES;
+    const void* kernel = (const void*)executor_kernel;
+    const size_t smem = SMEM_BYTES;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     ExecParams pp = p;
@@ -806,9 +546,9 @@ cudaError_t launch_executor(const ExecParams& p, int grid, cudaStream_t stream) 
 }
 
 cudaError_t launch_diag_bench(double* pool, int iters, long long* cycles, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(diag_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_LUB);
+    cudaError_t e = cudaFuncSetAttribute(diag_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    diag_bench_kernel<<<1, N_THREADS, SMEM_BYTES_LUB, stream>>>(pool, iters, cycles);
+    diag_bench_kernel<<<1, N_THREADS, SMEM_BYTES, stream>>>(pool, iters, cycles);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,6 @@ struct ExecParams {
     int32_t n_hi_ctas;     // CTAs dedicated to queue 0; -1 = shared: every CTA serves queue 0 first (option hi_shared)
     int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
     int32_t prefetch;      // bit 0: operand-pair lookahead in the scheduler lane; bit 1: releasing threads prefetch the successor's task record
-    int32_t lu_mode;       // 0: lu3_reg (one pivot per barrier, registers); 1: lu_blocked.cuh (16-column panels, DMMA)
     unsigned long long* trace;   // optional: 6 x u64 per task (published, claimed, loaded, computed, signalled, smid)
 };
 

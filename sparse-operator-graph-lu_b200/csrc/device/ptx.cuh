@@ -104,6 +104,19 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r;
 }
 
+// -1/x with the same seed and Newton steps.  The sign enters in the first step through operand negations (free in
+// SASS), so a consumer that needs the negated reciprocal -- a multiplier that is subtracted -- has no negation on its
+// dependency chain.
+__device__ __forceinline__ double fast_neg_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    double n = fma(-r, e, -r);       // -(r + r e)
+    e = fma(x, n, 1.0);              // 1 - x * (-n)
+    n = fma(n, e, n);
+    return n;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 }  // namespace ptx

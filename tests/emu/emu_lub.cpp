@@ -1,10 +1,13 @@
 // TEST INFRASTRUCTURE: host run of the blocked diagonal-block kernel (csrc/device/lu_blocked.cuh).  The device code
 // is compiled unchanged for the host and executed by 256 real threads, one per CUDA math thread: __syncwarp and the
 // CTA barrier are pthread barriers, warp shuffles and the m8n8k4 DMMA are emulated through per-warp exchange arrays
-// with the PTX fragment layout (lane 4g+t holds A[g][t], B[t][g], C[g][2t..2t+1]).  Checked against a plain
+// with the PTX fragment layout (lane 4g+t holds A[g][t], B[t][g], C[g][2t..2t+1]); the arrive-only side of barrier Y
+// and the shared-memory pivot counter (release / acquire) are host atomics.  Checked against a plain
 // no-pivoting LU with the reference's pivot clamp (MatrixStdDouble.cpp:2745) and against L^-1 L = I, U U^-1 = I.
 #define SOGLU_LUB_HOST 1
 #include <pthread.h>
+
+#include <atomic>
 
 #include <cmath>
 #include <cstdio>
@@ -15,6 +18,7 @@
 #include "../../sparse-operator-graph-lu_b200/csrc/device/lu_blocked.cuh"
 
 namespace {
+std::vector<double>* g_scr_ptr = nullptr;
 pthread_barrier_t g_cta, g_warp[8];
 double g_xa[8][32], g_xb[8][32];
 thread_local int tl_ct = 0;
@@ -50,6 +54,27 @@ void dmma(double& c0, double& c1, double a, double b) {
     sync_warp();
 }
 double rcp(double x) { return 1.0 / x; }
+double neg_rcp(double x) { return -1.0 / x; }
+// barrier Y: 32 threads (warp 0) arrive and go on, 224 wait for all 256 (PTX bar.arrive / bar.sync on one barrier)
+static std::atomic<int> y_count{0}, y_gen{0};
+static bool y_enter() {
+    if (y_count.fetch_add(1) + 1 == 256) { y_count.store(0); y_gen.fetch_add(1); return true; }
+    return false;
+}
+void arrive_y() { jitter(); y_enter(); }
+void sync_y() {
+    jitter();
+    const int g = y_gen.load();
+    if (!y_enter()) while (y_gen.load() == g) std::this_thread::yield();
+    jitter();
+}
+// an mbarrier with one arrival per phase = a counter of completed phases; the phase with parity p has completed
+// iff (count & 1) != p, which is also what the hardware answers on a fresh barrier asked for parity 1
+void pivot_init(unsigned long long* b) { __atomic_store_n(b, 0ull, __ATOMIC_RELAXED); }
+void pivot_init_done() {}
+void pivot_signal(unsigned long long* b) { jitter(); __atomic_fetch_add(b, 1ull, __ATOMIC_RELEASE); }
+bool pivot_ready(const unsigned long long* b, int parity) { std::this_thread::yield(); return (int)(__atomic_load_n(b, __ATOMIC_ACQUIRE) & 1) != parity; }
+void prof(int) {}
 }}}  // namespace soglu::lub::hw
 
 using namespace soglu::lub;
@@ -58,7 +83,7 @@ template <bool WITH_INV>
 static void run(const std::vector<double>& A, std::vector<double>& S, std::vector<double>& W) {
     S.assign(64 * LD, 0.0);
     W.assign(64 * LD, 7.7e300);          // poison: the kernel has to clear it
-    std::vector<double> scr(SCRATCH_DOUBLES, 3.3e300);
+    std::vector<double>& scr = *g_scr_ptr;    // persists across calls like the CTA's shared memory (barrier phases!)
     for (int i = 0; i < 64; i++) for (int j = 0; j < 64; j++) S[i * LD + j] = A[i * 64 + j];
     std::vector<std::thread> th;
     for (int ct = 0; ct < 256; ct++)
@@ -70,7 +95,7 @@ static void run(const std::vector<double>& A, std::vector<double>& S, std::vecto
 static void run_llt(const std::vector<double>& A, std::vector<double>& S, std::vector<double>& W) {
     S.assign(64 * LD, 0.0);
     W.assign(64 * LD, 7.7e300);
-    std::vector<double> scr(SCRATCH_DOUBLES, 3.3e300);
+    std::vector<double>& scr = *g_scr_ptr;
     for (int i = 0; i < 64; i++) for (int j = 0; j < 64; j++) S[i * LD + j] = A[i * 64 + j];
     std::vector<std::thread> th;
     for (int ct = 0; ct < 256; ct++)
@@ -104,6 +129,13 @@ static double maxabs_prod_minus_eye(const std::vector<double>& X, const std::vec
 int main() {
     pthread_barrier_init(&g_cta, nullptr, 256);
     for (auto& b : g_warp) pthread_barrier_init(&b, nullptr, 32);
+    std::vector<double> scr_store(SCRATCH_DOUBLES, 3.3e300);
+    g_scr_ptr = &scr_store;
+    {
+        std::vector<std::thread> th;
+        for (int ct = 0; ct < 256; ct++) th.emplace_back([&, ct]() { tl_ct = ct; lu_setup(scr_store.data(), ct); });
+        for (auto& t : th) t.join();
+    }
     unsigned long long st = 4242;
     auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return ((st >> 11) * (1.0 / 9007199254740992.0)) * 2 - 1; };
     double worst_lu = 0, worst_li = 0, worst_ui = 0, worst_noinv = 0, worst_clamped = 0;

@@ -1,4 +1,4 @@
-"""CPU check of the blocked diagonal-block kernel (csrc/device/lu_blocked.cuh, executor option lu_mode=1):
+"""CPU check of the blocked diagonal-block kernel (csrc/device/lu_blocked.cuh, the executor's T_LU / T_LLT tasks):
 tests/emu/emu_lub.cpp compiles the device header for the host and runs it with one host thread per CUDA thread
 (pthread barriers for __syncwarp / bar.sync, emulated DMMA fragments and shuffles) against a plain no-pivoting LU
 with the reference's pivot clamp (MatrixStdDouble.cpp:2745) and against L^-1 L = I, U U^-1 = I."""

@@ -10,11 +10,4 @@ p = sg.Problem.from_mtx(path); ctx = sg.Context(0); ctx.load(p); ctx.factor()
 cyc = (ctypes.c_longlong * 12)()
 L = sg.lib(); L.soglu_debug_diag_bench.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
 rc = L.soglu_debug_diag_bench(ctx.h, 20, cyc); assert rc == 0, L.soglu_last_error()
-print("cycles: lu+Linv+Uinv fused %d  lu only %d  lowerInv %d  upperInv %d   (per pivot: %.0f %.0f %.0f %.0f)" % (cyc[0], cyc[1], cyc[2], cyc[3], cyc[0] / 64, cyc[1] / 64, cyc[2] / 64, cyc[3] / 64))
-print('blocked kernel (lu_blocked.cuh, incl. write-out): lu+Linv+Uinv %d  lu only %d cycles' % (cyc[10], cyc[11]))
-print('lu-only variants (cycles): no-barrier %d | no-rcp %d | no-update %d | no-rcp+no-update %d | none of the three %d | full %d' % tuple(cyc[4:10]))
-# numerical check of the bench outputs (slots 2..7) against numpy on the same block
-import numpy as np
-def blk(slot):
-    # read by abusing get_block on ids is not possible for raw slots; use inputs: slot 1 = input id with slot 1
-    return None
+print("cycles incl. write-out: lu+Linv+Uinv fused %d (%.2f us at 1.965 GHz)  lu only %d  standalone lowerInv %d  upperInv %d" % (cyc[0], cyc[0] / 1965.0, cyc[1], cyc[2], cyc[3]))

@@ -11,15 +11,9 @@ import gen_mtx
 import soglu_b200 as sg
 
 VARIANTS = [
-    ("default", {}),
-    ("split_slack=100", {"split_slack": 100}),
+    ("default (split_slack=100)", {}),
+    ("split_slack=0", {"split_slack": 0}),
     ("chain_cuts=200", {"chain_cuts": 200}),
-    ("split_slack=100 chain_cuts=200", {"split_slack": 100, "chain_cuts": 200}),
-    ("prefetch=1", {"prefetch": 1}),
-    ("prefetch=3", {"prefetch": 3}),
-    ("hi_shared=1000", {"hi_shared": 1000}),
-    ("lu_mode=1", {"lu_mode": 1}),
-    ("lu_mode=1 split_slack=100 chain_cuts=200 prefetch=3", {"lu_mode": 1, "split_slack": 100, "chain_cuts": 200, "prefetch": 3}),
 ]
 
 kind, dims = sys.argv[1], [int(a) for a in sys.argv[2:]]
