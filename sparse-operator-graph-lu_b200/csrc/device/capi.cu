@@ -50,16 +50,13 @@ struct soglu_ctx {
     int64_t opt_fuse_inv = 1;
     int64_t opt_split_slack = 100; // GEMM tasks within this slack (us) of the longest chain are row-split in wide levels too (measured -5..6 % on the
                                    // latency-bound configs, profiles/r02_call1_options.md); 0 = narrow levels only
-    int64_t opt_prefetch = 0;      // executor prefetch bits (executor.cuh)
     int64_t opt_chain_cuts = 0;    // > 0: cut accumulation chains of tasks within this slack (us) of the critical path (two-pass compile)
-    int64_t opt_hi_shared = 0;     // > 0: tasks with less estimated slack than this (us) go to a high-priority queue every CTA serves first
-    int64_t opt_hi_ctas = 0;       // CTAs dedicated to a high-priority queue of small-slack tasks; 0 (default) = one FIFO
-                                   // queue: measured SLOWER with 16 (100^3: 2.58 -> 2.73 s on 1 GPU, 1.64 -> 1.91 s on 4)
     int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
     int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;
     int64_t opt_grid = 0;          // override CTA count (0 = all resident)
     int64_t opt_trace = 0;         // record per-task timestamps (debug; adds overhead)
+    int64_t opt_watchdog_ms = 60000;   // a kernel whose waiters see no progress for this long aborts with SOGLU_ERR_CUDA (0 = off)
     DevBuf trace;
 
     // multi-GPU (one process per GPU): process grid, localized task graph, peer mappings
@@ -93,6 +90,9 @@ struct soglu_ctx {
     std::vector<int32_t> level_order;   // tasks sorted by level (debug executor)
     std::vector<int64_t> level_ptr;
     DevBuf pool, tasks, pairs, succ, dep0, dep, ready, ready0, counters, counters0;
+    // watchdog word {flag, queue slot / block row, CTA, rank}: the 64 bytes behind the queue counters (one allocation,
+    // so the peers reach it through the IPC mapping of the counters)
+    int32_t* abort_word() const { return counters.as<int32_t>() + counters0.bytes / 4; }
     int64_t opt_max_slots = 0;     // debug: cap the block pool (forces segments + slot recycling)
     // solve structures
     DevBuf l_ptr, l_col, l_slot, l_diag, l_dinv, u_ptr, u_col, u_slot, u_diag, u_dinv, d_b, d_y, d_x;
@@ -115,6 +115,20 @@ namespace {
     } while (0)
 
 int fail(int code, const std::string& msg) { soglu::set_error(msg); return code; }
+
+// after the stream has been synchronised: did a kernel's watchdog give up?  (clears the word for the next call)
+int check_watchdog(soglu_ctx* c, const char* what) {
+    int32_t w[4] = {0, 0, 0, 0};
+    if (cudaMemcpy(w, c->abort_word(), sizeof w, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(SOGLU_ERR_CUDA, "cannot read the watchdog word");
+    if (w[0] == 0) return SOGLU_OK;
+    cudaMemset(c->abort_word(), 0, 64);
+    char m[320];
+    if (w[0] == 2) snprintf(m, sizeof m, "%s aborted: a peer GPU's watchdog gave up (see its error)", what);
+    else snprintf(m, sizeof m, "%s aborted by the watchdog after %lld ms without progress: CTA %d was waiting for %s %d%s", what, (long long)c->opt_watchdog_ms,
+                  w[2], c->factored && what[0] == 's' ? "block row" : "ready-queue slot", w[1],
+                  " (a lost dependency signal: a peer that failed, or an operation list with a missing edge)");
+    return fail(SOGLU_ERR_CUDA, m);
+}
 
 template <typename T, typename A>
 int upload(DevBuf& b, const std::vector<T, A>& v, soglu_ctx* c) {
@@ -232,8 +246,6 @@ int finalize(soglu_ctx* c) {
     co.split_narrow = (int)c->opt_split;
     co.n_sms = c->sms;
     co.split_slack_us = (double)std::max<int64_t>(0, c->opt_split_slack);
-    co.hi_ctas = (int)std::max<int64_t>(0, std::min<int64_t>(c->opt_hi_ctas, c->exec_grid / 2));
-    if (c->opt_hi_shared > 0) { co.hi_ctas = 0; co.hi_slack_us = (double)c->opt_hi_shared; }
     {
         // pool capacity: what is free now minus the graph arrays (estimated from the op count) and a margin
         size_t free_b = 0, total_b = 0;
@@ -304,26 +316,22 @@ int finalize(soglu_ctx* c) {
         if ((rc = upload(c->dep0, d0, c))) return rc;
     }
     {
-        // ready queue image: per segment slice, the initially ready tasks first, -1 elsewhere;
-        // counter image: per segment one 256-byte record {head = 0, ..., tail = #initial at int 32}
-        // ready-queue image: per segment slice [hi queue | bulk queue], the initially ready tasks first in each,
-        // -1 elsewhere; counter image: per segment one 512-byte record {head_hi @0, tail_hi @32, head_lo @64, tail_lo @96}
+        // ready-queue image: per segment slice the initially ready tasks first, -1 elsewhere;
+        // counter image: per segment one 512-byte record {head @ int 0, tail = #initial @ int 32}
         const std::vector<int32_t>& sb = c->dist ? c->D.seg_begin : G.seg_begin;
         const std::vector<int32_t>& si = c->dist ? c->D.seg_init : G.seg_init;
-        const std::vector<int32_t>& nh = c->dist ? c->D.seg_nhi : G.seg_nhi;
         const std::vector<int32_t>& ini = c->dist ? c->D.initial : G.initial;
         const int nseg = (int)sb.size() - 1;
         std::vector<int32_t> r0(std::max<size_t>(tasks_up.size(), 1), -1), c0((size_t)std::max(nseg, 1) * 128, 0);
-        for (int sg = 0; sg < nseg; sg++)
-            for (int cls = 0; cls < 2; cls++) {
-                const int32_t base = sb[sg] + (cls ? nh[sg] : 0);
-                const int32_t nb = si[2 * sg + cls + 1] - si[2 * sg + cls];
-                for (int32_t k = 0; k < nb; k++) r0[base + k] = ini[si[2 * sg + cls] + k];
-                c0[(size_t)sg * 128 + 32 + 64 * cls] = nb;
-            }
+        for (int sg = 0; sg < nseg; sg++) {
+            const int32_t nb = si[sg + 1] - si[sg];
+            for (int32_t k = 0; k < nb; k++) r0[sb[sg] + k] = ini[si[sg] + k];
+            c0[(size_t)sg * 128 + 32] = nb;
+        }
         if ((rc = upload(c->ready0, r0, c))) return rc;
         if ((rc = upload(c->counters0, c0, c))) return rc;
-        CU(c->counters.alloc(c0.size() * 4));
+        CU(c->counters.alloc(c0.size() * 4 + 64));
+        CU(cudaMemsetAsync(c->counters.as<char>() + c0.size() * 4, 0, 64, c->stream));
     }
     CU(c->dep.alloc(std::max<size_t>(tasks_up.size(), 1) * 4));
     CU(c->ready.alloc(std::max<size_t>(tasks_up.size(), 1) * 4));
@@ -528,11 +536,9 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
     else if (k == "split_slack") { if (c->compiled) return fail(SOGLU_ERR_ARG, "split_slack must be set before the first factor"); c->opt_split_slack = value; }
     else if (k == "chain_cuts") { if (c->compiled) return fail(SOGLU_ERR_ARG, "chain_cuts must be set before the first factor"); c->opt_chain_cuts = value; }
-    else if (k == "hi_shared") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_shared must be set before the first factor"); c->opt_hi_shared = value; }
-    else if (k == "hi_ctas") { if (c->compiled) return fail(SOGLU_ERR_ARG, "hi_ctas must be set before the first factor"); c->opt_hi_ctas = value; }
-    else if (k == "prefetch") c->opt_prefetch = value;
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
+    else if (k == "watchdog_ms") c->opt_watchdog_ms = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
     return SOGLU_OK;
 }
@@ -677,7 +683,9 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     P.succ = c->succ.as<int32_t>();
     P.dep = c->dep.as<int32_t>();
     P.trace = nullptr;
-    P.prefetch = (int32_t)c->opt_prefetch;
+    P.abort = c->abort_word();
+    P.watchdog_ns = (unsigned long long)std::max<int64_t>(0, c->opt_watchdog_ms) * 1000000ull;
+    if (c->dist) for (int g = 0; g < c->world; g++) P.aborts[g] = (int32_t*)c->peer_counters[g] + c->counters0.bytes / 4;
     if (c->opt_trace && nt > 0) {
         if (!c->trace.p) CU(c->trace.alloc((size_t)nt * 6 * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->trace.p, 0, (size_t)nt * 6 * sizeof(unsigned long long), c->stream));
@@ -686,23 +694,14 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     // queue pointers of one segment (this GPU and, sharded, the peers' queues of the same segment)
     auto set_segment = [&](int sg) {
         const std::vector<int32_t>& sb = c->dist ? c->D.seg_begin : G.seg_begin;
-        const std::vector<int32_t>& nh = c->dist ? c->D.seg_nhi : G.seg_nhi;
         int32_t* cnt = c->counters.as<int32_t>() + (size_t)sg * 128;
-        P.ready[0] = c->ready.as<int32_t>() + sb[sg];
-        P.ready[1] = P.ready[0] + nh[sg];
-        P.head[0] = cnt; P.tail[0] = cnt + 32; P.head[1] = cnt + 64; P.tail[1] = cnt + 96;
-        P.n_tasks[0] = nh[sg];
-        P.n_tasks[1] = sb[sg + 1] - sb[sg] - nh[sg];
-        const int32_t want = (sg < (int)G.seg_hi_ctas.size()) ? G.seg_hi_ctas[sg] : (int32_t)c->opt_hi_ctas;
-        P.n_hi_ctas = (P.n_tasks[0] > 0 && P.n_tasks[1] > 0) ? (int32_t)std::min<int64_t>(want, grid / 2) : (P.n_tasks[0] > 0 ? grid : 0);
-        if (c->opt_hi_ctas <= 0) P.n_hi_ctas = 0;
-        if (c->opt_hi_shared > 0) P.n_hi_ctas = -1;     // shared high-priority queue (executor.cu)
+        P.ready = c->ready.as<int32_t>() + sb[sg];
+        P.head = cnt; P.tail = cnt + 32;
+        P.n_tasks = sb[sg + 1] - sb[sg];
         if (c->dist)
             for (int g = 0; g < c->world; g++) {
-                int32_t* rb = (int32_t*)c->peer_ready[g] + c->D.seg_begin_all[g][sg];
-                int32_t* cb = (int32_t*)c->peer_counters[g] + (size_t)sg * 128;
-                P.readys[g][0] = rb; P.readys[g][1] = rb + c->D.seg_nhi_all[g][sg];
-                P.tails[g][0] = cb + 32; P.tails[g][1] = cb + 96;
+                P.readys[g] = (int32_t*)c->peer_ready[g] + c->D.seg_begin_all[g][sg];
+                P.tails[g] = (int32_t*)c->peer_counters[g] + (size_t)sg * 128 + 32;
             }
     };
     CU(cudaEventRecord(c->ev0, c->stream));
@@ -715,7 +714,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
             if (sg < 0 || sg >= nseg) return fail(SOGLU_ERR_ARG, "segment out of range");
             set_segment(sg);
             P.signal = 1;
-            if (P.n_tasks[0] + P.n_tasks[1] > 0) {
+            if (P.n_tasks > 0) {
                 CU(launch_executor(P, grid, c->stream));
                 c->launches++;
             }
@@ -728,7 +727,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
             // one persistent launch per segment (a single one unless the pool forces slot recycling)
             for (int sg = 0; sg < nseg; sg++) {
                 set_segment(sg);
-                if (P.n_tasks[0] + P.n_tasks[1] == 0) continue;
+                if (P.n_tasks == 0) continue;
                 CU(launch_executor(P, grid, c->stream));
                 c->launches++;
             }
@@ -739,11 +738,9 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
                 CU(cudaMemcpyAsync(c->ready.p, c->level_order.data() + b, (size_t)(e - b) * 4, cudaMemcpyHostToDevice, c->stream));
                 CU(cudaMemsetAsync(c->counters.p, 0, 512, c->stream));
                 int32_t* cnt = c->counters.as<int32_t>();
-                P.ready[0] = P.ready[1] = c->ready.as<int32_t>();
-                P.head[0] = cnt; P.tail[0] = cnt + 32; P.head[1] = cnt + 64; P.tail[1] = cnt + 96;
-                P.n_tasks[0] = 0;
-                P.n_tasks[1] = (int32_t)(e - b);
-                P.n_hi_ctas = 0;
+                P.ready = c->ready.as<int32_t>();
+                P.head = cnt; P.tail = cnt + 32;
+                P.n_tasks = (int32_t)(e - b);
                 P.signal = 0;
                 CU(launch_executor(P, (int)std::min<int64_t>(grid, e - b), c->stream));
                 c->launches++;
@@ -752,6 +749,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if ((rc = check_watchdog(c, "factorisation"))) return rc;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->factored = true;
@@ -787,6 +785,8 @@ static int run_trsv(soglu_ctx* c, const double* d_rhs, double* d_sol) {
     P.n_rows = c->n_block_rows;
     P.b = d_rhs; P.y = c->d_y.as<double>(); P.x = d_sol;
     P.symmetric = c->symmetric;
+    P.abort = c->abort_word();
+    P.watchdog_ns = (unsigned long long)std::max<int64_t>(0, c->opt_watchdog_ms) * 1000000ull;
     CU(launch_trsv(P, std::min(c->trsv_grid, c->n_block_rows), c->stream));
     c->launches += 2;   // sentinel fill + solve kernel
     return SOGLU_OK;
@@ -820,6 +820,7 @@ static int solve_impl(soglu_ctx* c, const double* b_ext, double* x_ext, int refi
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaMemcpyAsync(x_ext, refine > 0 ? c->d_xacc.p : c->d_x.p, next, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if ((rc = check_watchdog(c, "solve"))) return rc;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->h2d += (double)next;
@@ -839,23 +840,21 @@ static int solve_impl(soglu_ctx* c, const double* b_ext, double* x_ext, int refi
     return SOGLU_OK;
 }
 
-int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* out) { return solve_impl(c, b_ext, x_ext, 0, out); }
+static int solve_guarded(soglu_ctx* c, const double* b_ext, double* x_ext, int refine, soglu_stats* out) {
+    try {
+        return solve_impl(c, b_ext, x_ext, refine, out);
+    } catch (const std::bad_alloc&) {
+        return fail(SOGLU_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
+    }
+}
+
+int soglu_solve(soglu_ctx* c, const double* b_ext, double* x_ext, soglu_stats* out) { return solve_guarded(c, b_ext, x_ext, 0, out); }
 
 // solve + `steps` rounds of iterative refinement on the device (needs soglu_set_matrix)
 int soglu_solve_refined(soglu_ctx* c, const double* b_ext, double* x_ext, int steps, soglu_stats* out) {
-    try {
-    try {
-    return solve_impl(c, b_ext, x_ext, steps < 0 ? 0 : steps, out);
-    } catch (const std::bad_alloc&) {
-        return fail(SOGLU_ERR_OOM, "out of host memory");
-    } catch (const std::exception& e) {
-        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
-    }
-    } catch (const std::bad_alloc&) {
-        return fail(SOGLU_ERR_OOM, "out of host memory");
-    } catch (const std::exception& e) {
-        return fail(SOGLU_ERR_ARG, std::string("internal error: ") + e.what());
-    }
+    return solve_guarded(c, b_ext, x_ext, steps < 0 ? 0 : steps, out);
 }
 
 // CSR of the permuted system padded with the identity to n_block_rows*64 rows (what the factors factorise)

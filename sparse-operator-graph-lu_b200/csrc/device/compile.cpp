@@ -12,7 +12,7 @@
 //     that chain: R = S2 -/+ sum A*B   (removes one level of the critical path
 //     lu -> inv -> mul -> mul -> sub -> lu and one block write + two block reads).
 #include "tasks.h"
-#include "model.h"
+#include "cost_model.h"
 
 #include <algorithm>
 #include <cmath>
@@ -713,7 +713,7 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         if (opt.split_slack_us > 0) {
             // A task on (or near) the longest dependent chain delays everything behind it even when its level is wide:
             // split those too.  Slack = longest chain - longest chain through the task, under the cost model of
-            // model.h with the width-based slices chosen above.
+            // cost_model.h with the width-based slices chosen above.
             const ModelParams M;
             std::vector<float> dur(nt), tl(nt, 0.f), bl(nt, 0.f);
             for (int64_t t = 0; t < nt; t++) dur[t] = (float)model_hop_us(G.tasks[t], M, 4 / split[t]);
@@ -772,89 +772,33 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         }
     }
     lap("row split");
-    // ---- priority classes -----------------------------------------------------------------------------
-    // Estimated times (us): slack = critical path of the segment - longest path through the task.  With one
-    // FIFO queue a released critical-chain task waits behind every bulk update published before it (247 us
-    // on average at 100^3), which stretches the chain; the small-slack tasks get their own queue.
-    G.seg_nhi.assign(G.seg_begin.size() - 1, 0);
-    if ((opt.hi_ctas > 0 || opt.hi_slack_us > 0) && !G.tasks.empty()) {
-        const int64_t n2 = (int64_t)G.tasks.size();
-        std::vector<float> dur(n2), tl(n2, 0.f), bl(n2, 0.f);
-        const ModelParams M;     // one dependent hop through a task under the measured cost model (model.h)
-        for (int64_t t = 0; t < n2; t++) dur[t] = (float)model_hop_us(G.tasks[t], M);
-        for (int64_t t = 0; t < n2; t++)     // tasks are in topological order; successors are group leaders
-            for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
-                const int32_t s2 = G.succ[e];
-                for (int q = 0, g = task_group_size(G.tasks[s2]); q < g; q++) tl[s2 + q] = std::max(tl[s2 + q], tl[t] + dur[t]);
-            }
-        for (int64_t t = n2 - 1; t >= 0; t--) {
-            float m = 0.f;
-            for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) m = std::max(m, bl[G.succ[e]]);   // slices are alike
-            bl[t] = dur[t] + m;
-        }
-        const int nseg = (int)G.seg_begin.size() - 1;
-        std::vector<float> cp(nseg, 0.f);
-        for (int sg = 0; sg < nseg; sg++)
-            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) cp[sg] = std::max(cp[sg], tl[t] + bl[t]);
-        // dedicated CTAs (hi_ctas): the threshold shrinks until those CTAs are at most half busy; shared queue
-        // (hi_slack_us): every CTA serves the high-priority queue first, the threshold is fixed
-        float theta = opt.hi_slack_us > 0 ? (float)opt.hi_slack_us : 400.f;
-        for (int round = 0; round < 10 && opt.hi_slack_us <= 0; round++) {
-            bool ok = true;
-            for (int sg = 0; sg < nseg && ok; sg++) {
-                double busy = 0;
-                for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
-                    if (cp[sg] - (tl[t] + bl[t]) < theta) busy += dur[t];
-                ok = busy <= 0.5 * opt.hi_ctas * std::max(1, G.n_owners) * (double)cp[sg];
-            }
-            if (ok) break;
-            theta *= 0.5f;
-        }
-        G.seg_hi_ctas.assign(nseg, 0);
-        for (int sg = 0; sg < nseg; sg++) {
-            double busy = 0;
-            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
-                if (cp[sg] - (tl[t] + bl[t]) < theta) { G.tasks[t].flags |= TF_HI; G.n_hi++; busy += dur[t]; }
-            // one class per group: the slices follow their leader
-            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
-                if (!task_is_leader(G.tasks[t])) {
-                    const int32_t lead = t - ((G.tasks[t].flags >> TF_ROW0_SHIFT) & 3) / std::max(1, (G.tasks[t].flags >> TF_NROWS_SHIFT) & 7);
-                    const bool hi = G.tasks[lead].flags & TF_HI, mine = G.tasks[t].flags & TF_HI;
-                    if (hi != mine) { G.tasks[t].flags ^= TF_HI; G.n_hi += hi ? 1 : -1; }
-                }
-            G.critical_path_us = std::max(G.critical_path_us, (double)cp[sg]);
-            // dedicated CTAs per GPU for this segment: 4x the average load of the high-priority tasks, at least 4
-            const double avg = busy / std::max(1.0, (double)cp[sg]) / std::max(1, G.n_owners);
-            G.seg_hi_ctas[sg] = (int32_t)std::min<double>(opt.hi_ctas, std::max(4.0, std::ceil(4.0 * avg)));
-        }
-        G.hi_threshold_us = theta;
-    }
+    // successor references; a group with exactly one predecessor task (unsplit) carries the "sole predecessor" bit
     G.succ_enc.resize(G.succ.size());
 #pragma omp parallel for schedule(static)
-    for (int64_t e = 0; e < (int64_t)G.succ.size(); e++) {
-        const Task& S = G.tasks[G.succ[e]];
-        G.succ_enc[e] = make_task_ref(0, S.flags & TF_HI, task_log2_slices(S), G.succ[e]);
+    for (int64_t t = 0; t < (int64_t)G.tasks.size(); t++) {
+        const Task& T = G.tasks[t];
+        if (!task_is_leader(T)) continue;              // the slices of one task share their leader's list
+        const bool single = task_group_size(T) == 1;
+        for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+            const Task& S = G.tasks[G.succ[e]];
+            G.succ_enc[e] = make_task_ref(0, single && S.n_deps == 1, task_log2_slices(S), G.succ[e]);
+        }
     }
     if ((int64_t)G.tasks.size() > TASK_LOCAL_MASK) return "too many tasks";
 
-    // per-segment lists of initially ready tasks, high-priority ones first (single GPU: every task is owned
-    // by GPU 0; the multi-GPU split is redone per rank in localize_tasks)
+    // per-segment lists of initially ready tasks (single GPU: every task is owned by GPU 0; the multi-GPU split is
+    // redone per rank in localize_tasks)
     {
         const int nseg = (int)G.seg_begin.size() - 1;
         G.initial.clear();
         G.seg_init.assign(1, 0);
         for (int sg = 0; sg < nseg; sg++) {
-            for (int cls = 0; cls < 2; cls++) {
-                for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
-                    const bool hi = G.tasks[t].flags & TF_HI;
-                    if (cls == 0 && hi) G.seg_nhi[sg]++;
-                    if (G.tasks[t].n_deps == 0 && hi == (cls == 0)) G.initial.push_back(t);
-                }
-                G.seg_init.push_back((int32_t)G.initial.size());
-            }
+            for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++)
+                if (G.tasks[t].n_deps == 0) G.initial.push_back(t);
+            G.seg_init.push_back((int32_t)G.initial.size());
         }
     }
-    lap("priority + initial");
+    lap("successor refs + initial");
     // ---- chain analysis (diagnostics + input of a second compile, CompileOptions::analyze_chains) --------------
     // Under the cost model of model.h: fin[t] = earliest time a successor of t can start, as compiled (a task starts
     // when ALL operands are ready), and fin_e[t] = the same if every accumulation chain may be cut once into an
@@ -1022,19 +966,13 @@ std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {
     const int nseg = (int)G.seg_begin.size() - 1;
     D.seg_begin.assign(1, 0);
     D.seg_init.assign(1, 0);
-    D.seg_nhi.assign(nseg, 0);
     D.seg_begin_all.assign(G.n_owners, std::vector<int32_t>(nseg + 1, 0));
-    D.seg_nhi_all.assign(G.n_owners, std::vector<int32_t>(nseg, 0));
     for (int sg = 0; sg < nseg; sg++) {
         for (int o = 0; o < G.n_owners; o++) D.seg_begin_all[o][sg + 1] = D.seg_begin_all[o][sg];
-        for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
-            D.seg_begin_all[G.task_owner[t]][sg + 1]++;
-            if (G.tasks[t].flags & TF_HI) D.seg_nhi_all[G.task_owner[t]][sg]++;
-        }
+        for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) D.seg_begin_all[G.task_owner[t]][sg + 1]++;
     }
     int32_t shared_from = -1, shared_begin = 0, shared_end = 0;
     for (int sg = 0; sg < nseg; sg++) {
-        std::vector<int32_t> init_lo;
         for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
             if (G.task_owner[t] != rank) continue;
             Task T = G.tasks[t];
@@ -1050,19 +988,16 @@ std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {
                 shared_begin = (int32_t)D.succ.size();
                 for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
                     const int32_t s2 = G.succ[e];
-                    D.succ.push_back(make_task_ref(G.task_owner[s2], G.tasks[s2].flags & TF_HI, task_log2_slices(G.tasks[s2]), D.task_local[s2]));
+                    D.succ.push_back(make_task_ref(G.task_owner[s2], (G.succ_enc[e] & TASK_SOLE_BIT) != 0, task_log2_slices(G.tasks[s2]), D.task_local[s2]));
                 }
                 shared_end = (int32_t)D.succ.size();
             }
             for (int32_t e = T.succ_begin; e < T.succ_end; e++) D.remote_edges += G.task_owner[G.succ[e]] != rank;
             T.succ_begin = shared_begin;
             T.succ_end = shared_end;
-            if (T.n_deps == 0) { if (T.flags & TF_HI) D.initial.push_back((int32_t)D.tasks.size()); else init_lo.push_back((int32_t)D.tasks.size()); }
-            if (T.flags & TF_HI) D.seg_nhi[sg]++;
+            if (T.n_deps == 0) D.initial.push_back((int32_t)D.tasks.size());
             D.tasks.push_back(T);
         }
-        D.seg_init.push_back((int32_t)D.initial.size());
-        D.initial.insert(D.initial.end(), init_lo.begin(), init_lo.end());
         D.seg_init.push_back((int32_t)D.initial.size());
         D.seg_begin.push_back((int32_t)D.tasks.size());
     }

@@ -1,17 +1,17 @@
-// Timed host model of the persistent executor: see model.cpp.  Diagnostics only.
+// Cost model of one task hop (microseconds), used by the task compiler's slack estimates (row split of near-critical
+// GEMM tasks, chain analysis).  Durations measured with the executor's trace option and tools/diag_bench.py on a B200.
 #pragma once
 #include "tasks.h"
 
 namespace soglu {
 
 struct ModelParams {        // microseconds, measured with the executor's trace option on a B200
-    int n_ctas = 148;
     double t_pair = 2.38;          // one 64x64x64 product, whole block, 8 math warps of one SM
     double t_pair_half = 1.25;     // 32-row slice
     double t_pair_quarter = 0.72;  // 16-row slice
-    double t_lu_fused = 18.8;      // lu + both inverses in one sweep (37 k cycles) + write-back
-    double t_lu = 12.0;
-    double t_llt_fused = 17.0;
+    double t_lu_fused = 11.7;      // lu + both inverses, blocked kernel (23 k cycles incl. write-out)
+    double t_lu = 9.1;
+    double t_llt_fused = 10.5;
     double t_inv = 7.0;
     double t_sub = 0.6;
     double t_epilogue = 0.4;       // result write-back + barrier
@@ -20,13 +20,6 @@ struct ModelParams {        // microseconds, measured with the executor's trace 
     double t_poll_hit = 0.8;       // the task was already there when the slot was claimed
     double t_desc = 0.6;           // task record fetch
     double t_load = 1.3;           // bulk copy of one operand pair into shared memory
-    double t_launch = 30.0;        // per segment (cooperative launch + drain)
-    double t_release_remote = 5.5; // successor on a peer GPU: system-scope fence + two NVLink atomics + remote store
-    double t_load_remote = 4.0;    // operand pair with a block in a peer's HBM (fetch tasks, unmirrored operands)
-    double t_launch_dist = 300.0;  // per segment with a host barrier across ranks
-    double t_cas = 0.5;            // policy 2: extra compare-and-swap to take a high-priority task
-    double hi_slack_us = 100.0;    // policy 2: tasks with less slack than this are high priority
-    int policy = 0;                // 0 = the executor's FIFO ready queue; 1 = ideal list scheduling by longest remaining path (what-if)
 };
 
 // ---- the cost model, shared by the executor model and by the task compiler's slack / chain estimates ---------------
@@ -51,19 +44,5 @@ inline double model_out_us(const ModelParams& M) { return M.t_epilogue + M.t_rel
 inline double model_hop_us(const Task& T, const ModelParams& M, int rows16 = -1) {
     return model_in_us(M) + model_stages(T) * model_stage_us(T, M, rows16) + model_out_us(M);
 }
-
-struct ModelResult {
-    double makespan_us = 0;        // sum over segments
-    double critical_path_us = 0;   // longest dependent chain under the same durations (infinite SMs)
-    double busy_us = 0;            // sum of math time over all CTAs
-    int64_t n_tasks = 0;
-    int64_t remote_loads = 0, remote_releases = 0;
-    // the longest dependent chain by task kind: 0 GEMM whole block, 1 half, 2 quarter, 3 lu / llt, 4 sub / copy, 5 inverse
-    int64_t chain_tasks[6] = {0, 0, 0, 0, 0, 0}, chain_pairs[6] = {0, 0, 0, 0, 0, 0}, chain_remote_hops = 0;
-    double chain_math_us[6] = {0, 0, 0, 0, 0, 0}, chain_overhead_us = 0;
-    int64_t n_hi = 0;              // policy 2: tasks in the high-priority class
-};
-
-ModelResult model_executor(const TaskGraph& G, const ModelParams& M);
 
 }  // namespace soglu

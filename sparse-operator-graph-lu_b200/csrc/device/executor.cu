@@ -20,15 +20,20 @@
 //               publishes the whole group (a task, or the 2 / 4 row slices of a split GEMM task,
 //               which share their leader's counter) at the tail of the ready queue.
 //
-// Memory-ordering protocol: writer CTA: st.global data -> bar.sync -> __threadfence ->
-// atomicSub(dep) [-> __threadfence -> atomicAdd(tail) -> st.release(ready)]; reader CTA:
-// ld.acquire(ready) -> fence.proxy.async -> cp.async.bulk of the data.  Successors on the same GPU
-// use gpu scope; successors on a peer GPU (multi-GPU run: counters, queues and block pools of the
-// peers are mapped through CUDA IPC) use system-scope fences and atomics over NVLink.
+// Memory-ordering protocol: writer CTA: st.global data -> bar.sync -> fence.acq_rel.gpu -> atomicSub(dep)
+// [-> fence.acq_rel.gpu -> atomicAdd(tail) -> st.relaxed(ready)]; reader CTA: ld.acquire(ready) -> fence.proxy.async ->
+// cp.async.bulk of the data.  (acq_rel fences, not __threadfence(): that one is MEMBAR.SC + an L1 invalidate.)  A
+// successor whose only predecessor is the finishing task skips the counter: fence -> atomicAdd(tail) -> st.relaxed.
+// Successors on the same GPU use gpu scope; successors on a peer GPU (multi-GPU run: counters, queues and block pools
+// of the peers are mapped through CUDA IPC) use system-scope fences and atomics over NVLink.
+//
+// Watchdog: a claim-then-wait queue under a cooperative launch hangs for good if a signal is lost (a peer that died,
+// a graph with a missing edge).  Every scheduler lane therefore checks, once per 1024 polls, the abort word of its
+// GPU and %globaltimer against the launch's deadline; on a timeout it raises the abort word (on every GPU of the
+// run) with the queue slot it was stuck at, all CTAs drain and soglu_factor returns SOGLU_ERR_CUDA.
 #include "executor.cuh"
 #include "ptx.cuh"
 #include "lu_blocked.cuh"
-#include "ready_queue.cuh"
 
 namespace soglu {
 
@@ -225,6 +230,20 @@ __device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const do
         }
 }
 
+// scheduler lane, once per 1024 polls: has somebody aborted the run, or has the deadline passed?  On a timeout the
+// abort word {1, queue slot, CTA, rank} is raised on every GPU of the run.
+__device__ __noinline__ bool watchdog_expired(const ExecParams& P, int slot, unsigned long long deadline) {
+    if (*reinterpret_cast<volatile int32_t*>(P.abort) != 0) return true;
+    if (deadline == 0 || gtime() < deadline) return false;
+    if (atomicCAS(P.abort, 0, 1) == 0) {
+        P.abort[1] = slot; P.abort[2] = (int32_t)blockIdx.x; P.abort[3] = P.rank;
+    }
+    for (int g = 0; g < P.world; g++)
+        if (g != P.rank && P.aborts[g]) atomicCAS_system(P.aborts[g], 0, 2);     // 2 = raised by a peer
+    __threadfence_system();
+    return true;
+}
+
 __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
@@ -251,20 +270,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 ptx::fence_proxy_async();
                 const int nst = (T.type == T_GEMM) ? T.n_pairs : 1;
                 const bool two = (T.type == T_GEMM || T.type == T_SUB);
-                // option prefetch bit 0: the operand pair of stage p + 1 is fetched before the wait for stage p's buffer,
-                // so its latency (the pair list of a long chain lives in HBM) overlaps the wait instead of following it
-                const bool ahead = P.prefetch & 1;
-                Pair nxt = T.first[0];
                 for (int p = 0; p < nst; p++, it++) {
                     const int s = it % N_STAGES;
-                    Pair pa = nxt;
-                    if (ahead && p + 1 < nst) nxt = (p == 0) ? T.first[1] : P.pairs[T.pair_begin + p + 1];
                     ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);
                     StageDesc d;
                     d.type = T.type; d.flags = T.flags; d.task = t; d.out = T.out; d.out2 = T.out2; d.init = T.init; d.out4 = T.out4;
                     d.first_last = (p == 0 ? 1 : 0) | (p == nst - 1 ? 2 : 0);
                     ctl->desc[s] = d;
-                    const Pair pr = ahead ? pa : ((p == 0) ? T.first[0] : ((p == 1) ? T.first[1] : P.pairs[T.pair_begin + p]));
+                    const Pair pr = (p == 0) ? T.first[0] : ((p == 1) ? T.first[1] : P.pairs[T.pair_begin + p]);
                     double* As = stage_base + (size_t)s * (STAGE_BYTES / 8);
                     // GEMM row slice: only rows [16*row0, 16*(row0+nrows)) of A are needed (same place in smem)
                     const int a_off = (T.type == T_GEMM) ? ((T.flags >> TF_ROW0_SHIFT) & 3) * 16 * BLK_LD : 0;
@@ -281,31 +294,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 ctl->desc[s].type = T_EXIT;
                 ptx::mbar_arrive(&ctl->full[s]);
             };
-            if (P.n_hi_ctas >= 0) {
-                // CTAs 0..n_hi_ctas-1 serve the high-priority queue, the others the bulk queue; each claims the next
-                // slot of its queue and waits until a finishing CTA publishes a task there
-                const int q = (blockIdx.x < (unsigned)P.n_hi_ctas) ? 0 : 1;
+            // claim the next slot of the ready queue and wait until a finishing CTA publishes a task there
+            const unsigned long long deadline = P.watchdog_ns ? gtime() + P.watchdog_ns : 0;
+            bool aborted = false;
+            while (!aborted) {
+                const int slot = atomicAdd(P.head, 1);
+                if (slot >= P.n_tasks) break;
+                int t;
+                uint32_t polls = 0;
                 while (true) {
-                    const int slot = atomicAdd(P.head[q], 1);
-                    if (slot >= P.n_tasks[q]) break;
-                    int t;
-                    if (P.world > 1) { while ((t = ptx::ld_acquire_sys(P.ready[q] + slot)) < 0) {} }
-                    else { while ((t = ptx::ld_acquire(P.ready[q] + slot)) < 0) {} }
-                    issue(t);
+                    t = (P.world > 1) ? ptx::ld_acquire_sys(P.ready + slot) : ptx::ld_acquire(P.ready + slot);
+                    if (t >= 0) break;
+                    if ((++polls & 1023u) == 0 && watchdog_expired(P, slot, deadline)) { aborted = true; break; }
                 }
-            } else {
-                // Shared high-priority queue (option hi_shared): every CTA takes published entries of queue 0 before it
-                // looks at its pre-claimed slot of the bulk queue (ready_queue.cuh; the same loop runs on the host in
-                // tests/emu/emu_queue.cpp)
-                struct DevQueues {
-                    const ExecParams& P;
-                    __device__ __forceinline__ int head_hi() { return *(volatile int*)P.head[0]; }
-                    __device__ __forceinline__ int ready_hi(int s) { return (P.world > 1) ? ptx::ld_acquire_sys(P.ready[0] + s) : ptx::ld_acquire(P.ready[0] + s); }
-                    __device__ __forceinline__ bool cas_head_hi(int h) { return atomicCAS(P.head[0], h, h + 1) == h; }
-                    __device__ __forceinline__ int claim_lo() { return atomicAdd(P.head[1], 1); }
-                    __device__ __forceinline__ int ready_lo(int s) { return (P.world > 1) ? ptx::ld_acquire_sys(P.ready[1] + s) : ptx::ld_acquire(P.ready[1] + s); }
-                } dq{P};
-                serve_shared_queues(dq, P.n_tasks[0], P.n_tasks[1], issue);
+                if (!aborted) issue(t);
             }
             quit();
         }
@@ -401,38 +403,36 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 // Successors on this GPU are released at gpu scope (cheap); only successors on peer GPUs pay for
                 // system-scope fences and atomics over NVLink.  A counter may be decremented from both scopes:
                 // the atomics themselves are performed at the owning GPU's L2 either way.
-                __threadfence();
+                ptx::fence_acq_rel_gpu();
                 bool remote = false;
                 for (int e = sb + ct; e < se; e += N_MATH) {
                     const int32_t ref = P.succ[e];
-                    const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
+                    const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK;
                     if (o != P.rank) { remote = true; continue; }
-                    // option prefetch bit 1: pull the successor's task record (HBM: the table does not fit L2) towards L2
-                    // while the counter is being decremented, for the scheduler that will read it after the pick-up
-                    if (P.prefetch & 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.tasks + nx));
-                    if (atomicSub(P.dep + nx, 1) == 1) {
+                    // sole predecessor: ready now, no counter; otherwise the thread that brings the counter to zero publishes
+                    if ((ref & TASK_SOLE_BIT) || atomicSub(P.dep + nx, 1) == 1) {
                         // the whole group (all row slices of the successor) becomes ready at once
-                        // (the fence below + the strong relaxed stores form the release; the consumers ld.acquire)
+                        // (the fence + the strong relaxed stores form the release; the consumers ld.acquire)
                         const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
-                        __threadfence();
-                        const int pos = atomicAdd(P.tail[qq], g);
+                        if (!(ref & TASK_SOLE_BIT)) ptx::fence_acq_rel_gpu();
+                        const int pos = atomicAdd(P.tail, g);
                         for (int k = 0; k < g; k++) {
                             if (P.trace) P.trace[6 * (size_t)(nx + k) + 0] = gtime();
-                            ptx::st_relaxed(P.ready[qq] + pos + k, nx + k);
+                            ptx::st_relaxed(P.ready + pos + k, nx + k);
                         }
                     }
                 }
                 if (remote) {
-                    __threadfence_system();
+                    ptx::fence_acq_rel_sys();
                     for (int e = sb + ct; e < se; e += N_MATH) {
                         const int32_t ref = P.succ[e];
-                        const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK, qq = (ref & TASK_HI_BIT) ? 0 : 1;
+                        const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK;
                         if (o == P.rank) continue;
-                        if (atomicSub_system(P.deps[o] + nx, 1) == 1) {
+                        if ((ref & TASK_SOLE_BIT) || atomicSub_system(P.deps[o] + nx, 1) == 1) {
                             const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
-                            __threadfence_system();
-                            const int pos = atomicAdd_system(P.tails[o][qq], g);
-                            for (int k = 0; k < g; k++) ptx::st_relaxed_sys(P.readys[o][qq] + pos + k, nx + k);
+                            if (!(ref & TASK_SOLE_BIT)) ptx::fence_acq_rel_sys();
+                            const int pos = atomicAdd_system(P.tails[o], g);
+                            for (int k = 0; k < g; k++) ptx::st_relaxed_sys(P.readys[o] + pos + k, nx + k);
                         }
                     }
                 }

@@ -10,25 +10,24 @@ namespace soglu {
 struct ExecParams {
     // Multi-GPU: per-owner base pointers (peer-mapped through CUDA IPC); block / task references carry
     // the owner in their top 3 bits (tasks.h make_ref).  Single GPU: world = 1, index 0 only.
-    // Two ready queues per GPU: [0] high priority (small-slack tasks, served by CTAs 0..n_hi_ctas-1),
-    // [1] everything else (served by the remaining CTAs).
     double* pools[MAX_GPUS];
     int32_t* deps[MAX_GPUS];
-    int32_t* readys[MAX_GPUS][2];
-    int32_t* tails[MAX_GPUS][2];
+    int32_t* readys[MAX_GPUS];     // ready queue slice of this launch on every GPU
+    int32_t* tails[MAX_GPUS];
     int32_t world, rank;
     double* pool;          // this GPU's block pool, slot s at pool + s*BLK_ELEMS
     const Task* tasks;
     const Pair* pairs;
-    const int32_t* succ;   // task references: owner | priority bit | local id
+    const int32_t* succ;   // task references: owner | sole-predecessor bit | log2(slices) | local id (tasks.h)
     int32_t* dep;          // live dependency counters (reset before every run)
-    int32_t* ready[2];     // ready queues of this launch, -1 = not yet published
-    int32_t* head[2];      // next queue slot to claim
-    int32_t* tail[2];      // next queue slot to publish
-    int32_t n_tasks[2];    // queue lengths for this launch
-    int32_t n_hi_ctas;     // CTAs dedicated to queue 0; -1 = shared: every CTA serves queue 0 first (option hi_shared)
+    int32_t* ready;        // ready queue of this launch (FIFO), -1 = not yet published
+    int32_t* head;         // next queue slot to claim
+    int32_t* tail;         // next queue slot to publish
+    int32_t n_tasks;       // queue length for this launch
     int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
-    int32_t prefetch;      // bit 0: operand-pair lookahead in the scheduler lane; bit 1: releasing threads prefetch the successor's task record
+    int32_t* abort;        // watchdog word of this GPU {flag, queue slot, CTA, rank}; aborts[g] = the peers' (multi-GPU)
+    int32_t* aborts[MAX_GPUS];
+    unsigned long long watchdog_ns;   // a scheduler lane that has waited this long since the launch gives up (0 = never)
     unsigned long long* trace;   // optional: 6 x u64 per task (published, claimed, loaded, computed, signalled, smid)
 };
 
@@ -57,6 +56,8 @@ struct TrsvParams {
     double* y;             // forward result  (pre-filled with the NaN sentinel by launch_trsv)
     double* x;             // backward result (idem)
     int32_t symmetric;     // U = L^T: backward sweep reads L blocks transposed (CSC of L passed in u_*)
+    int32_t* abort;        // watchdog word (as in ExecParams): a consumer that has polled for watchdog_ns raises it
+    unsigned long long watchdog_ns;
 };
 cudaError_t launch_trsv(const TrsvParams& p, int grid, cudaStream_t stream);
 int trsv_max_grid(int device);

@@ -47,6 +47,11 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // order generic-proxy accesses against later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// acq_rel fences: MEMBAR.ALL.{GPU,SYS}.  __threadfence() is fence.sc (MEMBAR.SC + an L1 invalidate) -- the release /
+// acquire patterns of the executor need no sequential consistency.
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -85,11 +90,6 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
 // D(8x8) += A(8x4, row) * B(4x8, col); lane = 4*g + t holds A[g][t], B[t][g], C[g][2t..2t+1]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// x = fma(-a, b, x) executed under a predicate (a predicated DFMA: no select, no branch)
-__device__ __forceinline__ void pfnma(double& x, double a, double b, bool pred) {
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}" : "+d"(x) : "d"(-a), "d"(b), "r"((int)pred));
 }
 
 // 1/x for finite |x| >= 1e-9: hardware seed (MUFU.RCP64H) + two Newton steps, branch-free

@@ -27,13 +27,15 @@ constexpr int32_t REF_MASK = (1 << REF_SHIFT) - 1;
 constexpr int MAX_GPUS = 8;
 inline int32_t make_ref(int owner, int32_t local) { return (int32_t)(((uint32_t)owner << REF_SHIFT) | (uint32_t)local); }
 // Task references in successor lists name a task GROUP (a task, or the 2 / 4 consecutive row slices of a
-// split GEMM task, which share the dependency counter of their first slice): owner | priority class of the
-// group | log2(group size) | local index of the first slice.
-constexpr int32_t TASK_HI_BIT = 1 << 28;
+// split GEMM task, which share the dependency counter of their first slice): owner | "sole predecessor" |
+// log2(group size) | local index of the first slice.  A group whose ONLY predecessor is the referring task (one
+// predecessor task, unsplit) is ready the moment that task has finished: the releasing thread publishes it without
+// touching its dependency counter (one fence and one atomic round trip less on that hop, e.g. Schur update -> lu).
+constexpr int32_t TASK_SOLE_BIT = 1 << 28;
 constexpr int TASK_SPLIT_SHIFT = 26;                       // 2 bits: log2(slices)
 constexpr int32_t TASK_LOCAL_MASK = (1 << TASK_SPLIT_SHIFT) - 1;
-inline int32_t make_task_ref(int owner, bool hi, int log2_slices, int32_t local) {
-    return make_ref(owner, local) | (hi ? TASK_HI_BIT : 0) | (log2_slices << TASK_SPLIT_SHIFT);
+inline int32_t make_task_ref(int owner, bool sole, int log2_slices, int32_t local) {
+    return make_ref(owner, local) | (sole ? TASK_SOLE_BIT : 0) | (log2_slices << TASK_SPLIT_SHIFT);
 }
 
 enum TaskType : int32_t {
@@ -51,7 +53,6 @@ enum TaskFlags : int32_t {
     TF_INIT = 4,     // GEMM: start from block `init` instead of zero (fused sub)
     TF_LINV = 8,     // LU/LLT: also produce out3 = L^-1 (fused lowerInv)
     TF_UINV = 16,    // LU: also produce out4 = U^-1 (fused upperInv)
-    TF_HI = 32,      // small scheduling slack: goes to the high-priority queue served by dedicated CTAs
     // GEMM row split: the task computes rows [16*row0, 16*row0 + 16*nrows) of the target block
     TF_ROW0_SHIFT = 8,    // 2 bits: first row / 16
     TF_NROWS_SHIFT = 12   // 3 bits: rows / 16 (4 = whole block, 2 = half, 1 = quarter)
@@ -100,13 +101,8 @@ struct TaskGraph {
     // unless the block pool is smaller than the number of blocks; then slots are recycled at
     // segment boundaries (every reader of the previous occupant finished with the launch).
     std::vector<int32_t> seg_begin;     // n_segments + 1 task indices
-    std::vector<int32_t> seg_init;      // 2 * n_segments + 1 offsets into `initial`: per segment the high-priority
-                                        // initially-ready tasks, then the others
-    std::vector<int32_t> seg_nhi;       // per segment: number of high-priority tasks (length of its hi queue)
-    std::vector<int32_t> seg_hi_ctas;   // per segment: CTAs (per GPU) dedicated to the hi queue
-    BigVec<int32_t> succ_enc;           // succ with the successor's priority bit (single-GPU upload)
-    int64_t n_hi = 0;                   // high-priority tasks
-    double hi_threshold_us = 0, critical_path_us = 0;
+    std::vector<int32_t> seg_init;      // n_segments + 1 offsets into `initial`
+    BigVec<int32_t> succ_enc;           // succ as task references (single-GPU upload)
     std::vector<uint8_t> recycled;      // block id -> its slot is reused later (contents do not survive)
     // multi-GPU (n_owners > 1): slots are numbered per owner and every block / zero-block reference in
     // tasks and pairs carries its owner (make_ref); slot_of[] stays the owner-local slot
@@ -142,14 +138,6 @@ struct CompileOptions {
     const int8_t* owner_of_id = nullptr;
     int n_owners = 1;
     int mirror_min = 1;
-    // priority scheduling: tasks whose estimated slack (critical path - longest path through the task) is below a
-    // threshold go to a separate queue served by `hi_ctas` dedicated CTAs; the threshold shrinks until those
-    // CTAs are at most half busy.  0 = one FIFO queue.
-    int hi_ctas = 0;
-    // shared high-priority queue: tasks with less estimated slack than this (us) go to a second FIFO queue that EVERY
-    // CTA looks at before it claims its next bulk slot (executor option hi_shared).  0 = off.  Model (tools/model.py,
-    // policy 2) at 100^3 on one GPU: 2.65 s -> 2.51 s with 1000 us; ideal list scheduling would give 2.48 s.
-    double hi_slack_us = 0;
     // Chain splitting (compile.cpp, "chain analysis"): a GEMM task waits for ALL its operand pairs although most
     // of an accumulation chain is ready long before the last pair arrives.  analyze_chains estimates, per task,
     // when each pair becomes ready and proposes cuts (TaskGraph::cuts); a second compile with chain_cuts applies
@@ -173,9 +161,8 @@ struct DistLayout {     // one GPU's share of an owner-compiled TaskGraph
     BigVec<Pair> pairs;
     BigVec<int32_t> succ;
     std::vector<int32_t> initial;        // local task ids, grouped by segment
-    std::vector<int32_t> seg_begin, seg_init, seg_nhi;   // as in TaskGraph, for this GPU's tasks
+    std::vector<int32_t> seg_begin, seg_init;            // as in TaskGraph, for this GPU's tasks
     std::vector<std::vector<int32_t>> seg_begin_all;     // [owner][segment] first local task (peers' queue slices)
-    std::vector<std::vector<int32_t>> seg_nhi_all;       // [owner][segment] length of the peer's hi queue
     int64_t remote_edges = 0, remote_operands = 0, mirrored = 0;
 };
 std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& out);

@@ -33,9 +33,26 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const double* p) {
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ double poll_value(const double* p) {
-    unsigned long long v;
-    while ((v = ld_volatile_u64(p)) == SENTINEL) {}
+// Watchdog (see executor.cu): a consumer that is still polling after watchdog_ns raises the abort word and goes on
+// with the sentinel (a NaN); every other poll loop sees the word at its next check and does the same, the kernel
+// drains and soglu_solve reports SOGLU_ERR_CUDA with the block row that never arrived.
+__device__ __noinline__ bool trsv_watchdog(const TrsvParams& P, const double* p, unsigned long long t0) {
+    if (*reinterpret_cast<volatile int32_t*>(P.abort) != 0) return true;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    if (P.watchdog_ns == 0 || now - t0 < P.watchdog_ns) return false;
+    if (atomicCAS(P.abort, 0, 1) == 0) { P.abort[1] = (int32_t)((p - ((p >= P.x && p < P.x + (size_t)P.n_rows * BLK) ? P.x : P.y)) / BLK); P.abort[2] = (int32_t)blockIdx.x; }
+    return true;
+}
+__device__ __forceinline__ double poll_value(const TrsvParams& P, const double* p) {
+    unsigned long long v = ld_volatile_u64(p);
+    if (v == SENTINEL) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        uint32_t polls = 0;
+        while ((v = ld_volatile_u64(p)) == SENTINEL)
+            if ((++polls & 4095u) == 0 && trsv_watchdog(P, p, t0)) break;
+    }
     return __longlong_as_double((long long)v);
 }
 __device__ __forceinline__ void publish_value(double* p, double x) {
@@ -121,7 +138,7 @@ __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restric
         ptx::bulk_g2s(S.diag, blk_ptr(P, inv_slot != 0 ? inv_slot : diag[row]), BLK_BYTES, &S.bar);
         if (nb > 0) ptx::bulk_g2s(S.last, blk_ptr(P, slot[kcrit]), BLK_BYTES, &S.bar);
     }
-    if (tid < BLK) S.r[tid] = rhs_is_computed ? poll_value(rhs + (size_t)row * BLK + tid) : rhs[(size_t)row * BLK + tid];
+    if (tid < BLK) S.r[tid] = rhs_is_computed ? poll_value(P, rhs + (size_t)row * BLK + tid) : rhs[(size_t)row * BLK + tid];
     const int rrow = tid >> 2, part = tid & 3;
     // non-critical blocks, far to near, RING bulk copies in flight
     auto blk_of = [&](int q) -> int64_t { return UPPER ? (e - 1 - q) : (b + q); };
@@ -135,7 +152,7 @@ __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restric
         const int64_t k = blk_of(q);
         const int rs = q % RING;
         __syncthreads();
-        if (tid < BLK) S.v[tid] = poll_value(sol + (size_t)col[k] * BLK + tid);
+        if (tid < BLK) S.v[tid] = poll_value(P, sol + (size_t)col[k] * BLK + tid);
         ptx::mbar_wait(&S.ring_bar[rs], (ring_phase >> rs) & 1);
         ring_phase ^= 1u << rs;
         __syncthreads();
@@ -152,7 +169,7 @@ __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restric
     ptx::mbar_wait(&S.bar, phase);
     phase ^= 1;
     if (nb > 0) {
-        if (tid < BLK) S.v[tid] = poll_value(sol + (size_t)col[kcrit] * BLK + tid);
+        if (tid < BLK) S.v[tid] = poll_value(P, sol + (size_t)col[kcrit] * BLK + tid);
         __syncthreads();
         const double s = quad_sum(gemv_part_smem<TRANS>(S.last, S.v, rrow, part));
         if (part == 0) S.t[rrow] = S.r[rrow] - s;

@@ -291,6 +291,8 @@ extern "C" int soglu_debug_simulate(const soglu_problem* pp, int split, int pr, 
         for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
             const int32_t ref = D[r].succ[e];
             const int o = (uint32_t)ref >> soglu::REF_SHIFT, nx = ref & soglu::TASK_LOCAL_MASK, g = 1 << ((ref >> soglu::TASK_SPLIT_SHIFT) & 3);
+            // a "sole predecessor" reference publishes without touching the counter (executor.cu): it must be the last one
+            if (ref & soglu::TASK_SOLE_BIT) { if (dep[o][nx] != 1) bad++; dep[o][nx] = 1; }
             if (--dep[o][nx] == 0)
                 for (int q = 0; q < g; q++) ready.push_back({(int8_t)o, nx + q});
         }
@@ -357,129 +359,5 @@ extern "C" int soglu_debug_compile_raw(int64_t n_ids, int64_t n_input, const int
     std::string err = soglu::compile_tasks(n_ids, n_input, input_ids, n_ops, src, src2, op, result, result2, keep, co, G);
     if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
     if (out) { out[0] = (int64_t)G.tasks.size(); out[1] = (int64_t)G.pairs.size(); out[2] = G.n_slots; out[3] = (int64_t)G.seg_begin.size() - 1; }
-    return SOGLU_OK;
-}
-
-// Timed model of the executor on the compiled graph of a problem (device/model.cpp; diagnostics, host only).
-// opts[10] = {split_narrow, max_slots, pr, pc, nb, chains, policy, hi_slack_us for the compiler, split_slack_us, n_sms for the split rule}; params: n_params doubles overriding ModelParams in
-// declaration order (NaN = keep the default); out[12] = {makespan_us, critical_path_us, busy_us, tasks, segments, pairs, hi tasks, cp_us, cp_early_us, proposed cuts,
-// cp_us after the cuts, cuts applied, operand pairs loaded from a peer, successor groups released on a peer,
-// longest chain: tasks[6], math us[6], pairs[6] by kind (GEMM whole / half / quarter, lu, sub, inverse), overhead us, remote hops,
-// shared-operand task pairs, operand pairs in them}.
-#include "../device/model.h"
-#include <cmath>
-extern "C" int soglu_debug_model(const soglu_problem* pp, const int64_t* opts, const double* params, int n_params, double* out) {
-    const Problem* p = reinterpret_cast<const Problem*>(pp);
-    if (!p || !opts || !out) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
-    const soglu::Plan& pl = p->plan;
-    const int64_t n = (int64_t)pl.ops.size();
-    soglu::BigVec<int32_t> src(n), src2(n), res(n), res2(n);
-    soglu::BigVec<uint8_t> op(n);
-#pragma omp parallel for schedule(static)
-    for (int64_t k = 0; k < n; k++) { const soglu::Op& o = pl.ops[k]; src[k] = o.src; src2[k] = o.src2; res[k] = o.result; res2[k] = o.result2; op[k] = o.op; }
-    std::vector<int32_t> in_ids(pl.inputs.size()), keep;
-    for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = (int32_t)(k + 1);
-    for (const auto& r : pl.L) keep.push_back(r.id);
-    for (const auto& r : pl.U) keep.push_back(r.id);
-    soglu::CompileOptions co;
-    co.split_narrow = (int)opts[0]; co.max_slots = opts[1];
-    const int pr = (int)std::max<int64_t>(1, opts[2]), pc = (int)std::max<int64_t>(1, opts[3]), nb = (int)std::max<int64_t>(1, opts[4]), world = pr * pc;
-    if (world > soglu::MAX_GPUS) { soglu::set_error("bad process grid"); return SOGLU_ERR_ARG; }
-    std::vector<int8_t> owners;
-    if (world > 1) {     // 2D block-cyclic ownership of nb x nb squares, as soglu_create_dist
-        owners.assign(pl.storage, 0);
-        for (int64_t id = 1; id < pl.storage; id++)
-            if (pl.brow[id] >= 0 && pl.bcol[id] >= 0) owners[id] = (int8_t)(((pl.brow[id] / nb) % pr) * pc + ((pl.bcol[id] / nb) % pc));
-        co.owner_of_id = owners.data(); co.n_owners = world;
-    }
-    const int chains = (int)opts[5];   // 0 = off, 1 = analyse only, 2 = analyse + recompile with the proposed cuts
-    co.analyze_chains = chains > 0;
-    const int policy = (int)opts[6];
-    co.hi_slack_us = (double)opts[7];   // > 0: the compiler classifies (as the executor option hi_shared does)
-    co.split_slack_us = (double)opts[8];
-    if (opts[9] > 0) co.n_sms = (int)opts[9];     // width against which a level counts as narrow (what-if; the model keeps 148 CTAs)
-    soglu::TaskGraph G;
-    std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
-    if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
-    out[7] = G.cp_us; out[8] = G.cp_early_us; out[9] = (double)G.cuts.size();
-    out[34] = (double)G.dual_pairs; out[35] = (double)G.dual_covered_pairs;
-    if (chains > 1 && !G.cuts.empty()) {
-        const std::vector<soglu::ChainCut> cuts = std::move(G.cuts);
-        co.analyze_chains = true;
-        co.chain_cuts = &cuts;
-        err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
-        if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
-        out[10] = G.cp_us; out[11] = (double)G.chain_splits;
-    }
-    soglu::ModelParams M;
-    M.policy = policy;
-    double* field[] = {nullptr, &M.t_pair, &M.t_pair_half, &M.t_pair_quarter, &M.t_lu_fused, &M.t_lu, &M.t_llt_fused, &M.t_inv, &M.t_sub,
-                       &M.t_epilogue, &M.t_release, &M.t_poll, &M.t_poll_hit, &M.t_desc, &M.t_load, &M.t_launch, &M.t_cas, &M.hi_slack_us, &M.t_release_remote, &M.t_load_remote, &M.t_launch_dist};
-    for (int k = 0; k < n_params && k < (int)(sizeof field / sizeof field[0]); k++) {
-        if (!params || std::isnan(params[k])) continue;
-        if (k == 0) M.n_ctas = (int)params[0]; else *field[k] = params[k];
-    }
-    const soglu::ModelResult R = soglu::model_executor(G, M);
-    out[0] = R.makespan_us; out[1] = R.critical_path_us; out[2] = R.busy_us; out[3] = (double)G.tasks.size();
-    out[4] = (double)G.seg_begin.size() - 1; out[5] = (double)G.pairs.size(); out[6] = (double)R.n_hi;
-    out[12] = (double)R.remote_loads; out[13] = (double)R.remote_releases;
-    for (int k = 0; k < 6; k++) { out[14 + k] = (double)R.chain_tasks[k]; out[20 + k] = R.chain_math_us[k]; out[26 + k] = (double)R.chain_pairs[k]; }
-    out[32] = R.chain_overhead_us; out[33] = (double)R.chain_remote_hops;
-    return SOGLU_OK;
-}
-
-// Consistency of the two ready queues the executor gets when tasks are classified by slack (option hi_shared /
-// CompileOptions::hi_slack_us), host only.  out = {tasks, high-priority tasks, segments, violations}: per segment the
-// high-priority queue must have exactly as many slots as there are high-priority tasks, the slices of one group share
-// a class, every successor reference carries its target's class and group size, and the initially ready tasks are
-// listed high-priority first.
-extern "C" int soglu_debug_check_queues(const soglu_problem* pp, int64_t hi_slack_us, int64_t max_slots, int64_t* out) {
-    const Problem* p = reinterpret_cast<const Problem*>(pp);
-    if (!p || !out) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
-    const soglu::Plan& pl = p->plan;
-    const int64_t n = (int64_t)pl.ops.size();
-    std::vector<int32_t> src(n), src2(n), res(n), res2(n);
-    std::vector<uint8_t> op(n);
-    for (int64_t k = 0; k < n; k++) { const soglu::Op& o = pl.ops[k]; src[k] = o.src; src2[k] = o.src2; res[k] = o.result; res2[k] = o.result2; op[k] = o.op; }
-    std::vector<int32_t> in_ids(pl.inputs.size()), keep;
-    for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = (int32_t)(k + 1);
-    for (const auto& r : pl.L) keep.push_back(r.id);
-    for (const auto& r : pl.U) keep.push_back(r.id);
-    soglu::CompileOptions co;
-    co.max_slots = max_slots;
-    co.hi_slack_us = (double)hi_slack_us;
-    soglu::TaskGraph G;
-    std::string err = soglu::compile_tasks(pl.storage, (int64_t)in_ids.size(), in_ids.data(), n, src.data(), src2.data(), op.data(), res.data(), res2.data(), keep, co, G);
-    if (!err.empty()) { soglu::set_error(err); return SOGLU_ERR_GRAPH; }
-    int64_t bad = 0, nhi = 0;
-    const int nseg = (int)G.seg_begin.size() - 1;
-    for (int sg = 0; sg < nseg; sg++) {
-        int64_t c = 0;
-        for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) {
-            const soglu::Task& T = G.tasks[t];
-            c += (T.flags & soglu::TF_HI) != 0;
-            if (!soglu::task_is_leader(T)) {
-                const int32_t lead = t - ((T.flags >> soglu::TF_ROW0_SHIFT) & 3) / std::max(1, (T.flags >> soglu::TF_NROWS_SHIFT) & 7);
-                if ((G.tasks[lead].flags & soglu::TF_HI) != (T.flags & soglu::TF_HI)) bad++;
-            }
-        }
-        if (c != G.seg_nhi[sg]) bad++;
-        nhi += c;
-        for (int cls = 0; cls < 2; cls++)
-            for (int32_t k = G.seg_init[2 * sg + cls]; k < G.seg_init[2 * sg + cls + 1]; k++) {
-                const soglu::Task& T = G.tasks[G.initial[k]];
-                if (((T.flags & soglu::TF_HI) != 0) != (cls == 0) || T.n_deps != 0) bad++;
-                if (G.initial[k] < G.seg_begin[sg] || G.initial[k] >= G.seg_begin[sg + 1]) bad++;
-            }
-    }
-    if (nhi != G.n_hi) bad++;
-    for (size_t e = 0; e < G.succ.size(); e++) {
-        const soglu::Task& S = G.tasks[G.succ[e]];
-        const int32_t ref = G.succ_enc[e];
-        if (((ref & soglu::TASK_HI_BIT) != 0) != ((S.flags & soglu::TF_HI) != 0)) bad++;
-        if (((ref >> soglu::TASK_SPLIT_SHIFT) & 3) != soglu::task_log2_slices(S)) bad++;
-        if ((ref & soglu::TASK_LOCAL_MASK) != G.succ[e]) bad++;
-    }
-    out[0] = (int64_t)G.tasks.size(); out[1] = nhi; out[2] = nseg; out[3] = bad;
     return SOGLU_OK;
 }

@@ -128,7 +128,7 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
         std::vector<int32_t> dep(G.tasks.size());
         for (size_t t = 0; t < G.tasks.size(); t++) dep[t] = G.tasks[t].n_deps;
         for (size_t sg = 0; sg + 1 < G.seg_begin.size(); sg++) {
-            std::vector<int32_t> ready(G.initial.begin() + G.seg_init[2 * sg], G.initial.begin() + G.seg_init[2 * sg + 2]);
+            std::vector<int32_t> ready(G.initial.begin() + G.seg_init[sg], G.initial.begin() + G.seg_init[sg + 1]);
             size_t ran = 0;
             while (!ready.empty()) {
                 rng = rng * 6364136223846793005ull + 1442695040888963407ull;
@@ -140,6 +140,8 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
                 ran++;
                 for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
                     const int32_t nx = G.succ[e];
+                    // "sole predecessor" references publish without the counter in the executor: it must stand at 1
+                    if ((G.succ_enc[e] & soglu::TASK_SOLE_BIT) && dep[nx] != 1) { std::fprintf(stderr, "sole-predecessor bit on a task with %d open dependencies\n", dep[nx]); return 3; }
                     if (--dep[nx] == 0)
                         for (int q = 0, g = task_group_size(G.tasks[nx]); q < g; q++) ready.push_back(nx + q);
                 }

@@ -464,3 +464,26 @@ def test_slack_split(sg, tmp_path, name):
     np.testing.assert_array_equal(x, x0)
     ctx.close()
     ref.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_watchdog_aborts_and_recovers(sg, tmp_path):
+    """The executor's watchdog (executor.cu): with a deadline far below the run time of the factorisation some scheduler
+    lane is still waiting for its queue slot when it expires, raises the abort word, every CTA drains and soglu_factor
+    returns SOGLU_ERR_CUDA naming the slot instead of hanging in cudaStreamSynchronize.  The context stays usable:
+    with the default deadline the next factorisation gives the golden solution."""
+    g = load_golden("lap3d_24")
+    p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    ctx.set_option("watchdog_ms", 1)   # the factorisation is chain-bound and takes ~10 ms: most schedulers are waiting at 1 ms
+    with pytest.raises(sg.SogluError) as e:
+        ctx.factor()
+    assert "watchdog" in str(e.value) and "ready-queue slot" in str(e.value)
+    ctx.set_option("watchdog_ms", 60000)
+    ctx.factor()
+    x, _ = ctx.solve(p)
+    assert _rel(x, g["x"]) <= TOL_X
+    ctx.close()
