@@ -24,7 +24,7 @@ N > 1  = ONE factorisation sharded over the N GPUs (2D block-cyclic block owners
 --impl reference times the UNMODIFIED reference (oracle/_ref/ref_harness --lean, its own OpenMP path on
 the host cores, timers around BlockPlanner::calculate + BlockPlanner::solve) on the SAME workload: ONE full
 run (steps_effective = 1; 100^3 needs ~110 GB and several minutes), falling back to the 64^3 sample of the same
-stencil family only when the host has too little memory, and to the oracle port when the prebuilt reference
+stencil family only when the host has too little memory (100^3: > 205 GB resident, the GPU box has 196 GB), and to the oracle port when the prebuilt reference
 cannot run at all.  Its x and timings are cached under /tmp for the `ours` arm that the driver runs next on the
 same box: the cpu_baseline leg reuses them instead of repeating the run, and reports rel_diff_vs_reference.
 """
@@ -150,7 +150,11 @@ def mem_available_gb():
     return 0.0
 
 
-REF_MEM_GB = {"lap3d_100": 120.0, "nine2d_1024": 24.0, "lap3d_64": 12.0, "banded_200k": 10.0}   # what the reference's arena needs (measured / SURVEY 8d)
+# Host memory the reference needs (resident set, measured with oracle/_ref on the GPU box).  lap3d_100: the process was
+# OOM-killed at 204.8 GB anon-rss on the box's 196 GB host, 3 min 14 s into BlockPlanner::calculate
+# (profiles/r02_reference_100_oom.md), so the reference cannot run BASELINE config 5 on this hardware at all; the gate
+# keeps bench.py from trying (an OOM kill can hit this process instead of the child).
+REF_MEM_GB = {"lap3d_100": 240.0, "nine2d_1024": 40.0, "lap3d_64": 14.0, "banded_200k": 12.0}
 
 
 def reference_on(sg, name, tmp, threads, use_cache):

@@ -247,15 +247,20 @@ int finalize(soglu_ctx* c) {
     co.n_sms = c->sms;
     co.split_slack_us = (double)std::max<int64_t>(0, c->opt_split_slack);
     {
-        // pool capacity: what is free now minus the graph arrays (estimated from the op count) and a margin
+        // Pool capacity: what is free now minus the graph arrays (estimated from the op count) and a margin.
+        // Sharded runs: every rank compiles the WHOLE graph and must arrive at the same slot numbers and segment
+        // boundaries for every GPU, so the capacity must not depend on rank-local state (a few MB of difference in
+        // free memory would shift the recycling boundaries): it is derived from the device's TOTAL memory, the same
+        // number on the identical GPUs of one box, with a fixed 7 % reserve for contexts and NCCL buffers; the
+        // resulting layout is hashed into the peer blob and soglu_dist_import rejects a mismatch.
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         const double graph_est = (double)c->n_ops * 40.0 + (double)c->n_block_rows * 64 * 8 * 4 + 1.5e9;
-        double cap = ((double)free_b - graph_est) / (double)BLK_BYTES;
+        const double budget = c->dist ? 0.93 * (double)total_b : (double)free_b;
+        double cap = (budget - graph_est / (c->dist ? c->world : 1)) / (double)BLK_BYTES;
         if (cap < 16) cap = 16;
         co.max_slots = (int64_t)cap;
         if (c->opt_max_slots > 0 && c->opt_max_slots < co.max_slots) co.max_slots = c->opt_max_slots;
-
     }
     std::vector<int8_t> owners;
     if (c->dist) {
@@ -287,11 +292,6 @@ int finalize(soglu_ctx* c) {
         err = localize_tasks(G, c->rank, c->D);
         if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
     }
-    // the op arrays are no longer needed on the host
-    BigVec<int32_t>().swap(c->src); BigVec<int32_t>().swap(c->src2);
-    BigVec<int32_t>().swap(c->result); BigVec<int32_t>().swap(c->result2);
-    BigVec<uint8_t>().swap(c->op);
-
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     const BigVec<Task>& tasks_up = c->dist ? c->D.tasks : G.tasks;
@@ -355,6 +355,11 @@ int finalize(soglu_ctx* c) {
     const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
     CU(c->d_b.alloc(next)); CU(c->d_y.alloc(next)); CU(c->d_x.alloc(next));
     c->compiled = true;
+    // only now are the op arrays no longer needed on the host: a failure above (pool does not fit, a factor without
+    // diagonal block, ...) leaves the context uncompiled WITH its graph, so a retry with other options is possible
+    BigVec<int32_t>().swap(c->src); BigVec<int32_t>().swap(c->src2);
+    BigVec<int32_t>().swap(c->result); BigVec<int32_t>().swap(c->result2);
+    BigVec<uint8_t>().swap(c->op);
     return pack_pending_inputs(c);
 }
 
@@ -397,7 +402,17 @@ int soglu_create(soglu_ctx** out, int n_gpus, const int* device_ids) {
 }
 
 // ---- multi-GPU: one process per GPU, peers mapped through CUDA IPC -------------------------------
-struct DistBlob { cudaIpcMemHandle_t pool, dep, ready, counters; int32_t rank, valid; };
+struct DistBlob { cudaIpcMemHandle_t pool, dep, ready, counters; int32_t rank, valid; uint64_t layout_hash; };
+
+// FNV-1a over what every rank must agree on: tasks and pool slots per GPU, segment boundaries of every GPU
+static uint64_t dist_layout_hash(const soglu_ctx* c) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+    mix(c->D.tasks_per_rank.data(), c->D.tasks_per_rank.size() * sizeof(int64_t));
+    mix(c->D.slots_per_rank.data(), c->D.slots_per_rank.size() * sizeof(int64_t));
+    for (const auto& v : c->D.seg_begin_all) mix(v.data(), v.size() * sizeof(int32_t));
+    return h;
+}
 
 int soglu_create_dist(soglu_ctx** out, int device, int rank, int world, int grid_rows, int grid_cols) {
     if (world < 1 || world > MAX_GPUS || grid_rows * grid_cols != world || rank < 0 || rank >= world)
@@ -424,6 +439,7 @@ int soglu_dist_export(soglu_ctx* c, void* blob) {
     std::memset(&b, 0, sizeof b);
     b.rank = c->rank; b.valid = 1;
     if (c->dist) {
+        b.layout_hash = dist_layout_hash(c);
         CU(cudaIpcGetMemHandle(&b.pool, c->pool.p));
         CU(cudaIpcGetMemHandle(&b.dep, c->dep.p));
         CU(cudaIpcGetMemHandle(&b.ready, c->ready.p));
@@ -443,6 +459,7 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
     try {
     if (!c || !all_blobs) return fail(SOGLU_ERR_ARG, "bad argument");
     if (!c->compiled) return fail(SOGLU_ERR_ARG, "soglu_dist_export must precede soglu_dist_import");
+    if (c->peers_ready) return fail(SOGLU_ERR_ARG, "peer handles are already imported (one import per context; destroy it and build a new one to re-shard)");
     CU(cudaSetDevice(c->device));
     const DistBlob* bl = reinterpret_cast<const DistBlob*>(all_blobs);
     for (int g = 0; g < c->world; g++) {
@@ -451,6 +468,9 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
             continue;
         }
         if (!bl[g].valid || bl[g].rank != g) return fail(SOGLU_ERR_ARG, "peer handle blob " + std::to_string(g) + " is missing or out of order");
+        if (bl[g].layout_hash != dist_layout_hash(c))
+            return fail(SOGLU_ERR_ARG, "rank " + std::to_string(g) + " compiled a different sharded layout (tasks / pool slots / segments per GPU): the ranks must "
+                                       "load the same problem with the same options; set max_slots explicitly if the GPUs differ");
         CU(cudaIpcOpenMemHandle(&c->peer_pool[g], bl[g].pool, cudaIpcMemLazyEnablePeerAccess));
         CU(cudaIpcOpenMemHandle(&c->peer_dep[g], bl[g].dep, cudaIpcMemLazyEnablePeerAccess));
         CU(cudaIpcOpenMemHandle(&c->peer_ready[g], bl[g].ready, cudaIpcMemLazyEnablePeerAccess));

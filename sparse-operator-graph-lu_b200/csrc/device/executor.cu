@@ -15,10 +15,12 @@
 //               the blocked diagonal-block kernel for the rest (lu_blocked.cuh: LU / Cholesky that also form
 //               L^-1 and U^-1, one warp on the pivot chain, four streaming behind it, DMMA trailing updates),
 //               standalone triangular inverses, subtract.
-//               After the write-back ALL math threads walk the task's successor list: one atomicSub
-//               on the successor group's dependency counter each; the thread that brings it to zero
-//               publishes the whole group (a task, or the 2 / 4 row slices of a split GEMM task,
-//               which share their leader's counter) at the tail of the ready queue.
+//   warp 9      signal: the math warps hand a finished task over (mbarrier, 8 arrivals) and go straight on to
+//               the next task's MMAs; this warp makes the result visible (one fence) and walks the successor
+//               list: one atomicSub on the successor group's dependency counter per lane; the lane that brings
+//               it to zero publishes the whole group (a task, or the 2 / 4 row slices of a split GEMM task,
+//               which share their leader's counter) at the tail of the ready queue.  (With the release on the
+//               math warps, 2-3 us of fence + atomic round trips per task kept the tensor cores idle.)
 //
 // Memory-ordering protocol: writer CTA: st.global data -> bar.sync -> fence.acq_rel.gpu -> atomicSub(dep)
 // [-> fence.acq_rel.gpu -> atomicAdd(tail) -> st.relaxed(ready)]; reader CTA: ld.acquire(ready) -> fence.proxy.async ->
@@ -42,7 +44,8 @@ namespace {
 constexpr int N_STAGES = 3;
 constexpr int N_MATH_WARPS = 8;
 constexpr int N_MATH = N_MATH_WARPS * 32;          // 256
-constexpr int N_THREADS = N_MATH + 32;             // + producer warp
+constexpr int N_THREADS = N_MATH + 64;             // + producer warp (warp 0) + signal warp (warp 9)
+constexpr int SIG_RING = 4;                        // finished tasks in flight between the math warps and the signal warp
 constexpr int STAGE_BYTES = 2 * BLK_BYTES;         // A and B
 constexpr int BAR_MATH = 1;                        // named barrier id for the math warps
 
@@ -70,6 +73,9 @@ struct __align__(16) SmemCtl {
     uint64_t full[N_STAGES];
     uint64_t empty[N_STAGES];
     StageDesc desc[N_STAGES];
+    uint64_t sig_full[SIG_RING];     // math warps -> signal warp: task sig_task[q] has issued all its stores (8 arrivals)
+    uint64_t sig_empty[SIG_RING];    // signal warp -> math warps: entry q may be reused
+    int32_t sig_task[SIG_RING];      // task id, -1 = leave
     double scratch[192];   // row exchange buffer + reciprocals of the standalone triangular inverses
 };
 
@@ -230,6 +236,17 @@ __device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const do
         }
 }
 
+// math warp -> signal warp: this warp has issued all its stores of `task` (task < 0: tell the signal warp to leave)
+__device__ __forceinline__ void hand_over(SmemCtl* ctl, uint32_t sig_it, int task, int mw, int lane) {
+    const int q = sig_it % SIG_RING;
+    if (lane == 0) {
+        ptx::mbar_wait(&ctl->sig_empty[q], ((sig_it / SIG_RING) & 1) ^ 1);
+        if (mw == 0) ctl->sig_task[q] = task;
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&ctl->sig_full[q]);
+}
+
 // scheduler lane, once per 1024 polls: has somebody aborted the run, or has the deadline passed?  On a timeout the
 // abort word {1, queue slot, CTA, rank} is raised on every GPU of the run.
 __device__ __noinline__ bool watchdog_expired(const ExecParams& P, int slot, unsigned long long deadline) {
@@ -244,7 +261,7 @@ __device__ __noinline__ bool watchdog_expired(const ExecParams& P, int slot, uns
     return true;
 }
 
-__global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
+__global__ void __maxnreg__(200) executor_kernel(const __grid_constant__ ExecParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (size_t)N_STAGES * STAGE_BYTES);
@@ -254,6 +271,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
         for (int s = 0; s < N_STAGES; s++) {
             ptx::mbar_init(&ctl->full[s], 1);
             ptx::mbar_init(&ctl->empty[s], N_MATH_WARPS);
+        }
+        for (int q = 0; q < SIG_RING; q++) {
+            ptx::mbar_init(&ctl->sig_full[q], N_MATH_WARPS);
+            ptx::mbar_init(&ctl->sig_empty[q], 1);
         }
         ptx::fence_mbar_init();
     }
@@ -314,17 +335,73 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
         return;
     }
 
+    if (warp == N_MATH_WARPS + 1) {
+        // ================= signal warp: release the successors of finished tasks ====================
+        for (uint32_t it = 0;; it++) {
+            const int q = it % SIG_RING;
+            ptx::mbar_wait(&ctl->sig_full[q], (it / SIG_RING) & 1);
+            const int t = ctl->sig_task[q];
+            if (t < 0) break;
+            if (P.signal) {
+                const Task* T = P.tasks + t;
+                const int sb = T->succ_begin, se = T->succ_end;
+                // The math threads' stores happen before this fence (their mbarrier arrivals were observed above), so it
+                // releases them at gpu scope.  Successors on this GPU are released at gpu scope (cheap); only successors on
+                // peer GPUs pay for system-scope fences and atomics over NVLink.  A counter may be decremented from both
+                // scopes: the atomics themselves are performed at the owning GPU's L2 either way.
+                ptx::fence_acq_rel_gpu();
+                bool remote = false;
+                for (int e = sb + lane; e < se; e += 32) {
+                    const int32_t ref = P.succ[e];
+                    const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK;
+                    if (o != P.rank) { remote = true; continue; }
+                    // sole predecessor: ready now, no counter; otherwise the lane that brings the counter to zero publishes
+                    if ((ref & TASK_SOLE_BIT) || atomicSub(P.dep + nx, 1) == 1) {
+                        // the whole group (all row slices of the successor) becomes ready at once
+                        // (the fence + the strong relaxed stores form the release; the consumers ld.acquire)
+                        const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
+                        if (!(ref & TASK_SOLE_BIT)) ptx::fence_acq_rel_gpu();
+                        const int pos = atomicAdd(P.tail, g);
+                        for (int k = 0; k < g; k++) {
+                            if (P.trace) P.trace[6 * (size_t)(nx + k) + 0] = gtime();
+                            ptx::st_relaxed(P.ready + pos + k, nx + k);
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, remote)) {
+                    ptx::fence_acq_rel_sys();
+                    for (int e = sb + lane; e < se; e += 32) {
+                        const int32_t ref = P.succ[e];
+                        const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK;
+                        if (o == P.rank) continue;
+                        if ((ref & TASK_SOLE_BIT) || atomicSub_system(P.deps[o] + nx, 1) == 1) {
+                            const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
+                            if (!(ref & TASK_SOLE_BIT)) ptx::fence_acq_rel_sys();
+                            const int pos = atomicAdd_system(P.tails[o], g);
+                            for (int k = 0; k < g; k++) ptx::st_relaxed_sys(P.readys[o] + pos + k, nx + k);
+                        }
+                    }
+                }
+                if (P.trace && lane == 0) P.trace[6 * (size_t)t + 4] = gtime();
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ctl->sig_empty[q]);
+        }
+        return;
+    }
+
     // ======================= math warps ====================================================
     const int mw = warp - 1;                 // 0..7
     const int ct = threadIdx.x - 32;         // 0..255
     double* lub_scr = reinterpret_cast<double*>(ctl + 1);
     lub::lu_setup(lub_scr, ct);              // pivot barriers of the diagonal-block kernel, once per launch
     double acc[4][2][2];
+    uint32_t sig_it = 0;
     for (uint32_t it = 0;; it++) {
         const int s = it % N_STAGES;
         ptx::mbar_wait(&ctl->full[s], (it / N_STAGES) & 1);
         const StageDesc d = ctl->desc[s];
-        if (d.type == T_EXIT) break;
+        if (d.type == T_EXIT) { hand_over(ctl, sig_it++, -1, mw, lane); break; }
         double* As = stage_base + (size_t)s * (STAGE_BYTES / 8);
         double* Bs = As + BLK_ELEMS;
 
@@ -359,6 +436,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
             if (nrows16 == 4) gemm_epilogue<4, 2>(out, ini, acc, rb, cb, lane, neg, has_init);
             else if (nrows16 == 2) gemm_epilogue<2, 2>(out, ini, acc, rb, cb, lane, neg, has_init);
             else gemm_epilogue<2, 1>(out, ini, acc, rb, cb, lane, neg, has_init);
+            // no CTA barrier: each warp hands its part over and goes on to the next task
+            if (P.trace && ct == 0) P.trace[6 * (size_t)d.task + 3] = gtime();
+            hand_over(ctl, sig_it++, d.task, mw, lane);
+            continue;
         } else {
             double* out = blk_ptr(P, d.out);
             switch (d.type) {
@@ -390,58 +471,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(ExecParams P) {
                 default: break;
             }
         }
-        // ---- task complete: make the result visible, then release the successors ---------
+        // ---- diagonal / copy task complete: the stage (work space of these kernels) is free again ---------
         math_sync();
-        if (d.type != T_GEMM) {
-            if (lane == 0) ptx::mbar_arrive(&ctl->empty[s]);
-        }
+        if (lane == 0) ptx::mbar_arrive(&ctl->empty[s]);
         if (P.trace && ct == 0) P.trace[6 * (size_t)d.task + 3] = gtime();
-        if (P.signal) {
-            const Task* T = P.tasks + d.task;
-            const int sb = T->succ_begin, se = T->succ_end;
-            if (sb + ct < se) {
-                // Successors on this GPU are released at gpu scope (cheap); only successors on peer GPUs pay for
-                // system-scope fences and atomics over NVLink.  A counter may be decremented from both scopes:
-                // the atomics themselves are performed at the owning GPU's L2 either way.
-                ptx::fence_acq_rel_gpu();
-                bool remote = false;
-                for (int e = sb + ct; e < se; e += N_MATH) {
-                    const int32_t ref = P.succ[e];
-                    const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK;
-                    if (o != P.rank) { remote = true; continue; }
-                    // sole predecessor: ready now, no counter; otherwise the thread that brings the counter to zero publishes
-                    if ((ref & TASK_SOLE_BIT) || atomicSub(P.dep + nx, 1) == 1) {
-                        // the whole group (all row slices of the successor) becomes ready at once
-                        // (the fence + the strong relaxed stores form the release; the consumers ld.acquire)
-                        const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
-                        if (!(ref & TASK_SOLE_BIT)) ptx::fence_acq_rel_gpu();
-                        const int pos = atomicAdd(P.tail, g);
-                        for (int k = 0; k < g; k++) {
-                            if (P.trace) P.trace[6 * (size_t)(nx + k) + 0] = gtime();
-                            ptx::st_relaxed(P.ready + pos + k, nx + k);
-                        }
-                    }
-                }
-                if (remote) {
-                    ptx::fence_acq_rel_sys();
-                    for (int e = sb + ct; e < se; e += N_MATH) {
-                        const int32_t ref = P.succ[e];
-                        const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK;
-                        if (o == P.rank) continue;
-                        if ((ref & TASK_SOLE_BIT) || atomicSub_system(P.deps[o] + nx, 1) == 1) {
-                            const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
-                            if (!(ref & TASK_SOLE_BIT)) ptx::fence_acq_rel_sys();
-                            const int pos = atomicAdd_system(P.tails[o], g);
-                            for (int k = 0; k < g; k++) ptx::st_relaxed_sys(P.readys[o] + pos + k, nx + k);
-                        }
-                    }
-                }
-            }
-            if (P.trace) {
-                math_sync();
-                if (ct == 0) P.trace[6 * (size_t)d.task + 4] = gtime();
-            }
-        }
+        hand_over(ctl, sig_it++, d.task, mw, lane);
     }
 }
 
@@ -453,7 +487,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
     double* Ws = As + BLK_ELEMS;
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (size_t)N_STAGES * STAGE_BYTES);
     double* scr = reinterpret_cast<double*>(ctl + 1);
-    if (threadIdx.x < 32) return;
+    if (threadIdx.x < 32 || threadIdx.x >= 32 + N_MATH) return;
     const int ct = threadIdx.x - 32;
     lub::lu_setup(scr, ct);
     auto slot = [&](int sl) { return pool + (size_t)sl * BLK_ELEMS; };

@@ -118,6 +118,7 @@ long read_mtx(const std::string& path, Coo& out) {
     const size_t chunk = (n_lines + nth - 1) / std::max(nth, 1);
     std::vector<std::vector<int>> ci(nth), cj(nth);
     std::vector<std::vector<double>> cv(nth);
+    long below_one = 0;
 #pragma omp parallel for schedule(static, 1) num_threads(nth)
     for (int t = 0; t < nth; t++) {
         const size_t lo = first + t * chunk, hi = std::min(nl, lo + chunk);
@@ -134,12 +135,14 @@ long read_mtx(const std::string& path, Coo& out) {
             double val = std::strtod(p2, nullptr);
             if (val == 0) continue;
             if (r > rows || c > rows) continue;
+            if (r < 1 || c < 1) { __atomic_fetch_add(&below_one, 1L, __ATOMIC_RELAXED); continue; }   // the reference would index [-1]
             ci[t].push_back((int)r - 1);
             cj[t].push_back((int)c - 1);
             cv[t].push_back(val);
         }
     }
     lap("parse");
+    if (below_one) std::fprintf(stderr, "%s: %ld entries with a row or column index below 1 were dropped (MatrixMarket indices are 1-based)\n", path.c_str(), below_one);
     std::vector<size_t> off(nth + 1, 0);
     for (int t = 0; t < nth; t++) off[t + 1] = off[t] + cv[t].size();
     const size_t keep = std::min<size_t>(off[nth], declared > 0 ? (size_t)declared : 0);   // the reference would overrun its arrays here

@@ -4,7 +4,7 @@
 // explicit triangular inverses, first on coarse "L2" blocks, then expanded to 64-blocks,
 // each pass followed by liveness pruning, ASAP stage numbering and the reference's
 // total ordering.  The emitted lists (ops, ids, stages, sequence/group numbers) equal the
-// reference's bit for bit; tests/test_planner_parity.py checks that against dumps of the
+// reference's bit for bit; tests/test_planner_golden.py checks that against dumps of the
 // unmodified reference.
 //
 // Reference: BlockPlanner.cpp:865-939 (LU), 941-989 (LLT), 1019-1092 (triangular

@@ -17,6 +17,8 @@ using soglu::Problem;
 
 extern "C" {
 
+static int upload_matrix(soglu_ctx* ctx, const Problem* p);
+
 int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
     try {
     const Problem* p = reinterpret_cast<const Problem*>(pp);
@@ -49,8 +51,10 @@ int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
     std::vector<int32_t> li, lr, lc, ui, ur, uc;
     split(pl.L, li, lr, lc);
     split(pl.U, ui, ur, uc);
-    return soglu_set_factors(ctx, (int64_t)li.size(), li.data(), lr.data(), lc.data(), (int64_t)ui.size(), ui.data(), ur.data(), uc.data(),
-                             p->cfg.blockRows, p->symmetric ? 1 : 0);
+    rc = soglu_set_factors(ctx, (int64_t)li.size(), li.data(), lr.data(), lc.data(), (int64_t)ui.size(), ui.data(), ur.data(), uc.data(),
+                           p->cfg.blockRows, p->symmetric ? 1 : 0);
+    if (rc) return rc;
+    return upload_matrix(ctx, p);
     } catch (const std::bad_alloc&) {
         soglu::set_error("out of host memory");
         return SOGLU_ERR_OOM;
@@ -60,26 +64,28 @@ int soglu_load_problem(soglu_ctx* ctx, const soglu_problem* pp) {
     }
 }
 
+// CSR of the permuted matrix, padded with the identity like the planner does (BlockPlanner.cpp:1520-1539); duplicates
+// keep the last value, as in the block scatter (BlockPlanner.cpp:1510).  Uploaded once per loaded problem: the
+// residual of the iterative refinement (soglu_solve_refined) is formed with it on the device.
+static int upload_matrix(soglu_ctx* ctx, const Problem* p) {
+    const int64_t n = p->n_ext, nnz = (int64_t)p->pv.size();
+    std::vector<int64_t> rp(n + 1, 0);
+    for (int64_t k = 0; k < nnz; k++) rp[p->pi[k] + 1]++;
+    for (int64_t i = p->dim; i < n; i++) rp[i + 1]++;
+    for (int64_t i = 0; i < n; i++) rp[i + 1] += rp[i];
+    std::vector<int32_t> ci(rp[n]);
+    std::vector<double> cv(rp[n]);
+    std::vector<int64_t> pos(rp.begin(), rp.end() - 1);
+    for (int64_t k = 0; k < nnz; k++) { ci[pos[p->pi[k]]] = p->pj[k]; cv[pos[p->pi[k]]++] = p->pv[k]; }
+    for (int64_t i = p->dim; i < n; i++) { ci[pos[i]] = (int32_t)i; cv[pos[i]++] = 1.0; }
+    return soglu_set_matrix(ctx, n, rp[n], rp.data(), ci.data(), cv.data());
+}
+
 int soglu_solve_problem(soglu_ctx* ctx, const soglu_problem* pp, const double* b, double* x, int refine, soglu_stats* out) {
     try {
     const Problem* p = reinterpret_cast<const Problem*>(pp);
     if (!ctx || !p || !x) { soglu::set_error("bad argument"); return SOGLU_ERR_ARG; }
-    if (refine > 0) {
-        // CSR of the permuted matrix, padded with the identity like the planner does (BlockPlanner.cpp:1520-1539);
-        // duplicates keep the last value, as in the block scatter (BlockPlanner.cpp:1510)
-        const int64_t n = p->n_ext, nnz = (int64_t)p->pv.size();
-        std::vector<int64_t> rp(n + 1, 0);
-        for (int64_t k = 0; k < nnz; k++) rp[p->pi[k] + 1]++;
-        for (int64_t i = p->dim; i < n; i++) rp[i + 1]++;
-        for (int64_t i = 0; i < n; i++) rp[i + 1] += rp[i];
-        std::vector<int32_t> ci(rp[n]);
-        std::vector<double> cv(rp[n]);
-        std::vector<int64_t> pos(rp.begin(), rp.end() - 1);
-        for (int64_t k = 0; k < nnz; k++) { ci[pos[p->pi[k]]] = p->pj[k]; cv[pos[p->pi[k]]++] = p->pv[k]; }
-        for (int64_t i = p->dim; i < n; i++) { ci[pos[i]] = (int32_t)i; cv[pos[i]++] = 1.0; }
-        int rcm = soglu_set_matrix(ctx, n, rp[n], rp.data(), ci.data(), cv.data());
-        if (rcm) return rcm;
-    }
+    // (the CSR of the permuted matrix for the refinement's residual was uploaded by soglu_load_problem)
     std::vector<double> bext;
     const double* bp = p->b_perm.data();
     if (b) {   // permute + pad a caller-supplied rhs exactly like the problem's own (GPSOrder.cpp:435-447)
@@ -104,7 +110,10 @@ int soglu_solve_problem(soglu_ctx* ctx, const soglu_problem* pp, const double* b
 
 double* soglu_solveLU(int dim, int valcount, int symmetric, const int* index_i, const int* index_j, const double* vals, const double* b) {
     soglu_problem* prob = nullptr;
-    if (soglu_problem_from_coo(dim, valcount, symmetric, index_i, index_j, vals, b, &prob)) return nullptr;
+    if (soglu_problem_from_coo(dim, valcount, symmetric, index_i, index_j, vals, b, &prob)) {
+        std::cout << "soglu error: " << soglu_last_error() << std::endl;
+        return nullptr;
+    }
     const Problem* p = reinterpret_cast<const Problem*>(prob);
     std::cout << p->log;
     soglu_ctx* ctx = nullptr;
