@@ -170,11 +170,14 @@ class Problem:
 class Context:
     """One GPU context: block pool + compiled task graph + factor/solve."""
 
-    def __init__(self, device=0, rank=0, world=1, grid=None):
-        """world > 1: this process drives one GPU of a 2D block-cyclic process grid (rows, cols)."""
+    def __init__(self, device=0, rank=0, world=1, grid=None, n_gpus=1):
+        """world > 1: this process drives one GPU of a 2D block-cyclic process grid (rows, cols).
+        n_gpus > 1: ONE process shards the factorisation over GPUs 0..n_gpus-1 (soglu_create's in-process group)."""
         self.h = ctypes.c_void_p()
         self.rank, self.world = rank, world
-        if world == 1:
+        if n_gpus > 1:
+            _check(lib().soglu_create(ctypes.byref(self.h), int(n_gpus), None))
+        elif world == 1:
             dev = (ctypes.c_int * 1)(device)
             _check(lib().soglu_create(ctypes.byref(self.h), 1, dev))
         else:

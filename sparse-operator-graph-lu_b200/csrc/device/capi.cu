@@ -56,6 +56,7 @@ struct soglu_ctx {
     int64_t opt_split = 1;
     int64_t opt_grid = 0;          // override CTA count (0 = all resident)
     int64_t opt_trace = 0;         // record per-task timestamps (debug; adds overhead)
+    int64_t opt_debug_drop = -1;       // test hook: lose the completion signal of this task (the watchdog must catch the hang)
     int64_t opt_watchdog_ms = 60000;   // a kernel whose waiters see no progress for this long aborts with SOGLU_ERR_CUDA (0 = off)
     DevBuf trace;
 
@@ -65,6 +66,9 @@ struct soglu_ctx {
     DistLayout D;
     std::vector<int32_t> brow, bcol;      // per block id (ownership)
     bool peers_ready = false;
+    bool ipc_peers = true;              // peer pointers come from cudaIpcOpenMemHandle (one process per GPU); false: same process
+    std::vector<soglu_ctx*> members;    // in-process group: this context only forwards to its members (rank g on device g)
+    soglu_ctx* leader = nullptr;        // member of a group: rank 0 of it (owns the compiled graph)
     int dist_segment = 0;               // segment the next soglu_factor call runs (multi-GPU)
     void* peer_pool[MAX_GPUS] = {}, *peer_dep[MAX_GPUS] = {}, *peer_ready[MAX_GPUS] = {}, *peer_counters[MAX_GPUS] = {};
 
@@ -86,7 +90,8 @@ struct soglu_ctx {
     // compiled state
     bool compiled = false;
     bool factored = false;
-    TaskGraph G;
+    TaskGraph G_own;
+    TaskGraph* Gp = &G_own;          // members of an in-process group (soglu_create with n_gpus > 1) share rank 0's graph
     std::vector<int32_t> level_order;   // tasks sorted by level (debug executor)
     std::vector<int64_t> level_ptr;
     DevBuf pool, tasks, pairs, succ, dep0, dep, ready, ready0, counters, counters0;
@@ -140,8 +145,8 @@ int upload(DevBuf& b, const std::vector<T, A>& v, soglu_ctx* c) {
 
 // block id -> block reference used by the kernels (owner in the top bits; plain slot on one GPU)
 int32_t id_ref(const soglu_ctx* c, int32_t id) {
-    const int32_t sl = c->G.slot_of[id];
-    return sl > 0 ? make_ref(c->G.owner_of[id], sl) : 0;
+    const int32_t sl = c->Gp->slot_of[id];
+    return sl > 0 ? make_ref(c->Gp->owner_of[id], sl) : 0;
 }
 
 // CSR over off-diagonal factor blocks of one triangle; lower: cols < row, upper: cols > row.
@@ -191,7 +196,7 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
     if ((rc = upload(ddiag, diag, c))) return rc;
     // explicit inverses of the diagonal blocks, where the factorisation produced them (fused lu tasks)
     std::unordered_map<int32_t, int32_t> inv_of_ref;   // reference of a diagonal factor block -> reference of its inverse
-    for (const Task& T : c->G.tasks)
+    for (const Task& T : c->Gp->tasks)
         if (T.type == T_LU || T.type == T_LLT) {      // llt: L^-1 also serves the transposed sweep, (L^T)^-1 = (L^-1)^T
             if (T.flags & TF_LINV) inv_of_ref[T.out] = T.init;
             if (T.flags & TF_UINV) inv_of_ref[T.out2] = T.out4;
@@ -210,7 +215,7 @@ int pack_pending_inputs(soglu_ctx* c) {
     std::vector<int32_t> slots(c->n_input);
     for (int64_t k = 0; k < c->n_input; k++) {
         const int32_t id = c->input_ids[k];
-        slots[k] = (!c->dist || c->G.owner_of[id] == c->rank) ? c->G.slot_of[id] : -1;   // other GPUs' inputs are skipped
+        slots[k] = (!c->dist || c->Gp->owner_of[id] == c->rank) ? c->Gp->slot_of[id] : -1;   // other GPUs' inputs are skipped
     }
     DevBuf dslots;
     int rc = upload(dslots, slots, c);
@@ -234,8 +239,15 @@ int pack_pending_inputs(soglu_ctx* c) {
 
 int finalize(soglu_ctx* c) {
     if (c->compiled) return pack_pending_inputs(c);
-    if (!c->have_blocks || !c->have_graph || !c->have_factors)
+    const bool follower = c->leader && c->leader != c;     // in-process group: rank 0 compiled the graph for everyone
+    if (follower) {
+        if (!c->leader->compiled) return fail(SOGLU_ERR_ARG, "internal: group leader not compiled");
+        if (!c->have_blocks) return fail(SOGLU_ERR_ARG, "soglu_set_blocks must precede soglu_factor");
+        c->Gp = c->leader->Gp;
+    } else if (!c->have_blocks || !c->have_graph || !c->have_factors) {
         return fail(SOGLU_ERR_ARG, "soglu_set_blocks, soglu_set_graph and soglu_set_factors must precede soglu_factor");
+    }
+    if (!follower) {
     std::vector<int32_t> keep;
     keep.reserve(c->L_ids.size() + c->U_ids.size());
     keep.insert(keep.end(), c->L_ids.begin(), c->L_ids.end());
@@ -276,20 +288,21 @@ int finalize(soglu_ctx* c) {
     }
     if (c->opt_chain_cuts > 0) { co.analyze_chains = true; co.cut_max_slack_us = (double)c->opt_chain_cuts; }
     std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
-                                    c->result.data(), c->result2.data(), keep, co, c->G);
+                                    c->result.data(), c->result2.data(), keep, co, *c->Gp);
     if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
-    TaskGraph& G = c->G;
-    if (c->opt_chain_cuts > 0 && !G.cuts.empty()) {
+    if (c->opt_chain_cuts > 0 && !c->Gp->cuts.empty()) {
         // second pass: the early pairs of every proposed chain become their own task (compile.cpp, chain analysis)
-        const std::vector<ChainCut> cuts = std::move(G.cuts);
+        const std::vector<ChainCut> cuts = std::move(c->Gp->cuts);
         co.analyze_chains = false;
         co.chain_cuts = &cuts;
         err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
-                            c->result.data(), c->result2.data(), keep, co, c->G);
+                            c->result.data(), c->result2.data(), keep, co, *c->Gp);
         if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
     }
+    }   // !follower
+    TaskGraph& G = *c->Gp;
     if (c->dist) {
-        err = localize_tasks(G, c->rank, c->D);
+        std::string err = localize_tasks(G, c->rank, c->D);
         if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
     }
     size_t free_b = 0, total_b = 0;
@@ -336,7 +349,7 @@ int finalize(soglu_ctx* c) {
     CU(c->dep.alloc(std::max<size_t>(tasks_up.size(), 1) * 4));
     CU(c->ready.alloc(std::max<size_t>(tasks_up.size(), 1) * 4));
     // level order for the debug executor
-    {
+    if (!c->dist) {
         const int64_t nt = (int64_t)G.tasks.size();
         c->level_ptr.assign(G.n_levels + 1, 0);
         for (int64_t t = 0; t < nt; t++) c->level_ptr[G.tasks[t].level + 1]++;
@@ -345,7 +358,8 @@ int finalize(soglu_ctx* c) {
         std::vector<int64_t> pos(c->level_ptr.begin(), c->level_ptr.end() - 1);
         for (int64_t t = 0; t < nt; t++) c->level_order[pos[G.tasks[t].level]++] = (int32_t)t;
     }
-    // triangular-solve structures
+    // triangular-solve structures (the solve runs on rank 0 of a sharded run)
+    if (!follower) {
     if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, false, false, c->l_ptr, c->l_col, c->l_slot, c->l_diag, c->l_dinv, c->nL_off))) return rc;
     if (c->symmetric) {
         if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, true, true, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->u_dinv, c->nU_off))) return rc;
@@ -354,6 +368,7 @@ int finalize(soglu_ctx* c) {
     }
     const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
     CU(c->d_b.alloc(next)); CU(c->d_y.alloc(next)); CU(c->d_x.alloc(next));
+    }
     c->compiled = true;
     // only now are the op arrays no longer needed on the host: a failure above (pool does not fit, a factor without
     // diagonal block, ...) leaves the context uncompiled WITH its graph, so a retry with other options is possible
@@ -365,12 +380,15 @@ int finalize(soglu_ctx* c) {
 
 }  // namespace
 
+static int group_create(soglu_ctx** out, int n_gpus, const int* device_ids);
+
 extern "C" {
 
 int soglu_create(soglu_ctx** out, int n_gpus, const int* device_ids) {
     if (!out) return fail(SOGLU_ERR_ARG, "null output pointer");
     *out = nullptr;
-    if (n_gpus != 1) return fail(SOGLU_ERR_ARG, "this build shards over one GPU per context (n_gpus must be 1)");
+    if (n_gpus > 1) return group_create(out, n_gpus, device_ids);
+    if (n_gpus != 1) return fail(SOGLU_ERR_ARG, "n_gpus must be >= 1");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -431,6 +449,7 @@ int64_t soglu_dist_blob_bytes(void) { return (int64_t)sizeof(DistBlob); }
 // compile + allocate this GPU's share, then write the IPC handles of its pool / counters / queue
 int soglu_dist_export(soglu_ctx* c, void* blob) {
     try {
+    if (c && !c->members.empty()) return fail(SOGLU_ERR_ARG, "in-process multi-GPU context (soglu_create with n_gpus > 1): peers are wired by the library, the soglu_dist_* protocol is for one process per GPU");
     if (!c || !blob) return fail(SOGLU_ERR_ARG, "bad argument");
     CU(cudaSetDevice(c->device));
     int rc = finalize(c);
@@ -457,6 +476,7 @@ int soglu_dist_export(soglu_ctx* c, void* blob) {
 // all_blobs: world blobs in rank order (gathered by the caller, e.g. torch.distributed.all_gather)
 int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
     try {
+    if (c && !c->members.empty()) return fail(SOGLU_ERR_ARG, "in-process multi-GPU context (soglu_create with n_gpus > 1): peers are wired by the library, the soglu_dist_* protocol is for one process per GPU");
     if (!c || !all_blobs) return fail(SOGLU_ERR_ARG, "bad argument");
     if (!c->compiled) return fail(SOGLU_ERR_ARG, "soglu_dist_export must precede soglu_dist_import");
     if (c->peers_ready) return fail(SOGLU_ERR_ARG, "peer handles are already imported (one import per context; destroy it and build a new one to re-shard)");
@@ -488,11 +508,12 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
 // reset this GPU's dependency counters and ready queue; the caller must put a barrier across all
 // ranks between soglu_dist_reset and soglu_factor, and another one after soglu_factor
 int soglu_dist_reset(soglu_ctx* c) {
+    if (c && !c->members.empty()) return fail(SOGLU_ERR_ARG, "in-process multi-GPU context (soglu_create with n_gpus > 1): peers are wired by the library, the soglu_dist_* protocol is for one process per GPU");
     if (!c || !c->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled");
     CU(cudaSetDevice(c->device));
     int rc = pack_pending_inputs(c);
     if (rc) return rc;
-    const size_t nt = c->dist ? c->D.tasks.size() : c->G.tasks.size();
+    const size_t nt = c->dist ? c->D.tasks.size() : c->Gp->tasks.size();
     if (nt) {
         CU(cudaMemcpyAsync(c->dep.p, c->dep0.p, nt * 4, cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(c->ready.p, c->ready0.p, nt * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -505,11 +526,13 @@ int soglu_dist_reset(soglu_ctx* c) {
 
 // number of executor launches (segments) one factorisation needs; > 1 when the pools recycle slots
 int soglu_dist_segments(soglu_ctx* c) {
+    if (c && !c->members.empty()) c = c->members[0];
     if (!c || !c->compiled) return -1;
-    return (int)((c->dist ? c->D.seg_begin.size() : c->G.seg_begin.size()) - 1);
+    return (int)((c->dist ? c->D.seg_begin.size() : c->Gp->seg_begin.size()) - 1);
 }
 // select the segment the next soglu_factor call runs (all ranks the same one, barrier in between)
 int soglu_dist_set_segment(soglu_ctx* c, int seg) {
+    if (c && !c->members.empty()) return fail(SOGLU_ERR_ARG, "in-process multi-GPU context (soglu_create with n_gpus > 1): peers are wired by the library, the soglu_dist_* protocol is for one process per GPU");
     if (!c || !c->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled");
     c->dist_segment = seg;
     return SOGLU_OK;
@@ -517,9 +540,10 @@ int soglu_dist_set_segment(soglu_ctx* c, int seg) {
 
 // owned tasks / blocks / remote edges / remote operand reads of this rank
 int soglu_dist_info(soglu_ctx* c, int64_t* out4) {
+    if (c && !c->members.empty()) return fail(SOGLU_ERR_ARG, "soglu_dist_info: ask per rank (one process per GPU) -- an in-process group has no single rank");
     if (!c || !out4 || !c->compiled) return fail(SOGLU_ERR_ARG, "bad argument");
-    out4[0] = (int64_t)(c->dist ? c->D.tasks.size() : c->G.tasks.size());
-    out4[1] = c->G.slots_per_owner[c->dist ? c->rank : 0];
+    out4[0] = (int64_t)(c->dist ? c->D.tasks.size() : c->Gp->tasks.size());
+    out4[1] = c->Gp->slots_per_owner[c->dist ? c->rank : 0];
     out4[2] = c->dist ? c->D.remote_edges : 0;
     out4[3] = c->dist ? c->D.remote_operands : 0;
     out4[4] = c->dist ? c->D.mirrored : 0;
@@ -528,8 +552,14 @@ int soglu_dist_info(soglu_ctx* c, int64_t* out4) {
 
 void soglu_destroy(soglu_ctx* c) {
     if (!c) return;
+    if (!c->members.empty()) {
+        // all kernels of the group have been synchronised by the calls that launched them; members free their own memory
+        for (soglu_ctx* m : c->members) soglu_destroy(m);
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
-    if (c->dist)
+    if (c->dist && c->ipc_peers)
         for (int g = 0; g < c->world; g++) {
             if (g == c->rank) continue;
             for (void* p : {c->peer_pool[g], c->peer_dep[g], c->peer_ready[g], c->peer_counters[g]})
@@ -546,6 +576,10 @@ void soglu_destroy(soglu_ctx* c) {
 
 int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     if (!c || !key) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->members.empty()) {
+        for (soglu_ctx* m : c->members) { int rc = soglu_set_option(m, key, value); if (rc) return rc; }
+        return SOGLU_OK;
+    }
     std::string k(key);
     if (k == "exec_mode") c->opt_exec_mode = value;
     else if (k == "fuse_sub") { if (c->compiled) return fail(SOGLU_ERR_ARG, "fuse_sub must be set before the first factor"); c->opt_fuse_sub = value; }
@@ -559,6 +593,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else if (k == "watchdog_ms") c->opt_watchdog_ms = value;
+    else if (k == "debug_drop_task") c->opt_debug_drop = value;
     else return fail(SOGLU_ERR_ARG, "unknown option " + k);
     return SOGLU_OK;
 }
@@ -579,6 +614,10 @@ static int register_input_pattern(soglu_ctx* c, int64_t n_block_ids, int64_t n_i
 int soglu_set_blocks(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, const int32_t* input_ids, const double* dense) {
     try {
     if (!c || n_block_ids < 1 || n_input < 0 || (n_input > 0 && (!input_ids || !dense))) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->members.empty()) {      // every GPU stages the inputs and keeps its share
+        for (soglu_ctx* m : c->members) { int rc = soglu_set_blocks(m, n_block_ids, n_input, input_ids, dense); if (rc) return rc; }
+        return SOGLU_OK;
+    }
     CU(cudaSetDevice(c->device));
     int rc = register_input_pattern(c, n_block_ids, n_input, input_ids);
     if (rc) return rc;
@@ -605,6 +644,10 @@ int soglu_set_blocks_sparse(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, 
     if (!c || n_block_ids < 1 || n_input < 0 || n_entries < 0 || (n_input > 0 && !input_ids) || (n_entries > 0 && (!entry_input || !entry_pos || !vals)))
         return fail(SOGLU_ERR_ARG, "bad argument");
     int bad = 0;
+    if (!c->members.empty()) {
+        for (soglu_ctx* m : c->members) { int rc = soglu_set_blocks_sparse(m, n_block_ids, n_input, input_ids, n_entries, entry_input, entry_pos, vals); if (rc) return rc; }
+        return SOGLU_OK;
+    }
 #pragma omp parallel for schedule(static) reduction(| : bad)
     for (int64_t k = 0; k < n_entries; k++)
         if (entry_input[k] < 0 || entry_input[k] >= n_input || entry_pos[k] < 0 || entry_pos[k] >= BLK * BLK) bad = 1;
@@ -640,6 +683,10 @@ int soglu_set_graph(soglu_ctx* c, int64_t n_ops, const int32_t* src, const int32
     try {
     (void)stage;
     if (!c || n_ops < 0 || (n_ops > 0 && (!src || !src2 || !op || !result || !result2))) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->members.empty()) {      // ONE copy of the operation list, ONE compilation: rank 0 holds the graph for the group
+        if (!block_row || !block_col) return fail(SOGLU_ERR_ARG, "multi-GPU context: soglu_set_graph needs block_row / block_col (they decide the block ownership)");
+        return soglu_set_graph(c->members[0], n_ops, src, src2, op, result, result2, stage, block_row, block_col);
+    }
     if (c->compiled) return fail(SOGLU_ERR_ARG, "graph already compiled; create a new context for a new pattern");
     c->n_ops = n_ops;
     c->src.resize(n_ops); c->src2.resize(n_ops); c->result.resize(n_ops); c->result2.resize(n_ops); c->op.resize(n_ops);
@@ -663,6 +710,10 @@ int soglu_set_factors(soglu_ctx* c, int64_t nL, const int32_t* L_ids, const int3
                       const int32_t* U_ids, const int32_t* U_brow, const int32_t* U_bcol, int32_t n_block_rows, int symmetric) {
     try {
     if (!c || nL <= 0 || !L_ids || !L_brow || !L_bcol || n_block_rows <= 0) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->members.empty()) {
+        for (soglu_ctx* m : c->members) m->n_block_rows = n_block_rows;
+        return soglu_set_factors(c->members[0], nL, L_ids, L_brow, L_bcol, nU, U_ids, U_brow, U_bcol, n_block_rows, symmetric);
+    }
     if (!symmetric && (nU <= 0 || !U_ids || !U_brow || !U_bcol)) return fail(SOGLU_ERR_ARG, "U factor missing");
     if (c->compiled) return fail(SOGLU_ERR_ARG, "graph already compiled; create a new context for a new pattern");
     c->L_ids.assign(L_ids, L_ids + nL); c->L_brow.assign(L_brow, L_brow + nL); c->L_bcol.assign(L_bcol, L_bcol + nL);
@@ -678,14 +729,12 @@ int soglu_set_factors(soglu_ctx* c, int64_t nL, const int32_t* L_ids, const int3
     }
 }
 
-int soglu_factor(soglu_ctx* c, soglu_stats* out) {
-    try {
-    if (!c) return fail(SOGLU_ERR_ARG, "null context");
+// enqueue the executor launch(es) of one factorisation (sharded: of the selected segment) on the context's stream
+static int factor_launch(soglu_ctx* c) {
     CU(cudaSetDevice(c->device));
-    const int64_t launches0 = c->launches;
     int rc = finalize(c);
     if (rc) return rc;
-    TaskGraph& G = c->G;
+    TaskGraph& G = *c->Gp;
     const int32_t nt = (int32_t)(c->dist ? c->D.tasks.size() : G.tasks.size());
     int grid = c->exec_grid;
     if (c->opt_grid > 0 && c->opt_grid < grid) grid = (int)c->opt_grid;
@@ -705,6 +754,7 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     P.trace = nullptr;
     P.abort = c->abort_word();
     P.watchdog_ns = (unsigned long long)std::max<int64_t>(0, c->opt_watchdog_ms) * 1000000ull;
+    P.debug_drop = (int32_t)c->opt_debug_drop;
     if (c->dist) for (int g = 0; g < c->world; g++) P.aborts[g] = (int32_t*)c->peer_counters[g] + c->counters0.bytes / 4;
     if (c->opt_trace && nt > 0) {
         if (!c->trace.p) CU(c->trace.alloc((size_t)nt * 6 * sizeof(unsigned long long)));
@@ -768,19 +818,39 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
         }
     }
     CU(cudaEventRecord(c->ev1, c->stream));
+    return SOGLU_OK;
+}
+
+// wait for factor_launch, check the watchdog; ms = device time between the events
+static int factor_finish(soglu_ctx* c, float* ms) {
+    CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    if ((rc = check_watchdog(c, "factorisation"))) return rc;
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    int rc = check_watchdog(c, "factorisation");
+    if (rc) return rc;
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
     c->factored = true;
+    return SOGLU_OK;
+}
+
+static int group_factor(soglu_ctx* grp, soglu_stats* out);
+
+int soglu_factor(soglu_ctx* c, soglu_stats* out) {
+    try {
+    if (!c) return fail(SOGLU_ERR_ARG, "null context");
+    if (!c->members.empty()) return group_factor(c, out);
+    const int64_t launches0 = c->launches;
+    int rc = factor_launch(c);
+    if (rc) return rc;
+    float ms = 0;
+    if ((rc = factor_finish(c, &ms))) return rc;
     if (out) {
         std::memset(out, 0, sizeof *out);
         out->seconds = ms * 1e-3;
-        out->flops = G.flops;
+        out->flops = c->Gp->flops;
         out->bytes = 0;
         out->kernel_launches = c->launches - launches0;
-        out->tasks = nt;
-        out->pool_blocks = G.slots_per_owner[c->dist ? c->rank : 0];
+        out->tasks = (int64_t)(c->dist ? c->D.tasks.size() : c->Gp->tasks.size());
+        out->pool_blocks = c->Gp->slots_per_owner[c->dist ? c->rank : 0];
         out->h2d_bytes = c->h2d;
         out->d2h_bytes = c->d2h;
     }
@@ -814,6 +884,7 @@ static int run_trsv(soglu_ctx* c, const double* d_rhs, double* d_sol) {
 
 static int solve_impl(soglu_ctx* c, const double* b_ext, double* x_ext, int refine, soglu_stats* out) {
     if (!c || !b_ext || !x_ext) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->members.empty()) return solve_impl(c->members[0], b_ext, x_ext, refine, out);   // rank 0 solves over peer memory
     if (!c->factored) return fail(SOGLU_ERR_ARG, "soglu_factor must precede soglu_solve");
     if (c->dist && c->rank != 0) return fail(SOGLU_ERR_ARG, "multi-GPU context: the triangular solve runs on rank 0 (it reads the peers' factor blocks over NVLink)");
     if (refine > 0 && c->m_n == 0) return fail(SOGLU_ERR_ARG, "iterative refinement needs the matrix: call soglu_set_matrix first");
@@ -853,7 +924,7 @@ static int solve_impl(soglu_ctx* c, const double* b_ext, double* x_ext, int refi
         out->bytes = (double)BLK * BLK * 8.0 * nblk + 8.0 * 3.0 * c->n_block_rows * BLK * (1 + refine);
         out->kernel_launches = c->launches - launches0;
         out->tasks = 2 * (int64_t)c->n_block_rows * (1 + refine);
-        out->pool_blocks = c->G.slots_per_owner[c->dist ? c->rank : 0];
+        out->pool_blocks = c->Gp->slots_per_owner[c->dist ? c->rank : 0];
         out->h2d_bytes = (double)next;
         out->d2h_bytes = (double)next;
     }
@@ -881,6 +952,7 @@ int soglu_solve_refined(soglu_ctx* c, const double* b_ext, double* x_ext, int st
 int soglu_set_matrix(soglu_ctx* c, int64_t n_ext, int64_t nnz, const int64_t* row_ptr, const int32_t* col, const double* val) {
     try {
     if (!c || n_ext <= 0 || nnz < 0 || !row_ptr || (nnz > 0 && (!col || !val))) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->members.empty()) return soglu_set_matrix(c->members[0], n_ext, nnz, row_ptr, col, val);
     CU(cudaSetDevice(c->device));
     CU(c->m_rp.alloc((size_t)(n_ext + 1) * 8)); CU(c->m_ci.alloc(std::max<size_t>(nnz, 1) * 4)); CU(c->m_v.alloc(std::max<size_t>(nnz, 1) * 8));
     CU(cudaMemcpyAsync(c->m_rp.p, row_ptr, (size_t)(n_ext + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -901,7 +973,7 @@ int soglu_set_matrix(soglu_ctx* c, int64_t n_ext, int64_t nnz, const int64_t* ro
 
 // debug: cycles of lu / write-out / inverses / total for one diagonal block (slot 1 = first input)
 int soglu_debug_diag_bench(soglu_ctx* c, int iters, long long* cycles4) {
-    if (!c || !c->compiled || c->G.n_slots < 12) return fail(SOGLU_ERR_ARG, "need a compiled problem");
+    if (!c || !c->compiled || c->Gp->n_slots < 12) return fail(SOGLU_ERR_ARG, "need a compiled problem");
     DevBuf d;
     CU(d.alloc(128));
     CU(cudaMemsetAsync(d.p, 0, 128, c->stream));
@@ -916,14 +988,14 @@ int soglu_debug_diag_bench(soglu_ctx* c, int iters, long long* cycles4) {
 // n_deps per task) of the last traced soglu_factor; returns the number of tasks
 int64_t soglu_debug_trace(soglu_ctx* c, unsigned long long* trace_out, int32_t* task_info_out, int32_t* succ_ptr_out, int32_t* succ_out) {
     if (!c || !c->compiled) return -1;
-    const int64_t nt = (int64_t)c->G.tasks.size();
+    const int64_t nt = (int64_t)c->Gp->tasks.size();
     if (trace_out) {
         if (!c->trace.p) return -1;
         if (cudaMemcpy(trace_out, c->trace.p, (size_t)nt * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     }
     if (task_info_out)
         for (int64_t t = 0; t < nt; t++) {
-            const Task& T = c->G.tasks[t];
+            const Task& T = c->Gp->tasks[t];
             task_info_out[4 * t] = T.type; task_info_out[4 * t + 1] = T.n_pairs; task_info_out[4 * t + 2] = T.level; task_info_out[4 * t + 3] = T.n_deps;
         }
     // successor lists name group leaders and are shared by the slices of a task: export them expanded to
@@ -931,11 +1003,11 @@ int64_t soglu_debug_trace(soglu_ctx* c, unsigned long long* trace_out, int32_t* 
     if (succ_ptr_out || succ_out) {
         int64_t pos = 0;
         for (int64_t t = 0; t < nt; t++) {
-            const Task& T = c->G.tasks[t];
+            const Task& T = c->Gp->tasks[t];
             if (succ_ptr_out) succ_ptr_out[t] = (int32_t)pos;
             for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
-                const int32_t s2 = c->G.succ[e];
-                for (int q = 0, g = task_group_size(c->G.tasks[s2]); q < g; q++, pos++)
+                const int32_t s2 = c->Gp->succ[e];
+                for (int q = 0, g = task_group_size(c->Gp->tasks[s2]); q < g; q++, pos++)
                     if (succ_out) succ_out[pos] = s2 + q;
             }
         }
@@ -947,16 +1019,22 @@ int64_t soglu_debug_trace(soglu_ctx* c, unsigned long long* trace_out, int32_t* 
 int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {
     try {
     if (!c || !out_64x64) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->members.empty()) {
+        soglu_ctx* m0 = c->members[0];
+        if (!m0->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled yet");
+        if (id <= 0 || id >= m0->n_ids) return fail(SOGLU_ERR_ARG, "block id out of range");
+        return soglu_get_block(c->members[m0->Gp->owner_of[id]], id, out_64x64);
+    }
     if (!c->compiled) return fail(SOGLU_ERR_ARG, "nothing compiled yet");
     if (id <= 0 || id >= c->n_ids) return fail(SOGLU_ERR_ARG, "block id out of range");
-    const int32_t slot = c->G.slot_of[id];
-    if (c->G.recycled[id]) return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " was recycled (its pool slot was reused after its last reader)");
+    const int32_t slot = c->Gp->slot_of[id];
+    if (c->Gp->recycled[id]) return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " was recycled (its pool slot was reused after its last reader)");
     if (slot <= 0) return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " has no storage (never produced, or folded into a fused task)");
     CU(cudaSetDevice(c->device));
     DevBuf tmp;
     CU(tmp.alloc(BLK * BLK * sizeof(double)));
     const int32_t local = slot;
-    if (c->dist && c->G.owner_of[id] != c->rank) { tmp.release(); return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " lives on another GPU"); }
+    if (c->dist && c->Gp->owner_of[id] != c->rank) { tmp.release(); return fail(SOGLU_ERR_ARG, "block " + std::to_string(id) + " lives on another GPU"); }
     CU(launch_unpack_block(c->pool.as<double>(), local, tmp.as<double>(), c->stream));
     c->launches++;
     CU(cudaMemcpyAsync(out_64x64, tmp.p, BLK * BLK * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -971,3 +1049,99 @@ int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {
 }
 
 }  // extern "C"
+
+// ---- in-process multi-GPU: soglu_create(n_gpus > 1) ----------------------------------------------------------------
+// The group context owns one ordinary sharded context per GPU (rank g on device_ids[g], the same 2D block-cyclic
+// ownership as the one-process-per-GPU mode) and forwards the ABI to them.  Differences to that mode: ONE copy of the
+// operation list and ONE compilation (rank 0's TaskGraph, shared by pointer -- the other ranks only localise their
+// part), peers reached through cudaDeviceEnablePeerAccess pointers instead of IPC mappings, and the per-segment
+// barriers are this thread waiting for every stream.  This is what ./solve and SOGLU::solveLU use (SOGLU_GPUS=N).
+static void default_grid(int world, int* pr, int* pc) {
+    int r = 1;
+    while (r * r * 2 <= world) r *= 2;
+    if (world % r) r = 1;
+    *pr = r; *pc = world / r;
+}
+
+static int group_create(soglu_ctx** out, int n_gpus, const int* device_ids) {
+    if (n_gpus > MAX_GPUS) return fail(SOGLU_ERR_ARG, "at most 8 GPUs");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < n_gpus)
+        return fail(SOGLU_ERR_NO_DEVICE, "soglu_create: " + std::to_string(n_gpus) + " GPUs requested, " + std::to_string(count) + " visible (soglu-b200 has no CPU fallback)");
+    int pr, pc;
+    default_grid(n_gpus, &pr, &pc);
+    soglu_ctx* grp = new soglu_ctx();
+    for (int g = 0; g < n_gpus; g++) {
+        soglu_ctx* m = nullptr;
+        int rc = soglu_create_dist(&m, device_ids ? device_ids[g] : g, g, n_gpus, pr, pc);
+        if (rc) { soglu_destroy(grp); return rc; }
+        m->ipc_peers = false;
+        grp->members.push_back(m);
+    }
+    for (soglu_ctx* m : grp->members) m->leader = grp->members[0];
+    // peer access between every pair (an error other than "already enabled" means the box has no P2P path)
+    for (soglu_ctx* a : grp->members)
+        for (soglu_ctx* b : grp->members) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, a->device, b->device);
+            if (!can) { soglu_destroy(grp); return fail(SOGLU_ERR_NO_DEVICE, "GPUs " + std::to_string(a->device) + " and " + std::to_string(b->device) + " have no peer access"); }
+            cudaSetDevice(a->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { soglu_destroy(grp); return fail(SOGLU_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); }
+            cudaGetLastError();
+        }
+    grp->world = n_gpus;
+    *out = grp;
+    return SOGLU_OK;
+}
+
+static int group_factor(soglu_ctx* grp, soglu_stats* out) {
+    std::vector<soglu_ctx*>& M = grp->members;
+    int64_t launches0 = 0;
+    for (soglu_ctx* m : M) launches0 += m->launches;
+    int rc;
+    // compile on rank 0 (the first call), allocate + upload everywhere, wire the peers
+    for (soglu_ctx* m : M) {
+        cudaSetDevice(m->device);
+        if ((rc = finalize(m))) return rc;
+    }
+    if (!M[0]->peers_ready)
+        for (soglu_ctx* m : M) {
+            for (size_t g = 0; g < M.size(); g++) {
+                m->peer_pool[g] = M[g]->pool.p; m->peer_dep[g] = M[g]->dep.p; m->peer_ready[g] = M[g]->ready.p; m->peer_counters[g] = M[g]->counters.p;
+            }
+            m->peers_ready = true;
+        }
+    for (soglu_ctx* m : M) if ((rc = soglu_dist_reset(m))) return rc;
+    const int nseg = soglu_dist_segments(M[0]);
+    double seconds = 0;
+    for (int sg = 0; sg < nseg; sg++) {
+        for (soglu_ctx* m : M) { m->dist_segment = sg; if ((rc = factor_launch(m))) return rc; }
+        float worst = 0;
+        int first_err = 0;
+        std::string first_msg;
+        for (soglu_ctx* m : M) {          // wait for EVERY GPU even if one reports an error (its peers drain through the abort word)
+            float ms = 0;
+            rc = factor_finish(m, &ms);
+            if (rc && !first_err) { first_err = rc; first_msg = soglu_last_error(); }
+            worst = std::max(worst, ms);
+        }
+        if (first_err) return fail(first_err, first_msg);
+        seconds += worst * 1e-3;
+    }
+    if (out) {
+        std::memset(out, 0, sizeof *out);
+        out->seconds = seconds;
+        out->flops = M[0]->Gp->flops;
+        for (soglu_ctx* m : M) {
+            out->kernel_launches += m->launches;
+            out->tasks += (int64_t)m->D.tasks.size();
+            out->pool_blocks = std::max<int64_t>(out->pool_blocks, m->Gp->slots_per_owner[m->rank]);
+            out->h2d_bytes += m->h2d; out->d2h_bytes += m->d2h;
+        }
+        out->kernel_launches -= launches0;
+    }
+    return SOGLU_OK;
+}
+

@@ -261,7 +261,7 @@ __device__ __noinline__ bool watchdog_expired(const ExecParams& P, int slot, uns
     return true;
 }
 
-__global__ void __maxnreg__(200) executor_kernel(const __grid_constant__ ExecParams P) {
+__global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_constant__ ExecParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (size_t)N_STAGES * STAGE_BYTES);
@@ -342,7 +342,7 @@ __global__ void __maxnreg__(200) executor_kernel(const __grid_constant__ ExecPar
             ptx::mbar_wait(&ctl->sig_full[q], (it / SIG_RING) & 1);
             const int t = ctl->sig_task[q];
             if (t < 0) break;
-            if (P.signal) {
+            if (P.signal && t != P.debug_drop) {
                 const Task* T = P.tasks + t;
                 const int sb = T->succ_begin, se = T->succ_end;
                 // The math threads' stores happen before this fence (their mbarrier arrivals were observed above), so it

@@ -120,7 +120,11 @@ double* soglu_solveLU(int dim, int valcount, int symmetric, const int* index_i, 
     double* x = nullptr;
     soglu_stats fs, ss;
     do {
-        if (soglu_create(&ctx, 1, nullptr)) break;
+        // SOGLU_GPUS=N: shard the factorisation over GPUs 0..N-1 of this process (soglu_create with n_gpus > 1)
+        const char* env_gpus = std::getenv("SOGLU_GPUS");
+        const int n_gpus = env_gpus ? std::max(1, std::atoi(env_gpus)) : 1;
+        if (soglu_create(&ctx, n_gpus, nullptr)) break;
+        if (n_gpus > 1) std::cout << "sharded over " << n_gpus << " GPUs (2D block-cyclic block ownership)\n";
         if (soglu_load_problem(ctx, prob)) break;
         if (soglu_factor(ctx, &fs)) break;
         std::cout << "kernel time: " << fs.seconds << "  (" << fs.flops / fs.seconds * 1e-9 << " GFLOP/s, " << fs.tasks << " tasks)\n";

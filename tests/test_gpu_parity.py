@@ -267,6 +267,60 @@ def test_two_gpu_sharded_factorisation():
         assert sum(r["mirrored"] for r in rec["per_rank"]) > 0
 
 
+@pytest.mark.parametrize("name,opts", [("lap3d_24", {}), ("lap3d_24", {"max_slots": 4000}), ("lap2d_64_sym", {}), ("banded_3000", {"dist_nb": 2})])
+def test_in_process_two_gpus(sg, tmp_path, name, opts):
+    """soglu_create(n_gpus = 2): one process, one compilation, two GPUs wired with cudaDeviceEnablePeerAccess -- the
+    entry point SOGLU::solveLU / ./solve use with SOGLU_GPUS.  Bitwise the single-GPU solution (every block is produced
+    by the same task with the same operand order), with and without pool recycling (segments), and refinement on top."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    one = sg.Context(0)
+    one.load(p)
+    one.factor()
+    x1, _ = one.solve(p)
+    two = sg.Context(n_gpus=2)
+    for k, v in opts.items():
+        two.set_option(k, v)
+    two.load(p)
+    for _ in range(2):
+        fs = two.factor()
+        x2, _ = two.solve(p)
+        np.testing.assert_array_equal(x2, x1)
+    assert fs["tasks"] > 0 and fs["seconds"] > 0
+    if opts.get("max_slots"):
+        assert two.segments() > 1
+    xr1, _ = one.solve(p, refine=1)
+    xr2, _ = two.solve(p, refine=1)
+    np.testing.assert_array_equal(xr2, xr1)
+    lid = int(p.i32("L")[5, 0])
+    np.testing.assert_array_equal(two.get_block(lid), one.get_block(lid))
+    two.close()
+    one.close()
+
+
+def test_solve_cli_two_gpus(sg, tmp_path):
+    """SOGLU_GPUS=2 ./solve file.mtx (main.cpp:34-66 with the sharded context behind SOGLU::solveLU): same _x.mtx as on one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = load_golden("lap3d_24")
+    xs = []
+    for gpus in ("1", "2"):
+        d = tmp_path / ("g" + gpus)
+        d.mkdir()
+        path = write_case_mtx("lap3d_24", d)
+        r = subprocess.run([sg.SOLVE_PATH, path], capture_output=True, text=True, timeout=300, env=dict(os.environ, SOGLU_GPUS=gpus))
+        assert r.returncode == 0, r.stdout + r.stderr
+        if gpus == "2":
+            assert "sharded over 2 GPUs" in r.stdout
+        vals = [float(l) for l in open(path[: path.find(".mtx")] + "_x.mtx").read().split("\n")[2:] if l.strip()]
+        xs.append(np.array(vals))
+    np.testing.assert_array_equal(xs[0], xs[1])
+    assert _rel(xs[1], g["x"]) <= TOL_X
+
+
 def test_iterative_refinement_lowers_residual(sg, tmp_path):
     """Device-side refinement (r = b - A x in FP64, re-solve, update) drives the residual to the FP64 floor
     (SURVEY.md 0.9): on the 2D Laplacian, where the raw solve sits near 1e-12, one step must not be worse
@@ -469,19 +523,22 @@ def test_slack_split(sg, tmp_path, name):
 @pytest.mark.gpu
 @pytest.mark.timeout(300)
 def test_watchdog_aborts_and_recovers(sg, tmp_path):
-    """The executor's watchdog (executor.cu): with a deadline far below the run time of the factorisation some scheduler
-    lane is still waiting for its queue slot when it expires, raises the abort word, every CTA drains and soglu_factor
-    returns SOGLU_ERR_CUDA naming the slot instead of hanging in cudaStreamSynchronize.  The context stays usable:
-    with the default deadline the next factorisation gives the golden solution."""
+    """The executor's watchdog (executor.cu).  The test hook debug_drop_task loses the completion signal of one task, so
+    its successors are never published and the claim-then-wait queue would spin forever; with a 300 ms deadline the
+    scheduler lanes raise the abort word, every CTA drains and soglu_factor returns SOGLU_ERR_CUDA naming the queue slot
+    instead of hanging in cudaStreamSynchronize.  The context stays usable: without the fault the next factorisation
+    gives the golden solution."""
     g = load_golden("lap3d_24")
     p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
     ctx = sg.Context(0)
     ctx.load(p)
     ctx.factor()
-    ctx.set_option("watchdog_ms", 1)   # the factorisation is chain-bound and takes ~10 ms: most schedulers are waiting at 1 ms
+    ctx.set_option("watchdog_ms", 300)
+    ctx.set_option("debug_drop_task", 1000)
     with pytest.raises(sg.SogluError) as e:
         ctx.factor()
     assert "watchdog" in str(e.value) and "ready-queue slot" in str(e.value)
+    ctx.set_option("debug_drop_task", -1)
     ctx.set_option("watchdog_ms", 60000)
     ctx.factor()
     x, _ = ctx.solve(p)
