@@ -18,7 +18,8 @@ e2e    = same metric through the C ABI from HOST buffers: every step re-uploads 
          blocks and the right-hand side (H2D) and reads x back (D2H) inside the timed region.
 N > 1  = ONE factorisation sharded over the N GPUs (2D block-cyclic block ownership, owner computes,
          remote operands pulled over NVLink into local mirrors; one process per GPU, peers mapped with
-         CUDA IPC; NCCL only for bootstrap / barriers); the solve runs on rank 0 over peer memory.
+         CUDA IPC; NCCL only for bootstrap / barriers); the solve is sharded too: every GPU substitutes the block rows
+         whose diagonal block it owns and publishes its segments into every GPU's copy of y / x.
          Total work is fixed -> "scaling": "strong".  value = op-list FLOPs / max-over-ranks time.
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/ref_harness --lean, its own OpenMP path on
@@ -374,19 +375,15 @@ def main():
         factor = ctx.factor
     first = factor()                           # includes the one-time task-graph compilation + upload
     t_first = time.perf_counter() - t0
-    x = None
-    if rank == 0:
-        x, _ = ctx.solve(prob, refine=1)       # also uploads the CSR of the permuted system (soglu_set_matrix), once
+    x, _ = ctx.solve(prob, refine=1)           # collective in a sharded run: every GPU solves its block rows; rank 0 holds x
     barrier()
 
     # ---- device-resident steps ---------------------------------------------------------------
     def step():
         fs = factor()
-        ss = {"kernel_launches": 0, "seconds": 0.0}
-        if rank == 0:
-            _, ss = ctx.solve(prob, refine=1)
+        _, ss = ctx.solve(prob, refine=1)       # every rank (sharded solve); refinement residual on rank 0
         if use_dist:
-            barrier()                           # peers keep their factor blocks mapped until rank 0 has solved
+            barrier()                           # no rank may refill its solve vectors while a peer still publishes into them
         return fs, ss
     for _ in range(max(args.warmup, 3)):
         step()
@@ -425,9 +422,8 @@ def main():
     def e2e_step():
         ctx.set_blocks_sparse(prob.size("storage"), ids, ent_in_np, ent_pos_np, vals_np)   # H2D: matrix entries (every rank: it keeps its share)
         factor()
-        if rank == 0:
-            rc = L.soglu_solve_refined(ctx.h, b_np.ctypes.data_as(ctypes.c_void_p), x_np.ctypes.data_as(ctypes.c_void_p), 1, ctypes.byref(st))  # H2D b, D2H x
-            assert rc == 0
+        rc = L.soglu_solve_refined(ctx.h, b_np.ctypes.data_as(ctypes.c_void_p), x_np.ctypes.data_as(ctypes.c_void_p), 1, ctypes.byref(st))  # H2D b (every rank), D2H x (rank 0)
+        assert rc == 0, L.soglu_last_error()
         if use_dist:
             barrier()
     for _ in range(2):
@@ -487,7 +483,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][2], "name": args.workload, "n": prob.size("dim"), "ops": prob.size("n_ops"),
                        "tasks": int(first["tasks"]), "pool_blocks": int(first["pool_blocks"]),
-                       "parallelism": "1 GPU" if world == 1 else "one factorisation sharded over %d GPUs: 2D block-cyclic (%dx%d grid, 16x16-block squares), owner computes, NVLink peer pulls; solve on rank 0" % ((world,) + sg.default_grid(world)),
+                       "parallelism": "1 GPU" if world == 1 else "one factorisation sharded over %d GPUs: 2D block-cyclic (%dx%d grid, 16x16-block squares), owner computes, NVLink peer pulls; solve sharded by block-row owner" % ((world,) + sg.default_grid(world)),
                        "segments": n_segments,   # executor launches per factorisation (pool recycling)
                        "l2": "inputs_exceed_l2 (block pool %.1f GB >> 126 MB L2)" % (first["pool_blocks"] * 34816 * 1e-9),
                        "factor_ms": t_factor * 1e3, "solve_ms": t_solve * 1e3, "factor_gflops": flops / t_factor * 1e-9,

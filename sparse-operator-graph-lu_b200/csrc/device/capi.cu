@@ -100,9 +100,14 @@ struct soglu_ctx {
     int32_t* abort_word() const { return counters.as<int32_t>() + counters0.bytes / 4; }
     int64_t opt_max_slots = 0;     // debug: cap the block pool (forces segments + slot recycling)
     // solve structures
-    DevBuf l_ptr, l_col, l_slot, l_diag, l_dinv, u_ptr, u_col, u_slot, u_diag, u_dinv, d_b, d_y, d_x;
+    DevBuf l_ptr, l_col, l_slot, l_diag, l_dinv, u_ptr, u_col, u_slot, u_diag, u_dinv, d_b;
+    // solve vectors, peer-visible in a sharded run: [y0 | x0 | y1 | x1 | r0 | r1], n_ext doubles each (two sets so that a
+    // refinement step never refills a vector a slower peer may still read)
+    DevBuf sv, my_rows;
+    int32_t n_my_rows = 0;
+    void* peer_sv[MAX_GPUS] = {};
     int64_t nL_off = 0, nU_off = 0;
-    DevBuf m_rp, m_ci, m_v, d_r, d_xacc;   // CSR of the permuted padded matrix (iterative refinement)
+    DevBuf m_rp, m_ci, m_v, d_xacc;   // CSR of the permuted padded matrix (iterative refinement)
     int64_t m_n = 0, m_nnz = 0;
     int64_t launches = 0;
     double h2d = 0, d2h = 0;
@@ -152,7 +157,8 @@ int32_t id_ref(const soglu_ctx* c, int32_t id) {
 // CSR over off-diagonal factor blocks of one triangle; lower: cols < row, upper: cols > row.
 // transpose = true builds the structure of the transposed factor (CSC of L for L^T).
 int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<int32_t>& br, const std::vector<int32_t>& bc,
-              bool upper, bool transpose, DevBuf& dptr, DevBuf& dcol, DevBuf& dslot, DevBuf& ddiag, DevBuf& ddinv, int64_t& n_off) {
+              bool upper, bool transpose, DevBuf& dptr, DevBuf& dcol, DevBuf& dslot, DevBuf& ddiag, DevBuf& ddinv, int64_t& n_off,
+              std::vector<int32_t>* diag_out = nullptr) {
     const int n = c->n_block_rows;
     std::vector<int64_t> ptr(n + 1, 0);
     std::vector<int32_t> diag(n, -1);
@@ -207,6 +213,7 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
         if (it != inv_of_ref.end()) dinv[r] = it->second;
     }
     if ((rc = upload(ddinv, dinv, c))) return rc;
+    if (diag_out) *diag_out = diag;
     return SOGLU_OK;
 }
 
@@ -358,16 +365,26 @@ int finalize(soglu_ctx* c) {
         std::vector<int64_t> pos(c->level_ptr.begin(), c->level_ptr.end() - 1);
         for (int64_t t = 0; t < nt; t++) c->level_order[pos[G.tasks[t].level]++] = (int32_t)t;
     }
-    // triangular-solve structures (the solve runs on rank 0 of a sharded run)
-    if (!follower) {
-    if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, false, false, c->l_ptr, c->l_col, c->l_slot, c->l_diag, c->l_dinv, c->nL_off))) return rc;
-    if (c->symmetric) {
-        if ((rc = build_tri(c, c->L_ids, c->L_brow, c->L_bcol, true, true, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->u_dinv, c->nU_off))) return rc;
-    } else {
-        if ((rc = build_tri(c, c->U_ids, c->U_brow, c->U_bcol, true, false, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->u_dinv, c->nU_off))) return rc;
-    }
-    const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
-    CU(c->d_b.alloc(next)); CU(c->d_y.alloc(next)); CU(c->d_x.alloc(next));
+    // triangular-solve structures, on every rank: a sharded solve gives each GPU the block rows whose diagonal block it owns
+    {
+        const soglu_ctx* fac = follower ? c->leader : c;       // the factor lists live with the group's rank 0
+        c->n_block_rows = fac->n_block_rows;
+        c->symmetric = fac->symmetric;
+        std::vector<int32_t> ldiag;
+        if ((rc = build_tri(c, fac->L_ids, fac->L_brow, fac->L_bcol, false, false, c->l_ptr, c->l_col, c->l_slot, c->l_diag, c->l_dinv, c->nL_off, &ldiag))) return rc;
+        if (c->symmetric) {
+            if ((rc = build_tri(c, fac->L_ids, fac->L_brow, fac->L_bcol, true, true, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->u_dinv, c->nU_off))) return rc;
+        } else {
+            if ((rc = build_tri(c, fac->U_ids, fac->U_brow, fac->U_bcol, true, false, c->u_ptr, c->u_col, c->u_slot, c->u_diag, c->u_dinv, c->nU_off))) return rc;
+        }
+        std::vector<int32_t> mine;
+        for (int r = 0; r < c->n_block_rows; r++)
+            if (!c->dist || (int)((uint32_t)ldiag[r] >> REF_SHIFT) == c->rank) mine.push_back(r);
+        c->n_my_rows = (int32_t)mine.size();
+        if ((rc = upload(c->my_rows, mine, c))) return rc;
+        const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
+        CU(c->d_b.alloc(next));
+        CU(c->sv.alloc(6 * next));
     }
     c->compiled = true;
     // only now are the op arrays no longer needed on the host: a failure above (pool does not fit, a factor without
@@ -420,7 +437,7 @@ int soglu_create(soglu_ctx** out, int n_gpus, const int* device_ids) {
 }
 
 // ---- multi-GPU: one process per GPU, peers mapped through CUDA IPC -------------------------------
-struct DistBlob { cudaIpcMemHandle_t pool, dep, ready, counters; int32_t rank, valid; uint64_t layout_hash; };
+struct DistBlob { cudaIpcMemHandle_t pool, dep, ready, counters, sv; int32_t rank, valid; uint64_t layout_hash; };
 
 // FNV-1a over what every rank must agree on: tasks and pool slots per GPU, segment boundaries of every GPU
 static uint64_t dist_layout_hash(const soglu_ctx* c) {
@@ -463,6 +480,7 @@ int soglu_dist_export(soglu_ctx* c, void* blob) {
         CU(cudaIpcGetMemHandle(&b.dep, c->dep.p));
         CU(cudaIpcGetMemHandle(&b.ready, c->ready.p));
         CU(cudaIpcGetMemHandle(&b.counters, c->counters.p));
+        CU(cudaIpcGetMemHandle(&b.sv, c->sv.p));
     }
     std::memcpy(blob, &b, sizeof b);
     return SOGLU_OK;
@@ -484,7 +502,7 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
     const DistBlob* bl = reinterpret_cast<const DistBlob*>(all_blobs);
     for (int g = 0; g < c->world; g++) {
         if (g == c->rank || !c->dist) {
-            c->peer_pool[g] = c->pool.p; c->peer_dep[g] = c->dep.p; c->peer_ready[g] = c->ready.p; c->peer_counters[g] = c->counters.p;
+            c->peer_pool[g] = c->pool.p; c->peer_dep[g] = c->dep.p; c->peer_ready[g] = c->ready.p; c->peer_counters[g] = c->counters.p; c->peer_sv[g] = c->sv.p;
             continue;
         }
         if (!bl[g].valid || bl[g].rank != g) return fail(SOGLU_ERR_ARG, "peer handle blob " + std::to_string(g) + " is missing or out of order");
@@ -495,6 +513,7 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
         CU(cudaIpcOpenMemHandle(&c->peer_dep[g], bl[g].dep, cudaIpcMemLazyEnablePeerAccess));
         CU(cudaIpcOpenMemHandle(&c->peer_ready[g], bl[g].ready, cudaIpcMemLazyEnablePeerAccess));
         CU(cudaIpcOpenMemHandle(&c->peer_counters[g], bl[g].counters, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&c->peer_sv[g], bl[g].sv, cudaIpcMemLazyEnablePeerAccess));
     }
     c->peers_ready = true;
     return SOGLU_OK;
@@ -562,11 +581,11 @@ void soglu_destroy(soglu_ctx* c) {
     if (c->dist && c->ipc_peers)
         for (int g = 0; g < c->world; g++) {
             if (g == c->rank) continue;
-            for (void* p : {c->peer_pool[g], c->peer_dep[g], c->peer_ready[g], c->peer_counters[g]})
+            for (void* p : {c->peer_pool[g], c->peer_dep[g], c->peer_ready[g], c->peer_counters[g], c->peer_sv[g]})
                 if (p) cudaIpcCloseMemHandle(p);
         }
     for (DevBuf* b : {&c->in_dense, &c->in_entry_input, &c->in_entry_pos, &c->in_entry_val, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
-                      &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->d_y, &c->d_x, &c->trace, &c->m_rp, &c->m_ci, &c->m_v, &c->d_r, &c->d_xacc})
+                      &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->sv, &c->my_rows, &c->trace, &c->m_rp, &c->m_ci, &c->m_v, &c->d_xacc})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -862,56 +881,96 @@ int soglu_factor(soglu_ctx* c, soglu_stats* out) {
     }
 }
 
-// one forward/back substitution on device buffers: rhs (n_ext) -> sol (n_ext)
-static int run_trsv(soglu_ctx* c, const double* d_rhs, double* d_sol) {
+// vector k of GPU g's solve buffer: 0 / 1 = y, x of set 0; 2 / 3 = y, x of set 1; 4 / 5 = r of refinement step 0 / 1
+static double* sv_vec(const soglu_ctx* c, int g, int k) {
+    char* base = (char*)(c->dist ? c->peer_sv[g] : c->sv.p);
+    return (double*)(base + (size_t)k * c->n_block_rows * BLK * sizeof(double));
+}
+
+// one forward/back substitution: rhs (n_ext, local; polled if it is a refinement residual) -> x of `set` on every GPU
+static int run_trsv(soglu_ctx* c, const double* d_rhs, bool rhs_polled, int set) {
     TrsvParams P = {};
     P.pool = c->pool.as<double>();
-    if (c->dist) { for (int g = 0; g < c->world; g++) P.pools[g] = (const double*)c->peer_pool[g]; }
-    else P.pools[0] = c->pool.as<double>();
+    P.world = c->dist ? c->world : 1;
+    P.rank = c->dist ? c->rank : 0;
+    for (int g = 0; g < P.world; g++) {
+        P.pools[g] = c->dist ? (const double*)c->peer_pool[g] : c->pool.as<double>();
+        P.y_all[g] = sv_vec(c, g, 2 * set);
+        P.x_all[g] = sv_vec(c, g, 2 * set + 1);
+    }
+    P.y = P.y_all[P.rank]; P.x = P.x_all[P.rank];
     P.l_ptr = c->l_ptr.as<int64_t>(); P.l_col = c->l_col.as<int32_t>(); P.l_slot = c->l_slot.as<int32_t>(); P.l_diag = c->l_diag.as<int32_t>();
     P.l_dinv = c->l_dinv.as<int32_t>();
     P.u_ptr = c->u_ptr.as<int64_t>(); P.u_col = c->u_col.as<int32_t>(); P.u_slot = c->u_slot.as<int32_t>(); P.u_diag = c->u_diag.as<int32_t>();
     P.u_dinv = c->u_dinv.as<int32_t>();
     P.n_rows = c->n_block_rows;
-    P.b = d_rhs; P.y = c->d_y.as<double>(); P.x = d_sol;
+    P.my_rows = c->my_rows.as<int32_t>(); P.n_my_rows = c->n_my_rows;
+    P.b = d_rhs; P.b_polled = rhs_polled ? 1 : 0;
     P.symmetric = c->symmetric;
     P.abort = c->abort_word();
     P.watchdog_ns = (unsigned long long)std::max<int64_t>(0, c->opt_watchdog_ms) * 1000000ull;
-    CU(launch_trsv(P, std::min(c->trsv_grid, c->n_block_rows), c->stream));
-    c->launches += 2;   // sentinel fill + solve kernel
+    if (c->n_my_rows > 0) {
+        CU(launch_trsv(P, std::min(c->trsv_grid, (int)c->n_my_rows), c->stream));
+        c->launches++;
+    }
     return SOGLU_OK;
 }
 
-static int solve_impl(soglu_ctx* c, const double* b_ext, double* x_ext, int refine, soglu_stats* out) {
-    if (!c || !b_ext || !x_ext) return fail(SOGLU_ERR_ARG, "bad argument");
-    if (!c->members.empty()) return solve_impl(c->members[0], b_ext, x_ext, refine, out);   // rank 0 solves over peer memory
+// Enqueue solve + `refine` refinement steps on the context's stream.  Sharded: EVERY rank calls this with the same b and
+// the same `refine` (a collective, like soglu_factor); each GPU solves its block rows, rank 0 forms the residuals
+// (soglu_set_matrix is only needed there) and holds the answer.
+static int solve_launch(soglu_ctx* c, const double* b_ext, int refine) {
     if (!c->factored) return fail(SOGLU_ERR_ARG, "soglu_factor must precede soglu_solve");
-    if (c->dist && c->rank != 0) return fail(SOGLU_ERR_ARG, "multi-GPU context: the triangular solve runs on rank 0 (it reads the peers' factor blocks over NVLink)");
-    if (refine > 0 && c->m_n == 0) return fail(SOGLU_ERR_ARG, "iterative refinement needs the matrix: call soglu_set_matrix first");
+    const bool lead = !c->dist || c->rank == 0;
+    if (refine > 0 && lead && c->m_n == 0) return fail(SOGLU_ERR_ARG, "iterative refinement needs the matrix: call soglu_set_matrix first");
+    if (refine > 1 && c->dist) return fail(SOGLU_ERR_ARG, "a sharded solve supports at most one refinement step");
     CU(cudaSetDevice(c->device));
-    const int64_t launches0 = c->launches;
     const int64_t n = (int64_t)c->n_block_rows * BLK;
     const size_t next = (size_t)n * sizeof(double);
     CU(cudaMemcpyAsync(c->d_b.p, b_ext, next, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev0, c->stream));
-    int rc = run_trsv(c, c->d_b.as<double>(), c->d_x.as<double>());
+    // every vector of this call starts as "not yet computed" BEFORE the first kernel: a peer's residual / segments may
+    // arrive any time after this GPU's first solve kernel has started
+    CU(launch_fill_sentinel(c->sv.as<double>(), (refine > 0 ? 6 : 2) * n, c->stream));
+    c->launches++;
+    int rc = run_trsv(c, c->d_b.as<double>(), false, 0);
     if (rc) return rc;
-    if (refine > 0) {
-        // x_acc = x; repeat: r = b - A x_acc; solve A d = r; x_acc += d   (all FP64, on the device)
-        if (!c->d_r.p) { CU(c->d_r.alloc(next)); CU(c->d_xacc.alloc(next)); }
-        CU(cudaMemcpyAsync(c->d_xacc.p, c->d_x.p, next, cudaMemcpyDeviceToDevice, c->stream));
-        for (int it = 0; it < refine; it++) {
-            CU(launch_residual(c->m_rp.as<int64_t>(), c->m_ci.as<int32_t>(), c->m_v.as<double>(), c->d_b.as<double>(), c->d_xacc.as<double>(),
-                               c->d_r.as<double>(), n, c->stream));
-            if ((rc = run_trsv(c, c->d_r.as<double>(), c->d_x.as<double>()))) return rc;
-            CU(launch_axpy(c->d_xacc.as<double>(), c->d_x.as<double>(), n, c->stream));
-            c->launches += 2;
+    int set = 0;
+    for (int it = 0; it < refine; it++) {
+        // x_acc = x; r = b - A x_acc (rank 0, written into every GPU's r); solve A d = r; x_acc += d   (all FP64, on the device)
+        double* r_mine = sv_vec(c, c->dist ? c->rank : 0, 4 + (it & 1));
+        if (lead) {
+            if (!c->d_xacc.p) CU(c->d_xacc.alloc(next));
+            if (it == 0) CU(cudaMemcpyAsync(c->d_xacc.p, sv_vec(c, c->dist ? c->rank : 0, 1), next, cudaMemcpyDeviceToDevice, c->stream));
+            double* r_all[MAX_GPUS];
+            const int world = c->dist ? c->world : 1;
+            for (int g = 0; g < world; g++) r_all[g] = sv_vec(c, g, 4 + (it & 1));
+            CU(launch_residual(c->m_rp.as<int64_t>(), c->m_ci.as<int32_t>(), c->m_v.as<double>(), c->d_b.as<double>(), c->d_xacc.as<double>(), r_all, world, n, c->stream));
+            c->launches++;
+        }
+        set ^= 1;
+        if (it >= 1) {      // (single GPU only) the set and the r vector of two steps ago are reused: same stream, so refilling is safe
+            CU(launch_fill_sentinel(sv_vec(c, 0, 2 * set), 2 * n, c->stream));
+        }
+        if ((rc = run_trsv(c, r_mine, true, set))) return rc;
+        if (lead) {
+            CU(launch_axpy(c->d_xacc.as<double>(), sv_vec(c, c->dist ? c->rank : 0, 2 * set + 1), n, c->stream));
+            c->launches++;
+            if (it + 2 < refine) CU(launch_fill_sentinel(sv_vec(c, 0, 4 + (it & 1)), n, c->stream));   // r of this step, reused at it + 2
         }
     }
     CU(cudaEventRecord(c->ev1, c->stream));
-    CU(cudaMemcpyAsync(x_ext, refine > 0 ? c->d_xacc.p : c->d_x.p, next, cudaMemcpyDeviceToHost, c->stream));
+    return SOGLU_OK;
+}
+
+static int solve_finish(soglu_ctx* c, double* x_ext, int refine, int64_t launches0, soglu_stats* out) {
+    CU(cudaSetDevice(c->device));
+    const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
+    const bool lead = !c->dist || c->rank == 0;
+    if (lead && x_ext) CU(cudaMemcpyAsync(x_ext, refine > 0 ? c->d_xacc.p : (void*)sv_vec(c, c->dist ? c->rank : 0, 1), next, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if ((rc = check_watchdog(c, "solve"))) return rc;
+    int rc = check_watchdog(c, "solve");
+    if (rc) return rc;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->h2d += (double)next;
@@ -929,6 +988,29 @@ static int solve_impl(soglu_ctx* c, const double* b_ext, double* x_ext, int refi
         out->d2h_bytes = (double)next;
     }
     return SOGLU_OK;
+}
+
+static int solve_impl(soglu_ctx* c, const double* b_ext, double* x_ext, int refine, soglu_stats* out) {
+    if (!c || !b_ext) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (!c->members.empty()) {
+        // in-process group: launch on every GPU, then collect; rank 0 holds x
+        if (!x_ext) return fail(SOGLU_ERR_ARG, "bad argument");
+        std::vector<int64_t> l0;
+        for (soglu_ctx* m : c->members) { l0.push_back(m->launches); int rc = solve_launch(m, b_ext, refine); if (rc) return rc; }
+        int first_err = 0;
+        std::string first_msg;
+        for (size_t g = c->members.size(); g-- > 0;) {       // rank 0 last: its stats are the ones reported
+            int rc = solve_finish(c->members[g], g == 0 ? x_ext : nullptr, refine, l0[g], g == 0 ? out : nullptr);
+            if (rc && !first_err) { first_err = rc; first_msg = soglu_last_error(); }
+        }
+        return first_err ? fail(first_err, first_msg) : SOGLU_OK;
+    }
+    if (!x_ext && (!c->dist || c->rank == 0)) return fail(SOGLU_ERR_ARG, "bad argument");
+    if (c->dist && !c->peers_ready) return fail(SOGLU_ERR_ARG, "multi-GPU context: exchange peer handles first (soglu_dist_export / soglu_dist_import)");
+    const int64_t launches0 = c->launches;
+    int rc = solve_launch(c, b_ext, refine);
+    if (rc) return rc;
+    return solve_finish(c, x_ext, refine, launches0, out);
 }
 
 static int solve_guarded(soglu_ctx* c, const double* b_ext, double* x_ext, int refine, soglu_stats* out) {
@@ -1109,7 +1191,7 @@ static int group_factor(soglu_ctx* grp, soglu_stats* out) {
     if (!M[0]->peers_ready)
         for (soglu_ctx* m : M) {
             for (size_t g = 0; g < M.size(); g++) {
-                m->peer_pool[g] = M[g]->pool.p; m->peer_dep[g] = M[g]->dep.p; m->peer_ready[g] = M[g]->ready.p; m->peer_counters[g] = M[g]->counters.p;
+                m->peer_pool[g] = M[g]->pool.p; m->peer_dep[g] = M[g]->dep.p; m->peer_ready[g] = M[g]->ready.p; m->peer_counters[g] = M[g]->counters.p; m->peer_sv[g] = M[g]->sv.p;
             }
             m->peers_ready = true;
         }

@@ -46,6 +46,9 @@ cudaError_t launch_scatter_entries(double* pool, const int32_t* slots, int64_t n
 cudaError_t launch_unpack_block(const double* pool, int32_t slot, double* dense, cudaStream_t stream);
 
 // ---- block triangular solve -----------------------------------------------------------
+// Sharded run: every GPU processes the block rows whose diagonal block it owns (my_rows), reads the factor blocks of
+// those rows (its own, or a peer's over NVLink) and publishes each finished 64-value segment into EVERY GPU's copy of
+// y / x, so consumers always poll local memory.
 struct TrsvParams {
     const double* pools[MAX_GPUS];   // factor blocks may live on peer GPUs (references as in ExecParams)
     const double* pool;
@@ -53,18 +56,25 @@ struct TrsvParams {
     const int64_t* l_ptr; const int32_t* l_col; const int32_t* l_slot; const int32_t* l_diag; const int32_t* l_dinv;
     const int64_t* u_ptr; const int32_t* u_col; const int32_t* u_slot; const int32_t* u_diag; const int32_t* u_dinv;
     int32_t n_rows;        // block rows
-    const double* b;       // n_rows*64
-    double* y;             // forward result  (pre-filled with the NaN sentinel by launch_trsv)
+    const int32_t* my_rows;   // the block rows this GPU processes, ascending (all of them on one GPU)
+    int32_t n_my_rows;
+    int32_t world, rank;
+    const double* b;       // n_rows*64: right-hand side (local copy)
+    int32_t b_polled;      // b arrives through the sentinel protocol (the refinement's residual, written by rank 0)
+    double* y;             // forward result, this GPU's copy (pre-filled with the NaN sentinel)
     double* x;             // backward result (idem)
+    double* y_all[MAX_GPUS];   // every GPU's copy: a finished segment is stored into all of them
+    double* x_all[MAX_GPUS];
     int32_t symmetric;     // U = L^T: backward sweep reads L blocks transposed (CSC of L passed in u_*)
     int32_t* abort;        // watchdog word (as in ExecParams): a consumer that has polled for watchdog_ns raises it
     unsigned long long watchdog_ns;
 };
 cudaError_t launch_trsv(const TrsvParams& p, int grid, cudaStream_t stream);
 int trsv_max_grid(int device);
-// iterative refinement: r = b - A x (CSR of the permuted padded system), x += d
-cudaError_t launch_residual(const int64_t* rp, const int32_t* ci, const double* v, const double* b, const double* x, double* r, int64_t n,
-                            cudaStream_t stream);
+cudaError_t launch_fill_sentinel(double* a, int64_t n, cudaStream_t stream);
+// iterative refinement: r = b - A x (CSR of the permuted padded system), written into every GPU's copy of r; x += d
+cudaError_t launch_residual(const int64_t* rp, const int32_t* ci, const double* v, const double* b, const double* x, double* const* r_all, int world,
+                            int64_t n, cudaStream_t stream);
 cudaError_t launch_axpy(double* x, const double* d, int64_t n, cudaStream_t stream);
 
 }  // namespace soglu

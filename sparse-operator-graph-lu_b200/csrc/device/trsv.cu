@@ -55,10 +55,17 @@ __device__ __forceinline__ double poll_value(const TrsvParams& P, const double* 
     }
     return __longlong_as_double((long long)v);
 }
-__device__ __forceinline__ void publish_value(double* p, double x) {
+__device__ __forceinline__ void store_value(double* p, double x) {
     unsigned long long v = (unsigned long long)__double_as_longlong(x);
     if (v == SENTINEL) v = 0x7FF8000000000000ull;   // never publish the sentinel itself
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// a finished value goes into every GPU's copy of the vector (8-byte stores are single-copy atomic over NVLink too);
+// the local copy last, so that a local consumer never runs ahead of what the peers can see by more than the link latency
+__device__ __forceinline__ void publish_value(const TrsvParams& P, double* const* all, size_t idx, double x) {
+    for (int g = 0; g < P.world; g++)
+        if (g != P.rank) store_value(all[g] + idx, x);
+    store_value(all[P.rank] + idx, x);
 }
 
 __device__ __forceinline__ const double* blk_ptr(const TrsvParams& P, int32_t ref) {
@@ -125,7 +132,7 @@ __device__ __forceinline__ double quad_sum(double s) {
 template <bool UPPER, bool TRANS>
 __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restrict__ ptr, const int32_t* __restrict__ col,
                           const int32_t* __restrict__ slot, const int32_t* __restrict__ diag, const int32_t* __restrict__ dinv,
-                          const double* __restrict__ rhs, bool rhs_is_computed, double* __restrict__ sol, TrsvSmem& S,
+                          const double* __restrict__ rhs, bool rhs_is_computed, const double* __restrict__ sol, double* const* sol_all, TrsvSmem& S,
                           uint32_t& phase, uint32_t& ring_phase, int tid) {
     const int64_t b = ptr[row], e = ptr[row + 1];
     const int nb = (int)(e - b);
@@ -180,7 +187,7 @@ __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restric
     if (inv_slot != 0) {
         // x = D^-1 t with the explicit inverse (a GEMV instead of a 64-step substitution)
         const double s = quad_sum(gemv_part_smem<TRANS>(S.diag, S.t, rrow, part));
-        if (part == 0) publish_value(sol + (size_t)row * BLK + rrow, s);
+        if (part == 0) publish_value(P, sol_all, (size_t)row * BLK + rrow, s);
     } else if (tid < 32) {
         // substitution with the stored diagonal (lowerSolver / upperSolver, BlockPlanner.cpp:757, 821)
         const int lane = tid;
@@ -203,8 +210,8 @@ __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restric
                 if (lane + 32 < k) r1 -= (TRANS ? D[k * BLK_LD + lane + 32] : D[(lane + 32) * BLK_LD + k]) * xk;
             }
         }
-        publish_value(sol + (size_t)row * BLK + lane, r0);
-        publish_value(sol + (size_t)row * BLK + lane + 32, r1);
+        publish_value(P, sol_all, (size_t)row * BLK + lane, r0);
+        publish_value(P, sol_all, (size_t)row * BLK + lane + 32, r1);
     }
     __syncthreads();
 }
@@ -221,35 +228,33 @@ __global__ void __launch_bounds__(TR_THREADS) trsv_kernel(TrsvParams P) {
     }
     __syncthreads();
     uint32_t phase = 0, ring_phase = 0;
-    // forward sweep: L y = b
-    for (int row = blockIdx.x; row < P.n_rows; row += G)
-        solve_row<false, false>(P, row, P.l_ptr, P.l_col, P.l_slot, P.l_diag, P.l_dinv, P.b, false, P.y, S, phase, ring_phase, tid);
+    // forward sweep: L y = b, over the block rows this GPU owns
+    for (int k = blockIdx.x; k < P.n_my_rows; k += G)
+        solve_row<false, false>(P, P.my_rows[k], P.l_ptr, P.l_col, P.l_slot, P.l_diag, P.l_dinv, P.b, P.b_polled != 0, P.y, P.y_all, S, phase, ring_phase, tid);
     // backward sweep: U x = y (or L^T x = y); its right-hand side is the forward result
-    for (int r = blockIdx.x; r < P.n_rows; r += G) {
-        const int row = P.n_rows - 1 - r;
+    for (int k = blockIdx.x; k < P.n_my_rows; k += G) {
+        const int row = P.my_rows[P.n_my_rows - 1 - k];
         if (P.symmetric)
-            solve_row<true, true>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, ring_phase, tid);
+            solve_row<true, true>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, P.x_all, S, phase, ring_phase, tid);
         else
-            solve_row<true, false>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, S, phase, ring_phase, tid);
+            solve_row<true, false>(P, row, P.u_ptr, P.u_col, P.u_slot, P.u_diag, P.u_dinv, P.y, true, P.x, P.x_all, S, phase, ring_phase, tid);
     }
 }
 
-__global__ void fill_sentinel_kernel(double* __restrict__ a, double* __restrict__ b, int64_t n) {
+__global__ void fill_sentinel_kernel(double* __restrict__ a, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        reinterpret_cast<unsigned long long*>(a)[i] = SENTINEL;
-        reinterpret_cast<unsigned long long*>(b)[i] = SENTINEL;
-    }
+    if (i < n) reinterpret_cast<unsigned long long*>(a)[i] = SENTINEL;
 }
 
 // ---- iterative refinement helpers: r = b - A x on the permuted, padded system (CSR), x += d ------
+struct RAll { double* p[MAX_GPUS]; };
 __global__ void residual_kernel(const int64_t* __restrict__ rp, const int32_t* __restrict__ ci, const double* __restrict__ v,
-                                const double* __restrict__ b, const double* __restrict__ x, double* __restrict__ r, int64_t n) {
+                                const double* __restrict__ b, const double* __restrict__ x, RAll r_all, int world, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s = b[i];
     for (int64_t k = rp[i]; k < rp[i + 1]; k++) s = fma(-v[k], x[ci[k]], s);
-    r[i] = s;
+    for (int g = 0; g < world; g++) store_value(r_all.p[g] + i, s);     // the peers' solve polls its copy (sentinel protocol)
 }
 __global__ void axpy_kernel(double* __restrict__ x, const double* __restrict__ d, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,9 +263,15 @@ __global__ void axpy_kernel(double* __restrict__ x, const double* __restrict__ d
 
 }  // namespace
 
-cudaError_t launch_residual(const int64_t* rp, const int32_t* ci, const double* v, const double* b, const double* x, double* r, int64_t n,
-                            cudaStream_t stream) {
-    residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rp, ci, v, b, x, r, n);
+cudaError_t launch_residual(const int64_t* rp, const int32_t* ci, const double* v, const double* b, const double* x, double* const* r_all, int world,
+                            int64_t n, cudaStream_t stream) {
+    RAll ra = {};
+    for (int g = 0; g < world; g++) ra.p[g] = r_all[g];
+    residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rp, ci, v, b, x, ra, world, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_sentinel(double* a, int64_t n, cudaStream_t stream) {
+    fill_sentinel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, n);
     return cudaGetLastError();
 }
 cudaError_t launch_axpy(double* x, const double* d, int64_t n, cudaStream_t stream) {
@@ -278,10 +289,6 @@ int trsv_max_grid(int device) {
 
 cudaError_t launch_trsv(const TrsvParams& p, int grid, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsvSmem));
-    if (e != cudaSuccess) return e;
-    const int64_t n = (int64_t)p.n_rows * BLK;
-    fill_sentinel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p.y, p.x, n);
-    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     TrsvParams pp = p;
     void* args[] = {&pp};

@@ -1,4 +1,4 @@
-"""One rank of a multi-GPU factorisation (torchrun, NCCL): sharded factor, solve on rank 0,
+"""One rank of a multi-GPU factorisation (torchrun, NCCL): sharded factor, sharded solve (x on rank 0),
 comparison with a single-GPU run of the same problem on rank 0.  Prints one JSON line on rank 0."""
 import json
 import os
@@ -51,8 +51,7 @@ def run(kind, dims, steps=2):
         t0 = time.perf_counter()
         fs = ctx.factor_dist(barrier)
         times.append(time.perf_counter() - t0)
-        if rank == 0:
-            x, ss = ctx.solve(p)
+        x, ss = ctx.solve(p)        # collective: every GPU solves the block rows it owns, rank 0 holds x
         dist.barrier()
     tt = torch.tensor([min(times)], dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)

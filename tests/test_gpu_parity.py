@@ -146,6 +146,27 @@ def test_solve_cli(sg, tmp_path):
     assert _rel(np.array(xs), g["x"]) <= TOL_X
 
 
+@pytest.mark.parametrize("name", ["lap3d_24", "nine2d_40", "banded_3000", "lap2d_64_sym"])
+def test_reference_side_adapter(sg, tmp_path, name):
+    """The boundary seen from the reference: oracle/_ref/ref_adapter is the UNMODIFIED reference (reader, GPS ordering,
+    both planner passes, iniBlockStorage, result un-permutation) linked with oracle/soglu_adapter.cpp -- the binding of
+    INTEGRATION.md section 2 -- so that BlockPlanner::calculate / ::solve (solver.cpp:106, 115) run in libsoglu_b200.so
+    through the array ABI (dense 64x64 input blocks, op list from data::graph, factor leaves from the quadtrees).
+    Its x must be the reference's own x (golden vector)."""
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_adapter")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_adapter not built (needs the reference sources at build time)")
+    g = load_golden(name)
+    path = write_case_mtx(name, tmp_path)
+    out = str(tmp_path / "x.f64")
+    r = subprocess.run([exe, path, out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ADAPTER factor_s" in r.stdout and "ADAPTER solve_s" in r.stdout
+    x = np.fromfile(out)
+    assert _rel(x, g["x"]) <= TOL_X
+
+
 def test_solve_lu_dropin(sg):
     import gen_mtx
     n, r, c, v = gen_mtx.generate("lap2d", 40, 33)
