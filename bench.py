@@ -322,6 +322,7 @@ def main():
     ap.add_argument("--workload", default="lap3d_100", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", default="lap3d_64", choices=sorted(WORKLOADS), help="workload the CPU reference is timed on (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="after the timed region: one traced factorisation, per-rank SM utilisation over time on stderr (diagnostics)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="executor option passed to soglu_set_option before the first factorisation (chain_cuts, split_slack, dist_nb, ...); recorded in config.options")
     args = ap.parse_args()
@@ -443,6 +444,29 @@ def main():
         x_e2e = x_np[prob.i32("perm_old2new")]
         assert np.array_equal(x_e2e, x), "end-to-end path produced a different solution"
 
+    if args.trace:
+        # one traced factorisation (last segment of a multi-segment run): busy share of the CTAs over time, per rank
+        ctx.set_option("trace", 1)
+        fs_t = factor()
+        ctx.set_option("trace", 0)
+        nb = 20
+        outb = np.zeros(8 + nb)
+        L.soglu_debug_trace_summary.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        rc = L.soglu_debug_trace_summary(ctx.h, nb, outb.ctypes.data_as(ctypes.c_void_p))
+        msg = "rank %d: trace failed" % rank
+        if rc == 0 and outb[1] > 0:
+            util = outb[8:] / (outb[1] / nb * outb[5])
+            msg = "rank %d: traced launch %.1f ms (events %.1f ms), %d tasks, math busy %.0f%% of CTA time, operand wait %.0f%%; busy per 5%% of the time: %s" % (
+                rank, outb[1] * 1e-6, fs_t["seconds"] * 1e3, int(outb[0]), 100 * outb[3] / (outb[1] * outb[5]), 100 * outb[2] / (outb[1] * outb[5]),
+                " ".join("%2.0f" % (100 * u) for u in util))
+        if use_dist:
+            msgs = [None] * world
+            dist.all_gather_object(msgs, msg)
+        else:
+            msgs = [msg]
+        if rank == 0:
+            sys.stderr.write("\n".join(msgs) + "\n")
+        barrier()
     if rank == 0:
         peak, peak_how = measure_fp64_peak()
         t_factor = t_factor_all

@@ -103,8 +103,9 @@ struct soglu_ctx {
     DevBuf l_ptr, l_col, l_slot, l_diag, l_dinv, u_ptr, u_col, u_slot, u_diag, u_dinv, d_b;
     // solve vectors, peer-visible in a sharded run: [y0 | x0 | y1 | x1 | r0 | r1], n_ext doubles each (two sets so that a
     // refinement step never refills a vector a slower peer may still read)
-    DevBuf sv, my_rows;
+    DevBuf sv, my_rows;       // (sv: + 64 bytes of epoch slots for the device-side barrier of the sharded solve)
     int32_t n_my_rows = 0;
+    int32_t solve_epoch = 0;  // collective solves so far (the ranks call in lockstep)
     void* peer_sv[MAX_GPUS] = {};
     int64_t nL_off = 0, nU_off = 0;
     DevBuf m_rp, m_ci, m_v, d_xacc;   // CSR of the permuted padded matrix (iterative refinement)
@@ -134,6 +135,8 @@ int check_watchdog(soglu_ctx* c, const char* what) {
     cudaMemset(c->abort_word(), 0, 64);
     char m[320];
     if (w[0] == 2) snprintf(m, sizeof m, "%s aborted: a peer GPU's watchdog gave up (see its error)", what);
+    else if (w[1] < 0) snprintf(m, sizeof m, "%s aborted by the watchdog after %lld ms: GPU %d never reached the collective call (every rank of a sharded run must call it)", what,
+                                (long long)c->opt_watchdog_ms, -1 - w[1]);
     else snprintf(m, sizeof m, "%s aborted by the watchdog after %lld ms without progress: CTA %d was waiting for %s %d%s", what, (long long)c->opt_watchdog_ms,
                   w[2], c->factored && what[0] == 's' ? "block row" : "ready-queue slot", w[1],
                   " (a lost dependency signal: a peer that failed, or an operation list with a missing edge)");
@@ -384,7 +387,8 @@ int finalize(soglu_ctx* c) {
         if ((rc = upload(c->my_rows, mine, c))) return rc;
         const size_t next = (size_t)c->n_block_rows * BLK * sizeof(double);
         CU(c->d_b.alloc(next));
-        CU(c->sv.alloc(6 * next));
+        CU(c->sv.alloc(6 * next + 64));
+        CU(cudaMemsetAsync(c->sv.as<char>() + 6 * next, 0, 64, c->stream));
     }
     c->compiled = true;
     // only now are the op arrays no longer needed on the host: a failure above (pool does not fit, a factor without
@@ -777,7 +781,7 @@ static int factor_launch(soglu_ctx* c) {
     if (c->dist) for (int g = 0; g < c->world; g++) P.aborts[g] = (int32_t*)c->peer_counters[g] + c->counters0.bytes / 4;
     if (c->opt_trace && nt > 0) {
         if (!c->trace.p) CU(c->trace.alloc((size_t)nt * 6 * sizeof(unsigned long long)));
-        CU(cudaMemsetAsync(c->trace.p, 0, (size_t)nt * 6 * sizeof(unsigned long long), c->stream));
+        if (!c->dist || c->dist_segment == 0) CU(cudaMemsetAsync(c->trace.p, 0, (size_t)nt * 6 * sizeof(unsigned long long), c->stream));   // (all segments of one factorisation)
         P.trace = c->trace.as<unsigned long long>();
     }
     // queue pointers of one segment (this GPU and, sharded, the peers' queues of the same segment)
@@ -933,6 +937,14 @@ static int solve_launch(soglu_ctx* c, const double* b_ext, int refine) {
     // arrive any time after this GPU's first solve kernel has started
     CU(launch_fill_sentinel(c->sv.as<double>(), (refine > 0 ? 6 : 2) * n, c->stream));
     c->launches++;
+    if (c->dist) {
+        // ... and no GPU publishes into a peer's vectors before that peer has filled them: device-side barrier
+        int32_t* flags_all[MAX_GPUS];
+        for (int g = 0; g < c->world; g++) flags_all[g] = (int32_t*)((char*)c->peer_sv[g] + 6 * next);
+        CU(launch_peer_epoch(flags_all, c->world, c->rank, ++c->solve_epoch, c->abort_word(),
+                             (unsigned long long)std::max<int64_t>(0, c->opt_watchdog_ms) * 1000000ull, c->stream));
+        c->launches++;
+    }
     int rc = run_trsv(c, c->d_b.as<double>(), false, 0);
     if (rc) return rc;
     int set = 0;
@@ -1096,6 +1108,46 @@ int64_t soglu_debug_trace(soglu_ctx* c, unsigned long long* trace_out, int32_t* 
         if (succ_ptr_out) succ_ptr_out[nt] = (int32_t)pos;
     }
     return nt;
+}
+
+// debug: utilisation profile of the last traced factorisation on THIS GPU (works per rank of a sharded run; the idle
+// time between the segments of a recycled pool is part of the makespan).  out[0] = tasks with a trace, out[1] = makespan (ns, first claim to last signal), out[2..4] = summed ns
+// of operand wait (claimed -> loaded), math (loaded -> computed), release (computed -> signalled), out[5] = CTAs,
+// out[8 + b] = busy CTA-ns (loaded -> computed) in time bin b of nbins equal bins over the makespan.
+int soglu_debug_trace_summary(soglu_ctx* c, int nbins, double* out) {
+    if (!c || !out || nbins < 1 || !c->compiled || !c->trace.p) return fail(SOGLU_ERR_ARG, "no trace (set option trace = 1 before soglu_factor)");
+    if (!c->members.empty()) return fail(SOGLU_ERR_ARG, "ask the members (one process per GPU)");
+    const int64_t nt = (int64_t)(c->dist ? c->D.tasks.size() : c->Gp->tasks.size());
+    std::vector<unsigned long long> tr((size_t)nt * 6);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpy(tr.data(), c->trace.p, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull, t1 = 0;
+    int64_t seen = 0;
+    for (int64_t t = 0; t < nt; t++) {
+        const unsigned long long* r = &tr[6 * t];
+        if (r[1] == 0 || r[3] == 0) continue;
+        seen++;
+        t0 = std::min(t0, r[1]);
+        t1 = std::max(t1, std::max(r[3], r[4]));
+    }
+    for (int k = 0; k < 8 + nbins; k++) out[k] = 0;
+    out[0] = (double)seen;
+    if (!seen) return SOGLU_OK;
+    const double span = (double)(t1 - t0), bw = span / nbins;
+    out[1] = span;
+    for (int64_t t = 0; t < nt; t++) {
+        const unsigned long long* r = &tr[6 * t];
+        if (r[1] == 0 || r[3] == 0) continue;
+        out[2] += (double)(r[2] - r[1]);
+        out[3] += (double)(r[3] - r[2]);
+        if (r[4] > r[3]) out[4] += (double)(r[4] - r[3]);
+        double a = (double)(r[2] - t0), b = (double)(r[3] - t0);
+        for (int k = std::max(0, (int)(a / bw)); k < nbins && k * bw < b; k++) out[8 + k] += std::min(b, (k + 1) * bw) - std::max(a, k * bw);
+    }
+    int grid = c->exec_grid;
+    if (c->opt_grid > 0 && c->opt_grid < grid) grid = (int)c->opt_grid;
+    out[5] = grid;
+    return SOGLU_OK;
 }
 
 int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {

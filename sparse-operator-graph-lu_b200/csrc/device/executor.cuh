@@ -72,6 +72,8 @@ struct TrsvParams {
 cudaError_t launch_trsv(const TrsvParams& p, int grid, cudaStream_t stream);
 int trsv_max_grid(int device);
 cudaError_t launch_fill_sentinel(double* a, int64_t n, cudaStream_t stream);
+// device-side barrier across the GPUs of a sharded solve (flags_all[g] = GPU g's array of world epoch slots)
+cudaError_t launch_peer_epoch(int32_t* const* flags_all, int world, int rank, int32_t epoch, int32_t* abort, unsigned long long watchdog_ns, cudaStream_t stream);
 // iterative refinement: r = b - A x (CSR of the permuted padded system), written into every GPU's copy of r; x += d
 cudaError_t launch_residual(const int64_t* rp, const int32_t* ci, const double* v, const double* b, const double* x, double* const* r_all, int world,
                             int64_t n, cudaStream_t stream);

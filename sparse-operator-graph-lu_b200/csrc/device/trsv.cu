@@ -216,7 +216,7 @@ __device__ void solve_row(const TrsvParams& P, int row, const int64_t* __restric
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TR_THREADS) trsv_kernel(TrsvParams P) {
+__global__ void __launch_bounds__(TR_THREADS) trsv_kernel(const __grid_constant__ TrsvParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TrsvSmem& S = *reinterpret_cast<TrsvSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -246,6 +246,31 @@ __global__ void fill_sentinel_kernel(double* __restrict__ a, int64_t n) {
     if (i < n) reinterpret_cast<unsigned long long*>(a)[i] = SENTINEL;
 }
 
+// Barrier across the GPUs of a sharded solve, on the device: every rank stores `epoch` into its slot of every peer's
+// flag array and waits until all slots of its own array carry it.  It runs between the sentinel fill and the solve
+// kernel: no GPU may publish a segment into a peer's vectors before that peer has filled them (the fill would wipe it
+// and the peer would wait for ever -- which is how the watchdog found this).
+struct FlagsAll { int32_t* p[MAX_GPUS]; };
+__global__ void peer_epoch_kernel(FlagsAll f, int world, int rank, int32_t epoch, int32_t* abort, unsigned long long watchdog_ns) {
+    const int g = threadIdx.x;
+    if (g >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f.p[g] + rank), "r"(epoch) : "memory");
+    unsigned long long t0, now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    int32_t v;
+    uint32_t polls = 0;
+    while (true) {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f.p[rank] + g) : "memory");
+        if (v >= epoch) break;
+        if ((++polls & 1023u) == 0) {
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (*reinterpret_cast<volatile int32_t*>(abort) != 0) break;
+            if (watchdog_ns && now - t0 > watchdog_ns) { if (atomicCAS(abort, 0, 1) == 0) { abort[1] = -1 - g; abort[2] = 0; } break; }
+        }
+    }
+}
+
 // ---- iterative refinement helpers: r = b - A x on the permuted, padded system (CSR), x += d ------
 struct RAll { double* p[MAX_GPUS]; };
 __global__ void residual_kernel(const int64_t* __restrict__ rp, const int32_t* __restrict__ ci, const double* __restrict__ v,
@@ -268,6 +293,12 @@ cudaError_t launch_residual(const int64_t* rp, const int32_t* ci, const double* 
     RAll ra = {};
     for (int g = 0; g < world; g++) ra.p[g] = r_all[g];
     residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rp, ci, v, b, x, ra, world, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_peer_epoch(int32_t* const* flags_all, int world, int rank, int32_t epoch, int32_t* abort, unsigned long long watchdog_ns, cudaStream_t stream) {
+    FlagsAll f = {};
+    for (int g = 0; g < world; g++) f.p[g] = flags_all[g];
+    peer_epoch_kernel<<<1, 32, 0, stream>>>(f, world, rank, epoch, abort, watchdog_ns);
     return cudaGetLastError();
 }
 cudaError_t launch_fill_sentinel(double* a, int64_t n, cudaStream_t stream) {

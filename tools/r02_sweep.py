@@ -11,9 +11,8 @@ import gen_mtx
 import soglu_b200 as sg
 
 VARIANTS = [
-    ("default (split_slack=100)", {}),
-    ("split_slack=0", {"split_slack": 0}),
-    ("chain_cuts=200", {"chain_cuts": 200}),
+    ("default", {}),
+    ("lazy_claim=0", {"lazy_claim": 0}),
 ]
 
 kind, dims = sys.argv[1], [int(a) for a in sys.argv[2:]]

@@ -59,12 +59,17 @@ def main():
         cat["publish-gap"] += max(0.0, pub[b] - sig[a]) if pub[b] > 0 else 0.0
     for c in chain:
         cat["q-wait"] += clm[c] - pub[c]; cat["load"] += lod[c] - clm[c]; cat["compute"] += cmp_[c] - lod[c]; cat["signal"] += sig[c] - cmp_[c]
-        nm = TYPES[info[c, 0]]; d = bytype.setdefault(nm, [0, 0.0, 0.0]); d[0] += 1; d[1] += sig[c] - pub[c]; d[2] += cmp_[c] - lod[c]
+        nm = TYPES[info[c, 0]]; d = bytype.setdefault(nm, [0, 0.0, 0.0, 0]); d[0] += 1; d[1] += sig[c] - pub[c]; d[2] += cmp_[c] - lod[c]; d[3] += int(info[c, 1])
     print("critical chain: %d tasks, spans %.3f ms of %.3f ms" % (len(chain), (sig[chain[-1]] - clm[chain[0]]) * 1e-3, total * 1e-3))
     print("  by phase (ms):", {k: round(v * 1e-3, 3) for k, v in cat.items()})
-    print("  by type: ", {k: (v[0], "%.2f us/task total" % (v[1] / v[0]), "%.2f us compute" % (v[2] / v[0])) for k, v in bytype.items()})
+    print("  by type: ", {k: (v[0], "%.2f us/task total" % (v[1] / v[0]), "%.2f us compute" % (v[2] / v[0]), "%.1f pairs/task" % (v[3] / v[0])) for k, v in bytype.items()})
+    # distribution of the chain's GEMM tasks by accumulation-chain length
+    gl = np.array([info[c, 1] for c in chain if info[c, 0] == 0])
+    if len(gl):
+        print("  chain GEMM tasks by pairs: " + ", ".join("%s: %d" % (lab, int(((gl >= lo) & (gl < hi)).sum())) for lab, lo, hi in (("1", 1, 2), ("2-3", 2, 4), ("4-7", 4, 8), ("8-15", 8, 16), ("16-31", 16, 32), ("32+", 32, 10 ** 9))))
+        print("  compute time of the chain's GEMM tasks by pairs (ms): " + ", ".join("%s: %.2f" % (lab, sum((cmp_[c] - lod[c]) for c in chain if info[c, 0] == 0 and lo <= info[c, 1] < hi) * 1e-3) for lab, lo, hi in (("1", 1, 2), ("2-3", 2, 4), ("4-7", 4, 8), ("8-15", 8, 16), ("16-31", 16, 32), ("32+", 32, 10 ** 9))))
     n = max(1, len(chain))
-    print("  for tools/model.py (means along the chain): t_release=%.2f t_poll=%.2f t_desc+t_load=%.2f  (signal phase %.2f us is part of t_release when it precedes the publication)"
+    print("  means along the chain (us): release (signal end -> publication of the successor) %.2f, queue wait %.2f, descriptor + operand load %.2f, signal phase %.2f"
           % (cat["publish-gap"] / n, cat["q-wait"] / n, cat["load"] / n, cat["signal"] / n))
     # SM utilisation: busy = sum over tasks of (sig - lod) / (n_sm * total)
     busy = (sig - lod).sum()
