@@ -50,7 +50,6 @@ struct soglu_ctx {
     int64_t opt_fuse_inv = 1;
     int64_t opt_split_slack = 100; // GEMM tasks within this slack (us) of the longest chain are row-split in wide levels too (measured -5..6 % on the
                                    // latency-bound configs, profiles/r02_call1_options.md); 0 = narrow levels only
-    int64_t opt_chain_cuts = 0;    // > 0: cut accumulation chains of tasks within this slack (us) of the critical path (two-pass compile)
     int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
     int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;
@@ -296,19 +295,9 @@ int finalize(soglu_ctx* c) {
         co.n_owners = c->world;
         co.mirror_min = (int)std::max<int64_t>(1, c->opt_mirror_min);
     }
-    if (c->opt_chain_cuts > 0) { co.analyze_chains = true; co.cut_max_slack_us = (double)c->opt_chain_cuts; }
     std::string err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
                                     c->result.data(), c->result2.data(), keep, co, *c->Gp);
     if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
-    if (c->opt_chain_cuts > 0 && !c->Gp->cuts.empty()) {
-        // second pass: the early pairs of every proposed chain become their own task (compile.cpp, chain analysis)
-        const std::vector<ChainCut> cuts = std::move(c->Gp->cuts);
-        co.analyze_chains = false;
-        co.chain_cuts = &cuts;
-        err = compile_tasks(c->n_ids, c->n_input, c->input_ids.data(), c->n_ops, c->src.data(), c->src2.data(), c->op.data(),
-                            c->result.data(), c->result2.data(), keep, co, *c->Gp);
-        if (!err.empty()) return fail(SOGLU_ERR_GRAPH, err);
-    }
     }   // !follower
     TaskGraph& G = *c->Gp;
     if (c->dist) {
@@ -612,7 +601,6 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
     else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
     else if (k == "split_slack") { if (c->compiled) return fail(SOGLU_ERR_ARG, "split_slack must be set before the first factor"); c->opt_split_slack = value; }
-    else if (k == "chain_cuts") { if (c->compiled) return fail(SOGLU_ERR_ARG, "chain_cuts must be set before the first factor"); c->opt_chain_cuts = value; }
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
     else if (k == "watchdog_ms") c->opt_watchdog_ms = value;

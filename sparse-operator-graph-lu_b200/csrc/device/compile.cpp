@@ -40,42 +40,91 @@ struct IdInfo {
 };
 }  // namespace
 
-std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* input_ids, int64_t n_ops,
-                          const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,
-                          const int32_t* result2, const std::vector<int32_t>& keep_ids, const CompileOptions& opt,
-                          TaskGraph& G) {
-    G = TaskGraph();
+namespace {
+// The compilation is a sequence of passes over the operation list / the task array; what one pass leaves for the next
+// lives here.  compile_tasks() runs them in order; each returns "" or the violated invariant.
+struct Compiler {
+    // ---- input (borrowed) -----------------------------------------------------------------------------------------
+    const int64_t n_ids_caller, n_input;
+    const int32_t* const input_ids;
+    const int64_t n_ops;
+    const int32_t *const src, *const src2;
+    const uint8_t* const op;
+    const int32_t *const result, *const result2;
+    const std::vector<int32_t>& keep_ids;
+    const CompileOptions& opt;
+    TaskGraph& G;
+    // ---- state shared by the passes -------------------------------------------------------------------------------
     char msg[256];
+    const int64_t n_ids;                    // block ids of the caller (mirrors are appended: nid)
+    std::vector<IdInfo> info;
+    std::vector<int64_t> fused_sub_of;      // product id -> index of the sub op it is folded into
+    std::vector<char> op_fused;             // per op: 1 = folded into an lu task, 2 = alias of an earlier inverse
+    std::vector<int32_t> alias_to;          // result id -> canonical result id
+    std::vector<int64_t> inv_of;            // source id -> first inverse op
+    int64_t nt = 0;                         // tasks so far
+    int64_t nid = 0;                        // block ids including mirrors
+    int nown = 1;
+    std::vector<int32_t> seg_of;            // task -> segment
+    std::vector<int64_t> poff;              // predecessor lists: offsets into pflat (capacity per task), pcnt entries each
+    BigVec<int32_t> pflat;
+    std::vector<int32_t> pcnt;
     // SOGLU_TIMING=1 prints the phase times to stderr (diagnostics only)
     const bool timing = std::getenv("SOGLU_TIMING") != nullptr;
-    auto t_last = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
+    std::chrono::steady_clock::time_point t_last = std::chrono::steady_clock::now();
+
+    static constexpr int64_t NONE = INT64_MAX;
+    static bool is_acc(uint8_t o) { return o == OP_MUL || o == OP_MULNEG || o == OP_MULT; }
+    static void atomic_min(int64_t* p, int64_t v) {
+        int64_t cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+        while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    }
+    void lap(const char* what) {
         if (!timing) return;
         auto t1 = std::chrono::steady_clock::now();
         std::fprintf(stderr, "[compile] %-25s %8.3f s\n", what, std::chrono::duration<double>(t1 - t_last).count());
         t_last = t1;
-    };
-    if (n_ids_caller < 1) return "n_block_ids must be >= 1";
-    // Chain cuts (CompileOptions::chain_cuts): the early part of a cut accumulation chain writes a temporary block;
-    // the temporaries get the ids n_ids_caller .. n_ids-1 and are ordinary blocks for everything below.
-    const int64_t n_cuts = opt.chain_cuts ? (int64_t)opt.chain_cuts->size() : 0;
-    const int64_t n_ids = n_ids_caller + n_cuts;
-    if (n_ids > 0x7fffffff) return "too many block ids";
-    if (n_ops > 0x7fffffff) return "too many operations";
-    std::vector<IdInfo> info(n_ids);
-    for (int64_t k = 0; k < n_input; k++) {
-        int32_t id = input_ids[k];
-        if (id <= 0 || id >= n_ids_caller) return "input block id out of range";
-        info[id].is_input = true;
     }
-    for (int32_t id : keep_ids)
-        if (id > 0 && id < n_ids_caller) info[id].keep = true;
 
+    Compiler(int64_t n_ids_caller_, int64_t n_input_, const int32_t* input_ids_, int64_t n_ops_, const int32_t* src_, const int32_t* src2_,
+             const uint8_t* op_, const int32_t* result_, const int32_t* result2_, const std::vector<int32_t>& keep_ids_, const CompileOptions& opt_,
+             TaskGraph& G_)
+        : n_ids_caller(n_ids_caller_), n_input(n_input_), input_ids(input_ids_), n_ops(n_ops_), src(src_), src2(src2_), op(op_), result(result_),
+          result2(result2_), keep_ids(keep_ids_), opt(opt_), G(G_), n_ids(n_ids_caller_) {}
+
+    std::string run() {
+        G = TaskGraph();
+        if (n_ids_caller < 1) return "n_block_ids must be >= 1";
+        if (n_ids > 0x7fffffff) return "too many block ids";
+        if (n_ops > 0x7fffffff) return "too many operations";
+        info.assign(n_ids, IdInfo());
+        for (int64_t k = 0; k < n_input; k++) {
+            int32_t id = input_ids[k];
+            if (id <= 0 || id >= n_ids_caller) return "input block id out of range";
+            info[id].is_input = true;
+        }
+        for (int32_t id : keep_ids)
+            if (id > 0 && id < n_ids_caller) info[id].keep = true;
+        std::string e;
+        if (!(e = validate()).empty()) return e;
+        if (!(e = decide_fusions()).empty()) return e;
+        if (!(e = make_tasks()).empty()) return e;
+        if (!(e = fill_pairs()).empty()) return e;
+        if (!(e = shard()).empty()) return e;
+        if (!(e = assign_slots()).empty()) return e;
+        if (!(e = dependencies()).empty()) return e;
+        if (!(e = levels()).empty()) return e;
+        if (!(e = split_rows()).empty()) return e;
+        if (!(e = finish()).empty()) return e;
+        return "";
+    }
+
+    // ==== validation + per-block writer / reader statistics ===================================================
+    std::string validate() {
     // ---- validation + per-block writer / reader statistics --------------------------------------
     // All passes over the op list run on every host thread; where the serial order matters (first writer
     // of a block, first inverse of a factor, the lowest offending op) it is recovered with atomic minima.
     auto bad_id = [&](int32_t id) { return id < 0 || id >= n_ids_caller; };
-    auto is_acc = [](uint8_t o) { return o == OP_MUL || o == OP_MULNEG || o == OP_MULT; };
     auto op_error = [&](int64_t i) -> const char* {          // checks that need no other op
         const uint8_t o = op[i];
         if (!(o == OP_LU || o == OP_LOWERINV || o == OP_UPPERINV || o == OP_SUB || o == OP_MUL || o == OP_MULNEG || o == OP_LLT || o == OP_MULT))
@@ -87,11 +136,6 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         if (info[result[i]].is_input || (o == OP_LU && info[result2[i]].is_input)) return "writes an input block";
         return nullptr;
     };
-    auto atomic_min = [](int64_t* p, int64_t v) {
-        int64_t cur = __atomic_load_n(p, __ATOMIC_RELAXED);
-        while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-    };
-    const int64_t NONE = INT64_MAX;
 #pragma omp parallel for schedule(static)
     for (int64_t id = 0; id < n_ids; id++) info[id].first_writer = NONE;
     {
@@ -143,9 +187,13 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         }
     }
     lap("validate + id info");
+        return "";
+    }
 
+    // ==== which subs / inverses are folded into other tasks ===================================================
+    std::string decide_fusions() {
     // ---- fusion decisions ------------------------------------------------------------
-    std::vector<int64_t> fused_sub_of(opt.fuse_sub ? n_ids : 0, -1);  // product id -> index of the sub op
+    fused_sub_of.assign(opt.fuse_sub ? n_ids : 0, -1);
     if (opt.fuse_sub) {
         int64_t nf = 0;
 #pragma omp parallel for schedule(static) reduction(+ : nf)
@@ -168,9 +216,9 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
     // same computation on the same input -> its result id aliases the first one's block
     // (the planner re-derives bottom-right inverses at every recursion level, BlockPlanner.cpp:
     // 1035-1036, 1081-1082); (b) the first inverse of an lu factor is folded into the lu task.
-    std::vector<char> op_fused(n_ops, 0);                 // 1 = folded into an lu task, 2 = alias
-    std::vector<int32_t> alias_to(n_ids, 0);              // result id -> canonical result id
-    std::vector<int64_t> inv_of(n_ids, NONE);             // source id -> first inverse op
+    op_fused.assign(n_ops, 0);
+    alias_to.assign(n_ids, 0);
+    inv_of.assign(n_ids, NONE);
     {
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n_ops; i++)
@@ -206,7 +254,11 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         G.fused_invs = n_fused;
     }
     lap("fusion decisions");
+        return "";
+    }
 
+    // ==== one task per produced block =========================================================================
+    std::string make_tasks() {
     // ---- one task per produced block (lu: one task, two blocks) -------------------------
     // task order = order of the first contributing op, i.e. the reference's stage order
     G.task_of.assign(n_ids, -1);
@@ -215,29 +267,6 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         const IdInfo& w = info[result[i]];
         return w.first_writer == i && !w.fused_away && !op_fused[i];   // fused products are opened by their sub, folded inverses by their lu
     };
-    // chain cuts by the block id the (uncut) task produces; a cut is applied if it still fits the chain
-    std::vector<int32_t> cut_of(n_cuts ? n_ids : 0, -1);
-    for (int64_t c = 0; c < n_cuts; c++) {
-        const ChainCut& cc = (*opt.chain_cuts)[c];
-        if (cc.out_id > 0 && cc.out_id < n_ids_caller && cut_of[cc.out_id] < 0) cut_of[cc.out_id] = (int32_t)c;
-    }
-    // number of operand pairs of the task op i opens, if it is a GEMM task (0 otherwise)
-    auto chain_len = [&](int64_t i) -> int32_t {
-        const uint8_t o = op[i];
-        if (is_acc(o)) return info[result[i]].n_writers;
-        if (o == OP_SUB && src[i] > 0 && info[src[i]].fused_away && fused_sub_of[src[i]] == i) return info[src[i]].n_writers;
-        return 0;
-    };
-    auto cut_for = [&](int64_t i) -> int32_t {       // index of the applicable cut of the task op i opens, or -1
-        if (!n_cuts) return -1;
-        const int32_t c = cut_of[result[i]];
-        if (c < 0) return -1;
-        const ChainCut& cc = (*opt.chain_cuts)[c];
-        const int32_t n = chain_len(i);
-        if (cc.n_early <= 0 || cc.n_early >= n || (int32_t)cc.early_pos.size() != cc.n_early || cc.early_pos.back() >= n) return -1;
-        return c;
-    };
-    std::vector<int32_t> cut_of_task;                // final task of a cut chain -> cut index (its early task precedes it)
     {
         int nth = 1;
 #ifdef _OPENMP
@@ -249,13 +278,12 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         for (int c = 0; c < nth; c++) {
             int64_t k = 0;
             for (int64_t i = c * chunk, e = std::min(n_ops, i + chunk); i < e; i++)
-                if (opens_task(i)) k += (cut_for(i) >= 0) ? 2 : 1;
+                if (opens_task(i)) k++;
             first_task[c + 1] = k;
         }
         for (int c = 0; c < nth; c++) first_task[c + 1] += first_task[c];
         if (first_task[nth] > 0x7fffffff) return "too many tasks";
         G.tasks.resize(first_task[nth]);
-        if (n_cuts) cut_of_task.assign(first_task[nth], -1);
 #pragma omp parallel for schedule(static, 1) num_threads(nth)
         for (int c = 0; c < nth; c++) {
             int64_t tid = first_task[c];
@@ -296,23 +324,6 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
                         break;
                     }
                 }
-                const int32_t cut = (t.type == T_GEMM) ? cut_for(i) : -1;
-                if (cut >= 0) {
-                    // early part: tmp = init -/+ sum over the early pairs; the final task starts from tmp
-                    const ChainCut& cc = (*opt.chain_cuts)[cut];
-                    const int32_t tmp = (int32_t)(n_ids_caller + cut);
-                    Task e1 = t;
-                    e1.out = tmp;
-                    e1.n_pairs = cc.n_early;
-                    IdInfo& tw = info[tmp];
-                    tw.n_writers = 1; tw.n_readers = 1; tw.kind = OP_MUL; tw.first_writer = i;
-                    G.task_of[tmp] = (int32_t)tid;
-                    G.tasks[tid++] = e1;
-                    t.n_pairs -= cc.n_early;
-                    t.flags = (t.flags & (TF_NEGATE | TF_TRANSB)) | TF_INIT;
-                    t.init = tmp;
-                    cut_of_task[tid] = cut;
-                }
                 G.task_of[r] = (int32_t)tid;
                 if (t.type == T_LU) G.task_of[t.out2] = (int32_t)tid;
                 if (t.type == T_LU || t.type == T_LLT) {
@@ -323,7 +334,7 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
             }
         }
     }
-    int64_t nt = (int64_t)G.tasks.size();
+    nt = (int64_t)G.tasks.size();
     // redirect fused products to the task of their sub's result
     if (opt.fuse_sub) {
 #pragma omp parallel for schedule(static)
@@ -335,7 +346,11 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
     for (int64_t id = 1; id < n_ids; id++)
         if (alias_to[id]) G.task_of[id] = G.task_of[alias_to[id]];
     lap("tasks");
+        return "";
+    }
 
+    // ==== operand pairs of the accumulation chains, in op-list order ==========================================
+    std::string fill_pairs() {
     // ---- pairs ------------------------------------------------------------------------------
     {
         int64_t total = 0;
@@ -354,9 +369,7 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
             Task& t = G.tasks[tid];
             if (is_acc(o)) {
                 const int32_t k = __atomic_fetch_add(&fill[tid], 1, __ATOMIC_RELAXED);
-                int32_t pb = t.pair_begin, np = t.n_pairs;
-                if (n_cuts && cut_of_task[tid] >= 0) { pb = G.tasks[tid - 1].pair_begin; np += G.tasks[tid - 1].n_pairs; }
-                if (k < np) { G.pairs[pb + k] = Pair{src[i], src2[i]}; pair_op[pb + k] = (int32_t)i; }
+                if (k < t.n_pairs) { G.pairs[t.pair_begin + k] = Pair{src[i], src2[i]}; pair_op[t.pair_begin + k] = (int32_t)i; }
                 flops += 524288.0;
                 gemm_pairs++;
             } else if (o == OP_SUB) {
@@ -374,42 +387,33 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         for (int64_t t = 0; t < nt; t++) {
             const Task& T = G.tasks[t];
             if (T.type != T_GEMM) continue;
-            const int32_t cut = n_cuts ? cut_of_task[t] : -1;
-            if (n_cuts && cut < 0 && t + 1 < nt && cut_of_task[t + 1] >= 0) continue;   // early part: filled through its final task
-            int32_t n = T.n_pairs, pb = T.pair_begin;
-            if (cut >= 0) { pb = G.tasks[t - 1].pair_begin; n += G.tasks[t - 1].n_pairs; }
+            const int32_t n = T.n_pairs, pb = T.pair_begin;
             if (fill[t] != n) { mismatch = 1; continue; }
             bool sorted = true;
             for (int32_t k = 1; k < n; k++) sorted = sorted && pair_op[pb + k - 1] < pair_op[pb + k];
-            if (sorted && cut < 0) continue;
+            if (sorted) continue;
             // sort by op index (chains are short: up to a few hundred operands)
             std::vector<std::pair<int32_t, Pair>> tmp(n);
             for (int32_t k = 0; k < n; k++) tmp[k] = {pair_op[pb + k], G.pairs[pb + k]};
-            if (!sorted) std::sort(tmp.begin(), tmp.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-            if (cut < 0) {
-                for (int32_t k = 0; k < n; k++) G.pairs[pb + k] = tmp[k].second;
-            } else {
-                // the early positions (in op order) first, then the rest (in op order)
-                const ChainCut& cc = (*opt.chain_cuts)[cut];
-                std::vector<char> early(n, 0);
-                for (int32_t q : cc.early_pos) early[q] = 1;
-                int32_t w = pb;
-                for (int32_t k = 0; k < n; k++) if (early[k]) G.pairs[w++] = tmp[k].second;
-                for (int32_t k = 0; k < n; k++) if (!early[k]) G.pairs[w++] = tmp[k].second;
-            }
+            std::sort(tmp.begin(), tmp.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            for (int32_t k = 0; k < n; k++) G.pairs[pb + k] = tmp[k].second;
         }
         if (mismatch) return "internal: pair count mismatch";
-        if (n_cuts) for (int64_t t = 0; t < nt; t++) G.chain_splits += cut_of_task[t] >= 0;
     }
     lap("pairs");
+        return "";
+    }
+
+    // ==== multi-GPU: owners, mirrors of remote blocks and their fetch tasks ===================================
+    std::string shard() {
     // ---- multi-GPU: owners, mirrors of remote blocks and their fetch tasks ---------------------------
     // A task runs on the GPU that owns its result block.  A produced block that a GPU reads at least
     // mirror_min times from a peer is MIRRORED there: a fetch task (a T_SUB "copy": out = remote - 0)
     // owned by the reader copies it once over NVLink as soon as it is complete, and the reader's
     // tasks use the copy (the panel broadcast of the north star, pulled by the consumer).  Mirrors
     // are ordinary blocks (ids appended after the caller's) so slot recycling and segments cover them.
-    int64_t nid = n_ids;                       // block ids including mirrors
-    const int nown = std::max(1, opt.n_owners);
+    nid = n_ids;
+    nown = std::max(1, opt.n_owners);
     G.n_owners = nown;
     G.owner_of.assign(n_ids, 0);
     if (nown > 1) {
@@ -419,10 +423,6 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
                 if (opt.owner_of_id[id] < 0 || opt.owner_of_id[id] >= nown) return "block owner out of range";
                 G.owner_of[id] = opt.owner_of_id[id];
             }
-        for (int64_t c = 0; c < n_cuts; c++) {       // a temporary lives where the block it becomes lives
-            const int32_t o = (*opt.chain_cuts)[c].out_id;
-            if (o > 0 && o < n_ids_caller) G.owner_of[n_ids_caller + c] = G.owner_of[o];
-        }
         for (int64_t id = 1; id < n_ids; id++)
             if (alias_to[id]) G.owner_of[id] = G.owner_of[alias_to[id]];
         auto cn = [&](int32_t id) { return alias_to[id] ? alias_to[id] : id; };
@@ -514,6 +514,11 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
     }
 
     lap("owners + mirrors");
+        return "";
+    }
+
+    // ==== pool slots, segments and slot recycling =============================================================
+    std::string assign_slots() {
     // ---- pool slots and segments -------------------------------------------------------------------
     // Unlimited pool: every input / produced block gets its own slot, one segment.  Limited pool
     // (opt.max_slots): walk the tasks in order (a topological order: the op list is stage-sorted),
@@ -521,7 +526,7 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
     // every block whose producer and readers all lie before it is dead and its slot returns to the
     // free list.  Inputs, kept blocks (L, U) and the diagonal inverses the solve uses are pinned.
     auto canon = [&](int32_t id) { return alias_to[id] ? alias_to[id] : id; };
-    std::vector<int32_t> seg_of(nt, 0);
+    seg_of.assign(nt, 0);
     G.recycled.assign(nid, 0);
     G.seg_begin.assign(1, 0);
     G.slots_per_owner.assign(nown, 1);          // local slot 0 of every GPU is its all-zero block
@@ -606,13 +611,18 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
     }
 
     lap("slots + segments");
+        return "";
+    }
+
+    // ==== producer -> consumer edges, successor lists =========================================================
+    std::string dependencies() {
     // ---- dependencies: distinct producer tasks of every source, inside the same segment ----------
     // (producers in earlier segments have finished before the launch starts)
     // predecessor lists in one flat array (capacity = operand count per task), sorted and made unique per task
-    std::vector<int64_t> poff(nt + 1, 0);
+    poff.assign(nt + 1, 0);
     for (int64_t t = 0; t < nt; t++) poff[t + 1] = poff[t] + 2 * (int64_t)G.tasks[t].n_pairs + ((G.tasks[t].flags & TF_INIT) ? 1 : 0);
-    BigVec<int32_t> pflat(poff[nt]);
-    std::vector<int32_t> pcnt(nt, 0);
+    pflat = BigVec<int32_t>(poff[nt]);
+    pcnt.assign(nt, 0);
     {
         int order_error = 0;
 #pragma omp parallel for schedule(dynamic, 2048) reduction(| : order_error)
@@ -668,6 +678,11 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         for (int64_t t = 0; t < nt; t++) { G.tasks[t].succ_begin = cnt[t]; G.tasks[t].succ_end = cnt[t + 1]; }
     }
     lap("dependencies");
+        return "";
+    }
+
+    // ==== ASAP levels =========================================================================================
+    std::string levels() {
     // ---- levels: longest path from a source (every predecessor precedes its task, checked above) -----------
     {
         int32_t maxlev = 0;
@@ -690,6 +705,11 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         G.n_levels = nt ? maxlev + 1 : 0;
     }
     lap("levels");
+        return "";
+    }
+
+    // ==== row slices of GEMM tasks in narrow levels / near the critical path ==================================
+    std::string split_rows() {
     // ---- row split of GEMM tasks in narrow levels -------------------------------------------------
     // In a level with fewer GEMM tasks than SMs the factorisation is latency-bound: one 64x64x64
     // product occupies one SM for ~2.4 us per pair while the others idle.  Such tasks are split
@@ -772,6 +792,11 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         }
     }
     lap("row split");
+        return "";
+    }
+
+    // ==== successor references, initially ready tasks, block ids -> block references ==========================
+    std::string finish() {
     // successor references; a group with exactly one predecessor task (unsplit) carries the "sole predecessor" bit
     G.succ_enc.resize(G.succ.size());
 #pragma omp parallel for schedule(static)
@@ -799,124 +824,6 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         }
     }
     lap("successor refs + initial");
-    // ---- chain analysis (diagnostics + input of a second compile, CompileOptions::analyze_chains) --------------
-    // Under the cost model of model.h: fin[t] = earliest time a successor of t can start, as compiled (a task starts
-    // when ALL operands are ready), and fin_e[t] = the same if every accumulation chain may be cut once into an
-    // early part (the pairs that are ready first, plus the initial value) and a late part that starts from it.
-    // A cut is proposed when it moves the task's own finish by cut_min_gain_us and the task has little slack.
-    if (opt.analyze_chains && !G.tasks.empty()) {
-        const ModelParams M;
-        const int64_t n2 = (int64_t)G.tasks.size();
-        const float o_in = (float)model_in_us(M), o_out = (float)model_out_us(M);
-        auto stage_us = [&](const Task& T) -> float { return (float)model_stage_us(T, M); };
-        std::vector<float> fin(n2, 0.f), fin_e(n2, 0.f);
-        std::vector<int32_t> best_k(n2, 0);
-        std::vector<std::pair<float, int32_t>> rs;   // (ready time, position) of the pairs of one chain
-        for (int64_t t = 0; t < n2; t++) {
-            const Task& T = G.tasks[t];
-            if (!task_is_leader(T)) {
-                const int64_t lead = t - ((T.flags >> TF_ROW0_SHIFT) & 3) / std::max(1, (T.flags >> TF_NROWS_SHIFT) & 7);
-                fin[t] = fin[lead]; fin_e[t] = fin_e[lead];
-                continue;
-            }
-            const float ts = stage_us(T);
-            const int n = (T.type == T_GEMM) ? T.n_pairs : 1;
-            auto ready = [&](int32_t id, const std::vector<float>& f) -> float {
-                if (id <= 0) return 0.f;
-                const int32_t p = G.task_of[id];
-                return (p >= 0 && p != t) ? f[p] : 0.f;
-            };
-            float r_all = 0.f, ri = 0.f, ri_e = 0.f;
-            if (T.flags & TF_INIT) { ri = ready(T.init, fin); ri_e = ready(T.init, fin_e); }
-            rs.clear();
-            for (int k = 0; k < T.n_pairs; k++) {
-                const Pair& pr = G.pairs[T.pair_begin + k];
-                r_all = std::max(r_all, std::max(ready(pr.a, fin), ready(pr.b, fin)));
-                if (T.type == T_GEMM) rs.push_back({std::max(ready(pr.a, fin_e), ready(pr.b, fin_e)), k});
-            }
-            fin[t] = std::max(r_all, ri) + o_in + n * ts + o_out;
-            if (T.type != T_GEMM) {
-                float r = 0.f;
-                for (int k = 0; k < T.n_pairs; k++) r = std::max(r, std::max(ready(G.pairs[T.pair_begin + k].a, fin_e), ready(G.pairs[T.pair_begin + k].b, fin_e)));
-                fin_e[t] = r + o_in + n * ts + o_out;
-                continue;
-            }
-            std::stable_sort(rs.begin(), rs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-            const float r_last = rs.back().first;
-            float best = std::max(r_last, ri_e) + o_in + n * ts + o_out;
-            int bk = 0;
-            for (int k = 1; k < n; k++) {
-                const float fe = std::max(rs[k - 1].first, ri_e) + o_in + k * ts + o_out;
-                const float f = std::max(fe, r_last) + o_in + (n - k) * ts + o_out;
-                if (f < best - (float)opt.cut_min_gain_us) { best = f; bk = k; }
-            }
-            fin_e[t] = best;
-            best_k[t] = bk;
-        }
-        for (int64_t t = 0; t < n2; t++) { G.cp_us = std::max(G.cp_us, (double)fin[t]); G.cp_early_us = std::max(G.cp_early_us, (double)fin_e[t]); }
-        // slack under the early-start times: a cut only matters on (near-)critical tasks
-        std::vector<float> bot(n2, 0.f);     // longest path from the END of the task to the end of the factorisation
-        for (int64_t t = n2 - 1; t >= 0; t--) {
-            const Task& T = G.tasks[t];
-            float m = 0.f;
-            for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
-                const Task& S = G.tasks[G.succ[e]];
-                m = std::max(m, bot[G.succ[e]] + o_in + ((S.type == T_GEMM) ? S.n_pairs : 1) * stage_us(S) + o_out);
-            }
-            bot[t] = m;
-        }
-        for (int64_t t = 0; t < n2; t++) {
-            const Task& T = G.tasks[t];
-            if (T.type != T_GEMM || !task_is_leader(T) || best_k[t] == 0) continue;
-            if (G.cp_early_us - (fin_e[t] + bot[t]) > opt.cut_max_slack_us) continue;
-            // recompute the order of the chain (cheap: only the chosen tasks)
-            rs.clear();
-            for (int k = 0; k < T.n_pairs; k++) {
-                const Pair& pr = G.pairs[T.pair_begin + k];
-                auto rd = [&](int32_t id) { if (id <= 0) return 0.f; const int32_t p = G.task_of[id]; return (p >= 0 && p != t) ? fin_e[p] : 0.f; };
-                rs.push_back({std::max(rd(pr.a), rd(pr.b)), k});
-            }
-            std::stable_sort(rs.begin(), rs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-            ChainCut c;
-            c.out_id = T.out;
-            c.n_early = best_k[t];
-            for (int k = 0; k < best_k[t]; k++) c.early_pos.push_back(rs[k].second);
-            std::sort(c.early_pos.begin(), c.early_pos.end());
-            G.cuts.push_back(std::move(c));
-        }
-        // Shared-operand pairs (diagnostics): two bulk GEMM tasks with the same left-operand sequence could
-        // run as ONE task that loads every A block once (3 instead of 4 block loads per two products).  Candidates:
-        // whole-block tasks with plenty of slack, the same flags and chain, ready at about the same time, and no
-        // successor of the first in between (the pair would sit at the second task's place in the order).
-        {
-            struct Cand { uint64_t key; int32_t task; };
-            std::vector<Cand> cand;
-            for (int64_t t = 0; t < n2; t++) {
-                const Task& T = G.tasks[t];
-                if (T.type != T_GEMM || T.n_pairs < 2 || ((T.flags >> TF_NROWS_SHIFT) & 7) != 4) continue;
-                if (G.cp_early_us - (fin_e[t] + bot[t]) < opt.dual_min_slack_us) continue;
-                uint64_t h = 1469598103934665603ull ^ (uint64_t)(T.flags & (TF_NEGATE | TF_TRANSB | TF_INIT)) ^ ((uint64_t)T.n_pairs << 8) ^ ((uint64_t)G.task_owner[t] << 40);
-                for (int k = 0; k < T.n_pairs; k++) { h ^= (uint64_t)(uint32_t)G.pairs[T.pair_begin + k].a; h *= 1099511628211ull; }
-                cand.push_back({h, (int32_t)t});
-            }
-            std::sort(cand.begin(), cand.end(), [](const Cand& x, const Cand& y) { return x.key != y.key ? x.key < y.key : x.task < y.task; });
-            int64_t pairs_formed = 0, covered = 0;
-            for (size_t q = 0; q + 1 < cand.size();) {
-                const int32_t t1 = cand[q].task, t2 = cand[q + 1].task;
-                bool ok = cand[q].key == cand[q + 1].key && std::fabs(fin_e[t1] - fin_e[t2]) < 50.f;
-                if (ok) {
-                    const Task &A = G.tasks[t1], &B = G.tasks[t2];
-                    for (int k = 0; k < A.n_pairs && ok; k++) ok = G.pairs[A.pair_begin + k].a == G.pairs[B.pair_begin + k].a;
-                    for (int32_t e = A.succ_begin; e < A.succ_end && ok; e++) ok = G.succ[e] > t2;
-                }
-                if (ok) { pairs_formed++; covered += 2 * (int64_t)G.tasks[t1].n_pairs; q += 2; }
-                else q++;
-            }
-            G.dual_pairs = pairs_formed;
-            G.dual_covered_pairs = covered;
-        }
-        lap("chain analysis");
-    }
     // ---- patch block ids -> block references (owner in the top bits; plain slots on one GPU) --------
     {
         auto ref = [&](int32_t id, int reader) -> int32_t {
@@ -946,8 +853,19 @@ std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* 
         }
     }
     lap("patch refs");
-    return "";
+        return "";
+    }
+
+};
+}  // namespace
+
+std::string compile_tasks(int64_t n_ids_caller, int64_t n_input, const int32_t* input_ids, int64_t n_ops,
+                          const int32_t* src, const int32_t* src2, const uint8_t* op, const int32_t* result,
+                          const int32_t* result2, const std::vector<int32_t>& keep_ids, const CompileOptions& opt,
+                          TaskGraph& G) {
+    return Compiler(n_ids_caller, n_input, input_ids, n_ops, src, src2, op, result, result2, keep_ids, opt, G).run();
 }
+
 
 
 std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {

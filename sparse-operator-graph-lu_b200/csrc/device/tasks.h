@@ -83,12 +83,6 @@ inline int task_group_size(const Task& t) {
 inline bool task_is_leader(const Task& t) { return t.type != T_GEMM || ((t.flags >> TF_ROW0_SHIFT) & 3) == 0; }
 inline int task_log2_slices(const Task& t) { const int g = task_group_size(t); return g == 4 ? 2 : (g == 2 ? 1 : 0); }
 
-struct ChainCut {        // split of one accumulation chain, keyed by the block id its task produces
-    int32_t out_id;
-    int32_t n_early;                 // pairs (in op-list order positions) that go to the early task
-    std::vector<int32_t> early_pos;  // positions within the chain, ascending
-};
-
 struct TaskGraph {
     BigVec<Task> tasks;
     BigVec<Pair> pairs;
@@ -118,12 +112,6 @@ struct TaskGraph {
     int64_t fused_invs = 0;
     int64_t aliased_invs = 0;
     int64_t split_tasks = 0;   // GEMM tasks that were row-split
-    // chain analysis (CompileOptions::analyze_chains): critical path in us under the cost model, as compiled and
-    // with every accumulation chain started as early as its operands allow; proposed cuts
-    double cp_us = 0, cp_early_us = 0;
-    std::vector<ChainCut> cuts;
-    int64_t chain_splits = 0;  // cuts applied (CompileOptions::chain_cuts)
-    int64_t dual_pairs = 0, dual_covered_pairs = 0;   // chain analysis: task pairs that could share their left operands, operand pairs in them
 };
 
 struct CompileOptions {
@@ -138,15 +126,6 @@ struct CompileOptions {
     const int8_t* owner_of_id = nullptr;
     int n_owners = 1;
     int mirror_min = 1;
-    // Chain splitting (compile.cpp, "chain analysis"): a GEMM task waits for ALL its operand pairs although most
-    // of an accumulation chain is ready long before the last pair arrives.  analyze_chains estimates, per task,
-    // when each pair becomes ready and proposes cuts (TaskGraph::cuts); a second compile with chain_cuts applies
-    // them: the early pairs become their own task writing a temporary block that the late part starts from.
-    bool analyze_chains = false;
-    double cut_min_gain_us = 1.5;     // propose a cut only if the estimated finish of the task moves by at least this
-    double dual_min_slack_us = 300.0; // shared-operand pairs are only looked for among tasks with at least this slack
-    double cut_max_slack_us = 200.0;  // ... and the task lies within this slack of the critical path
-    const std::vector<ChainCut>* chain_cuts = nullptr;
 };
 
 // ---- multi-GPU: 2D block-cyclic owner-computes sharding -------------------------------------------

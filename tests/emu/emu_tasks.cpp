@@ -73,8 +73,7 @@ void inv_upper(const double* u, double* y) {     // U Y = I
 }  // namespace
 
 // split: bit 0 = row slices in narrow levels, bit 1 = also near-critical tasks (split_slack), bit 2 = 8 SMs.
-// mode: 0 = default compile, 1 = analyse chains + recompile with the proposed cuts.  max_slots > 0 forces slot
-// recycling.  keep_out: n_keep dense 64x64 blocks.  stats = {tasks, segments, slots, chain cuts applied, row-split tasks}.
+// mode: unused (0).  max_slots > 0 forces slot recycling.  keep_out: n_keep dense 64x64 blocks.  stats = {tasks, segments, slots, chain cuts applied, row-split tasks}.
 // grid = {pr, pc, nb} with brow / bcol per block id: the graph is compiled for pr*pc owners (2D block-cyclic squares of
 // nb blocks, mirrors of remote blocks filled by fetch tasks) and every owner gets its own pool here.
 extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids, const double* input_dense, int64_t n_ops, const int32_t* src,
@@ -98,16 +97,9 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
         co.owner_of_id = owners.data();
         co.n_owners = world;
     }
-    if (mode == 1) { co.analyze_chains = true; co.cut_max_slack_us = cut_max_slack_us; }
+    (void)mode; (void)cut_max_slack_us;     // (kept in the signature: the chain-cut compile mode they selected was measured and removed)
     std::string err = compile_tasks(n_ids, n_input, input_ids, n_ops, src, src2, op, result, result2, keep, co, G);
     if (!err.empty()) return fail(err);
-    if (mode == 1) {
-        const std::vector<ChainCut> cuts = std::move(G.cuts);
-        co.analyze_chains = false;
-        co.chain_cuts = &cuts;
-        err = compile_tasks(n_ids, n_input, input_ids, n_ops, src, src2, op, result, result2, keep, co, G);
-        if (!err.empty()) return fail(err);
-    }
     // one pool per owner; slot 0 of each stays its zero block
     int64_t stride = 0;
     for (int64_t sl : G.slots_per_owner) stride = std::max(stride, sl);
@@ -207,7 +199,7 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
         if (G.recycled[keep_ids[k]]) return fail("a kept block was recycled");
         std::memcpy(keep_out + k * NN, blk(ref_of(keep_ids[k])), NN * sizeof(double));
     }
-    stats[0] = (int64_t)G.tasks.size(); stats[1] = (int64_t)G.seg_begin.size() - 1; stats[2] = stride; stats[3] = G.chain_splits; stats[4] = G.split_tasks;
+    stats[0] = (int64_t)G.tasks.size(); stats[1] = (int64_t)G.seg_begin.size() - 1; stats[2] = stride; stats[3] = 0; stats[4] = G.split_tasks;
     stats[5] = 0;
     for (int64_t m : G.mirrors_per_owner) stats[5] += m;
     return 0;

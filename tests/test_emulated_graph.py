@@ -1,7 +1,7 @@
 """The compiled task graph, executed on the host (tests/emu/emu_tasks.cpp, test infrastructure), must reproduce the
 factors the reference's operation list defines -- checked against the oracle, no GPU.  Covers what the task compiler
-does to the list: fused sub / inverse tasks, aliased inverses, row slices, slot recycling, and the chain cuts of
-option chain_cuts (early part of an accumulation chain as its own task)."""
+does to the list: fused sub / inverse tasks, aliased inverses, row slices, slot recycling, and
+pool recycling across segments."""
 import ctypes
 import os
 import subprocess
@@ -88,20 +88,6 @@ def test_slot_recycling_keeps_the_factors(sg, emu, oracle, tmp_path, name, max_s
     check_against_oracle(oracle, p, keep, blocks)
 
 
-@pytest.mark.parametrize("name,slack,split", [("lap3d_24", 1e9, 1), ("lap3d_24", 50.0, 1), ("lap3d_24", 1e9, 0), ("nine2d_40", 1e9, 1),
-                                              ("lap3d_16_sym", 1e9, 1), ("banded_3000", 1e9, 1), ("lap2d_64", 1e9, 1)])
-def test_chain_cuts_keep_the_factors(sg, emu, oracle, tmp_path, name, slack, split):
-    """Option chain_cuts: tasks near the critical path start their accumulation chain before the last operands exist;
-    the early pairs become a task of their own that writes a temporary block.  Same factors within the tolerance."""
-    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
-    _, _, st0 = run_emu(emu, p, split=split)
-    keep, blocks, st = run_emu(emu, p, mode=1, slack=slack, split=split)
-    if name in ("lap3d_24", "banded_3000"):
-        assert st["cuts"] > 0
-    assert st["tasks"] >= st0["tasks"] + st["cuts"]          # one more task per cut (more with row slices)
-    check_against_oracle(oracle, p, keep, blocks)
-
-
 @pytest.mark.parametrize("name", ["lap3d_24", "banded_3000"])
 def test_slack_based_row_split_is_bitwise_neutral(sg, emu, oracle, tmp_path, name):
     """Option split_slack: near-critical GEMM tasks are cut into row slices in wide levels too.  A slice computes its rows
@@ -117,32 +103,22 @@ def test_slack_based_row_split_is_bitwise_neutral(sg, emu, oracle, tmp_path, nam
 def test_execution_order_does_not_matter(sg, emu, tmp_path):
     """Task order and two random dependency-driven orders give bitwise the same factors (each task's arithmetic is fixed)."""
     p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
-    for mode in (0, 1):
-        _, b0, _ = run_emu(emu, p, mode=mode, seed=0)
-        for seed in (1, 2):
-            _, b, _ = run_emu(emu, p, mode=mode, seed=seed)
-            np.testing.assert_array_equal(b, b0)
+    _, b0, _ = run_emu(emu, p, seed=0)
+    for seed in (1, 2):
+        _, b, _ = run_emu(emu, p, seed=seed)
+        np.testing.assert_array_equal(b, b0)
 
 
-@pytest.mark.parametrize("grid,mode,max_slots", [((2, 1, 2), 0, 0), ((2, 2, 1), 0, 0), ((4, 2, 4), 0, 0), ((2, 2, 2), 1, 0), ((2, 1, 4), 0, 4000), ((2, 2, 2), 1, 2500)])
-def test_sharded_graph_reproduces_the_factors(sg, emu, oracle, tmp_path, grid, mode, max_slots):
+@pytest.mark.parametrize("grid,max_slots", [((2, 1, 2), 0), ((2, 2, 1), 0), ((4, 2, 4), 0), ((2, 2, 2), 0), ((2, 1, 4), 4000), ((2, 2, 2), 2500)])
+def test_sharded_graph_reproduces_the_factors(sg, emu, oracle, tmp_path, grid, max_slots):
     """The graph compiled for several GPUs (owner-computes, remote blocks mirrored by fetch tasks, per-owner pools), with
-    and without chain cuts and pool recycling, run in a dependency-driven random order: same factors as the oracle."""
+    and without pool recycling, run in a dependency-driven random order: same factors as the oracle."""
     p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
     _, _, st0 = run_emu(emu, p)
-    keep, blocks, st = run_emu(emu, p, mode=mode, max_slots=max_slots, grid=grid)
+    keep, blocks, st = run_emu(emu, p, max_slots=max_slots, grid=grid)
     assert st["mirrors"] > 0 and st["tasks"] > st0["tasks"]
     if max_slots:
         assert st["segments"] > 1
-    if mode:
-        assert st["cuts"] > 0
-    check_against_oracle(oracle, p, keep, blocks)
-
-
-def test_chain_cuts_with_recycling(sg, emu, oracle, tmp_path):
-    p = sg.Problem.from_mtx(write_case_mtx("lap3d_24", tmp_path))
-    keep, blocks, st = run_emu(emu, p, mode=1, slack=1e9, max_slots=6000)
-    assert st["cuts"] > 0 and st["segments"] > 1
     check_against_oracle(oracle, p, keep, blocks)
 
 
@@ -210,7 +186,7 @@ def random_op_list(seed, n_steps=60):
 
 
 @pytest.mark.parametrize("seed", range(12))
-@pytest.mark.parametrize("variant", ["default", "cuts", "small_pool"])
+@pytest.mark.parametrize("variant", ["default", "small_pool"])
 def test_random_operation_lists(emu, oracle, seed, variant):
     n_ids, inputs, dense, ops, keep, n_input = random_op_list(seed)
     ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
@@ -227,7 +203,7 @@ def test_random_operation_lists(emu, oracle, seed, variant):
     out = np.zeros((len(keep), 64, 64))
     stats = np.zeros(6, dtype=np.int64)
     err = ctypes.create_string_buffer(256)
-    mode, slack, max_slots = (1, 1e9, 0) if variant == "cuts" else (0, 0.0, 0)
+    mode, slack, max_slots = 0, 0.0, 0
     if variant == "small_pool":
         max_slots = n_input + len(keep) + 14
     rc = emu.emu_run(n_ids, len(inputs), ptr(inputs), ptr(dense), len(ops), ptr(src), ptr(src2), ptr(opc), ptr(res), ptr(res2), len(keep), ptr(keep),

@@ -469,30 +469,6 @@ def test_sparse_input_upload_rejects_bad_entries(sg):
 # ---- compiler / kernel variants ------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("name,slack", [("lap3d_24", 10 ** 9), ("lap3d_24", 50), ("banded_3000", 10 ** 9), ("lap3d_16_sym", 10 ** 9)])
-def test_chain_cuts(sg, tmp_path, name, slack):
-    """Option chain_cuts: near-critical accumulation chains are cut into an early task (writes a temporary block) and a
-    late task that starts from it.  Same solution within the parity tolerance (the summation order changes)."""
-    g = load_golden(name)
-    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
-    ref = sg.Context(0)
-    ref.load(p)
-    f0 = ref.factor()
-    x0, _ = ref.solve(p)
-    ctx = sg.Context(0)
-    ctx.set_option("chain_cuts", slack)
-    ctx.load(p)
-    fs = ctx.factor()
-    assert fs["tasks"] > f0["tasks"]
-    x, _ = ctx.solve(p)
-    assert _rel(x, x0) <= 1e-12
-    assert _rel(x, g["x"]) <= TOL_X
-    ctx.close()
-    ref.close()
-
-
-@pytest.mark.gpu
-@pytest.mark.timeout(300)
 @pytest.mark.parametrize("name", ["lap2d_64", "lap3d_24", "nine2d_40", "banded_3000", "lap3d_13x11x9", "lap2d_64_sym", "lap3d_16_sym"])
 def test_diagonal_kernel_factors(sg, oracle, tmp_path, name):
     """The blocked diagonal-block kernel (lu_blocked.cuh: 16-column panels, one warp on the pivot chain, DMMA trailing
