@@ -66,8 +66,11 @@ int soglu_abi_version(void);
 
 /* ---------------- A. device hot path ------------------------------------------------- */
 
-/* one context per GPU; device_ids may be NULL (devices 0..n_gpus-1).  n_gpus > 1 shards the
- * factorisation by block ownership inside ONE process (peer access required). */
+/* n_gpus = 1: one context on one GPU (device_ids may be NULL: device 0).
+ * n_gpus = 2..8: ONE process shards the factorisation and the solve over devices device_ids[0..n_gpus-1] (NULL: 0..n_gpus-1)
+ * by 2D block-cyclic block ownership (the scheme of section A2) -- peer access between the GPUs is required, the
+ * operation list is held and compiled once, and every call below works on the group as on a single GPU.  This is what
+ * SOGLU::solveLU / ./solve use when the environment variable SOGLU_GPUS is set. */
 int soglu_create(soglu_ctx** out, int n_gpus, const int* device_ids);
 void soglu_destroy(soglu_ctx* ctx);
 
@@ -100,8 +103,16 @@ int soglu_set_factors(soglu_ctx* ctx, int64_t nL, const int32_t* L_ids, const in
 /* replaces BlockPlanner::calculate() */
 int soglu_factor(soglu_ctx* ctx, soglu_stats* out);
 
+/* The reference's numeric sanity signal: number of diagonal blocks of the last soglu_factor whose U * U^-1 fails
+ * MatrixStdDouble::inv_check_diag (diagonal within 1 +- 1e-3; MatrixStdDouble.cpp:2871-2937, printed as
+ * " upper out of tolerance" at BlockPlanner.cpp:575-577).  0 for a healthy factorisation; in effect it counts NaN / Inf pivots. */
+int64_t soglu_diag_warnings(soglu_ctx* ctx);
+
 /* replaces BlockPlanner::solve(): b_ext = permuted rhs padded with 1.0 to n_block_rows*64
- * (NOT overwritten, unlike the reference); x_ext receives n_block_rows*64 values. */
+ * (NOT overwritten, unlike the reference); x_ext receives n_block_rows*64 values.
+ * One process per GPU (A2): the solve is sharded like the factorisation and therefore COLLECTIVE -- every rank calls it
+ * with the same b_ext; x_ext is filled on rank 0 only (may be NULL elsewhere); put a barrier across the ranks between
+ * two collective calls. */
 int soglu_solve(soglu_ctx* ctx, const double* b_ext, double* x_ext, soglu_stats* out);
 
 /* Iterative refinement on the device (the reference has none): soglu_set_matrix takes the
@@ -113,15 +124,21 @@ int soglu_solve_refined(soglu_ctx* ctx, const double* b_ext, double* x_ext, int 
 /* parity helpers: read back one block (dense 64x64) after soglu_factor; error if the block
  * was recycled (only inputs of later ops, L and U are guaranteed to survive). */
 int soglu_get_block(soglu_ctx* ctx, int32_t id, double* out_64x64);
-/* Tuning / debug knobs, to be set before the first soglu_factor (INTEGRATION.md lists them all).  None changes what is
- * computed.  "exec_mode" = 1 runs the op list one dependency level at a time with plain per-level launches instead of
- * the persistent executor (cross-check path; same kernels' math); "max_slots" caps the block pool; "split", "fuse_sub",
- * "fuse_inv" switch compiler transformations; "hi_shared", "split_slack", "chain_cuts", "lu_mode", "prefetch" select
- * scheduling / kernel variants that are off by default; "trace" records per-task timestamps. */
+/* Tuning / debug knobs, to be set before the first soglu_factor.  None changes what is computed.
+ *   "exec_mode" = 1   run the op list one dependency level at a time with plain per-level launches instead of the
+ *                     persistent executor (cross-check path; the same kernels' math); single GPU only
+ *   "max_slots"       cap of the block pool in blocks (forces slot recycling / several executor launches)
+ *   "split" "split_slack" "fuse_sub" "fuse_inv"   compiler transformations (row slices of GEMM tasks in narrow levels /
+ *                     within split_slack us of the critical path, default 100; folding of sub / inverse operations)
+ *   "dist_nb" "mirror_min"   multi-GPU: side of the ownership squares in blocks (16), reads that justify a local mirror
+ *   "grid"            number of CTAs of the executor (0 = one per SM)
+ *   "watchdog_ms"     a kernel whose waiters see no progress for this long aborts; the call returns SOGLU_ERR_CUDA with
+ *                     the queue slot / block row that never arrived (default 60000, 0 = off); may be set at any time
+ *   "trace"           record per-task timestamps (tools/trace_analyze.py, bench.py --trace) */
 int soglu_set_option(soglu_ctx* ctx, const char* key, int64_t value);
 
 /* ---------------- A2. multi-GPU: one process per GPU, 2D block-cyclic block ownership -------
- * Block (brow, bcol) lives on GPU (brow mod grid_rows) * grid_cols + (bcol mod grid_cols); an
+ * Block (brow, bcol) lives on GPU ((brow / 16) mod grid_rows) * grid_cols + ((bcol / 16) mod grid_cols); an
  * operation runs where its result lives and pulls remote operands over NVLink (peer memory
  * mapped through CUDA IPC); dependency counters and ready queues of peers are updated with
  * system-scope atomics.  The reference has no multi-device path; this extends
@@ -129,7 +146,7 @@ int soglu_set_option(soglu_ctx* ctx, const char* key, int64_t value);
  *   soglu_create_dist -> soglu_set_blocks / soglu_set_graph (with block_row / block_col) /
  *   soglu_set_factors (the same full problem on every rank) -> soglu_dist_export ->
  *   [all-gather the blobs] -> soglu_dist_import -> per factorisation: soglu_dist_reset ->
- *   [barrier] -> soglu_factor -> [barrier] -> soglu_solve on rank 0 -> [barrier]. */
+ *   [barrier] -> soglu_factor -> [barrier] -> soglu_solve on EVERY rank (x on rank 0) -> [barrier]. */
 int soglu_create_dist(soglu_ctx** out, int device, int rank, int world, int grid_rows, int grid_cols);
 int64_t soglu_dist_blob_bytes(void);
 int soglu_dist_export(soglu_ctx* ctx, void* blob);
@@ -143,6 +160,10 @@ int soglu_dist_set_segment(soglu_ctx* ctx, int segment);
 /* out5: tasks run here (incl. fetch tasks), pool slots (owned + mirrors), dependency edges to other GPUs,
  * operand block reads from other GPUs, remote blocks mirrored locally */
 int soglu_dist_info(soglu_ctx* ctx, int64_t* out5);
+/* Collective calls in this mode: soglu_factor (per segment), soglu_solve / soglu_solve_refined (at most one refinement
+ * step; the residual is formed on rank 0, which alone needs soglu_set_matrix).  The ranks must load the same problem
+ * with the same options: soglu_dist_import rejects peers whose sharded layout (tasks, pool slots, segment boundaries per
+ * GPU) differs -- the pool capacity is derived from the device's TOTAL memory for that reason, not from what is free. */
 
 /* ---------------- B. host front-end (bit-exact integer planning) ------------------------ */
 

@@ -21,6 +21,7 @@ ABI_SYMBOLS = [
     "soglu_problem_log", "soglu_load_problem", "soglu_solve_problem", "soglu_solveLU", "soglu_free", "soglu_write_stencil_mtx",
     "soglu_create_dist", "soglu_dist_blob_bytes", "soglu_dist_export", "soglu_dist_import", "soglu_dist_reset", "soglu_dist_info",
     "soglu_dist_segments", "soglu_dist_set_segment", "soglu_set_matrix", "soglu_solve_refined", "soglu_set_host_threads", "soglu_set_blocks_sparse",
+    "soglu_diag_warnings",
 ]
 
 OP_NAMES = {1: "lu", 2: "lowerInv", 3: "upperInv", 4: "sub", 8: "mul", 9: "mulneg", 10: "llt", 11: "mult"}
@@ -87,6 +88,8 @@ def lib():
     L.soglu_dist_info.argtypes = [vp, vp]
     L.soglu_dist_segments.argtypes = [vp]
     L.soglu_dist_set_segment.argtypes = [vp, ctypes.c_int]
+    L.soglu_diag_warnings.argtypes = [vp]
+    L.soglu_diag_warnings.restype = i64
     _lib = L
     return L
 
@@ -256,6 +259,10 @@ class Context:
             ui, ur, uc = c(U[:, 0]), c(U[:, 1]), c(U[:, 2])
             _check(lib().soglu_set_factors(self.h, len(li), _ptr(li), _ptr(lr), _ptr(lc), len(ui), _ptr(ui), _ptr(ur), _ptr(uc),
                                            n_block_rows, int(symmetric)))
+
+    def diag_warnings(self):
+        """Diagonal blocks of the last factorisation that fail the reference's inv_check_diag (0 when healthy)."""
+        return int(lib().soglu_diag_warnings(self.h))
 
     def segments(self):
         """Executor launches per factorisation (more than one when pool slots are recycled); valid once compiled."""

@@ -25,6 +25,12 @@ namespace {
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    // grow-only: a buffer that is already large enough is kept (cudaMalloc / cudaFree cost milliseconds each once tens of
+    // GB and peer mappings exist -- the per-step staging buffers of a refactorisation must not pay that)
+    cudaError_t reserve(size_t n) {
+        if (p && bytes >= n) return cudaSuccess;
+        return alloc(n);
+    }
     cudaError_t alloc(size_t n) {
         release();
         if (n == 0) return cudaSuccess;
@@ -75,7 +81,8 @@ struct soglu_ctx {
     int64_t n_ids = 0, n_input = 0;
     std::vector<int32_t> input_ids;
     DevBuf in_dense;               // staging for dense input blocks until slots are known
-    DevBuf in_entry_input, in_entry_pos, in_entry_val;   // staging for a sparse entry list (soglu_set_blocks_sparse)
+    DevBuf in_entry_input, in_entry_pos, in_entry_val;   // staging for a sparse entry list (soglu_set_blocks_sparse); kept for the next upload
+    DevBuf in_slots;               // pool slot of every input block on this GPU (-1: another GPU's), built once
     int64_t n_entries = -1;        // >= 0: the pending inputs are an entry list
     bool inputs_pending = false;
     int64_t n_ops = 0;
@@ -104,6 +111,7 @@ struct soglu_ctx {
     // refinement step never refills a vector a slower peer may still read)
     DevBuf sv, my_rows;       // (sv: + 64 bytes of epoch slots for the device-side barrier of the sharded solve)
     int32_t n_my_rows = 0;
+    int64_t diag_warnings = 0; // diagonal blocks of the last factorisation that failed inv_check_diag (NaN / Inf pivots)
     int32_t solve_epoch = 0;  // collective solves so far (the ranks call in lockstep)
     void* peer_sv[MAX_GPUS] = {};
     int64_t nL_off = 0, nU_off = 0;
@@ -128,8 +136,12 @@ int fail(int code, const std::string& msg) { soglu::set_error(msg); return code;
 
 // after the stream has been synchronised: did a kernel's watchdog give up?  (clears the word for the next call)
 int check_watchdog(soglu_ctx* c, const char* what) {
-    int32_t w[4] = {0, 0, 0, 0};
+    int32_t w[12] = {};
     if (cudaMemcpy(w, c->abort_word(), sizeof w, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(SOGLU_ERR_CUDA, "cannot read the watchdog word");
+    if (what[0] == 'f') {           // factorisation: the inv_check_diag counter (reset for the next one)
+        c->diag_warnings = w[8];
+        if (w[8]) cudaMemset(c->abort_word() + 8, 0, 4);
+    }
     if (w[0] == 0) return SOGLU_OK;
     cudaMemset(c->abort_word(), 0, 64);
     char m[320];
@@ -221,26 +233,25 @@ int build_tri(soglu_ctx* c, const std::vector<int32_t>& ids, const std::vector<i
 
 int pack_pending_inputs(soglu_ctx* c) {
     if (!c->inputs_pending) return SOGLU_OK;
-    std::vector<int32_t> slots(c->n_input);
-    for (int64_t k = 0; k < c->n_input; k++) {
-        const int32_t id = c->input_ids[k];
-        slots[k] = (!c->dist || c->Gp->owner_of[id] == c->rank) ? c->Gp->slot_of[id] : -1;   // other GPUs' inputs are skipped
+    if (!c->in_slots.p) {
+        std::vector<int32_t> slots(c->n_input);
+        for (int64_t k = 0; k < c->n_input; k++) {
+            const int32_t id = c->input_ids[k];
+            slots[k] = (!c->dist || c->Gp->owner_of[id] == c->rank) ? c->Gp->slot_of[id] : -1;   // other GPUs' inputs are skipped
+        }
+        int rc = upload(c->in_slots, slots, c);
+        if (rc) return rc;
     }
-    DevBuf dslots;
-    int rc = upload(dslots, slots, c);
-    if (rc) return rc;
     if (c->n_entries >= 0) {
-        CU(launch_scatter_entries(c->pool.as<double>(), dslots.as<int32_t>(), c->n_input, c->in_entry_input.as<int32_t>(), c->in_entry_pos.as<int32_t>(),
+        CU(launch_scatter_entries(c->pool.as<double>(), c->in_slots.as<int32_t>(), c->n_input, c->in_entry_input.as<int32_t>(), c->in_entry_pos.as<int32_t>(),
                                   c->in_entry_val.as<double>(), c->n_entries, c->stream));
         c->launches += c->n_entries > 0 ? 2 : 1;
     } else {
-        CU(launch_pack_blocks(c->pool.as<double>(), c->in_dense.as<double>(), dslots.as<int32_t>(), c->n_input, c->stream));
+        CU(launch_pack_blocks(c->pool.as<double>(), c->in_dense.as<double>(), c->in_slots.as<int32_t>(), c->n_input, c->stream));
         c->launches++;
     }
     CU(cudaStreamSynchronize(c->stream));
-    dslots.release();
-    c->in_dense.release();
-    c->in_entry_input.release(); c->in_entry_pos.release(); c->in_entry_val.release();
+    c->in_dense.release();         // (dense staging is 30x larger than the entry list: not kept)
     c->n_entries = -1;
     c->inputs_pending = false;
     return SOGLU_OK;
@@ -577,7 +588,7 @@ void soglu_destroy(soglu_ctx* c) {
             for (void* p : {c->peer_pool[g], c->peer_dep[g], c->peer_ready[g], c->peer_counters[g], c->peer_sv[g]})
                 if (p) cudaIpcCloseMemHandle(p);
         }
-    for (DevBuf* b : {&c->in_dense, &c->in_entry_input, &c->in_entry_pos, &c->in_entry_val, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
+    for (DevBuf* b : {&c->in_dense, &c->in_entry_input, &c->in_entry_pos, &c->in_entry_val, &c->in_slots, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
                       &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->sv, &c->my_rows, &c->trace, &c->m_rp, &c->m_ci, &c->m_v, &c->d_xacc})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -666,9 +677,9 @@ int soglu_set_blocks_sparse(soglu_ctx* c, int64_t n_block_ids, int64_t n_input, 
     CU(cudaSetDevice(c->device));
     int rc = register_input_pattern(c, n_block_ids, n_input, input_ids);
     if (rc) return rc;
-    CU(c->in_entry_input.alloc(std::max<size_t>(n_entries, 1) * 4));
-    CU(c->in_entry_pos.alloc(std::max<size_t>(n_entries, 1) * 4));
-    CU(c->in_entry_val.alloc(std::max<size_t>(n_entries, 1) * 8));
+    CU(c->in_entry_input.reserve(std::max<size_t>(n_entries, 1) * 4));
+    CU(c->in_entry_pos.reserve(std::max<size_t>(n_entries, 1) * 4));
+    CU(c->in_entry_val.reserve(std::max<size_t>(n_entries, 1) * 8));
     if (n_entries) {
         CU(cudaMemcpyAsync(c->in_entry_input.p, entry_input, (size_t)n_entries * 4, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->in_entry_pos.p, entry_pos, (size_t)n_entries * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1136,6 +1147,14 @@ int soglu_debug_trace_summary(soglu_ctx* c, int nbins, double* out) {
     if (c->opt_grid > 0 && c->opt_grid < grid) grid = (int)c->opt_grid;
     out[5] = grid;
     return SOGLU_OK;
+}
+
+// diagonal blocks of the last soglu_factor whose U U^-1 failed the reference's inv_check_diag (1 +- 1e-3 on the diagonal;
+// MatrixStdDouble.cpp:2871, printed as " upper out of tolerance" at BlockPlanner.cpp:575-577): 0 for a healthy factorisation
+int64_t soglu_diag_warnings(soglu_ctx* c) {
+    if (!c) return -1;
+    if (!c->members.empty()) { int64_t n = 0; for (soglu_ctx* m : c->members) n += m->diag_warnings; return n; }
+    return c->diag_warnings;
 }
 
 int soglu_get_block(soglu_ctx* c, int32_t id, double* out_64x64) {

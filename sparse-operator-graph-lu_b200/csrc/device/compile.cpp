@@ -66,6 +66,7 @@ struct Compiler {
     int64_t nid = 0;                        // block ids including mirrors
     int nown = 1;
     std::vector<int32_t> seg_of;            // task -> segment
+    std::vector<uint8_t> reused_slot;       // block id -> its pool slot is shared in time with another block (recycling)
     std::vector<int64_t> poff;              // predecessor lists: offsets into pflat (capacity per task), pcnt entries each
     BigVec<int32_t> pflat;
     std::vector<int32_t> pcnt;
@@ -528,6 +529,7 @@ struct Compiler {
     auto canon = [&](int32_t id) { return alias_to[id] ? alias_to[id] : id; };
     seg_of.assign(nt, 0);
     G.recycled.assign(nid, 0);
+    reused_slot.assign(nid, 0);
     G.seg_begin.assign(1, 0);
     G.slots_per_owner.assign(nown, 1);          // local slot 0 of every GPU is its all-zero block
     {
@@ -567,9 +569,11 @@ struct Compiler {
             std::vector<std::vector<int32_t>> freelist(nown);
             for (int64_t id = 1; id < nid; id++)
                 if (info[id].is_input) G.slot_of[id] = (int32_t)G.slots_per_owner[G.owner_of[id]]++;
+            bool took_fresh = false;
             auto take = [&](int o) -> int32_t {
+                took_fresh = false;
                 if (!freelist[o].empty()) { int32_t sl = freelist[o].back(); freelist[o].pop_back(); return sl; }
-                if (G.slots_per_owner[o] < opt.max_slots) return (int32_t)G.slots_per_owner[o]++;
+                if (G.slots_per_owner[o] < opt.max_slots) { took_fresh = true; return (int32_t)G.slots_per_owner[o]++; }
                 return -1;
             };
             int32_t cur_seg = 0;
@@ -600,6 +604,7 @@ struct Compiler {
                         if (sl < 0) return "block pool too small for the live set of the factorisation";
                     }
                     G.slot_of[id] = sl;
+                    if (!took_fresh || !pinned[id]) reused_slot[id] = 1;    // the slot has held, or will hold, another block
                 }
                 seg_of[t] = cur_seg;
             }
@@ -835,6 +840,13 @@ struct Compiler {
         for (int64_t t = 0; t < (int64_t)G.tasks.size(); t++) {
             Task& T = G.tasks[t];
             const int o = G.task_owner[t];
+            if (T.type == T_LU || T.type == T_LLT) {
+                bool clean = !reused_slot[T.out];
+                if (T.type == T_LU) clean = clean && !reused_slot[T.out2];
+                if (T.flags & TF_LINV) clean = clean && !reused_slot[T.init];
+                if (T.flags & TF_UINV) clean = clean && !reused_slot[T.out4];
+                if (clean) T.flags |= TF_TRI_OUT;
+            }
             T.out = ref(T.out, o);
             if (T.type == T_LU) T.out2 = ref(T.out2, o);
             if (T.flags & (TF_INIT | TF_LINV)) T.init = ref(T.init, o);

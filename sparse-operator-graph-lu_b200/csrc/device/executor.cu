@@ -92,19 +92,29 @@ __device__ __forceinline__ void math_sync() { ptx::named_bar_sync(BAR_MATH, N_MA
 // (L, U) = LU(A) without pivoting, unit-diagonal L, |u_kk| < 1e-9 clamped sign-preserving (ludcmpSimple,
 // MatrixStdDouble.cpp:2711-2784; plain FP64 instead of x87 long double) and, fused, both triangular inverses
 // (inv_lower / inv_upper, MatrixStdDouble.cpp:2787-2802, 2829-2866).
-__device__ __forceinline__ void lu_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gU, double* gLi, double* gUi, int ct) {
+__device__ __forceinline__ void lu_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gU, double* gLi, double* gUi, bool tri, int32_t* warn, int ct) {
     const bool inv = gLi != nullptr || gUi != nullptr;
     if (inv) lub::lu_blocked<true, false>(As, Ws, scr, ct);
     else lub::lu_blocked<false, false>(As, nullptr, scr, ct);
+    // tri (TF_TRI_OUT): the identically-zero half of every result is already zero in its slot -- only the pairs that touch the
+    // triangle are stored (the write-out is bound by the SM's store bandwidth: 139 KB are 2.9 us, half of it 1.5 us)
     for (int e = ct; e < BLK * BLK / 2; e += N_MATH) {
         const int i = e >> 5, j = (e & 31) * 2, o = i * BLK_LD + j;
+        const bool lo = !tri || j <= i, up = !tri || j + 1 >= i;
         const double2 v = *reinterpret_cast<const double2*>(As + o);
-        *reinterpret_cast<double2*>(gL + o) = make_double2(j < i ? v.x : (j == i ? 1.0 : 0.0), j + 1 < i ? v.y : (j + 1 == i ? 1.0 : 0.0));
-        *reinterpret_cast<double2*>(gU + o) = make_double2(j >= i ? v.x : 0.0, j + 1 >= i ? v.y : 0.0);
+        if (lo) *reinterpret_cast<double2*>(gL + o) = make_double2(j < i ? v.x : (j == i ? 1.0 : 0.0), j + 1 < i ? v.y : (j + 1 == i ? 1.0 : 0.0));
+        if (up) *reinterpret_cast<double2*>(gU + o) = make_double2(j >= i ? v.x : 0.0, j + 1 >= i ? v.y : 0.0);
         if (inv) {
             const double2 w = *reinterpret_cast<const double2*>(Ws + o);
-            if (gLi) *reinterpret_cast<double2*>(gLi + o) = make_double2(j < i ? w.x : (j == i ? 1.0 : 0.0), j + 1 < i ? w.y : (j + 1 == i ? 1.0 : 0.0));
-            if (gUi) *reinterpret_cast<double2*>(gUi + o) = make_double2(j >= i ? w.x : 0.0, j + 1 >= i ? w.y : 0.0);
+            if (gLi && lo) *reinterpret_cast<double2*>(gLi + o) = make_double2(j < i ? w.x : (j == i ? 1.0 : 0.0), j + 1 < i ? w.y : (j + 1 == i ? 1.0 : 0.0));
+            if (gUi && up) *reinterpret_cast<double2*>(gUi + o) = make_double2(j >= i ? w.x : 0.0, j + 1 >= i ? w.y : 0.0);
+            // The reference's only numeric sanity signal, inv_check_diag after upperInv (MatrixStdDouble.cpp:2871-2937,
+            // BlockPlanner.cpp:575-577): diag(U U^-1) within 1 +- 1e-3.  For triangular factors that diagonal is u_ii times
+            // the inverse's ii entry (its off-diagonal probe is identically 0), so in effect it flags NaN / Inf pivots.
+            if (gUi && warn && (j == i || j + 1 == i)) {
+                const double p = (j == i) ? v.x * w.x : v.y * w.y;
+                if (!(p <= 1.0 + 1e-3 && p >= 1.0 - 1e-3)) atomicAdd(warn, 1);
+            }
         }
     }
     // the stage was written through the generic proxy; the next bulk copy into it comes through the async proxy
@@ -115,7 +125,7 @@ __device__ __forceinline__ void lu_task_blocked(double* As, double* Ws, double* 
 // that L (inv_lower uses the stored diagonal, 2787-2802).  The blocked sweep gives A = L1 D L1^T with unit L1, so
 // chol(A) = L1 sqrt(D) and chol(A)^-1 = D^-1/2 L1^-1.  Only the symmetric (LL^T) path of the planner emits this task
 // (BlockPlanner.cpp:941-989).
-__device__ __forceinline__ void llt_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gLi, int ct) {
+__device__ __forceinline__ void llt_task_blocked(double* As, double* Ws, double* scr, double* gL, double* gLi, bool tri, int ct) {
     if (gLi) lub::lu_blocked<true, true, false>(As, Ws, scr, ct);
     else lub::lu_blocked<false, true, false>(As, nullptr, scr, ct);
     double* sq = scr + lub::SCR_LDI;   // [64] sqrt(d_k), [64] 1 / sqrt(d_k)   (the panel-inverse scratch is free again)
@@ -127,6 +137,7 @@ __device__ __forceinline__ void llt_task_blocked(double* As, double* Ws, double*
     math_sync();
     for (int e = ct; e < BLK * BLK; e += N_MATH) {
         const int i = e >> 6, j = e & 63, o = i * BLK_LD + j;
+        if (tri && j > i) continue;
         gL[o] = (j < i) ? As[o] * sq[j] : (j == i ? sq[i] : 0.0);
         if (gLi) gLi[o] = ((j < i) ? Ws[o] : (j == i ? 1.0 : 0.0)) * sq[64 + i];
     }
@@ -457,10 +468,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
                 }
                 case T_LU:
                     lu_task_blocked(As, Bs, lub_scr, out, blk_ptr(P, d.out2), (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr,
-                                    (d.flags & TF_UINV) ? blk_ptr(P, d.out4) : nullptr, ct);
+                                    (d.flags & TF_UINV) ? blk_ptr(P, d.out4) : nullptr, (d.flags & TF_TRI_OUT) != 0, P.abort + 8, ct);
                     break;
                 case T_LLT:
-                    llt_task_blocked(As, Bs, lub_scr, out, (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr, ct);
+                    llt_task_blocked(As, Bs, lub_scr, out, (d.flags & TF_LINV) ? blk_ptr(P, d.init) : nullptr, (d.flags & TF_TRI_OUT) != 0, ct);
                     break;
                 case T_LOWERINV:
                     tri_inv_task<false>(As, ctl->scratch, out, ct);
@@ -496,13 +507,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) diag_bench_kernel(double* pool, 
         for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = slot(1)[i];
         math_sync();
         long long c0 = clock64();
-        lu_task_blocked(As, Ws, scr, slot(2), slot(3), slot(4), slot(5), ct);
+        lu_task_blocked(As, Ws, scr, slot(2), slot(3), slot(4), slot(5), true, nullptr, ct);
         math_sync();
         long long c1 = clock64();
         for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = slot(1)[i];
         math_sync();
         long long c2 = clock64();
-        lu_task_blocked(As, Ws, scr, slot(2), slot(3), nullptr, nullptr, ct);
+        lu_task_blocked(As, Ws, scr, slot(2), slot(3), nullptr, nullptr, true, nullptr, ct);
         math_sync();
         long long c3 = clock64();
         for (int i = ct; i < BLK_ELEMS; i += N_MATH) As[i] = slot(2)[i];

@@ -25,7 +25,8 @@ struct ExecParams {
     int32_t* tail;         // next queue slot to publish
     int32_t n_tasks;       // queue length for this launch
     int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
-    int32_t* abort;        // watchdog word of this GPU {flag, queue slot, CTA, rank}; aborts[g] = the peers' (multi-GPU)
+    int32_t* abort;        // watchdog word of this GPU {flag, queue slot, CTA, rank}; aborts[g] = the peers' (multi-GPU);
+                           // abort[8] counts diagonal blocks whose U U^-1 fails the reference's inv_check_diag
     int32_t* aborts[MAX_GPUS];
     unsigned long long watchdog_ns;   // a scheduler lane that has waited this long since the launch gives up (0 = never)
     int32_t debug_drop;    // test hook for the watchdog: the completion of this task is NOT propagated (-1 = none)

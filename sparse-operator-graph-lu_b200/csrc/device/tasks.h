@@ -53,6 +53,8 @@ enum TaskFlags : int32_t {
     TF_INIT = 4,     // GEMM: start from block `init` instead of zero (fused sub)
     TF_LINV = 8,     // LU/LLT: also produce out3 = L^-1 (fused lowerInv)
     TF_UINV = 16,    // LU: also produce out4 = U^-1 (fused upperInv)
+    TF_TRI_OUT = 32, // LU/LLT: every result block sits in a pool slot that no other block ever occupies, so the half of the triangle
+                     // that is identically zero still holds the zeros of the pool's initial memset and need not be written
     // GEMM row split: the task computes rows [16*row0, 16*row0 + 16*nrows) of the target block
     TF_ROW0_SHIFT = 8,    // 2 bits: first row / 16
     TF_NROWS_SHIFT = 12   // 3 bits: rows / 16 (4 = whole block, 2 = half, 1 = quarter)

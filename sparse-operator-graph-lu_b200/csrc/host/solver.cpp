@@ -127,6 +127,7 @@ double* soglu_solveLU(int dim, int valcount, int symmetric, const int* index_i, 
         if (n_gpus > 1) std::cout << "sharded over " << n_gpus << " GPUs (2D block-cyclic block ownership)\n";
         if (soglu_load_problem(ctx, prob)) break;
         if (soglu_factor(ctx, &fs)) break;
+        for (int64_t k = 0, n_bad = soglu_diag_warnings(ctx); k < n_bad && k < 8; k++) std::cout << " upper out of tolerance " << std::endl;   // (BlockPlanner.cpp:576; capped)
         std::cout << "kernel time: " << fs.seconds << "  (" << fs.flops / fs.seconds * 1e-9 << " GFLOP/s, " << fs.tasks << " tasks)\n";
         x = (double*)std::malloc(sizeof(double) * dim);
         if (soglu_solve_problem(ctx, prob, nullptr, x, 0, &ss)) { std::free(x); x = nullptr; break; }

@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+echo skip tests
 for w in lap3d_64 lap3d_100; do
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 3 --warmup 3 --workload $w --no-cpu-baseline --trace > gpurun_out/bench_n2_$w.json 2> gpurun_out/bench_n2_$w.err
 grep "^rank" gpurun_out/bench_n2_$w.err | cut -c1-300; python - <<PY
