@@ -479,6 +479,7 @@ def test_diagonal_kernel_factors(sg, oracle, tmp_path, name):
     ctx = sg.Context(0)
     ctx.load(p)
     ctx.factor()
+    assert ctx.diag_warnings() == 0
     x, _ = ctx.solve(p)
     assert _rel(x, g["x"]) <= TOL_X
     x_ext, h = oracle.run(p)
@@ -540,4 +541,20 @@ def test_watchdog_aborts_and_recovers(sg, tmp_path):
     ctx.factor()
     x, _ = ctx.solve(p)
     assert _rel(x, g["x"]) <= TOL_X
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_diag_warnings_flag_nan_pivots(sg):
+    """soglu_diag_warnings = the reference's inv_check_diag signal (MatrixStdDouble.cpp:2871, " upper out of tolerance"):
+    0 for a healthy matrix, > 0 when a NaN reaches the pivots."""
+    import gen_mtx
+    n, r, c, v = gen_mtx.generate("lap2d", 24)
+    v = v.copy()
+    v[(r == 100) & (c == 100)] = np.nan
+    p = sg.Problem.from_coo(n, r, c, v, gen_mtx.rhs(n))
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    assert ctx.diag_warnings() > 0
     ctx.close()
