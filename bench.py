@@ -475,7 +475,7 @@ def main():
         t_solve = sum(s_dev) / len(s_dev)
         achieved = flops / t_factor * 1e-12
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_executor_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_executor_traffic.json")
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))

@@ -198,6 +198,32 @@ def test_midsize_against_live_reference(sg, tmp_path):
     ctx.close()
 
 
+@pytest.mark.timeout(600)
+def test_config2_against_live_reference(sg, tmp_path):
+    """BASELINE config 2 (3D 7-pt 64^3) at full size against the UNMODIFIED reference run here on the host (about 13 s on
+    16 threads; the largest BASELINE stencil config whose reference run fits this box -- 100^3 is OOM-killed at 205 GB,
+    profiles/r02_reference_100_oom.md): relative solution difference <= 1e-10 (north-star gate), for the raw solve and
+    for the refined one the benchmark times."""
+    harness = ref_harness_path()
+    if harness is None:
+        pytest.skip("oracle/_ref not present on this box")
+    path = str(tmp_path / "l3d64.mtx")
+    sg.write_stencil_mtx("lap3d", path, 64)
+    out = tmp_path / "ref"
+    out.mkdir()
+    subprocess.run([harness, path, str(out), "--lean"], check=True, capture_output=True, env=dict(os.environ, OMP_NUM_THREADS="16"))
+    xref = np.fromfile(out / "x.f64")
+    p = sg.Problem.from_mtx(path)
+    ctx = sg.Context(0)
+    ctx.load(p)
+    ctx.factor()
+    x, _ = ctx.solve(p)
+    xr, _ = ctx.solve(p, refine=1)
+    assert _rel(x, xref) <= TOL_X
+    assert _rel(xr, xref) <= TOL_X
+    ctx.close()
+
+
 def test_config2_properties(sg, tmp_path):
     """BASELINE config 2 (3D 7-pt 64^3, n = 262 144, 7.1 M ops) at full size: residual gate,
     padding rows, and agreement with a second factorisation."""
