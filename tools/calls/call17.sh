@@ -1,1 +1,1 @@
-cd $GRAFT_REPO_ROOT; python tools/calls/dw.py
+cd $GRAFT_REPO_ROOT; timeout 60 tools/bin/poll_lat

@@ -1,0 +1,9 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 300 python tools/r02_sweep.py lap3d 64
+timeout 300 python tools/r02_sweep.py nine2d 1024
+timeout 300 python tools/r02_sweep.py banded 200000
+timeout 300 python tools/trace_analyze.py lap3d 64x64x64 2>&1 | head -12
+for h in 1 0; do timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --opt handoff=$h | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); c=d['config']; print('lap3d_100 handoff=$h: factor %.1f ms solve %.1f step %.1f e2e %.1f x %s' % (c['factor_ms'], c['solve_ms'], d['ms_per_step'], d['e2e']['ms_per_step'], d['x_sha256'][:16]))"; done
