@@ -1,8 +1,8 @@
 cd $GRAFT_REPO_ROOT
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 300 python tools/r02_sweep.py lap3d 64
-timeout 300 python tools/r02_sweep.py nine2d 1024
-timeout 300 python tools/r02_sweep.py banded 200000
+timeout 300 python tools/option_sweep.py lap3d 64
+timeout 300 python tools/option_sweep.py nine2d 1024
+timeout 300 python tools/option_sweep.py banded 200000
 timeout 300 python tools/trace_analyze.py lap3d 64x64x64 2>&1 | head -12
 for h in 1 0; do timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --opt handoff=$h | python -c "
 import json,sys

@@ -1,8 +1,7 @@
 #!/usr/bin/env python3
-"""Round-2 sweep: one BASELINE config, planned once, factorised with every prepared executor option (fresh context
-per variant); prints the factor time and the deviation of x from the default run.  Variants that touch unmeasured
-kernel code come last, so a hang there (kill it with `timeout`) does not lose the earlier lines.
-usage: r02_sweep.py <kind> <dims...>      e.g.  r02_sweep.py lap3d 64"""
+"""One BASELINE config, planned once, factorised with every listed set of executor options (fresh context per variant);
+prints the factor time and the deviation of x from the default run.
+usage: option_sweep.py <kind> <dims...>      e.g.  option_sweep.py lap3d 64"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,7 +11,7 @@ import soglu_b200 as sg
 
 VARIANTS = [
     ("default", {}),
-    ("lazy_claim=0", {"lazy_claim": 0}),
+    ("split_slack=0", {"split_slack": 0}),
 ]
 
 kind, dims = sys.argv[1], [int(a) for a in sys.argv[2:]]
