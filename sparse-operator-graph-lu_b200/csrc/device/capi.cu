@@ -59,6 +59,7 @@ struct soglu_ctx {
     int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
     int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;
+    int64_t opt_static_order = 1;  // 1: tasks sorted most-urgent-first (latest start time); 0: in the order of the operation list
     int64_t opt_grid = 0;          // override CTA count (0 = all resident)
     int64_t opt_trace = 0;         // record per-task timestamps (debug; adds overhead)
     int64_t opt_debug_drop = -1;       // test hook: lose the completion signal of this task (the watchdog must catch the hang)
@@ -278,6 +279,7 @@ int finalize(soglu_ctx* c) {
     co.split_narrow = (int)c->opt_split;
     co.n_sms = c->sms;
     co.split_slack_us = (double)std::max<int64_t>(0, c->opt_split_slack);
+    co.static_order = c->opt_static_order != 0;
     {
         // Pool capacity: what is free now minus the graph arrays (estimated from the op count) and a margin.
         // Sharded runs: every rank compiles the WHOLE graph and must arrive at the same slot numbers and segment
@@ -611,6 +613,7 @@ int soglu_set_option(soglu_ctx* c, const char* key, int64_t value) {
     else if (k == "max_slots") { if (c->compiled) return fail(SOGLU_ERR_ARG, "max_slots must be set before the first factor"); c->opt_max_slots = value; }
     else if (k == "mirror_min") { if (c->compiled) return fail(SOGLU_ERR_ARG, "mirror_min must be set before the first factor"); c->opt_mirror_min = value; }
     else if (k == "dist_nb") { if (c->compiled) return fail(SOGLU_ERR_ARG, "dist_nb must be set before the first factor"); c->opt_dist_nb = value; }
+    else if (k == "static_order") { if (c->compiled) return fail(SOGLU_ERR_ARG, "static_order must be set before the first factor"); c->opt_static_order = value; }
     else if (k == "split_slack") { if (c->compiled) return fail(SOGLU_ERR_ARG, "split_slack must be set before the first factor"); c->opt_split_slack = value; }
     else if (k == "grid") c->opt_grid = value;
     else if (k == "trace") c->opt_trace = value;
@@ -790,6 +793,7 @@ static int factor_launch(soglu_ctx* c) {
         P.ready = c->ready.as<int32_t>() + sb[sg];
         P.head = cnt; P.tail = cnt + 32;
         P.n_tasks = sb[sg + 1] - sb[sg];
+        P.task0 = sb[sg];
         if (c->dist)
             for (int g = 0; g < c->world; g++) {
                 P.readys[g] = (int32_t*)c->peer_ready[g] + c->D.seg_begin_all[g][sg];

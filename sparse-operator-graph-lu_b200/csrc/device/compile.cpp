@@ -116,6 +116,7 @@ struct Compiler {
         if (!(e = dependencies()).empty()) return e;
         if (!(e = levels()).empty()) return e;
         if (!(e = split_rows()).empty()) return e;
+        if (!(e = static_order()).empty()) return e;
         if (!(e = finish()).empty()) return e;
         return "";
     }
@@ -797,6 +798,78 @@ struct Compiler {
         }
     }
     lap("row split");
+        return "";
+    }
+
+    // ==== static execution order: most urgent first ===========================================================
+    std::string static_order() {
+    // The executor claims tasks IN TASK ORDER (slot s of a segment = its s-th task) and waits on the claimed task's
+    // dependency counter, so the order is the schedule's priority list.  Tasks are sorted by their latest start time
+    // under the cost model (longest chain of the segment minus the longest chain from the task to a sink): work on
+    // the critical chain comes first, bulk work is ordered by when the chain will need it.  A latest-start order is
+    // topological (lst(succ) >= lst(pred) + dur(pred)), so the lowest unfinished task of a run is always claimed and
+    // ready: no deadlock, on one GPU or on several (each GPU keeps its tasks in this global order).
+    if (!opt.static_order || G.tasks.empty()) return "";
+    const int64_t n = (int64_t)G.tasks.size();
+    const ModelParams M;
+    std::vector<double> bl(n, 0.0), key(n, 0.0);
+    std::vector<int32_t> seg(n, 0);
+    const int nseg = (int)G.seg_begin.size() - 1;
+    for (int sg = 0; sg < nseg; sg++)
+        for (int32_t t = G.seg_begin[sg]; t < G.seg_begin[sg + 1]; t++) seg[t] = sg;
+    // longest chain from the start of a task to a sink of its segment; successor lists name group leaders, the
+    // slices of one task share their leader's list
+    std::vector<double> cp(std::max(nseg, 1), 0.0);
+    for (int64_t t = n - 1; t >= 0; t--) {
+        const Task& T = G.tasks[t];
+        double m = 0.0;
+        for (int32_t e = T.succ_begin; e < T.succ_end; e++)
+            if (seg[G.succ[e]] == seg[t]) m = std::max(m, bl[G.succ[e]]);
+        bl[t] = model_hop_us(T, M) + m;
+    }
+    // a group's urgency is its most urgent slice's; groups stay contiguous, leader first
+    std::vector<int32_t> leaders;
+    leaders.reserve(n);
+    for (int64_t t = 0; t < n; t++) {
+        if (!task_is_leader(G.tasks[t])) continue;
+        double b = 0.0;
+        for (int q = 0, g = task_group_size(G.tasks[t]); q < g; q++) b = std::max(b, bl[t + q]);
+        bl[t] = b;
+        cp[seg[t]] = std::max(cp[seg[t]], b);
+        leaders.push_back((int32_t)t);
+    }
+    for (int32_t t : leaders) key[t] = cp[seg[t]] - bl[t];
+    std::stable_sort(leaders.begin(), leaders.end(), [&](int32_t a, int32_t b) {
+        if (seg[a] != seg[b]) return seg[a] < seg[b];
+        return key[a] < key[b];
+    });
+    std::vector<int32_t> new_of(n);
+    {
+        int32_t pos = 0;
+        for (int32_t t : leaders)
+            for (int q = 0, g = task_group_size(G.tasks[t]); q < g; q++) new_of[t + q] = pos++;
+    }
+    // a predecessor's latest start is at least its own duration earlier: the order must have stayed topological
+    for (int64_t t = 0; t < n; t++)
+        for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++)
+            if (new_of[G.succ[e]] <= new_of[t]) return "static order: a successor precedes its predecessor";
+    BigVec<Task> tasks2(n);
+    std::vector<int8_t> own2(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < n; t++) { tasks2[new_of[t]] = G.tasks[t]; own2[new_of[t]] = G.task_owner[t]; }
+    G.tasks.swap(tasks2);
+    G.task_owner.swap(own2);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < (int64_t)G.succ.size(); e++) G.succ[e] = new_of[G.succ[e]];
+    // successor lists most urgent first (the slices of a group share one list: the leader sorts it)
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t t = 0; t < n; t++)
+        if (task_is_leader(G.tasks[t]) && G.tasks[t].succ_end - G.tasks[t].succ_begin > 1)
+            std::sort(G.succ.begin() + G.tasks[t].succ_begin, G.succ.begin() + G.tasks[t].succ_end);
+#pragma omp parallel for schedule(static)
+    for (int64_t id = 0; id < (int64_t)G.task_of.size(); id++)
+        if (G.task_of[id] >= 0) G.task_of[id] = new_of[G.task_of[id]];
+    lap("static order");
         return "";
     }
 

@@ -296,9 +296,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
         if (lane == 0) {
             uint32_t it = 0;
             // stream the operand blocks of one ready task into the stage ring
-            auto issue = [&](int t) {
+            auto issue = [&](int t, const Task& T) {
                 if (P.trace) { P.trace[6 * (size_t)t + 1] = gtime(); P.trace[6 * (size_t)t + 5] = smid(); }
-                const Task T = P.tasks[t];
                 ptx::fence_proxy_async();
                 const int nst = (T.type == T_GEMM) ? T.n_pairs : 1;
                 const bool two = (T.type == T_GEMM || T.type == T_SUB);
@@ -326,20 +325,42 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
                 ctl->desc[s].type = T_EXIT;
                 ptx::mbar_arrive(&ctl->full[s]);
             };
-            // claim the next slot of the ready queue and wait until a finishing CTA publishes a task there
+            // Claim the next slot and wait for its task.  Static order (the product path): slot s IS the s-th task of the
+            // segment; the scheduler fetches its record and spins on the group's dependency counter, which the finishing
+            // predecessors count down with fire-and-forget reductions -- a release costs them one fence and one red, no
+            // atomic round trip and no queue tail.  Dynamic queue (debug executor, one launch per level): the slot holds
+            // a task index.
             const unsigned long long deadline = P.watchdog_ns ? gtime() + P.watchdog_ns : 0;
             bool aborted = false;
             while (!aborted) {
                 const int slot = atomicAdd(P.head, 1);
                 if (slot >= P.n_tasks) break;
                 int t;
+                Task T;
                 uint32_t polls = 0;
-                while (true) {
-                    t = (P.world > 1) ? ptx::ld_acquire_sys(P.ready + slot) : ptx::ld_acquire(P.ready + slot);
-                    if (t >= 0) break;
-                    if ((++polls & 1023u) == 0 && watchdog_expired(P, slot, deadline)) { aborted = true; break; }
+                if (P.signal) {
+                    t = P.task0 + slot;
+                    T = P.tasks[t];          // the record is fetched while the task is still waiting for its operands
+                    const int32_t fl = T.flags;
+                    const bool gemm = T.type == T_GEMM;
+                    const int rows16 = (fl >> TF_NROWS_SHIFT) & 7;
+                    // row slices wait on their leader's counter (slice index = first row / rows per slice)
+                    const int32_t* cnt = P.dep + t - ((gemm && rows16 > 0 && rows16 < 4) ? ((fl >> TF_ROW0_SHIFT) & 3) / rows16 : 0);
+                    while (true) {
+                        const int32_t d = (P.world > 1) ? ptx::ld_acquire_sys(cnt) : ptx::ld_acquire(cnt);
+                        if (d <= 0) break;
+                        if ((++polls & 1023u) == 0 && watchdog_expired(P, slot, deadline)) { aborted = true; break; }
+                    }
+                    if (P.trace) P.trace[6 * (size_t)t + 0] = gtime();
+                } else {
+                    while (true) {
+                        t = ptx::ld_acquire(P.ready + slot);
+                        if (t >= 0) break;
+                        if ((++polls & 1023u) == 0 && watchdog_expired(P, slot, deadline)) { aborted = true; break; }
+                    }
+                    if (!aborted) T = P.tasks[t];
                 }
-                if (!aborted) issue(t);
+                if (!aborted) issue(t, T);
             }
             quit();
         }
@@ -366,31 +387,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
                     const int32_t ref = P.succ[e];
                     const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK;
                     if (o != P.rank) { remote = true; continue; }
-                    // sole predecessor: ready now, no counter; otherwise the lane that brings the counter to zero publishes
-                    if ((ref & TASK_SOLE_BIT) || atomicSub(P.dep + nx, 1) == 1) {
-                        // the whole group (all row slices of the successor) becomes ready at once
-                        // (the fence + the strong relaxed stores form the release; the consumers ld.acquire)
-                        const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
-                        if (!(ref & TASK_SOLE_BIT)) ptx::fence_acq_rel_gpu();
-                        const int pos = atomicAdd(P.tail, g);
-                        for (int k = 0; k < g; k++) {
-                            if (P.trace) P.trace[6 * (size_t)(nx + k) + 0] = gtime();
-                            ptx::st_relaxed(P.ready + pos + k, nx + k);
-                        }
-                    }
+                    ptx::red_add(P.dep + nx, -1);
                 }
                 if (__any_sync(0xffffffffu, remote)) {
                     ptx::fence_acq_rel_sys();
                     for (int e = sb + lane; e < se; e += 32) {
                         const int32_t ref = P.succ[e];
                         const int o = (uint32_t)ref >> REF_SHIFT, nx = ref & TASK_LOCAL_MASK;
-                        if (o == P.rank) continue;
-                        if ((ref & TASK_SOLE_BIT) || atomicSub_system(P.deps[o] + nx, 1) == 1) {
-                            const int g = 1 << ((ref >> TASK_SPLIT_SHIFT) & 3);
-                            if (!(ref & TASK_SOLE_BIT)) ptx::fence_acq_rel_sys();
-                            const int pos = atomicAdd_system(P.tails[o], g);
-                            for (int k = 0; k < g; k++) ptx::st_relaxed_sys(P.readys[o] + pos + k, nx + k);
-                        }
+                        if (o != P.rank) ptx::red_add_sys(P.deps[o] + nx, -1);
                     }
                 }
                 if (P.trace && lane == 0) P.trace[6 * (size_t)t + 4] = gtime();

@@ -24,6 +24,7 @@ struct ExecParams {
     int32_t* head;         // next queue slot to claim
     int32_t* tail;         // next queue slot to publish
     int32_t n_tasks;       // queue length for this launch
+    int32_t task0;         // first task of the segment this launch executes (queue slot s = task task0 + s)
     int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
     int32_t* abort;        // watchdog word of this GPU {flag, queue slot, CTA, rank}; aborts[g] = the peers' (multi-GPU);
                            // abort[8] counts diagonal blocks whose U U^-1 fails the reference's inv_check_diag

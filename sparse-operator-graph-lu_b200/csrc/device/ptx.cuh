@@ -73,6 +73,14 @@ __device__ __forceinline__ void st_relaxed(int* p, int v) {
 __device__ __forceinline__ void st_relaxed_sys(int* p, int v) {
     asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// fire-and-forget counter updates (no return value: the issuing thread does not wait for the L2 round trip); after a
+// fence of the matching scope they complete a release pattern like the strong stores above
+__device__ __forceinline__ void red_add(int* p, int v) {
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_sys(int* p, int v) {
+    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

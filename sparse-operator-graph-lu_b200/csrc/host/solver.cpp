@@ -285,6 +285,51 @@ extern "C" int soglu_debug_simulate(const soglu_problem* pp, int split, int pr, 
     }
     uint64_t rng = seed * 6364136223846793005ull + 1442695040888963407ull;
     int64_t done = 0, bad = 0;
+    if (seed == 0) {
+        // The executor's own discipline (executor.cu): every GPU has a few workers, each claims the next task of its
+        // GPU IN TASK ORDER and waits until the group's counter is zero; a finished task counts every successor group
+        // down by one.  A sweep over all workers without progress while tasks remain = the order would deadlock.
+        const int workers = 3;
+        std::vector<int32_t> next(world, 0);
+        std::vector<std::vector<int32_t>> held(world, std::vector<int32_t>(workers, -1));
+        auto leader = [&](int r, int32_t t) {
+            const soglu::Task& T = D[r].tasks[t];
+            const int rows16 = (T.flags >> soglu::TF_NROWS_SHIFT) & 7;
+            return (T.type == soglu::T_GEMM && rows16 > 0 && rows16 < 4) ? t - ((T.flags >> soglu::TF_ROW0_SHIFT) & 3) / rows16 : t;
+        };
+        int64_t total0 = 0;
+        for (int r = 0; r < world; r++) total0 += (int64_t)D[r].tasks.size();
+        bool progress = true;
+        while (progress) {
+            progress = false;
+            for (int r = 0; r < world; r++)
+                for (int w = 0; w < workers; w++) {
+                    int32_t& h = held[r][(w + (int)(done % workers)) % workers];
+                    if (h < 0 && next[r] < (int32_t)D[r].tasks.size()) { h = next[r]++; progress = true; }
+                    if (h < 0 || dep[r][leader(r, h)] > 0) continue;
+                    const soglu::Task& T = D[r].tasks[h];
+                    if (runs[r][h]++) bad++;
+                    for (int32_t k = 0; k < T.n_pairs; k++) {
+                        const soglu::Pair& pq = D[r].pairs[T.pair_begin + k];
+                        if (writers[key(pq.a)] != 0) bad++;
+                        if ((T.type == soglu::T_GEMM || T.type == soglu::T_SUB) && writers[key(pq.b)] != 0) bad++;
+                    }
+                    if ((T.flags & soglu::TF_INIT) && writers[key(T.init)] != 0) bad++;
+                    for_outs(T, [&](int32_t ref) { writers[key(ref)]--; });
+                    for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
+                        const int32_t ref = D[r].succ[e];
+                        const int o = (uint32_t)ref >> soglu::REF_SHIFT, nx = ref & soglu::TASK_LOCAL_MASK;
+                        if ((ref & soglu::TASK_SOLE_BIT) && dep[o][nx] != 1) bad++;
+                        if (--dep[o][nx] < 0) bad++;
+                    }
+                    done++;
+                    h = -1;
+                    progress = true;
+                }
+        }
+        if (done != total0) bad++;      // stuck
+        ready.clear();
+    }
     while (!ready.empty()) {
         rng = rng * 6364136223846793005ull + 1442695040888963407ull;
         const size_t pick = (size_t)((rng >> 33) % ready.size());

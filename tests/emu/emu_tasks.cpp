@@ -72,7 +72,7 @@ void inv_upper(const double* u, double* y) {     // U Y = I
 }
 }  // namespace
 
-// split: bit 0 = row slices in narrow levels, bit 1 = also near-critical tasks (split_slack), bit 2 = 8 SMs.
+// split: bit 0 = row slices in narrow levels, bit 1 = also near-critical tasks (split_slack), bit 2 = 8 SMs, bit 3 = no static (latest-start) order.
 // mode: unused (0).  max_slots > 0 forces slot recycling.  keep_out: n_keep dense 64x64 blocks.  stats = {tasks, segments, slots, chain cuts applied, row-split tasks}.
 // grid = {pr, pc, nb} with brow / bcol per block id: the graph is compiled for pr*pc owners (2D block-cyclic squares of
 // nb blocks, mirrors of remote blocks filled by fetch tasks) and every owner gets its own pool here.
@@ -85,6 +85,7 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
     co.max_slots = max_slots;
     co.split_narrow = split & 1;
     if (split & 2) co.split_slack_us = 100.0;     // also split near-critical GEMM tasks of wide levels
+    if (split & 8) co.static_order = false;       // keep the tasks in the order of the operation list
     if (split & 4) co.n_sms = 8;                  // pretend the GPU is small: the small test cases get wide levels too
     TaskGraph G;
     auto fail = [&](const std::string& e) { std::snprintf(err_out, err_len, "%s", e.c_str()); return 1; };

@@ -112,11 +112,14 @@ def test_multi_gpu_with_small_pools_uses_segments(sg, prob):
     assert sum(t for t, _, _ in e["per_rank"]) == e["tasks"]
 
 
-@pytest.mark.parametrize("split,pr,pc,nb,seed", [(0, 1, 1, 1, 1), (1, 1, 1, 1, 2), (1, 1, 1, 1, 3), (1, 2, 1, 2, 4), (1, 2, 2, 1, 5), (1, 4, 2, 4, 6)])
+@pytest.mark.parametrize("split,pr,pc,nb,seed", [(0, 1, 1, 1, 1), (1, 1, 1, 1, 2), (1, 1, 1, 1, 3), (1, 2, 1, 2, 4), (1, 2, 2, 1, 5), (1, 4, 2, 4, 6),
+                                                 (1, 1, 1, 1, 0), (1, 2, 1, 2, 0), (1, 2, 2, 1, 0), (1, 4, 2, 4, 0)])
 def test_release_protocol_simulation(sg, prob, split, pr, pc, nb, seed):
-    """Host replay of the executor's dependency protocol on the per-GPU arrays it uploads, in a random
-    order: row slices of one task share their leader's counter and become ready together; every task
-    runs exactly once and never before all writers of its operands are done."""
+    """Host replay of the executor's dependency protocol on the per-GPU arrays it uploads: row slices of one task share
+    their leader's counter and become ready together; every task runs exactly once and never before all writers of its
+    operands are done.  seed > 0: tasks run in a random dependency-driven order.  seed 0: the executor's own discipline --
+    three workers per GPU claim their GPU's tasks in task order and wait on the claimed task's counter; the run must not
+    get stuck (the static order of every GPU is a filter of one global topological order)."""
     L = sg.lib()
     L.soglu_debug_simulate.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_uint64, ctypes.c_void_p]
     out = (ctypes.c_int64 * 3)()

@@ -109,6 +109,20 @@ def test_execution_order_does_not_matter(sg, emu, tmp_path):
         np.testing.assert_array_equal(b, b0)
 
 
+@pytest.mark.parametrize("name,grid,max_slots", [("lap3d_24", None, 0), ("banded_3000", None, 0), ("nine2d_40", None, 0), ("lap3d_24", (2, 2, 2), 0),
+                                                 ("lap3d_24", None, 5200), ("lap3d_24", (2, 2, 2), 2500)])
+def test_static_order_is_a_valid_schedule(sg, emu, oracle, tmp_path, name, grid, max_slots):
+    """The executor claims tasks in task order and waits on the claimed task's counter, so the compiled order (tasks sorted
+    by latest start time, Compiler::static_order) must be topological: executing the tasks one after the other in that order
+    gives the factors, bit for bit those of the operation-list order."""
+    p = sg.Problem.from_mtx(write_case_mtx(name, tmp_path))
+    keep, b_static, st = run_emu(emu, p, seed=0, grid=grid, max_slots=max_slots)
+    _, b_oplist, st2 = run_emu(emu, p, seed=0, split=1 | 8, grid=grid, max_slots=max_slots)
+    assert st["tasks"] == st2["tasks"]
+    np.testing.assert_array_equal(b_static, b_oplist)
+    check_against_oracle(oracle, p, keep, b_static)
+
+
 @pytest.mark.parametrize("grid,max_slots", [((2, 1, 2), 0), ((2, 2, 1), 0), ((4, 2, 4), 0), ((2, 2, 2), 0), ((2, 1, 4), 4000), ((2, 2, 2), 2500)])
 def test_sharded_graph_reproduces_the_factors(sg, emu, oracle, tmp_path, grid, max_slots):
     """The graph compiled for several GPUs (owner-computes, remote blocks mirrored by fetch tasks, per-owner pools), with

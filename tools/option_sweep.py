@@ -11,7 +11,7 @@ import soglu_b200 as sg
 
 VARIANTS = [
     ("default", {}),
-    ("split_slack=0", {"split_slack": 0}),
+    ("static_order=0 (op-list order)", {"static_order": 0}),
 ]
 
 kind, dims = sys.argv[1], [int(a) for a in sys.argv[2:]]
