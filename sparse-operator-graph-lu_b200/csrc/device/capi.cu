@@ -76,7 +76,7 @@ struct soglu_ctx {
     std::vector<soglu_ctx*> members;    // in-process group: this context only forwards to its members (rank g on device g)
     soglu_ctx* leader = nullptr;        // member of a group: rank 0 of it (owns the compiled graph)
     int dist_segment = 0;               // segment the next soglu_factor call runs (multi-GPU)
-    void* peer_pool[MAX_GPUS] = {}, *peer_dep[MAX_GPUS] = {}, *peer_ready[MAX_GPUS] = {}, *peer_counters[MAX_GPUS] = {};
+    void* peer_pool[MAX_GPUS] = {}, *peer_dep[MAX_GPUS] = {}, *peer_counters[MAX_GPUS] = {};
 
     // host-side description (borrowed arrays are copied)
     int64_t n_ids = 0, n_input = 0;
@@ -101,7 +101,7 @@ struct soglu_ctx {
     TaskGraph* Gp = &G_own;          // members of an in-process group (soglu_create with n_gpus > 1) share rank 0's graph
     std::vector<int32_t> level_order;   // tasks sorted by level (debug executor)
     std::vector<int64_t> level_ptr;
-    DevBuf pool, tasks, pairs, succ, dep0, dep, ready, ready0, counters, counters0;
+    DevBuf pool, tasks, pairs, succ, dep0, dep, ready, counters, counters0;
     // watchdog word {flag, queue slot / block row, CTA, rank}: the 64 bytes behind the queue counters (one allocation,
     // so the peers reach it through the IPC mapping of the counters)
     int32_t* abort_word() const { return counters.as<int32_t>() + counters0.bytes / 4; }
@@ -150,7 +150,7 @@ int check_watchdog(soglu_ctx* c, const char* what) {
     else if (w[1] < 0) snprintf(m, sizeof m, "%s aborted by the watchdog after %lld ms: GPU %d never reached the collective call (every rank of a sharded run must call it)", what,
                                 (long long)c->opt_watchdog_ms, -1 - w[1]);
     else snprintf(m, sizeof m, "%s aborted by the watchdog after %lld ms without progress: CTA %d was waiting for %s %d%s", what, (long long)c->opt_watchdog_ms,
-                  w[2], c->factored && what[0] == 's' ? "block row" : "ready-queue slot", w[1],
+                  w[2], c->factored && what[0] == 's' ? "block row" : "task (position in its segment)", w[1],
                   " (a lost dependency signal: a peer that failed, or an operation list with a missing edge)");
     return fail(SOGLU_ERR_CUDA, m);
 }
@@ -341,19 +341,10 @@ int finalize(soglu_ctx* c) {
         if ((rc = upload(c->dep0, d0, c))) return rc;
     }
     {
-        // ready-queue image: per segment slice the initially ready tasks first, -1 elsewhere;
-        // counter image: per segment one 512-byte record {head @ int 0, tail = #initial @ int 32}
+        // counter image: per segment one 512-byte record {next task to claim @ int 0}; the abort word sits behind it
         const std::vector<int32_t>& sb = c->dist ? c->D.seg_begin : G.seg_begin;
-        const std::vector<int32_t>& si = c->dist ? c->D.seg_init : G.seg_init;
-        const std::vector<int32_t>& ini = c->dist ? c->D.initial : G.initial;
         const int nseg = (int)sb.size() - 1;
-        std::vector<int32_t> r0(std::max<size_t>(tasks_up.size(), 1), -1), c0((size_t)std::max(nseg, 1) * 128, 0);
-        for (int sg = 0; sg < nseg; sg++) {
-            const int32_t nb = si[sg + 1] - si[sg];
-            for (int32_t k = 0; k < nb; k++) r0[sb[sg] + k] = ini[si[sg] + k];
-            c0[(size_t)sg * 128 + 32] = nb;
-        }
-        if ((rc = upload(c->ready0, r0, c))) return rc;
+        std::vector<int32_t> c0((size_t)std::max(nseg, 1) * 128, 0);
         if ((rc = upload(c->counters0, c0, c))) return rc;
         CU(c->counters.alloc(c0.size() * 4 + 64));
         CU(cudaMemsetAsync(c->counters.as<char>() + c0.size() * 4, 0, 64, c->stream));
@@ -443,7 +434,7 @@ int soglu_create(soglu_ctx** out, int n_gpus, const int* device_ids) {
 }
 
 // ---- multi-GPU: one process per GPU, peers mapped through CUDA IPC -------------------------------
-struct DistBlob { cudaIpcMemHandle_t pool, dep, ready, counters, sv; int32_t rank, valid; uint64_t layout_hash; };
+struct DistBlob { cudaIpcMemHandle_t pool, dep, counters, sv; int32_t rank, valid; uint64_t layout_hash; };
 
 // FNV-1a over what every rank must agree on: tasks and pool slots per GPU, segment boundaries of every GPU
 static uint64_t dist_layout_hash(const soglu_ctx* c) {
@@ -484,7 +475,6 @@ int soglu_dist_export(soglu_ctx* c, void* blob) {
         b.layout_hash = dist_layout_hash(c);
         CU(cudaIpcGetMemHandle(&b.pool, c->pool.p));
         CU(cudaIpcGetMemHandle(&b.dep, c->dep.p));
-        CU(cudaIpcGetMemHandle(&b.ready, c->ready.p));
         CU(cudaIpcGetMemHandle(&b.counters, c->counters.p));
         CU(cudaIpcGetMemHandle(&b.sv, c->sv.p));
     }
@@ -508,7 +498,7 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
     const DistBlob* bl = reinterpret_cast<const DistBlob*>(all_blobs);
     for (int g = 0; g < c->world; g++) {
         if (g == c->rank || !c->dist) {
-            c->peer_pool[g] = c->pool.p; c->peer_dep[g] = c->dep.p; c->peer_ready[g] = c->ready.p; c->peer_counters[g] = c->counters.p; c->peer_sv[g] = c->sv.p;
+            c->peer_pool[g] = c->pool.p; c->peer_dep[g] = c->dep.p; c->peer_counters[g] = c->counters.p; c->peer_sv[g] = c->sv.p;
             continue;
         }
         if (!bl[g].valid || bl[g].rank != g) return fail(SOGLU_ERR_ARG, "peer handle blob " + std::to_string(g) + " is missing or out of order");
@@ -517,7 +507,6 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
                                        "load the same problem with the same options; set max_slots explicitly if the GPUs differ");
         CU(cudaIpcOpenMemHandle(&c->peer_pool[g], bl[g].pool, cudaIpcMemLazyEnablePeerAccess));
         CU(cudaIpcOpenMemHandle(&c->peer_dep[g], bl[g].dep, cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&c->peer_ready[g], bl[g].ready, cudaIpcMemLazyEnablePeerAccess));
         CU(cudaIpcOpenMemHandle(&c->peer_counters[g], bl[g].counters, cudaIpcMemLazyEnablePeerAccess));
         CU(cudaIpcOpenMemHandle(&c->peer_sv[g], bl[g].sv, cudaIpcMemLazyEnablePeerAccess));
     }
@@ -541,7 +530,6 @@ int soglu_dist_reset(soglu_ctx* c) {
     const size_t nt = c->dist ? c->D.tasks.size() : c->Gp->tasks.size();
     if (nt) {
         CU(cudaMemcpyAsync(c->dep.p, c->dep0.p, nt * 4, cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->ready.p, c->ready0.p, nt * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     CU(cudaMemcpyAsync(c->counters.p, c->counters0.p, c->counters0.bytes, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -587,10 +575,10 @@ void soglu_destroy(soglu_ctx* c) {
     if (c->dist && c->ipc_peers)
         for (int g = 0; g < c->world; g++) {
             if (g == c->rank) continue;
-            for (void* p : {c->peer_pool[g], c->peer_dep[g], c->peer_ready[g], c->peer_counters[g], c->peer_sv[g]})
+            for (void* p : {c->peer_pool[g], c->peer_dep[g], c->peer_counters[g], c->peer_sv[g]})
                 if (p) cudaIpcCloseMemHandle(p);
         }
-    for (DevBuf* b : {&c->in_dense, &c->in_entry_input, &c->in_entry_pos, &c->in_entry_val, &c->in_slots, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->ready0, &c->counters, &c->counters0,
+    for (DevBuf* b : {&c->in_dense, &c->in_entry_input, &c->in_entry_pos, &c->in_entry_val, &c->in_slots, &c->pool, &c->tasks, &c->pairs, &c->succ, &c->dep0, &c->dep, &c->ready, &c->counters, &c->counters0,
                       &c->l_ptr, &c->l_col, &c->l_slot, &c->l_diag, &c->l_dinv, &c->u_ptr, &c->u_col, &c->u_slot, &c->u_diag, &c->u_dinv, &c->d_b, &c->sv, &c->my_rows, &c->trace, &c->m_rp, &c->m_ci, &c->m_v, &c->d_xacc})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -790,15 +778,10 @@ static int factor_launch(soglu_ctx* c) {
     auto set_segment = [&](int sg) {
         const std::vector<int32_t>& sb = c->dist ? c->D.seg_begin : G.seg_begin;
         int32_t* cnt = c->counters.as<int32_t>() + (size_t)sg * 128;
-        P.ready = c->ready.as<int32_t>() + sb[sg];
-        P.head = cnt; P.tail = cnt + 32;
+        P.ready = nullptr;
+        P.head = cnt;
         P.n_tasks = sb[sg + 1] - sb[sg];
         P.task0 = sb[sg];
-        if (c->dist)
-            for (int g = 0; g < c->world; g++) {
-                P.readys[g] = (int32_t*)c->peer_ready[g] + c->D.seg_begin_all[g][sg];
-                P.tails[g] = (int32_t*)c->peer_counters[g] + (size_t)sg * 128 + 32;
-            }
     };
     CU(cudaEventRecord(c->ev0, c->stream));
     if (nt > 0) {
@@ -817,7 +800,6 @@ static int factor_launch(soglu_ctx* c) {
         } else if (c->opt_exec_mode == 0) {
             const int nseg = (int)G.seg_begin.size() - 1;
             CU(cudaMemcpyAsync(c->dep.p, c->dep0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
-            CU(cudaMemcpyAsync(c->ready.p, c->ready0.p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, c->stream));
             CU(cudaMemcpyAsync(c->counters.p, c->counters0.p, c->counters0.bytes, cudaMemcpyDeviceToDevice, c->stream));
             P.signal = 1;
             // one persistent launch per segment (a single one unless the pool forces slot recycling)
@@ -835,7 +817,7 @@ static int factor_launch(soglu_ctx* c) {
                 CU(cudaMemsetAsync(c->counters.p, 0, 512, c->stream));
                 int32_t* cnt = c->counters.as<int32_t>();
                 P.ready = c->ready.as<int32_t>();
-                P.head = cnt; P.tail = cnt + 32;
+                P.head = cnt;
                 P.n_tasks = (int32_t)(e - b);
                 P.signal = 0;
                 CU(launch_executor(P, (int)std::min<int64_t>(grid, e - b), c->stream));
@@ -1254,7 +1236,7 @@ static int group_factor(soglu_ctx* grp, soglu_stats* out) {
     if (!M[0]->peers_ready)
         for (soglu_ctx* m : M) {
             for (size_t g = 0; g < M.size(); g++) {
-                m->peer_pool[g] = M[g]->pool.p; m->peer_dep[g] = M[g]->dep.p; m->peer_ready[g] = M[g]->ready.p; m->peer_counters[g] = M[g]->counters.p; m->peer_sv[g] = M[g]->sv.p;
+                m->peer_pool[g] = M[g]->pool.p; m->peer_dep[g] = M[g]->dep.p; m->peer_counters[g] = M[g]->counters.p; m->peer_sv[g] = M[g]->sv.p;
             }
             m->peers_ready = true;
         }

@@ -875,17 +875,13 @@ struct Compiler {
 
     // ==== successor references, initially ready tasks, block ids -> block references ==========================
     std::string finish() {
-    // successor references; a group with exactly one predecessor task (unsplit) carries the "sole predecessor" bit
+    // successor references (single-GPU upload)
     G.succ_enc.resize(G.succ.size());
 #pragma omp parallel for schedule(static)
     for (int64_t t = 0; t < (int64_t)G.tasks.size(); t++) {
         const Task& T = G.tasks[t];
         if (!task_is_leader(T)) continue;              // the slices of one task share their leader's list
-        const bool single = task_group_size(T) == 1;
-        for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
-            const Task& S = G.tasks[G.succ[e]];
-            G.succ_enc[e] = make_task_ref(0, single && S.n_deps == 1, task_log2_slices(S), G.succ[e]);
-        }
+        for (int32_t e = T.succ_begin; e < T.succ_end; e++) G.succ_enc[e] = make_task_ref(0, task_log2_slices(G.tasks[G.succ[e]]), G.succ[e]);
     }
     if ((int64_t)G.tasks.size() > TASK_LOCAL_MASK) return "too many tasks";
 
@@ -991,7 +987,7 @@ std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& D) {
                 shared_begin = (int32_t)D.succ.size();
                 for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
                     const int32_t s2 = G.succ[e];
-                    D.succ.push_back(make_task_ref(G.task_owner[s2], (G.succ_enc[e] & TASK_SOLE_BIT) != 0, task_log2_slices(G.tasks[s2]), D.task_local[s2]));
+                    D.succ.push_back(make_task_ref(G.task_owner[s2], task_log2_slices(G.tasks[s2]), D.task_local[s2]));
                 }
                 shared_end = (int32_t)D.succ.size();
             }

@@ -4,11 +4,13 @@
 //
 // One CTA per SM stays resident for a whole segment of the factorisation (one segment unless the block
 // pool is smaller than the number of blocks and slots are recycled between launches):
-//   warp 0      scheduler + TMA producer: claims the next slot of its ready queue (atomicAdd on the
-//               head), spins with ld.acquire until a finishing CTA publishes a task there, reads the
-//               64-byte task record and streams the operand blocks into a 3-stage shared-memory ring
-//               with cp.async.bulk (34 816 B per block, mbarrier complete_tx).  It runs ahead of the
-//               math warps, so the loads of task N+1 overlap the MMAs and the write-back of task N.
+//   warp 0      scheduler + TMA producer: claims the next task of the segment IN TASK ORDER (atomicAdd on a
+//               counter; the task compiler has sorted the tasks most-urgent-first, Compiler::static_order), reads
+//               its 64-byte record, spins with ld.acquire on the task group's dependency counter until it is zero
+//               and streams the operand blocks into a 3-stage shared-memory ring with cp.async.bulk (34 816 B per
+//               block, mbarrier complete_tx).  It runs ahead of the math warps, so the loads of task N+1 overlap
+//               the MMAs and the write-back of task N -- and in the latency-bound phases a CTA already holds the
+//               record of the task it is waiting for when the last predecessor finishes.
 //   warps 1..8  math: m8n8k4 FP64 tensor-core MMAs (DMMA) for the Schur updates
 //               C = init +/- sum_p A_p*B_p, the whole accumulation chain of one target block (or of
 //               a 16- / 32-row slice of it in narrow levels) kept in registers and written once;
@@ -17,22 +19,26 @@
 //               standalone triangular inverses, subtract.
 //   warp 9      signal: the math warps hand a finished task over (mbarrier, 8 arrivals) and go straight on to
 //               the next task's MMAs; this warp makes the result visible (one fence) and walks the successor
-//               list: one atomicSub on the successor group's dependency counter per lane; the lane that brings
-//               it to zero publishes the whole group (a task, or the 2 / 4 row slices of a split GEMM task,
-//               which share their leader's counter) at the tail of the ready queue.  (With the release on the
-//               math warps, 2-3 us of fence + atomic round trips per task kept the tensor cores idle.)
+//               list: one fire-and-forget red.add(-1) on the successor group's dependency counter per lane (a task,
+//               or the 2 / 4 row slices of a split GEMM task, which share their leader's counter).  Nobody waits for
+//               an atomic's return value and there is no queue to append to.
 //
-// Memory-ordering protocol: writer CTA: st.global data -> bar.sync -> fence.acq_rel.gpu -> atomicSub(dep)
-// [-> fence.acq_rel.gpu -> atomicAdd(tail) -> st.relaxed(ready)]; reader CTA: ld.acquire(ready) -> fence.proxy.async ->
-// cp.async.bulk of the data.  (acq_rel fences, not __threadfence(): that one is MEMBAR.SC + an L1 invalidate.)  A
-// successor whose only predecessor is the finishing task skips the counter: fence -> atomicAdd(tail) -> st.relaxed.
-// Successors on the same GPU use gpu scope; successors on a peer GPU (multi-GPU run: counters, queues and block pools
-// of the peers are mapped through CUDA IPC) use system-scope fences and atomics over NVLink.
+// Why a static order cannot deadlock: the order is topological, so the lowest unfinished task of a run has all its
+// predecessors finished; every lower task of its GPU is finished too, so it has been claimed (claims go in order) and
+// its scheduler sees the counter reach zero.  On several GPUs every GPU's order is a filter of ONE global order and
+// the argument holds for the globally lowest unfinished task.  (Cooperative launch: all CTAs are co-resident.)
 //
-// Watchdog: a claim-then-wait queue under a cooperative launch hangs for good if a signal is lost (a peer that died,
+// Memory-ordering protocol: writer CTA: st.global data -> mbarrier hand-over to the signal warp -> fence.acq_rel.gpu ->
+// red.relaxed.gpu.add(dep, -1); reader CTA: ld.acquire.gpu(dep) == 0 (the reds of all predecessors form one RMW chain on
+// the counter, so the acquire synchronises with every predecessor's fence) -> fence.proxy.async -> cp.async.bulk of the
+// data.  (acq_rel fences, not __threadfence(): that one is MEMBAR.SC + an L1 invalidate.)  Successors on the same GPU
+// use gpu scope; successors on a peer GPU (multi-GPU run: counters and block pools of the peers are mapped through
+// CUDA IPC or peer access) use a system-scope fence and red over NVLink, and the readers poll with ld.acquire.sys.
+//
+// Watchdog: a claim-then-wait executor under a cooperative launch hangs for good if a signal is lost (a peer that died,
 // a graph with a missing edge).  Every scheduler lane therefore checks, once per 1024 polls, the abort word of its
 // GPU and %globaltimer against the launch's deadline; on a timeout it raises the abort word (on every GPU of the
-// run) with the queue slot it was stuck at, all CTAs drain and soglu_factor returns SOGLU_ERR_CUDA.
+// run) with the task position it was stuck at, all CTAs drain and soglu_factor returns SOGLU_ERR_CUDA.
 #include "executor.cuh"
 #include "ptx.cuh"
 #include "lu_blocked.cuh"
@@ -205,33 +211,79 @@ __device__ __forceinline__ void tri_inv_task(const double* __restrict__ Tm, doub
     }
 }
 
-// ---- Schur update: acc += A(rows) * B(64x64) from shared memory, FP64 tensor cores ------------
-// A warp owns MT x NT DMMA tiles (8x8 each) starting at (row_base, col_base); 16 k-steps of 4.
+// ---- Schur update: out = init -/+ sum_p A_p(rows) * B_p(64x64) from shared memory, FP64 tensor cores ------------
+// A warp owns MT x NT DMMA tiles (8x8 each) starting at (row_base, col_base); 16 k-steps of 4 per operand stage.
 // Whole block (64 rows): 8 warps x (4 x 2 tiles); half (32 rows): 8 x (2 x 2); quarter: 8 x (2 x 1).
+// The warp runs ALL operand stages of the task in one software pipeline: the fragments of k-step k+1 are loaded while
+// the MMAs of step k issue, and on the last step of a stage the next stage's full barrier is awaited and its first
+// fragments are fetched under the last 8 MMAs -- the tensor pipe does not drain at stage boundaries (all 8 warps reach
+// them together: ~450 cycles per pair were lost there).  On the task's last stage the warp's tile of the initial value
+// (fused sub) is requested from global memory before the stage's MMAs, so its L2 latency runs under them; then
+// out = init -/+ acc with 16-byte stores straight from the accumulators.  `it` = ring position of the task's first
+// stage on entry, of its last stage on return.
 template <bool TRANSB, int MT, int NT>
-__device__ __forceinline__ void mma_block(const double* __restrict__ As, const double* __restrict__ Bs, double (&acc)[4][2][2],
-                                          int row_base, int col_base, int lane) {
+__device__ __forceinline__ void gemm_task(SmemCtl* ctl, double* stage_base, uint32_t& it, int32_t first_last, int32_t flags, int row_base, int col_base,
+                                          int lane, double* __restrict__ out, const double* __restrict__ ini) {
     const int g = lane >> 2, t = lane & 3;
-    const double* a0 = As + (row_base + g) * BLK_LD + t;
-    const double* b0 = TRANSB ? Bs + (col_base + g) * BLK_LD + t : Bs + t * BLK_LD + col_base + g;
+    double acc[MT][NT][2];
 #pragma unroll
-    for (int k0 = 0; k0 < BLK; k0 += 4) {
-        double a[MT], b[NT];
+    for (int mi = 0; mi < MT; mi++)
 #pragma unroll
-        for (int mi = 0; mi < MT; mi++) a[mi] = a0[mi * 8 * BLK_LD + k0];
+        for (int ni = 0; ni < NT; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const int a_off = (row_base + g) * BLK_LD + t;
+    const int b_off = TRANSB ? BLK_ELEMS + (col_base + g) * BLK_LD + t : BLK_ELEMS + t * BLK_LD + col_base + g;
+    auto frag = [&](const double* S, int k0, double (&a)[MT], double (&b)[NT]) {
 #pragma unroll
-        for (int ni = 0; ni < NT; ni++) b[ni] = TRANSB ? b0[ni * 8 * BLK_LD + k0] : b0[k0 * BLK_LD + ni * 8];
+        for (int mi = 0; mi < MT; mi++) a[mi] = S[a_off + mi * 8 * BLK_LD + k0];
 #pragma unroll
-        for (int mi = 0; mi < MT; mi++)
+        for (int ni = 0; ni < NT; ni++) b[ni] = TRANSB ? S[b_off + ni * 8 * BLK_LD + k0] : S[b_off + k0 * BLK_LD + ni * 8];
+    };
+    int s = it % N_STAGES;
+    const double* S = stage_base + (size_t)s * (STAGE_BYTES / 8);
+    double a[MT], b[NT];
+    frag(S, 0, a, b);
+    bool last = first_last & 2;
+    double2 c0[MT][NT];
 #pragma unroll
-            for (int ni = 0; ni < NT; ni++) ptx::dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NT; ni++) c0[mi][ni] = make_double2(0.0, 0.0);
+    while (true) {
+        if (last && (flags & TF_INIT)) {
+#pragma unroll
+            for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+                for (int ni = 0; ni < NT; ni++) c0[mi][ni] = ptx::ld_cg_f64x2(ini + (row_base + 8 * mi + g) * BLK_LD + col_base + 8 * ni + 2 * t);
+        }
+        const int s_cur = s;
+        const bool last_cur = last;
+#pragma unroll
+        for (int k0 = 0; k0 < BLK; k0 += 4) {
+            double ac[MT], bc[NT];
+#pragma unroll
+            for (int mi = 0; mi < MT; mi++) ac[mi] = a[mi];
+#pragma unroll
+            for (int ni = 0; ni < NT; ni++) bc[ni] = b[ni];
+            if (k0 + 4 < BLK) {
+                frag(S, k0 + 4, a, b);
+            } else if (!last_cur) {
+                it++;
+                s = it % N_STAGES;
+                ptx::mbar_wait(&ctl->full[s], (it / N_STAGES) & 1);
+                last = ctl->desc[s].first_last & 2;
+                S = stage_base + (size_t)s * (STAGE_BYTES / 8);
+                frag(S, 0, a, b);
+            }
+#pragma unroll
+            for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+                for (int ni = 0; ni < NT; ni++) ptx::dmma884(acc[mi][ni][0], acc[mi][ni][1], ac[mi], bc[ni]);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ctl->empty[s_cur]);
+        if (last_cur) break;
     }
-}
-
-template <int MT, int NT>
-__device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const double* __restrict__ ini, const double (&acc)[4][2][2],
-                                              int row_base, int col_base, int lane, bool neg, bool has_init) {
-    const int g = lane >> 2, t = lane & 3;
+    const bool neg = flags & TF_NEGATE;
 #pragma unroll
     for (int mi = 0; mi < MT; mi++)
 #pragma unroll
@@ -239,10 +291,7 @@ __device__ __forceinline__ void gemm_epilogue(double* __restrict__ out, const do
             const int off = (row_base + 8 * mi + g) * BLK_LD + col_base + 8 * ni + 2 * t;
             double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
             if (neg) { v.x = -v.x; v.y = -v.y; }
-            if (has_init) {
-                const double2 c0 = ptx::ld_cg_f64x2(ini + off);
-                v.x += c0.x; v.y += c0.y;
-            }
+            v.x += c0[mi][ni].x; v.y += c0[mi][ni].y;
             *reinterpret_cast<double2*>(out + off) = v;
         }
 }
@@ -325,11 +374,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
                 ctl->desc[s].type = T_EXIT;
                 ptx::mbar_arrive(&ctl->full[s]);
             };
-            // Claim the next slot and wait for its task.  Static order (the product path): slot s IS the s-th task of the
-            // segment; the scheduler fetches its record and spins on the group's dependency counter, which the finishing
-            // predecessors count down with fire-and-forget reductions -- a release costs them one fence and one red, no
-            // atomic round trip and no queue tail.  Dynamic queue (debug executor, one launch per level): the slot holds
-            // a task index.
+            // Claim the next position and wait for its task.  Product path: position s IS the s-th task of the segment;
+            // the scheduler fetches its record and spins on the group's dependency counter, which the finishing
+            // predecessors count down with fire-and-forget reductions.  Debug executor (one launch per dependency
+            // level, nothing to wait for): position s of the launch's task list.
             const unsigned long long deadline = P.watchdog_ns ? gtime() + P.watchdog_ns : 0;
             bool aborted = false;
             while (!aborted) {
@@ -353,12 +401,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
                     }
                     if (P.trace) P.trace[6 * (size_t)t + 0] = gtime();
                 } else {
-                    while (true) {
-                        t = ptx::ld_acquire(P.ready + slot);
-                        if (t >= 0) break;
-                        if ((++polls & 1023u) == 0 && watchdog_expired(P, slot, deadline)) { aborted = true; break; }
-                    }
-                    if (!aborted) T = P.tasks[t];
+                    t = P.ready[slot];
+                    T = P.tasks[t];
                 }
                 if (!aborted) issue(t, T);
             }
@@ -410,7 +454,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
     const int ct = threadIdx.x - 32;         // 0..255
     double* lub_scr = reinterpret_cast<double*>(ctl + 1);
     lub::lu_setup(lub_scr, ct);              // pivot barriers of the diagonal-block kernel, once per launch
-    double acc[4][2][2];
     uint32_t sig_it = 0;
     for (uint32_t it = 0;; it++) {
         const int s = it % N_STAGES;
@@ -420,37 +463,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
         double* As = stage_base + (size_t)s * (STAGE_BYTES / 8);
         double* Bs = As + BLK_ELEMS;
 
-        if (P.trace && (d.first_last & 1) && ct == 0) P.trace[6 * (size_t)d.task + 2] = gtime();
+        if (P.trace && ct == 0) P.trace[6 * (size_t)d.task + 2] = gtime();
         if (d.type == T_GEMM) {
-            if (d.first_last & 1) {
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            }
+            // all operand stages of the task in one go (`it` moves on to the task's last stage)
             const int nrows16 = (d.flags >> TF_NROWS_SHIFT) & 7, row0 = ((d.flags >> TF_ROW0_SHIFT) & 3) * 16;
-            const bool tb = d.flags & TF_TRANSB;
-            int rb, cb;
-            if (nrows16 == 4) {
-                rb = 32 * (mw >> 2); cb = 16 * (mw & 3);
-                if (tb) mma_block<true, 4, 2>(As, Bs, acc, rb, cb, lane); else mma_block<false, 4, 2>(As, Bs, acc, rb, cb, lane);
-            } else if (nrows16 == 2) {
-                rb = row0 + 16 * (mw >> 2); cb = 16 * (mw & 3);
-                if (tb) mma_block<true, 2, 2>(As, Bs, acc, rb, cb, lane); else mma_block<false, 2, 2>(As, Bs, acc, rb, cb, lane);
-            } else {
-                rb = row0; cb = 8 * mw;
-                if (tb) mma_block<true, 2, 1>(As, Bs, acc, rb, cb, lane); else mma_block<false, 2, 1>(As, Bs, acc, rb, cb, lane);
-            }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ctl->empty[s]);
-            if (!(d.first_last & 2)) continue;
-            // epilogue: out = init -/+ acc, 16-byte stores straight from the accumulators
             double* out = blk_ptr(P, d.out);
             const double* ini = blk_ptr(P, d.init);
-            const bool neg = d.flags & TF_NEGATE, has_init = d.flags & TF_INIT;
-            if (nrows16 == 4) gemm_epilogue<4, 2>(out, ini, acc, rb, cb, lane, neg, has_init);
-            else if (nrows16 == 2) gemm_epilogue<2, 2>(out, ini, acc, rb, cb, lane, neg, has_init);
-            else gemm_epilogue<2, 1>(out, ini, acc, rb, cb, lane, neg, has_init);
+            if (d.flags & TF_TRANSB) {
+                if (nrows16 == 4) gemm_task<true, 4, 2>(ctl, stage_base, it, d.first_last, d.flags, 32 * (mw >> 2), 16 * (mw & 3), lane, out, ini);
+                else if (nrows16 == 2) gemm_task<true, 2, 2>(ctl, stage_base, it, d.first_last, d.flags, row0 + 16 * (mw >> 2), 16 * (mw & 3), lane, out, ini);
+                else gemm_task<true, 2, 1>(ctl, stage_base, it, d.first_last, d.flags, row0, 8 * mw, lane, out, ini);
+            } else {
+                if (nrows16 == 4) gemm_task<false, 4, 2>(ctl, stage_base, it, d.first_last, d.flags, 32 * (mw >> 2), 16 * (mw & 3), lane, out, ini);
+                else if (nrows16 == 2) gemm_task<false, 2, 2>(ctl, stage_base, it, d.first_last, d.flags, row0 + 16 * (mw >> 2), 16 * (mw & 3), lane, out, ini);
+                else gemm_task<false, 2, 1>(ctl, stage_base, it, d.first_last, d.flags, row0, 8 * mw, lane, out, ini);
+            }
             // no CTA barrier: each warp hands its part over and goes on to the next task
             if (P.trace && ct == 0) P.trace[6 * (size_t)d.task + 3] = gtime();
             hand_over(ctl, sig_it++, d.task, mw, lane);
@@ -590,7 +617,7 @@ cudaError_t launch_executor(const ExecParams& p, int grid, cudaStream_t stream) 
     ExecParams pp = p;
     void* args[] = {&pp};
     // cooperative launch: the runtime guarantees that all CTAs are co-resident, which the
-    // claim-then-wait ready queue relies on
+    // claim-then-wait executor relies on
     return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(N_THREADS), args, smem, stream);
 }
 

@@ -12,20 +12,19 @@ struct ExecParams {
     // the owner in their top 3 bits (tasks.h make_ref).  Single GPU: world = 1, index 0 only.
     double* pools[MAX_GPUS];
     int32_t* deps[MAX_GPUS];
-    int32_t* readys[MAX_GPUS];     // ready queue slice of this launch on every GPU
-    int32_t* tails[MAX_GPUS];
     int32_t world, rank;
     double* pool;          // this GPU's block pool, slot s at pool + s*BLK_ELEMS
     const Task* tasks;
     const Pair* pairs;
-    const int32_t* succ;   // task references: owner | sole-predecessor bit | log2(slices) | local id (tasks.h)
+    const int32_t* succ;   // task references: owner | log2(slices) | local id (tasks.h)
     int32_t* dep;          // live dependency counters (reset before every run)
-    int32_t* ready;        // ready queue of this launch (FIFO), -1 = not yet published
-    int32_t* head;         // next queue slot to claim
-    int32_t* tail;         // next queue slot to publish
-    int32_t n_tasks;       // queue length for this launch
-    int32_t task0;         // first task of the segment this launch executes (queue slot s = task task0 + s)
-    int32_t signal;        // 1: propagate completions to successors (persistent DAG mode)
+    int32_t* head;         // next position to claim
+    int32_t n_tasks;       // tasks of this launch
+    int32_t task0;         // signal = 1: first task of the segment this launch executes (position s = task task0 + s)
+    int32_t signal;        // 1: the product path -- tasks are claimed in task order, wait on their dependency counters and
+                           //    count their successors' counters down; 0: debug executor (one launch per dependency
+                           //    level, no counters): position s = task ready[s]
+    const int32_t* ready;  // signal = 0: the task list of this launch
     int32_t* abort;        // watchdog word of this GPU {flag, queue slot, CTA, rank}; aborts[g] = the peers' (multi-GPU);
                            // abort[8] counts diagonal blocks whose U U^-1 fails the reference's inv_check_diag
     int32_t* aborts[MAX_GPUS];

@@ -27,15 +27,12 @@ constexpr int32_t REF_MASK = (1 << REF_SHIFT) - 1;
 constexpr int MAX_GPUS = 8;
 inline int32_t make_ref(int owner, int32_t local) { return (int32_t)(((uint32_t)owner << REF_SHIFT) | (uint32_t)local); }
 // Task references in successor lists name a task GROUP (a task, or the 2 / 4 consecutive row slices of a
-// split GEMM task, which share the dependency counter of their first slice): owner | "sole predecessor" |
-// log2(group size) | local index of the first slice.  A group whose ONLY predecessor is the referring task (one
-// predecessor task, unsplit) is ready the moment that task has finished: the releasing thread publishes it without
-// touching its dependency counter (one fence and one atomic round trip less on that hop, e.g. Schur update -> lu).
-constexpr int32_t TASK_SOLE_BIT = 1 << 28;
+// split GEMM task, which share the dependency counter of their first slice): owner | log2(group size) | local
+// index of the first slice.
 constexpr int TASK_SPLIT_SHIFT = 26;                       // 2 bits: log2(slices)
 constexpr int32_t TASK_LOCAL_MASK = (1 << TASK_SPLIT_SHIFT) - 1;
-inline int32_t make_task_ref(int owner, bool sole, int log2_slices, int32_t local) {
-    return make_ref(owner, local) | (sole ? TASK_SOLE_BIT : 0) | (log2_slices << TASK_SPLIT_SHIFT);
+inline int32_t make_task_ref(int owner, int log2_slices, int32_t local) {
+    return make_ref(owner, local) | (log2_slices << TASK_SPLIT_SHIFT);
 }
 
 enum TaskType : int32_t {
@@ -144,7 +141,7 @@ struct DistLayout {     // one GPU's share of an owner-compiled TaskGraph
     BigVec<int32_t> succ;
     std::vector<int32_t> initial;        // local task ids, grouped by segment
     std::vector<int32_t> seg_begin, seg_init;            // as in TaskGraph, for this GPU's tasks
-    std::vector<std::vector<int32_t>> seg_begin_all;     // [owner][segment] first local task (peers' queue slices)
+    std::vector<std::vector<int32_t>> seg_begin_all;     // [owner][segment] first local task (part of the layout hash the ranks compare)
     int64_t remote_edges = 0, remote_operands = 0, mirrored = 0;
 };
 std::string localize_tasks(const TaskGraph& G, int rank, DistLayout& out);

@@ -319,7 +319,6 @@ extern "C" int soglu_debug_simulate(const soglu_problem* pp, int split, int pr, 
                     for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
                         const int32_t ref = D[r].succ[e];
                         const int o = (uint32_t)ref >> soglu::REF_SHIFT, nx = ref & soglu::TASK_LOCAL_MASK;
-                        if ((ref & soglu::TASK_SOLE_BIT) && dep[o][nx] != 1) bad++;
                         if (--dep[o][nx] < 0) bad++;
                     }
                     done++;
@@ -350,8 +349,6 @@ extern "C" int soglu_debug_simulate(const soglu_problem* pp, int split, int pr, 
         for (int32_t e = T.succ_begin; e < T.succ_end; e++) {
             const int32_t ref = D[r].succ[e];
             const int o = (uint32_t)ref >> soglu::REF_SHIFT, nx = ref & soglu::TASK_LOCAL_MASK, g = 1 << ((ref >> soglu::TASK_SPLIT_SHIFT) & 3);
-            // a "sole predecessor" reference publishes without touching the counter (executor.cu): it must be the last one
-            if (ref & soglu::TASK_SOLE_BIT) { if (dep[o][nx] != 1) bad++; dep[o][nx] = 1; }
             if (--dep[o][nx] == 0)
                 for (int q = 0; q < g; q++) ready.push_back({(int8_t)o, nx + q});
         }

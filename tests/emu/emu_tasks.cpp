@@ -133,8 +133,6 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
                 ran++;
                 for (int32_t e = G.tasks[t].succ_begin; e < G.tasks[t].succ_end; e++) {
                     const int32_t nx = G.succ[e];
-                    // "sole predecessor" references publish without the counter in the executor: it must stand at 1
-                    if ((G.succ_enc[e] & soglu::TASK_SOLE_BIT) && dep[nx] != 1) { std::fprintf(stderr, "sole-predecessor bit on a task with %d open dependencies\n", dep[nx]); return 3; }
                     if (--dep[nx] == 0)
                         for (int q = 0, g = task_group_size(G.tasks[nx]); q < g; q++) ready.push_back(nx + q);
                 }

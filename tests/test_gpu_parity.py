@@ -561,7 +561,7 @@ def test_watchdog_aborts_and_recovers(sg, tmp_path):
     ctx.set_option("debug_drop_task", 1000)
     with pytest.raises(sg.SogluError) as e:
         ctx.factor()
-    assert "watchdog" in str(e.value) and "ready-queue slot" in str(e.value)
+    assert "watchdog" in str(e.value) and "task (position" in str(e.value)
     ctx.set_option("debug_drop_task", -1)
     ctx.set_option("watchdog_ms", 60000)
     ctx.factor()

@@ -11,7 +11,6 @@ import soglu_b200 as sg
 
 VARIANTS = [
     ("default", {}),
-    ("static_order=0 (op-list order)", {"static_order": 0}),
 ]
 
 kind, dims = sys.argv[1], [int(a) for a in sys.argv[2:]]

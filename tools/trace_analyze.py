@@ -35,7 +35,7 @@ def main():
     pub = np.where(tr[:, 0] == 0, 0.0, pub)
     total = sig.max()
     print("traced factor: %.3f ms device (events %.3f ms), %d tasks, %d levels" % (total * 1e-3, fs["seconds"] * 1e3, nt, info[:, 2].max() + 1))
-    print("%-9s %8s %7s | %8s %8s %8s %8s  (us, mean)" % ("type", "count", "pairs", "q-wait", "load", "compute", "signal"))
+    print("%-9s %8s %7s | %8s %8s %8s %8s  (us, mean)" % ("type", "count", "pairs", "seen->go", "load", "compute", "signal"))
     for ty, nm in TYPES.items():
         m = info[:, 0] == ty
         if not m.any(): continue
@@ -46,6 +46,9 @@ def main():
     order = np.argsort(succ, kind="stable")
     preds = src_of[order]
     cnt = np.bincount(succ, minlength=nt); pred_ptr[1:] = np.cumsum(cnt)
+    late = np.argsort(-sig)[:5]
+    print("last tasks to finish: " + "; ".join("#%d %s level %d deps %d preds %d sig %.1f us" % (c, TYPES[info[c, 0]], info[c, 2], info[c, 3], pred_ptr[c + 1] - pred_ptr[c], sig[c]) for c in late))
+    print("tasks without stamps: seen %d, issued %d, loaded %d, computed %d, signalled %d" % tuple(int((tr[:, k] == 0).sum()) for k in range(5)))
     cur = int(np.argmax(sig)); chain = []
     while True:
         chain.append(cur)
@@ -69,7 +72,8 @@ def main():
         print("  chain GEMM tasks by pairs: " + ", ".join("%s: %d" % (lab, int(((gl >= lo) & (gl < hi)).sum())) for lab, lo, hi in (("1", 1, 2), ("2-3", 2, 4), ("4-7", 4, 8), ("8-15", 8, 16), ("16-31", 16, 32), ("32+", 32, 10 ** 9))))
         print("  compute time of the chain's GEMM tasks by pairs (ms): " + ", ".join("%s: %.2f" % (lab, sum((cmp_[c] - lod[c]) for c in chain if info[c, 0] == 0 and lo <= info[c, 1] < hi) * 1e-3) for lab, lo, hi in (("1", 1, 2), ("2-3", 2, 4), ("4-7", 4, 8), ("8-15", 8, 16), ("16-31", 16, 32), ("32+", 32, 10 ** 9))))
     n = max(1, len(chain))
-    print("  means along the chain (us): release (signal end -> publication of the successor) %.2f, queue wait %.2f, descriptor + operand load %.2f, signal phase %.2f"
+    # (static order: column 0 of the trace = the moment the waiting scheduler saw the task's counter at zero)
+    print("  means along the chain (us): detection (predecessor's reds issued -> successor's scheduler sees zero) %.2f, seen -> issue %.2f, operand load %.2f, signal phase %.2f"
           % (cat["publish-gap"] / n, cat["q-wait"] / n, cat["load"] / n, cat["signal"] / n))
     # SM utilisation: busy = sum over tasks of (sig - lod) / (n_sm * total)
     busy = (sig - lod).sum()
