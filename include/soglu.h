@@ -130,18 +130,21 @@ int soglu_get_block(soglu_ctx* ctx, int32_t id, double* out_64x64);
  *   "max_slots"       cap of the block pool in blocks (forces slot recycling / several executor launches)
  *   "split" "split_slack" "fuse_sub" "fuse_inv"   compiler transformations (row slices of GEMM tasks in narrow levels /
  *                     within split_slack us of the critical path, default 100; folding of sub / inverse operations)
+ *   "static_order" "order_alpha"   the executor claims tasks in task order; 1 (default) = the compiler sorts them by
+ *                     order_alpha % latest start + (100 - order_alpha) % earliest start time under its cost model
+ *                     (default 50), 0 = they stay in the order of the operation list
  *   "dist_nb" "mirror_min"   multi-GPU: side of the ownership squares in blocks (16), reads that justify a local mirror
  *   "grid"            number of CTAs of the executor (0 = one per SM)
  *   "watchdog_ms"     a kernel whose waiters see no progress for this long aborts; the call returns SOGLU_ERR_CUDA with
- *                     the queue slot / block row that never arrived (default 60000, 0 = off); may be set at any time
+ *                     the task / block row that never arrived (default 60000, 0 = off); may be set at any time
  *   "trace"           record per-task timestamps (tools/trace_analyze.py, bench.py --trace) */
 int soglu_set_option(soglu_ctx* ctx, const char* key, int64_t value);
 
 /* ---------------- A2. multi-GPU: one process per GPU, 2D block-cyclic block ownership -------
  * Block (brow, bcol) lives on GPU ((brow / 16) mod grid_rows) * grid_cols + ((bcol / 16) mod grid_cols); an
  * operation runs where its result lives and pulls remote operands over NVLink (peer memory
- * mapped through CUDA IPC); dependency counters and ready queues of peers are updated with
- * system-scope atomics.  The reference has no multi-device path; this extends
+ * mapped through CUDA IPC); dependency counters of peers are counted down with
+ * system-scope reductions.  The reference has no multi-device path; this extends
  * BlockPlanner::calculate (BlockPlanner.cpp:376-651).  Call order on EVERY rank:
  *   soglu_create_dist -> soglu_set_blocks / soglu_set_graph (with block_row / block_col) /
  *   soglu_set_factors (the same full problem on every rank) -> soglu_dist_export ->

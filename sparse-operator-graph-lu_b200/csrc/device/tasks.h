@@ -119,6 +119,7 @@ struct CompileOptions {
     int split_narrow = 1;   // split GEMM tasks of narrow dependency levels by output rows (latency-bound phases)
     int n_sms = 148;        // width against which a level counts as narrow
     double split_slack_us = 0;   // > 0: GEMM tasks with less estimated slack than this are split 4-way in wide levels too
+    double order_alpha = 0.5;    // static order key = alpha * latest start + (1 - alpha) * earliest start
     bool static_order = true;    // tasks sorted by latest start time: the executor claims them in task order (see Compiler::static_order)
     int64_t max_slots = 0;  // block-pool capacity in slots PER GPU (0 = unlimited: no recycling)
     // multi-GPU: owner GPU of every block id (nullptr: everything on GPU 0).  Blocks a GPU reads at
