@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", action="store_true", help="after the timed region: one traced factorisation, per-rank SM utilisation over time on stderr (diagnostics)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
-                    help="executor option passed to soglu_set_option before the first factorisation (chain_cuts, split_slack, dist_nb, ...); recorded in config.options")
+                    help="executor option passed to soglu_set_option before the first factorisation (split_slack, order_alpha, dist_nb, ...); recorded in config.options")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
@@ -508,7 +508,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][2], "name": args.workload, "n": prob.size("dim"), "ops": prob.size("n_ops"),
                        "tasks": int(first["tasks"]), "pool_blocks": int(first["pool_blocks"]),
-                       "parallelism": "1 GPU" if world == 1 else "one factorisation sharded over %d GPUs: 2D block-cyclic (%dx%d grid, 16x16-block squares), owner computes, NVLink peer pulls; solve sharded by block-row owner" % ((world,) + sg.default_grid(world)),
+                       "parallelism": "1 GPU" if world == 1 else "one factorisation sharded over %d GPUs: 2D block-cyclic (%dx%d grid; ownership squares of 4x4 blocks when work-bound, 16x16 when chain-bound), owner computes, NVLink peer pulls; solve sharded by block-row owner" % ((world,) + sg.default_grid(world)),
                        "segments": n_segments,   # executor launches per factorisation (pool recycling)
                        "l2": "inputs_exceed_l2 (block pool %.1f GB >> 126 MB L2)" % (first["pool_blocks"] * 34816 * 1e-9),
                        "factor_ms": t_factor * 1e3, "solve_ms": t_solve * 1e3, "factor_gflops": flops / t_factor * 1e-9,

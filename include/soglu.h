@@ -133,7 +133,8 @@ int soglu_get_block(soglu_ctx* ctx, int32_t id, double* out_64x64);
  *   "static_order" "order_alpha"   the executor claims tasks in task order; 1 (default) = the compiler sorts them by
  *                     order_alpha % latest start + (100 - order_alpha) % earliest start time under its cost model
  *                     (default 50), 0 = they stay in the order of the operation list
- *   "dist_nb" "mirror_min"   multi-GPU: side of the ownership squares in blocks (16), reads that justify a local mirror
+ *   "dist_nb" "mirror_min"   multi-GPU: side of the ownership squares in blocks (0 = automatic: 4 for
+ *                     work-bound runs, 16 when the dependency chain bounds the run), reads that justify a local mirror
  *   "grid"            number of CTAs of the executor (0 = one per SM)
  *   "watchdog_ms"     a kernel whose waiters see no progress for this long aborts; the call returns SOGLU_ERR_CUDA with
  *                     the task / block row that never arrived (default 60000, 0 = off); may be set at any time
@@ -141,7 +142,7 @@ int soglu_get_block(soglu_ctx* ctx, int32_t id, double* out_64x64);
 int soglu_set_option(soglu_ctx* ctx, const char* key, int64_t value);
 
 /* ---------------- A2. multi-GPU: one process per GPU, 2D block-cyclic block ownership -------
- * Block (brow, bcol) lives on GPU ((brow / 16) mod grid_rows) * grid_cols + ((bcol / 16) mod grid_cols); an
+ * Block (brow, bcol) lives on GPU ((brow / nb) mod grid_rows) * grid_cols + ((bcol / nb) mod grid_cols), nb = option dist_nb; an
  * operation runs where its result lives and pulls remote operands over NVLink (peer memory
  * mapped through CUDA IPC); dependency counters of peers are counted down with
  * system-scope reductions.  The reference has no multi-device path; this extends

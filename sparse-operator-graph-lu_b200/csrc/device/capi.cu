@@ -56,7 +56,10 @@ struct soglu_ctx {
     int64_t opt_fuse_inv = 1;
     int64_t opt_split_slack = 100; // GEMM tasks within this slack (us) of the longest chain are row-split in wide levels too (measured -5..6 % on the
                                    // latency-bound configs, profiles/r02_call1_options.md); 0 = narrow levels only
-    int64_t opt_dist_nb = 16;      // multi-GPU ownership granularity (blocks): 16 x 16 squares measured best at 100^3 / 4 GPUs
+    int64_t opt_dist_nb = 0;       // multi-GPU ownership granularity (blocks); 0 = chosen in finalize(): 4 x 4 squares when the run is
+                                   // work-bound (finer squares balance the moving band: 100^3 on 2 GPUs, nb 16 / 8 / 4 / 2 = 1478 / 1377 /
+                                   // 1325 / 1322 ms), 16 x 16 when the dependency chain bounds it (every square boundary on the chain
+                                   // costs remote hops: 64^3 on 2 GPUs, nb 1 / 4 / 16 / 64 = 204 / 164 / 156 / 165 ms)
     int64_t opt_mirror_min = 1;    // mirror a remote block locally when it is read at least this often
     int64_t opt_split = 1;
     int64_t opt_static_order = 1;  // 1: tasks sorted most-urgent-first (latest start time); 0: in the order of the operation list
@@ -93,6 +96,7 @@ struct soglu_ctx {
     BigVec<uint8_t> op;
     std::vector<int32_t> L_ids, L_brow, L_bcol, U_ids, U_brow, U_bcol;
     int32_t n_block_rows = 0;
+    int dist_nb_used = 0;          // side of the ownership squares this context was compiled with
     int symmetric = 0;
     bool have_blocks = false, have_graph = false, have_factors = false;
 
@@ -303,7 +307,17 @@ int finalize(soglu_ctx* c) {
     if (c->dist) {
         // 2D block-cyclic ownership over nb x nb squares of blocks (coordinates from soglu_set_graph)
         if (c->brow.empty()) return fail(SOGLU_ERR_ARG, "multi-GPU context: soglu_set_graph needs block_row / block_col");
-        const int nb = (int)std::max<int64_t>(1, c->opt_dist_nb);
+        int nb = (int)c->opt_dist_nb;
+        if (nb <= 0) {
+            // work per GPU at the measured GEMM rate against the dependency chain (one diagonal block after the other,
+            // ~36 us per block row on one GPU): the same numbers on every rank
+            int64_t products = 0;
+            for (int64_t k = 0; k < c->n_ops; k++) products += (c->op[k] == 8 || c->op[k] == 9 || c->op[k] == 11);     // mul, mulneg, mult (soglu.h op codes)
+            const double t_work = (double)products * 2.0 * BLK * BLK * BLK / 33e12 / c->world;
+            const double t_chain = (double)c->n_block_rows * 36e-6;
+            nb = t_work > 1.3 * t_chain ? 4 : 16;
+        }
+        c->dist_nb_used = nb;
         owners.assign(c->n_ids, 0);
         for (int64_t id = 1; id < c->n_ids; id++)
             if (c->brow[id] >= 0 && c->bcol[id] >= 0) owners[id] = (int8_t)(((c->brow[id] / nb) % c->pr) * c->pc + ((c->bcol[id] / nb) % c->pc));

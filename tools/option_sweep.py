@@ -9,9 +9,11 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_mtx
 import soglu_b200 as sg
 
-VARIANTS = [
-    ("default", {}),
-]
+NGPU = int(os.environ.get("SWEEP_GPUS", "1"))          # > 1: the in-process group of soglu_create
+VARIANTS = [("default", {})]
+for spec in os.environ.get("SWEEP_VARIANTS", "").split(";"):      # e.g. "order_alpha=30;dist_nb=8,mirror_min=2"
+    if spec:
+        VARIANTS.append((spec, {kv.split("=")[0]: int(kv.split("=")[1]) for kv in spec.split(",")}))
 
 kind, dims = sys.argv[1], [int(a) for a in sys.argv[2:]]
 n, r, c, v = gen_mtx.generate(kind, *dims)
@@ -20,7 +22,7 @@ p = sg.Problem.from_coo(n, r, c, v, gen_mtx.rhs(n))
 print("%s %s: n=%d ops=%d planned in %.1f s" % (kind, dims, n, p.size("n_ops"), time.time() - t), flush=True)
 x0 = None
 for name, opts in VARIANTS:
-    ctx = sg.Context(0)
+    ctx = sg.Context(0) if NGPU == 1 else sg.Context(n_gpus=NGPU)
     for k, val in opts.items():
         ctx.set_option(k, val)
     t = time.time()
