@@ -4,9 +4,10 @@
   python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload lap3d_64]
 
 One "step" = one numeric factorisation (soglu_factor: the whole operation DAG, one persistent
-kernel) + one forward/back solve WITH one step of iterative refinement on the device (soglu_solve_refined,
-refine = 1: the raw residual of the 100^3 solve, 1.9e-12, misses the north-star gate of 1e-12; the refined
-one, 1.6e-13, meets it -- so the refinement is inside the timed region and `accuracy` reports both) of the same
+kernel) + one forward/back solve WITH iterative refinement on the device (soglu_solve_refined; as many steps as
+the north-star residual gate of 1e-12 needs on the workload, decided before the timed region: 1 at 100^3, where the
+raw solve's 1.9e-12 misses the gate and the refined 1.4e-13 meets it, 2 on the 9-point stencil -- so the refinement is
+inside the timed region and `accuracy` reports both) of the same
 planned problem.  The op list is
 planned once on the host (bit-exact reproduction of the reference planner; not timed, like the
 reference's own "plan time").  Input blocks are resident in HBM when the timed region starts;
@@ -376,13 +377,30 @@ def main():
         factor = ctx.factor
     first = factor()                           # includes the one-time task-graph compilation + upload
     t_first = time.perf_counter() - t0
-    x, _ = ctx.solve(prob, refine=1)           # collective in a sharded run: every GPU solves its block rows; rank 0 holds x
-    barrier()
+    # Refinement steps of the timed solve: as many as the north-star residual gate (1e-12) needs on this workload, at most 3
+    # -- decided here, before anything is timed (100^3, 64^3, banded: 1; the 9-point stencil: 2 on one GPU; the sharded
+    # solve supports one step).  Collective in a sharded run: every GPU solves its block rows, rank 0 holds x and tells
+    # the others.
+    refine = 1
+    A_chk, b_chk = workload_matrix(args.workload) if rank == 0 else (None, None)
+    while True:
+        x, _ = ctx.solve(prob, refine=refine)
+        barrier()
+        enough = 1
+        if rank == 0:
+            enough = int(residual_rel(A_chk, b_chk, x) <= 1e-12 or refine >= (1 if use_dist else 3))     # (a sharded solve refines at most once)
+        if use_dist:
+            flag = torch.tensor([enough], device="cuda")
+            dist.broadcast(flag, 0)
+            enough = int(flag.item())
+        if enough:
+            break
+        refine += 1
 
     # ---- device-resident steps ---------------------------------------------------------------
     def step():
         fs = factor()
-        _, ss = ctx.solve(prob, refine=1)       # every rank (sharded solve); refinement residual on rank 0
+        _, ss = ctx.solve(prob, refine=refine)  # every rank (sharded solve); refinement residual on rank 0
         if use_dist:
             barrier()                           # no rank may refill its solve vectors while a peer still publishes into them
         return fs, ss
@@ -423,7 +441,7 @@ def main():
     def e2e_step():
         ctx.set_blocks_sparse(prob.size("storage"), ids, ent_in_np, ent_pos_np, vals_np)   # H2D: matrix entries (every rank: it keeps its share)
         factor()
-        rc = L.soglu_solve_refined(ctx.h, b_np.ctypes.data_as(ctypes.c_void_p), x_np.ctypes.data_as(ctypes.c_void_p), 1, ctypes.byref(st))  # H2D b (every rank), D2H x (rank 0)
+        rc = L.soglu_solve_refined(ctx.h, b_np.ctypes.data_as(ctypes.c_void_p), x_np.ctypes.data_as(ctypes.c_void_p), refine, ctypes.byref(st))  # H2D b (every rank), D2H x (rank 0)
         assert rc == 0, L.soglu_last_error()
         if use_dist:
             barrier()
@@ -486,9 +504,10 @@ def main():
         # accuracy of the solution the timed step produces (refine = 1), next to the raw solve and -- when the reference
         # ran on this workload on this box -- to the reference's own x
         import hashlib
-        A, bb = workload_matrix(args.workload)
+        A, bb = A_chk, b_chk
         accuracy = {"residual_rel": residual_rel(A, bb, x), "residual_rel_raw_solve": residual_rel(A, bb, x_raw), "nan": int(np.isnan(x).sum()),
-                    "timed_solution": "solve + 1 step of iterative refinement on the device (FP64 residual of the original matrix + re-solve); residual_rel is that x",
+                    "refine_steps": refine,
+                    "timed_solution": "solve + %d step(s) of iterative refinement on the device (FP64 residual of the original matrix + re-solve), as many as the 1e-12 gate needs on this workload (decided before the timed region); residual_rel is that x" % refine,
                     "note": "||Ax-b||/||b||, north-star gate 1e-12"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
