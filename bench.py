@@ -6,7 +6,7 @@
 One "step" = one numeric factorisation (soglu_factor: the whole operation DAG, one persistent
 kernel) + one forward/back solve WITH iterative refinement on the device (soglu_solve_refined; as many steps as
 the north-star residual gate of 1e-12 needs on the workload, decided before the timed region: 1 at 100^3, where the
-raw solve's 1.9e-12 misses the gate and the refined 1.4e-13 meets it, 2 on the 9-point stencil -- so the refinement is
+raw solve's 1.9e-12 misses the gate and the refined 1.4e-13 meets it -- so the refinement is
 inside the timed region and `accuracy` reports both) of the same
 planned problem.  The op list is
 planned once on the host (bit-exact reproduction of the reference planner; not timed, like the
@@ -378,8 +378,8 @@ def main():
     first = factor()                           # includes the one-time task-graph compilation + upload
     t_first = time.perf_counter() - t0
     # Refinement steps of the timed solve: as many as the north-star residual gate (1e-12) needs on this workload, at most 3
-    # -- decided here, before anything is timed (100^3, 64^3, banded: 1; the 9-point stencil: 2 on one GPU; the sharded
-    # solve supports one step).  Collective in a sharded run: every GPU solves its block rows, rank 0 holds x and tells
+    # -- decided here, before anything is timed (100^3, 64^3, banded: 1 step meets it; the 9-point stencil sits at its FP64 floor
+    # of 8.9e-12 whatever the number of steps and keeps 1; the sharded solve supports one step).  Collective in a sharded run: every GPU solves its block rows, rank 0 holds x and tells
     # the others.
     refine = 1
     A_chk, b_chk = workload_matrix(args.workload) if rank == 0 else (None, None)
@@ -396,6 +396,11 @@ def main():
         if enough:
             break
         refine += 1
+    if not use_dist and refine > 1 and residual_rel(A_chk, b_chk, x) > 1e-12:
+        # more steps do not help: the residual sits at the FP64 floor of this system (9-point stencil 1024^2: 8.9e-12 after 1, 2
+        # and 3 steps) -- keep the single step
+        refine = 1
+        x, _ = ctx.solve(prob, refine=1)
 
     # ---- device-resident steps ---------------------------------------------------------------
     def step():
@@ -509,6 +514,7 @@ def main():
                     "refine_steps": refine,
                     "timed_solution": "solve + %d step(s) of iterative refinement on the device (FP64 residual of the original matrix + re-solve), as many as the 1e-12 gate needs on this workload (decided before the timed region); residual_rel is that x" % refine,
                     "note": "||Ax-b||/||b||, north-star gate 1e-12"}
+        accuracy["gate_met"] = bool(accuracy["residual_rel"] <= 1e-12)
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             t_cpu, cflops, ckind, ccores, csample, _, x_ref, cname = cpu_reference(sg, args, tmp, use_cache=True)
