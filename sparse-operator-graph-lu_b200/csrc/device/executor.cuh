@@ -30,7 +30,7 @@ struct ExecParams {
     int32_t* aborts[MAX_GPUS];
     unsigned long long watchdog_ns;   // a scheduler lane that has waited this long since the launch gives up (0 = never)
     int32_t debug_drop;    // test hook for the watchdog: the completion of this task is NOT propagated (-1 = none)
-    unsigned long long* trace;   // optional: 6 x u64 per task (published, claimed, loaded, computed, signalled, smid)
+    unsigned long long* trace;   // optional: 6 x u64 per task (counter seen at zero, issued, loaded = first math, computed, signalled, smid)
 };
 
 // persistent dependency-counted executor; grid = resident CTAs (1 per SM)
