@@ -73,7 +73,7 @@ void inv_upper(const double* u, double* y) {     // U Y = I
 }  // namespace
 
 // split: bit 0 = row slices in narrow levels, bit 1 = also near-critical tasks (split_slack), bit 2 = 8 SMs, bit 3 = no static (latest-start) order.
-// mode: unused (0).  max_slots > 0 forces slot recycling.  keep_out: n_keep dense 64x64 blocks.  stats = {tasks, segments, slots, chain cuts applied, row-split tasks}.
+// mode: 0 = default order key, m > 0 = order_alpha (m - 1) %.  max_slots > 0 forces slot recycling.  keep_out: n_keep dense 64x64 blocks.  stats = {tasks, segments, slots, chain cuts applied, row-split tasks}.
 // grid = {pr, pc, nb} with brow / bcol per block id: the graph is compiled for pr*pc owners (2D block-cyclic squares of
 // nb blocks, mirrors of remote blocks filled by fetch tasks) and every owner gets its own pool here.
 extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids, const double* input_dense, int64_t n_ops, const int32_t* src,
@@ -98,7 +98,8 @@ extern "C" int emu_run(int64_t n_ids, int64_t n_input, const int32_t* input_ids,
         co.owner_of_id = owners.data();
         co.n_owners = world;
     }
-    (void)mode; (void)cut_max_slack_us;     // (kept in the signature: the chain-cut compile mode they selected was measured and removed)
+    if (mode > 0) co.order_alpha = (mode - 1) / 100.0;
+    (void)cut_max_slack_us;     // (kept in the signature: the chain-cut compile mode it belonged to was measured and removed)
     std::string err = compile_tasks(n_ids, n_input, input_ids, n_ops, src, src2, op, result, result2, keep, co, G);
     if (!err.empty()) return fail(err);
     // one pool per owner; slot 0 of each stays its zero block

@@ -121,6 +121,10 @@ def test_static_order_is_a_valid_schedule(sg, emu, oracle, tmp_path, name, grid,
     assert st["tasks"] == st2["tasks"]
     np.testing.assert_array_equal(b_static, b_oplist)
     check_against_oracle(oracle, p, keep, b_static)
+    # the two ends of the order key (option order_alpha): earliest start only, latest start only
+    for alpha in (0, 100):
+        _, b, _ = run_emu(emu, p, mode=alpha + 1, seed=0, grid=grid, max_slots=max_slots)
+        np.testing.assert_array_equal(b, b_static)
 
 
 @pytest.mark.parametrize("grid,max_slots", [((2, 1, 2), 0), ((2, 2, 1), 0), ((4, 2, 4), 0), ((2, 2, 2), 0), ((2, 1, 4), 4000), ((2, 2, 2), 2500)])
