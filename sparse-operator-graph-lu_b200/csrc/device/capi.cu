@@ -108,7 +108,7 @@ struct soglu_ctx {
     std::vector<int32_t> level_order;   // tasks sorted by level (debug executor)
     std::vector<int64_t> level_ptr;
     DevBuf pool, tasks, pairs, succ, dep0, dep, ready, counters, counters0;
-    // watchdog word {flag, queue slot / block row, CTA, rank}: the 64 bytes behind the queue counters (one allocation,
+    // watchdog word {flag, task position / block row, CTA, rank}: the 64 bytes behind the claim counters (one allocation,
     // so the peers reach it through the IPC mapping of the counters)
     int32_t* abort_word() const { return counters.as<int32_t>() + counters0.bytes / 4; }
     int64_t opt_max_slots = 0;     // debug: cap the block pool (forces segments + slot recycling)
@@ -477,7 +477,7 @@ int soglu_create_dist(soglu_ctx** out, int device, int rank, int world, int grid
 
 int64_t soglu_dist_blob_bytes(void) { return (int64_t)sizeof(DistBlob); }
 
-// compile + allocate this GPU's share, then write the IPC handles of its pool / counters / queue
+// compile + allocate this GPU's share, then write the IPC handles of its pool / counters / solve vectors
 int soglu_dist_export(soglu_ctx* c, void* blob) {
     try {
     if (c && !c->members.empty()) return fail(SOGLU_ERR_ARG, "in-process multi-GPU context (soglu_create with n_gpus > 1): peers are wired by the library, the soglu_dist_* protocol is for one process per GPU");
@@ -536,7 +536,7 @@ int soglu_dist_import(soglu_ctx* c, const void* all_blobs) {
     }
 }
 
-// reset this GPU's dependency counters and ready queue; the caller must put a barrier across all
+// reset this GPU's dependency counters and claim counters; the caller must put a barrier across all
 // ranks between soglu_dist_reset and soglu_factor, and another one after soglu_factor
 int soglu_dist_reset(soglu_ctx* c) {
     if (c && !c->members.empty()) return fail(SOGLU_ERR_ARG, "in-process multi-GPU context (soglu_create with n_gpus > 1): peers are wired by the library, the soglu_dist_* protocol is for one process per GPU");
@@ -792,7 +792,7 @@ static int factor_launch(soglu_ctx* c) {
         if (!c->dist || c->dist_segment == 0) CU(cudaMemsetAsync(c->trace.p, 0, (size_t)nt * 6 * sizeof(unsigned long long), c->stream));   // (all segments of one factorisation)
         P.trace = c->trace.as<unsigned long long>();
     }
-    // queue pointers of one segment (this GPU and, sharded, the peers' queues of the same segment)
+    // claim counter and task range of one segment
     auto set_segment = [&](int sg) {
         const std::vector<int32_t>& sb = c->dist ? c->D.seg_begin : G.seg_begin;
         int32_t* cnt = c->counters.as<int32_t>() + (size_t)sg * 128;
@@ -804,7 +804,7 @@ static int factor_launch(soglu_ctx* c) {
     CU(cudaEventRecord(c->ev0, c->stream));
     if (nt > 0) {
         if (c->dist) {
-            // counters / queues were reset by soglu_dist_reset (all ranks, then a barrier) -- a late
+            // the counters were reset by soglu_dist_reset (all ranks, then a barrier) -- a late
             // reset here could wipe a signal a faster peer has already delivered
             const int nseg = (int)c->D.seg_begin.size() - 1;
             const int sg = c->dist_segment;

@@ -308,7 +308,7 @@ __device__ __forceinline__ void hand_over(SmemCtl* ctl, uint32_t sig_it, int tas
 }
 
 // scheduler lane, once per 1024 polls: has somebody aborted the run, or has the deadline passed?  On a timeout the
-// abort word {1, queue slot, CTA, rank} is raised on every GPU of the run.
+// abort word {1, task position, CTA, rank} is raised on every GPU of the run.
 __device__ __noinline__ bool watchdog_expired(const ExecParams& P, int slot, unsigned long long deadline) {
     if (*reinterpret_cast<volatile int32_t*>(P.abort) != 0) return true;
     if (deadline == 0 || gtime() < deadline) return false;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) executor_kernel(const __grid_con
                     if (two) ptx::bulk_g2s(As + BLK_ELEMS, blk_ptr(P, pr.b), BLK_BYTES, &ctl->full[s]);
                 }
             };
-            // tell the math warps to leave once every queue this CTA serves is exhausted
+            // tell the math warps to leave once the segment's tasks are all claimed
             auto quit = [&]() {
                 const int s = it % N_STAGES;
                 ptx::mbar_wait(&ctl->empty[s], ((it / N_STAGES) & 1) ^ 1);

@@ -25,7 +25,7 @@ struct ExecParams {
                            //    count their successors' counters down; 0: debug executor (one launch per dependency
                            //    level, no counters): position s = task ready[s]
     const int32_t* ready;  // signal = 0: the task list of this launch
-    int32_t* abort;        // watchdog word of this GPU {flag, queue slot, CTA, rank}; aborts[g] = the peers' (multi-GPU);
+    int32_t* abort;        // watchdog word of this GPU {flag, task position, CTA, rank}; aborts[g] = the peers' (multi-GPU);
                            // abort[8] counts diagonal blocks whose U U^-1 fails the reference's inv_check_diag
     int32_t* aborts[MAX_GPUS];
     unsigned long long watchdog_ns;   // a scheduler lane that has waited this long since the launch gives up (0 = never)

@@ -62,27 +62,14 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// strong relaxed stores: after ONE fence of the matching scope they complete a release pattern (fence + strong
-// write), so a thread that publishes several queue entries pays for one fence instead of one per st.release
-__device__ __forceinline__ void st_relaxed(int* p, int v) {
-    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_sys(int* p, int v) {
-    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// fire-and-forget counter updates (no return value: the issuing thread does not wait for the L2 round trip); after a
-// fence of the matching scope they complete a release pattern like the strong stores above
+// fire-and-forget counter updates (no return value: the issuing thread does not wait for the L2 round trip); after ONE
+// fence of the matching scope they complete a release pattern (fence + strong write), so a thread that releases
+// several successors pays for one fence
 __device__ __forceinline__ void red_add(int* p, int v) {
     asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_add_sys(int* p, int v) {
     asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ double2 ld_cg_f64x2(const double* p) {
     double2 v;
