@@ -1,5 +1,8 @@
 // Cost model of one task hop (microseconds), used by the task compiler's slack estimates (row split of near-critical
-// GEMM tasks, chain analysis).  Durations measured with the executor's trace option and tools/diag_bench.py on a B200.
+// GEMM tasks) and by the static execution order (earliest / latest start times).  Durations measured with the executor's
+// trace option and tools/diag_bench.py on a B200 -- on the executor with the dynamic ready queue; the static-order executor's
+// hops are cheaper (signal 1.9 us, detection 0.8 us, first operands 1.6 us: profiles/r02_static_order.md), but split_slack and
+// order_alpha were tuned by measurement WITH these constants, so they stay until both are re-measured together.
 #pragma once
 #include "tasks.h"
 
